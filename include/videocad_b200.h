@@ -1,0 +1,118 @@
+/* videocad_b200 -- C ABI of the B200-native (sm_100a) VideoCAD behaviour-cloning hot path.
+ *
+ * Drop-in boundary: the object returned by the reference's ModelFactory.create_model
+ * (/root/reference/model/model_factory.py:15-36) whose forward is
+ * AutoRegressiveTransformer.forward (/root/reference/model/autoregressive_transformer.py:121-220).
+ * The reference is pure Python/PyTorch and has no FFI of its own; the binding a maintainer adds is the
+ * ctypes stub shown in INTEGRATION.md (videocad_b200/lib.py is that stub).
+ *
+ * Rules of this ABI
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers on the current CUDA device unless
+ *     stated otherwise; `stream` is a cudaStream_t passed as void*;
+ *   - no function allocates device memory or synchronises the host; outputs/workspaces are caller-allocated;
+ *   - every function returns 0 on success, non-zero on error (message via vc_last_error());
+ *   - matrices are row-major with explicit leading dimensions in ELEMENTS;
+ *   - "split" operands are pairs of bf16 arrays (hi, lo) with x ~= hi + lo, hi = bf16_rn(x),
+ *     lo = bf16_rn(x - hi); bf16 values are passed as uint16_t bit patterns.
+ */
+#ifndef VIDEOCAD_B200_H_
+#define VIDEOCAD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t vc_bf16;
+
+enum { VC_ACT_NONE = 0, VC_ACT_GELU = 1, VC_ACT_RELU = 2, VC_ACT_TANH = 3 };
+enum { VC_MASK_NONE = 0, VC_MASK_CAUSAL = 1, VC_MASK_WINDOW = 2 };
+
+/* one dropout call site: keep-mask is a pure function of (seed, site, element index); p == 0 disables */
+typedef struct vc_drop {
+  float p;
+  uint32_t site;
+  uint64_t seed;
+} vc_drop;
+
+/* Tensor-core GEMM  acc[m,n] = sum_k A[m,k] * B[n,k]  with fused epilogue.
+ * Replaces every nn.Linear GEMM (and its dgrad/wgrad) on the path; see csrc/gemm_tc.cu.
+ *   A: a_mn_major == 0 -> stored [M,K] (lda >= K);  == 1 -> stored [K,M] (lda >= M)
+ *   B: b_mn_major == 0 -> stored [N,K] (ldb >= K);  == 1 -> stored [K,N] (ldb >= N)
+ *   passes: 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = hi*hi (bf16-grade)
+ * epilogue order: +bias[n], +rowadd[(m/rowadd_div)%rowadd_mod, n], store preact, act, dropout, +residual,
+ *   store out_f32 (atomicAdd when splitk > 1) and/or split (out_hi, out_lo). */
+typedef struct vc_gemm_desc {
+  const vc_bf16 *a_hi, *a_lo; int64_t lda; int a_mn_major;
+  const vc_bf16 *b_hi, *b_lo; int64_t ldb; int b_mn_major;
+  int M, N, K, passes, splitk;
+  const float* bias;
+  const float* rowadd; int64_t ld_rowadd; int rowadd_div, rowadd_mod;
+  float* preact; int64_t ld_preact;
+  int act;
+  vc_drop drop;
+  const float* residual; int64_t ld_res;
+  float* out_f32; int64_t ldo;
+  vc_bf16 *out_hi, *out_lo; int64_t ldo_split;
+} vc_gemm_desc;
+
+/* Multi-head attention core (replaces the bmm/softmax/dropout/bmm chain of vit_pytorch Attention and of
+ * F.multi_head_attention_forward).  Rows are (b*T + t); head h owns columns [h*d, (h+1)*d). */
+typedef struct vc_attn_desc {
+  const float *q, *k, *v; int64_t ldq, ldk, ldv;
+  int B, Tq, Tk, nh, d;
+  int mask, window;
+  float scale;
+  vc_drop drop;
+} vc_attn_desc;
+
+const char* vc_last_error(void);
+int vc_version(void);
+/* 1 if this library was built from the CUDA sources (product), 0 for the CPU emulation used by host-logic tests */
+int vc_is_cuda_build(void);
+
+/* ---- per-kernel entry points (unit parity tests call these; the model-level calls below chain them) ---- */
+void vc_gemm_desc_init(vc_gemm_desc* d);
+int vc_gemm(const vc_gemm_desc* d, void* stream);
+int vc_split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, vc_bf16* hi, vc_bf16* lo, int64_t ldo, void* stream);
+int vc_layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                     float* y, int64_t ldy, vc_bf16* y_hi, vc_bf16* y_lo, int64_t ldy_split, float* mean, float* rstd,
+                     void* stream);
+int vc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                     const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                     float* dgamma, float* dbeta, void* stream);
+int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
+                           vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream);
+int vc_patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
+                                  float* dgamma, float* dbeta, void* stream);
+int vc_vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, const float* pos, vc_drop drop, float* x,
+                        void* stream);
+int vc_vit_assemble_bwd(const float* dx, int F, int N, int C, vc_drop drop, float* de, float* dcls, float* dpos,
+                        void* stream);
+int vc_attention_fwd(const vc_attn_desc* a, vc_bf16* o_hi, vc_bf16* o_lo, int64_t ldo, float* lse, void* stream);
+int vc_attention_bwd(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
+                     const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                     int64_t lddv, void* stream);
+int vc_act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,
+                       const vc_bf16* aux_hi, int64_t ldaux_hi, vc_drop drop, float* g, int64_t ldg, vc_bf16* g_hi,
+                       vc_bf16* g_lo, int64_t ldg_split, float* colsum, void* stream);
+int vc_row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, void* stream);
+int vc_broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, float* dst, int64_t ldd, vc_bf16* d_hi,
+                      vc_bf16* d_lo, int64_t ldd_split, void* stream);
+int vc_embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E,
+                        int T, float* y, vc_bf16* y_hi, vc_bf16* y_lo, void* stream);
+int vc_embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW,
+                        float* db, float* dE, void* stream);
+int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream);
+int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
+                      int accumulate_dx, float* dW, float* db, void* stream);
+int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+int vc_zero_f32(float* x, int64_t n, void* stream);
+int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDEOCAD_B200_H_ */

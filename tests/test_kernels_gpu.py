@@ -1,0 +1,264 @@
+"""Unit parity tests of every CUDA kernel, through the C ABI, against plain torch (fp64 where it matters).
+
+Run on the B200 box: python -m pytest tests -m gpu
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from videocad_b200 import lib as L  # noqa: E402
+import kwrap as K  # noqa: E402
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+def _relerr(a, b):
+    return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30)).item()
+
+
+def test_library_is_cuda_build():
+    lib = L.load()
+    assert lib.vc_is_cuda_build() == 1
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 8), (300, 512), (1000, 1024)])
+def test_split_bit_exact(rows, cols):
+    x = _rand(rows, cols, seed=1) * 3.0
+    hi, lo = L.split(x)
+    rhi, rlo = K.ref_split(x)
+    assert torch.equal(hi.view(torch.int16), rhi.view(torch.int16))
+    assert torch.equal(lo.view(torch.int16), rlo.view(torch.int16))
+    assert ((hi.float() + lo.float()) - x).abs().max() <= x.abs().max() * 2.0 ** -16
+
+
+GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (300, 136, 200), (50, 8, 512), (1000, 3072, 512), (14400, 512, 1024)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    if (a_mn and M % 8) or (b_mn and N % 8):
+        pytest.skip("MN-major operand needs a 16-byte aligned leading dimension")
+    A = _rand(M, K, seed=2)
+    B = _rand(N, K, seed=3)
+    a_st = A.t().contiguous() if a_mn else A
+    b_st = B.t().contiguous() if b_mn else B
+    out = torch.full((M, N), float("nan"), device="cuda")
+    L.gemm(L.split(a_st), L.split(b_st), M, N, K, a_mn=a_mn, b_mn=b_mn, out_f32=out)
+    ref = A.double() @ B.double().t()
+    err = _relerr(out, ref)
+    assert err < 3e-5, f"gemm M{M} N{N} K{K} a_mn={a_mn} b_mn={b_mn}: rel err {err:.3e}"
+
+
+def test_gemm_single_pass_is_bf16_grade():
+    M, N, K = 512, 256, 512
+    A, B = _rand(M, K, seed=4), _rand(N, K, seed=5)
+    out = torch.empty(M, N, device="cuda")
+    L.gemm(L.split(A), L.split(B), M, N, K, passes=1, out_f32=out)
+    ref_bf = A.to(torch.bfloat16).double() @ B.to(torch.bfloat16).double().t()
+    assert _relerr(out, ref_bf) < 1e-5
+    ref = A.double() @ B.double().t()
+    assert 1e-4 < _relerr(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
+def test_gemm_epilogue(act):
+    M, N, K, T = 520, 264, 192, 8
+    A, B = _rand(M, K, seed=6, scale=0.5), _rand(N, K, seed=7, scale=0.2)
+    bias, rowadd, res = _rand(N, seed=8), _rand(T, N, seed=9), _rand(M, N, seed=10)
+    drop = L.make_drop(0.1, 17, 1234)
+    pre = torch.empty(M, N, device="cuda")
+    out = torch.empty(M, N, device="cuda")
+    outs = K.bf16_pair((M, N))
+    L.gemm(L.split(A), L.split(B), M, N, K, bias=bias, rowadd=rowadd, rowadd_div=1, rowadd_mod=T, preact=pre, act=act,
+           drop=drop, residual=res, out_f32=out, out_split=outs)
+    mask = K.dropout_mask(drop, M * N).reshape(M, N)
+    rows = torch.arange(M, device="cuda") % T
+    z = A.double() @ B.double().t() + bias.double() + rowadd.double()[rows]
+    f = {L.ACT_NONE: lambda t: t, L.ACT_GELU: lambda t: torch.nn.functional.gelu(t), L.ACT_RELU: torch.relu,
+         L.ACT_TANH: torch.tanh}[act]
+    ref = f(z) * mask.double() + res.double()
+    assert _relerr(pre, z) < 3e-5
+    assert _relerr(out, ref) < 3e-5
+    assert (K.join(outs) - out).abs().max() <= out.abs().max() * 2.0 ** -15
+    keep = (mask > 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01
+
+
+def test_gemm_rowadd_div():
+    M, N, K, T = 64, 128, 64, 8
+    A, B = _rand(M, K, seed=11), _rand(N, K, seed=12)
+    rowadd = _rand(M // T, N, seed=13)
+    out = torch.empty(M, N, device="cuda")
+    L.gemm(L.split(A), L.split(B), M, N, K, rowadd=rowadd, rowadd_div=T, rowadd_mod=M // T, out_f32=out)
+    ref = A.double() @ B.double().t() + rowadd.double().repeat_interleave(T, dim=0)
+    assert _relerr(out, ref) < 3e-5
+
+
+@pytest.mark.parametrize("splitk", [2, 4, 16])
+def test_gemm_splitk_wgrad_shape(splitk):
+    # wgrad: dW[N,K] = dY^T[N,M] X[M,K] -> both operands MN-major, contraction over the 3000 rows
+    rows, Nw, Kw = 3000, 512, 1024
+    dY, X = _rand(rows, Nw, seed=14), _rand(rows, Kw, seed=15)
+    bias = _rand(Kw, seed=16)
+    out = torch.zeros(Nw, Kw, device="cuda")
+    L.gemm(L.split(dY), L.split(X), Nw, Kw, rows, a_mn=True, b_mn=True, splitk=splitk, bias=bias, out_f32=out)
+    ref = dY.double().t() @ X.double() + bias.double()
+    assert _relerr(out, ref) < 3e-5
+
+
+def test_gemm_strided_outputs_and_views():
+    # output written into the left half of a wider buffer; B operand is a row-slice of a packed weight
+    M, H = 256, 256
+    A = _rand(M, 512, seed=17)
+    Wfull = _rand(3 * H, 512, seed=18)
+    wide = torch.zeros(M, 2 * H, device="cuda")
+    wide_s = (torch.zeros(M, 2 * H, dtype=torch.bfloat16, device="cuda"), torch.zeros(M, 2 * H, dtype=torch.bfloat16, device="cuda"))
+    whi, wlo = L.split(Wfull)
+    L.gemm(L.split(A), (whi[H:2 * H], wlo[H:2 * H]), M, H, 512, out_f32=wide, out_split=wide_s)
+    ref = A.double() @ Wfull[H:2 * H].double().t()
+    assert _relerr(wide[:, :H], ref) < 3e-5
+    assert wide[:, H:].abs().max() == 0
+    assert (K.join(wide_s)[:, :H] - wide[:, :H]).abs().max() <= wide.abs().max() * 2.0 ** -15
+
+
+@pytest.mark.parametrize("rows,C", [(5, 256), (1000, 512), (333, 1024)])
+def test_layernorm_fwd_bwd(rows, C):
+    x = _rand(rows, C, seed=20) * 2 + 0.3
+    gamma, beta = 1 + 0.1 * _rand(C, seed=21), 0.1 * _rand(C, seed=22)
+    y, ys, mean, rstd = K.layernorm_fwd(x, gamma, beta)
+    xd = x.double().requires_grad_(True)
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (C,), gd, bd, 1e-5)
+    assert (y.double() - ref).abs().max() < 2e-5
+    assert (K.join(ys) - y).abs().max() <= y.abs().max() * 2.0 ** -15
+    dy, dres = _rand(rows, C, seed=23), _rand(rows, C, seed=24)
+    ref.backward(dy.double())
+    dx, dg, db = K.layernorm_bwd(dy, x, mean, rstd, gamma, dres)
+    assert (dx.double() - (xd.grad + dres.double())).abs().max() < 5e-5
+    assert _relerr(dg, gd.grad) < 2e-5
+    assert _relerr(db, bd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("F,S", [(3, 64), (5, 224)])
+def test_patch_layernorm(F, S):
+    img = _rand(F, 1, S, S, seed=30).clamp(-1, 1)
+    gamma, beta = 1 + 0.1 * _rand(1024, seed=31), 0.1 * _rand(1024, seed=32)
+    ys, mean, rstd = K.patch_layernorm_fwd(img, gamma, beta)
+    h = S // 32
+    patches = img.reshape(F, 1, h, 32, h, 32).permute(0, 2, 4, 3, 5, 1).reshape(F * h * h, 1024)
+    pd = patches.double()
+    gd, bd = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(pd, (1024,), gd, bd, 1e-5)
+    assert (K.join(ys).double() - ref).abs().max() < 1e-4
+    dy = _rand(F * h * h, 1024, seed=33)
+    ref.backward(dy.double())
+    dg, db = K.patch_layernorm_bwd_params(img, mean, rstd, dy)
+    assert _relerr(dg, gd.grad) < 2e-5
+    assert _relerr(db, bd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_vit_assemble(p):
+    F, N, C = 9, 49, 512
+    e, cls, pos = _rand(F * N, C, seed=40), _rand(C, seed=41), _rand(N + 1, C, seed=42)
+    drop = L.make_drop(p, 3, 99)
+    x = K.vit_assemble_fwd(e, F, N, C, cls, pos, drop)
+    mask = K.dropout_mask(drop, F * (N + 1) * C).reshape(F, N + 1, C) if p > 0 else torch.ones(F, N + 1, C, device="cuda")
+    ref = torch.cat([cls.expand(F, 1, C), e.reshape(F, N, C)], 1) + pos
+    ref = ref * mask
+    assert (x.reshape(F, N + 1, C) - ref).abs().max() < 1e-6
+    dx = _rand(F * (N + 1), C, seed=43)
+    de, dcls, dpos = K.vit_assemble_bwd(dx, F, N, C, drop)
+    g = dx.reshape(F, N + 1, C) * mask
+    assert (de.reshape(F, N, C) - g[:, 1:]).abs().max() < 1e-6
+    assert (dpos - g.sum(0)).abs().max() < 1e-4
+    assert (dcls - g[:, 0].sum(0)).abs().max() < 1e-4
+
+
+def _attn_ref(q, k, v, B, Tq, Tk, nh, d, mask, window, pmask=None):
+    qh = q.reshape(B, Tq, nh, d).permute(0, 2, 1, 3)
+    kh = k.reshape(B, Tk, nh, d).permute(0, 2, 1, 3)
+    vh = v.reshape(B, Tk, nh, d).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(d)
+    if mask != L.MASK_NONE:
+        i = torch.arange(Tq, device=q.device)[:, None]
+        j = torch.arange(Tk, device=q.device)[None, :]
+        bad = j > i
+        if mask == L.MASK_WINDOW:
+            bad = bad | (j <= i - window)
+        s = s.masked_fill(bad, float("-inf"))
+    p = torch.softmax(s, -1)
+    if pmask is not None:
+        p = p * pmask
+    o = (p @ vh).permute(0, 2, 1, 3).reshape(B * Tq, nh * d)
+    return o, torch.logsumexp(s, -1)
+
+
+ATTN_CASES = [
+    # B, T, nh, d, mask, window, p
+    (6, 50, 16, 64, L.MASK_NONE, 1, 0.0),
+    (6, 50, 16, 64, L.MASK_NONE, 1, 0.1),
+    (3, 5, 16, 64, L.MASK_NONE, 1, 0.0),
+    (4, 8, 4, 128, L.MASK_CAUSAL, 1, 0.0),
+    (4, 8, 4, 128, L.MASK_WINDOW, 3, 0.1),
+    (2, 186, 4, 256, L.MASK_CAUSAL, 1, 0.0),
+    (2, 186, 4, 256, L.MASK_WINDOW, 10, 0.1),
+    (2, 100, 4, 64, L.MASK_WINDOW, 1, 0.0),
+    (2, 33, 4, 64, L.MASK_CAUSAL, 1, 0.1),
+]
+
+
+@pytest.mark.parametrize("B,T,nh,d,mask,window,p", ATTN_CASES)
+def test_attention_fwd_bwd(B, T, nh, d, mask, window, p):
+    H = nh * d
+    qkv = _rand(B * T, 3 * H, seed=50, scale=1.0)
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    drop = L.make_drop(p, 5, 77)
+    a = K.attn_desc(q, k, v, B, T, T, nh, d, mask=mask, window=window, drop=drop)
+    o, lse = K.attention_fwd(a, B, T, nh, d)
+    pmask = K.dropout_mask(drop, B * nh * T * T).reshape(B, nh, T, T).double() if p > 0 else None
+    qd = q.double().contiguous().requires_grad_(True)
+    kd = k.double().contiguous().requires_grad_(True)
+    vd = v.double().contiguous().requires_grad_(True)
+    ref, ref_lse = _attn_ref(qd, kd, vd, B, T, T, nh, d, mask, window, pmask)
+    assert (K.join(o).double() - ref).abs().max() < 5e-5, "forward output"
+    assert (lse.double() - ref_lse).abs().max() < 1e-4, "lse"
+    dout = _rand(B * T, H, seed=51)
+    ref.backward(dout.double())
+    dq, dk, dv = K.attention_bwd(a, o, lse, dout, B, T, T, nh, d)
+    for name, got, want in (("dq", dq, qd.grad), ("dk", dk, kd.grad), ("dv", dv, vd.grad)):
+        assert torch.isfinite(got).all(), name
+        assert _relerr(got, want) < 1e-4, f"{name}: {_relerr(got, want):.3e}"
+
+
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
+def test_act_dropout_bwd(act):
+    M, N = 777, 512
+    dy, pre = _rand(M, N, seed=60), _rand(M, N, seed=61)
+    drop = L.make_drop(0.1, 9, 5)
+    mask = K.dropout_mask(drop, M * N).reshape(M, N)
+    aux, aux_hi, deriv = None, None, torch.ones_like(pre)
+    if act == L.ACT_GELU:
+        aux = pre
+        t = pre.double().requires_grad_(True)
+        torch.nn.functional.gelu(t).sum().backward()
+        deriv = t.grad.float()
+    elif act == L.ACT_TANH:
+        aux = torch.tanh(pre)
+        deriv = 1 - aux * aux
+    elif act == L.ACT_RELU:
+        out = torch.relu(pre) * mask
+        aux_hi = out.to(torch.bfloat16)
+        deriv = (pre > 0).float()
+    g, gs, cs = K.act_dropout_bwd(dy, act, aux=aux, aux_hi=aux_hi, drop=drop)
+    ref = dy * mask * deriv
+    assert (g - ref).abs().max() < 1e-5
+    assert (K.join(gs) - g).abs().max() <= g.abs().max() * 2.0 ** -15
+    assert _relerr(cs, ref.double().sum(0)) < 1e-5

@@ -1,0 +1,95 @@
+// extern "C" surface of libvideocad_b200 (declared in include/videocad_b200.h).  Thin forwarding layer: every
+// entry point maps 1:1 onto a launcher of kernels.h or onto a model-level routine of model_*.cpp.
+#include "videocad_b200.h"
+#include "kernels.h"
+#include "host_util.h"
+
+#ifndef VC_CUDA_BUILD
+#define VC_CUDA_BUILD 0
+#endif
+
+extern "C" {
+
+const char* vc_last_error(void) { return vck::last_error(); }
+int vc_version(void) { return 100; }
+int vc_is_cuda_build(void) { return VC_CUDA_BUILD; }
+
+void vc_gemm_desc_init(vc_gemm_desc* d) { vck::gemm_desc_init(d); }
+int vc_gemm(const vc_gemm_desc* d, void* stream) {
+  if (!d) return vck::set_error("vc_gemm: null descriptor");
+  return vck::gemm(*d, stream);
+}
+int vc_split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, vc_bf16* hi, vc_bf16* lo, int64_t ldo, void* stream) {
+  return vck::split_f32(x, ldx, rows, cols, hi, lo, ldo, stream);
+}
+int vc_layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                     float* y, int64_t ldy, vc_bf16* y_hi, vc_bf16* y_lo, int64_t ldy_split, float* mean, float* rstd,
+                     void* stream) {
+  return vck::layernorm_fwd(x, ldx, rows, C, gamma, beta, eps, y, ldy, y_hi, y_lo, ldy_split, mean, rstd, stream);
+}
+int vc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                     const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                     float* dgamma, float* dbeta, void* stream) {
+  return vck::layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, rows, C, dres, lddres, dx, lddx, dgamma, dbeta, stream);
+}
+int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
+                           vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream) {
+  return vck::patch_layernorm_fwd(img, F, S, gamma, beta, eps, y_hi, y_lo, mean, rstd, stream);
+}
+int vc_patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
+                                  float* dgamma, float* dbeta, void* stream) {
+  return vck::patch_layernorm_bwd_params(img, F, S, mean, rstd, dy, dgamma, dbeta, stream);
+}
+int vc_vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, const float* pos, vc_drop drop, float* x,
+                        void* stream) {
+  return vck::vit_assemble_fwd(e, F, N, C, cls, pos, drop, x, stream);
+}
+int vc_vit_assemble_bwd(const float* dx, int F, int N, int C, vc_drop drop, float* de, float* dcls, float* dpos,
+                        void* stream) {
+  return vck::vit_assemble_bwd(dx, F, N, C, drop, de, dcls, dpos, stream);
+}
+int vc_attention_fwd(const vc_attn_desc* a, vc_bf16* o_hi, vc_bf16* o_lo, int64_t ldo, float* lse, void* stream) {
+  if (!a) return vck::set_error("vc_attention_fwd: null descriptor");
+  return vck::attention_fwd(*a, o_hi, o_lo, ldo, lse, stream);
+}
+int vc_attention_bwd(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
+                     const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                     int64_t lddv, void* stream) {
+  if (!a) return vck::set_error("vc_attention_bwd: null descriptor");
+  return vck::attention_bwd(*a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, stream);
+}
+int vc_act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,
+                       const vc_bf16* aux_hi, int64_t ldaux_hi, vc_drop drop, float* g, int64_t ldg, vc_bf16* g_hi,
+                       vc_bf16* g_lo, int64_t ldg_split, float* colsum, void* stream) {
+  return vck::act_dropout_bwd(dy, lddy, M, N, act, aux, ldaux, aux_hi, ldaux_hi, drop, g, ldg, g_hi, g_lo, ldg_split, colsum,
+                              stream);
+}
+int vc_row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, void* stream) {
+  return vck::row_reduce_mod(x, ldx, M, N, div, mod, out, stream);
+}
+int vc_broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, float* dst, int64_t ldd, vc_bf16* d_hi,
+                      vc_bf16* d_lo, int64_t ldd_split, void* stream) {
+  return vck::broadcast_rows(src, lds, M, N, div, dst, ldd, d_hi, d_lo, ldd_split, stream);
+}
+int vc_embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E,
+                        int T, float* y, vc_bf16* y_hi, vc_bf16* y_lo, void* stream) {
+  return vck::embed_action_fwd(actions, R, A, H, W, b, E, T, y, y_hi, y_lo, stream);
+}
+int vc_embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW,
+                        float* db, float* dE, void* stream) {
+  return vck::embed_action_bwd(dy, y, actions, R, A, H, T, dW, db, dE, stream);
+}
+int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream) {
+  return vck::head_small_fwd(x, R, H, W, b, C, out, stream);
+}
+int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
+                      int accumulate_dx, float* dW, float* db, void* stream) {
+  return vck::head_small_bwd(dout, x, R, H, W, C, dx, accumulate_dx, dW, db, stream);
+}
+int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) { return vck::add_f32(a, b, out, n, stream); }
+int vc_zero_f32(float* x, int64_t n, void* stream) { return vck::zero_f32(x, n, stream); }
+int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream) {
+  return vck::dropout_mask_debug(drop, n, out, stream);
+}
+
+}  // extern "C"

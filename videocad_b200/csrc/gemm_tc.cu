@@ -1,0 +1,447 @@
+// Split-bf16 tensor-core GEMM for sm_100a: TMA -> shared memory (128B swizzle) -> tcgen05.mma (kind::f16,
+// bf16 operands, fp32 accumulators in TMEM) -> tcgen05.ld epilogue with fused bias / row-add / activation /
+// dropout / residual and fp32 + split-bf16 outputs.
+//
+// Replaces the cuBLAS calls behind every nn.Linear on the reference hot path
+// (vit_pytorch Attention.to_qkv / to_out / FeedForward.net, nn.MultiheadAttention in/out_proj,
+// TransformerDecoderLayer.linear1/2, embed_state / embed_image / image_projection / predict_action_class_0_999;
+// /root/reference/model/autoregressive_transformer.py:54-65,76, base_transformer.py:53-54) and their
+// autograd dgrad / wgrad GEMMs.
+//
+// Structure (persistent, warp-specialised, one CTA per SM):
+//   warp 0      TMA producer        (one elected thread)
+//   warp 1      tcgen05.mma issuer  (one elected thread); 3 MMAs per k16 step in fp32-grade mode
+//   warps 2..5  epilogue            (TMEM lane quarter = warp % 4)
+//   smem ring of STAGES x {A_hi, A_lo, B_hi, B_lo} tiles, TMEM double-buffered accumulators (2 x BN columns)
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+#include "common.cuh"
+#include "kernels.h"
+#include "host_util.h"
+
+namespace vck {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+
+struct GemmParams {
+  int M, N, K, passes, splitk, kb_per_split, num_kb;
+  int a_mn, b_mn;
+  const float* bias;
+  const float* rowadd; long long ld_rowadd; int rowadd_div, rowadd_mod;
+  float* preact; long long ld_preact;
+  int act;
+  float drop_scale; uint32_t drop_thresh; uint32_t drop_site; uint64_t drop_seed; int drop_on;
+  const float* residual; long long ld_res;
+  float* out_f32; long long ldo;
+  __nv_bfloat16 *out_hi, *out_lo; long long ldo_split;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BN <= 128) ? 3 : 2;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
+};
+
+// shared-memory matrix descriptor (SWIZZLE_128B, version 1).  K-major: SBO = 1024 B between 8-row groups.
+// MN-major: LBO = 8192 B between 64-element MN groups (one TMA box each), SBO = 1024 B between 8-k groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int mn_major) {
+  const uint32_t lbo = mn_major ? 8192u : 16u;
+  const uint32_t sbo = 1024u;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row, int col0,
+                                               bool add_bias) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int col = col0 + 4 * q;
+    if (col >= p.N) break;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * q + i]);
+    if (p.bias != nullptr && add_bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (p.rowadd != nullptr && add_bias) {
+      const long long rr = (row / p.rowadd_div) % p.rowadd_mod;
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowadd + rr * p.ld_rowadd + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (p.preact != nullptr) {
+      *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (p.act != ACT_NONE) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+    }
+    if (p.drop_on) {
+      const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
+      const Philox4 w = dropout_words(p.drop_seed, p.drop_site, idx >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+    }
+    if (p.residual != nullptr) {
+      const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+    }
+    if (p.out_f32 != nullptr) {
+      float* o = p.out_f32 + row * p.ldo + col;
+      if (p.splitk > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
+      } else {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    if (p.out_hi != nullptr) {
+      uint2 hi, lo;
+      split4(v, hi, lo);
+      *reinterpret_cast<uint2*>(p.out_hi + row * p.ldo_split + col) = hi;
+      if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_off = ((raw_addr + C::BAR_BYTES + 1023u) & ~1023u) - raw_addr;
+  uint8_t* tiles = smem_raw + tiles_off;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (p.passes == 3) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int total_tiles = num_m * num_n * p.splitk;
+  const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * (A_TILE_BYTES + C::B_TILE_BYTES));
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_idx = tile % num_n;
+        const int t2 = tile / num_n;
+        const int m_idx = t2 % num_m;
+        const int split = t2 / num_m;
+        const int m0 = m_idx * BM, n0 = n_idx * BN;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = tiles + s * C::STAGE_BYTES;
+          uint8_t* sA_hi = st;
+          uint8_t* sA_lo = st + A_TILE_BYTES;
+          uint8_t* sB_hi = st + 2 * A_TILE_BYTES;
+          uint8_t* sB_lo = sB_hi + C::B_TILE_BYTES;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d(sA_hi, &tmA_hi, &full_bar[s], k0, m0);
+            if (p.passes == 3) tma_load_2d(sA_lo, &tmA_lo, &full_bar[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) {
+              tma_load_2d(sA_hi + j * 8192, &tmA_hi, &full_bar[s], m0 + 64 * j, k0);
+              if (p.passes == 3) tma_load_2d(sA_lo + j * 8192, &tmA_lo, &full_bar[s], m0 + 64 * j, k0);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB_hi, &tmB_hi, &full_bar[s], k0, n0);
+            if (p.passes == 3) tma_load_2d(sB_lo, &tmB_lo, &full_bar[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) {
+              tma_load_2d(sB_hi + j * 8192, &tmB_hi, &full_bar[s], n0 + 64 * j, k0);
+              if (p.passes == 3) tma_load_2d(sB_lo + j * 8192, &tmB_lo, &full_bar[s], n0 + 64 * j, k0);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, majors, N, M
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t adv_a = p.a_mn ? 2048u : 32u;  // bytes per k16 step
+      const uint32_t adv_b = p.b_mn ? 2048u : 32u;
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+        const int t2 = tile / num_n;
+        const int split = t2 / num_m;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const uint32_t a = acc_it & 1u;
+        const uint32_t aph = (acc_it >> 1) & 1u;
+        mbar_wait(&tempty_bar[a], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          const uint32_t ph = (it / C::STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sA_hi = smem_u32(tiles + s * C::STAGE_BYTES);
+          const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
+          const uint32_t sB_hi = sA_hi + 2 * A_TILE_BYTES;
+          const uint32_t sB_lo = sB_hi + C::B_TILE_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
+            const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
+            const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+            if (p.passes == 3) {
+              const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
+              const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
+              umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+              umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[a]);  // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue warps (TMEM -> registers -> global)
+    const int g = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
+      const int n_idx = tile % num_n;
+      const int t2 = tile / num_n;
+      const int m_idx = t2 % num_m;
+      const int split = t2 / num_m;
+      const int m0 = m_idx * BM, n0 = n_idx * BN;
+      const uint32_t a = acc_it & 1u;
+      const uint32_t aph = (acc_it >> 1) & 1u;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const long long row = (long long)m0 + g * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32;
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row < p.M && col0 < p.N) epilogue_chunk<BN>(p, r, row, col0, split == 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+// bf16 matrix stored [rows, cols] row-major with leading dimension ld; box = {box_cols (inner), box_rows}
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[256];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d): base=%p rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+             base, (long long)rows, (long long)cols, (long long)ld, box_cols, box_rows);
+    return set_error(msg);
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN>
+int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.passes = d.passes;
+  p.a_mn = d.a_mn_major ? 1 : 0;
+  p.b_mn = d.b_mn_major ? 1 : 0;
+  p.num_kb = (d.K + BK - 1) / BK;
+  int splitk = d.splitk < 1 ? 1 : d.splitk;
+  if (splitk > p.num_kb) splitk = p.num_kb;
+  p.kb_per_split = (p.num_kb + splitk - 1) / splitk;
+  p.splitk = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.bias = d.bias;
+  p.rowadd = d.rowadd; p.ld_rowadd = d.ld_rowadd;
+  p.rowadd_div = d.rowadd_div > 0 ? d.rowadd_div : 1;
+  p.rowadd_mod = d.rowadd_mod > 0 ? d.rowadd_mod : 1;
+  p.preact = d.preact; p.ld_preact = d.ld_preact;
+  p.act = d.act;
+  p.drop_on = d.drop.p > 0.f ? 1 : 0;
+  p.drop_scale = d.drop.p > 0.f ? 1.0f / (1.0f - d.drop.p) : 1.0f;
+  p.drop_thresh = dropout_threshold(d.drop.p);
+  p.drop_site = d.drop.site;
+  p.drop_seed = d.drop.seed;
+  p.residual = d.residual; p.ld_res = d.ld_res;
+  p.out_f32 = d.out_f32; p.ldo = d.ldo;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
+  p.ldo_split = d.ldo_split;
+
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  int rc = 0;
+  const bf16_t* a_lo = d.passes == 3 ? d.a_lo : d.a_hi;
+  const bf16_t* b_lo = d.passes == 3 ? d.b_lo : d.b_hi;
+  if (!p.a_mn) {
+    rc |= make_tmap(&tA_hi, d.a_hi, d.M, d.K, d.lda, BK, BM);
+    rc |= make_tmap(&tA_lo, a_lo, d.M, d.K, d.lda, BK, BM);
+  } else {
+    rc |= make_tmap(&tA_hi, d.a_hi, d.K, d.M, d.lda, 64, BK);
+    rc |= make_tmap(&tA_lo, a_lo, d.K, d.M, d.lda, 64, BK);
+  }
+  if (!p.b_mn) {
+    rc |= make_tmap(&tB_hi, d.b_hi, d.N, d.K, d.ldb, BK, BN);
+    rc |= make_tmap(&tB_lo, b_lo, d.N, d.K, d.ldb, BK, BN);
+  } else {
+    rc |= make_tmap(&tB_hi, d.b_hi, d.K, d.N, d.ldb, 64, BK);
+    rc |= make_tmap(&tB_lo, b_lo, d.K, d.N, d.ldb, 64, BK);
+  }
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_m = (d.M + BM - 1) / BM, num_n = (d.N + BN - 1) / BN;
+  const long long tiles = (long long)num_m * num_n * p.splitk;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace
+
+void gemm_desc_init(GemmDesc* d) {
+  memset(d, 0, sizeof *d);
+  d->passes = 3;
+  d->splitk = 1;
+  d->rowadd_div = 1;
+  d->rowadd_mod = 1;
+}
+
+int gemm(const GemmDesc& d, stream_t stream) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error("gemm: empty problem");
+  if (d.N % 8 != 0) return set_error("gemm: N must be a multiple of 8");
+  if (d.lda % 8 != 0 || d.ldb % 8 != 0) return set_error("gemm: lda/ldb must be multiples of 8 elements");
+  if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
+  if (d.a_hi == nullptr || d.b_hi == nullptr) return set_error("gemm: null operand");
+  if (d.passes == 3 && (d.a_lo == nullptr || d.b_lo == nullptr)) return set_error("gemm: passes=3 needs lo operands");
+  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact))
+    return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");
+  if (d.out_f32 == nullptr && d.out_hi == nullptr) return set_error("gemm: no output");
+  if ((d.out_f32 && d.ldo % 4 != 0) || (d.out_hi && d.ldo_split % 4 != 0) || (d.residual && d.ld_res % 4 != 0) ||
+      (d.preact && d.ld_preact % 4 != 0) || (d.rowadd && d.ld_rowadd % 4 != 0))
+    return set_error("gemm: epilogue leading dimensions must be multiples of 4");
+  return launch_gemm<128>(d, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // namespace vck

@@ -1,0 +1,16 @@
+// Host-side error plumbing shared by the CUDA translation units (and by the CPU emulation build).
+#pragma once
+#include <string>
+
+namespace vck {
+
+// stores msg as the calling thread's last error and returns a non-zero status
+int set_error(const char* msg);
+const char* last_error();
+
+#if defined(__CUDACC__)
+// checks cudaGetLastError() after a launch; returns 0 or sets the error
+int check_launch(const char* what);
+#endif
+
+}  // namespace vck

@@ -1,0 +1,111 @@
+// Host-callable launch API of the videocad_b200 kernels.
+//
+// Two implementations exist with IDENTICAL semantics:
+//   * videocad_b200/csrc/*.cu           -- the product: hand-written sm_100a CUDA kernels (device pointers)
+//   * oracle/csrc/kernels_cpu.cpp       -- test infrastructure: plain C++ loops on host pointers, used only
+//                                          to check the host orchestration (model_*.cpp) without a GPU.
+// The orchestration code (model_vit.cpp, model_seq.cpp) is written against this header only.
+//
+// Conventions
+//   * all matrices are row-major with an explicit leading dimension (elements);
+//   * "split" tensors are pairs of bf16 arrays (hi, lo) with x ~= hi + lo  (see common.cuh);
+//   * every function enqueues work on `stream` and returns 0 on success (no host sync);
+//   * no function allocates device memory.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include "videocad_b200.h"  // the C ABI structs (include/): vc_drop, vc_gemm_desc, vc_attn_desc
+
+namespace vck {
+
+typedef void* stream_t;
+typedef vc_bf16 bf16_t;  // raw bfloat16 bits
+typedef vc_drop Drop;    // dropout call site; p == 0 disables
+static inline Drop no_drop() { Drop d; d.p = 0.f; d.site = 0; d.seed = 0; return d; }
+static inline Drop make_drop(float p, uint32_t site, uint64_t seed) { Drop d; d.p = p; d.site = site; d.seed = seed; return d; }
+
+// -------------------------------------------------------------------------------------------------
+// tensor-core GEMM (tcgen05 / TMEM / TMA):   acc[m,n] = sum_k A[m,k] * B[n,k]
+//   A: a_mn_major == 0 -> stored [M,K] (lda >= K);  a_mn_major == 1 -> stored [K,M] (lda >= M)
+//   B: b_mn_major == 0 -> stored [N,K] (ldb >= K);  b_mn_major == 1 -> stored [K,N] (ldb >= N)
+//   passes == 3: hi*hi + lo*hi + hi*lo (fp32-grade), passes == 1: hi*hi only (bf16-grade)
+// epilogue, in this order:
+//   v = acc (+ bias[n]) (+ rowadd[((m / rowadd_div) % rowadd_mod), n]);  if (preact) preact[m,n] = v;
+//   v = act(v);  v = dropout(v);  if (residual) v += residual[m,n];
+//   out_f32[m,n] = v (or atomicAdd when splitk > 1);  (out_hi, out_lo)[m,n] = split(v)
+// constraints: contiguous dims and all ld multiples of 8 elements (16-byte TMA strides); N % 8 == 0;
+//   splitk > 1 only with bias/none epilogue and out_f32 pre-zeroed by the caller.
+// -------------------------------------------------------------------------------------------------
+typedef vc_gemm_desc GemmDesc;
+void gemm_desc_init(GemmDesc* d);
+int gemm(const GemmDesc& d, stream_t stream);
+
+// x[rows, cols] fp32 -> (hi, lo)
+int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t s);
+
+// LayerNorm over the last dim (biased variance, eps inside sqrt).  Outputs optional (may be null).
+int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  float* y, int64_t ldy, bf16_t* y_hi, bf16_t* y_lo, int64_t ldy_split, float* mean, float* rstd,
+                  stream_t s);
+// dx = (dres ? dres : 0) + LN_bwd(dy);  dgamma/dbeta are ACCUMULATED (atomicAdd) into caller-zeroed buffers.
+int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                  const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                  float* dgamma, float* dbeta, stream_t s);
+
+// ViT front end: 'f 1 (h 32) (w 32) -> (f h w) 1024' gather + LayerNorm(1024) -> split operand of the patch GEMM
+int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
+                        bf16_t* y_lo, float* mean, float* rstd, stream_t s);
+// parameter grads of that LayerNorm from dy[F*N, 1024] (accumulated into zeroed dgamma/dbeta); no input grad
+int patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
+                               float* dgamma, float* dbeta, stream_t s);
+
+// tokens: x[f, 0] = cls + pos[0]; x[f, 1+p] = e[f*N+p] + pos[1+p]; then dropout(site) on the whole [F*(N+1), C] tensor
+int vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, const float* pos, Drop drop, float* x,
+                     stream_t s);
+// de[f*N+p] = dx[f,1+p]*mask; dcls += sum_f dx[f,0]*mask; dpos[t] += sum_f dx[f,t]*mask  (dcls/dpos pre-zeroed)
+int vit_assemble_bwd(const float* dx, int F, int N, int C, Drop drop, float* de, float* dcls, float* dpos, stream_t s);
+
+// multi-head attention core on fp32 q/k/v with row strides; rows are (b * T + t); head h uses columns [h*d, (h+1)*d)
+//   s = scale * q k^T + mask;  p = softmax(s);  p~ = dropout(p) (element index ((b*nh+h)*Tq+i)*Tk+j);  o = p~ v
+//   mask: NONE | CAUSAL (j <= i) | WINDOW (i - window < j <= i)
+// fwd writes o as split [B*Tq, nh*d] (+ optional fp32) and lse[B, nh, Tq] (log-sum-exp of s) for the backward.
+typedef vc_attn_desc AttnDesc;
+int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s);
+// backward: recomputes p from (q, k, lse); needs do[B*Tq, nh*d] fp32 and o (split, as written by fwd)
+//   dq/dk/dv written (not accumulated) as fp32 with their own strides
+int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                  const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                  int64_t lddv, stream_t s);
+
+// backward of "v = dropout(act(pre))":  g = dy * mask*scale * act'(.)
+//   act GELU: aux = pre-activation fp32; TANH: aux = forward output fp32; RELU: aux_hi = forward output hi (bf16) != 0
+//   outputs (all optional): g fp32, g split, colsum[n] += sum_m g[m,n] (atomic, pre-zeroed)
+int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,
+                    const bf16_t* aux_hi, int64_t ldaux_hi, Drop drop, float* g, int64_t ldg, bf16_t* g_hi,
+                    bf16_t* g_lo, int64_t ldg_split, float* colsum, stream_t s);
+
+// out[((m / div) % mod), n] += x[m, n]   (atomic; out pre-zeroed by caller, ld = N)
+int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t s);
+// dst[m, n] = src[m / div, n] for m in [0, M): fp32 and/or split copies
+int broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, float* dst, int64_t ldd, bf16_t* d_hi,
+                   bf16_t* d_lo, int64_t ldd_split, stream_t s);
+
+// y[r, :] = tanh(a[r, 0:7] W^T + b + E[r % T])   (E may be null)  -> fp32 + split
+int embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E, int T,
+                     float* y, bf16_t* y_hi, bf16_t* y_lo, stream_t s);
+// dpre = dy * (1 - y^2); dW[H,A] += dpre^T a; db += colsum(dpre); dE[r % T] += dpre   (all accumulated, pre-zeroed)
+int embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW,
+                     float* db, float* dE, stream_t s);
+
+// narrow head: out[r, c] = x[r,:] . W[c,:] + b[c], C small (5)
+int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t s);
+// dx[r,:] (+)= dout[r,:] W ; dW += dout^T x ; db += colsum(dout)   (dW/db accumulated, pre-zeroed)
+int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,
+                   float* dW, float* db, stream_t s);
+
+// misc
+int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s);  // out = a + b (b may alias out)
+int zero_f32(float* x, int64_t n, stream_t s);
+int dropout_mask_debug(Drop drop, int64_t n, float* out, stream_t s);  // out[i] = keep ? 1/(1-p) : 0 (tests only)
+
+}  // namespace vck

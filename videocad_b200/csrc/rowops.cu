@@ -1,0 +1,637 @@
+// Row-wise / element-wise sm_100a kernels of the VideoCAD hot path (HBM-bound; 128-bit vectorised, warp-shuffle
+// reductions): LayerNorm fwd/bwd (vit_pytorch LayerNorms, TransformerDecoderLayer.norm1-3), patchify+LayerNorm
+// (vit_pytorch to_patch_embedding[0:2]), CLS/pos token assembly + embedding dropout, activation/dropout backward,
+// fp32 -> split-bf16 conversion, and the narrow linears that are not tensor-core shaped (embed_action K=7,
+// predict_action_class_0_4 N=5; /root/reference/model/autoregressive_transformer.py:64,77,110-113).
+#include <cuda_runtime.h>
+#include "common.cuh"
+#include "kernels.h"
+#include "host_util.h"
+
+namespace vck {
+
+namespace {
+
+inline cudaStream_t cs(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ void drop4(float (&v)[4], const Drop& d, uint32_t thresh, float scale, unsigned long long idx) {
+  const Philox4 w = dropout_words(d.seed, d.site, idx >> 2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= thresh) ? v[i] * scale : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------- split
+__global__ void split_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols4,
+                             __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4, c = (i % cols4) * 4;
+    const float4 v4 = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    uint2 h, l;
+    split4(v, h, l);
+    *reinterpret_cast<uint2*>(hi + r * ldo + c) = h;
+    *reinterpret_cast<uint2*>(lo + r * ldo + c) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm
+constexpr int LN_MAXV = 8;  // float4 chunks per lane -> C <= 1024
+constexpr int LN_WARPS = 4;
+
+struct RowLoader {  // plain strided rows
+  const float* x; long long ldx;
+  __device__ __forceinline__ float4 load(long long row, int c) const {
+    return *reinterpret_cast<const float4*>(x + row * ldx + c);
+  }
+};
+struct PatchLoader {  // 'f 1 (h 32) (w 32) -> (f h w) (32 32)' gather; C = 1024
+  const float* img; int S, wp, N;
+  __device__ __forceinline__ float4 load(long long row, int c) const {
+    const long long f = row / N;
+    const int pidx = (int)(row % N);
+    const int ph = pidx / wp, pw = pidx % wp;
+    const int p1 = c >> 5, p2 = c & 31;
+    return *reinterpret_cast<const float4*>(img + (f * S + (ph * 32 + p1)) * (long long)S + pw * 32 + p2);
+  }
+};
+
+template <class Loader>
+__device__ __forceinline__ void ln_load_stats(const Loader& ld, long long row, int C, int lane, float4 (&v)[LN_MAXV],
+                                              float& mean, float& rstd, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      v[i] = ld.load(row, c);
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+}
+
+template <class Loader>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(Loader ld, long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+              float* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
+              long long ldys, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[LN_MAXV];
+  float mean, rstd;
+  ln_load_stats(ld, row, C, lane, v, mean, rstd, eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float o[4];
+      o[0] = (v[i].x - mean) * rstd * g.x + b.x;
+      o[1] = (v[i].y - mean) * rstd * g.y + b.y;
+      o[2] = (v[i].z - mean) * rstd * g.z + b.z;
+      o[3] = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y) *reinterpret_cast<float4*>(y + row * ldy + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (y_hi) {
+        uint2 h, l;
+        split4(o, h, l);
+        *reinterpret_cast<uint2*>(y_hi + row * ldys + c) = h;
+        if (y_lo) *reinterpret_cast<uint2*>(y_lo + row * ldys + c) = l;
+      }
+    }
+  }
+}
+
+// backward: block loops over rows (grid-stride by warps); dgamma/dbeta partials in registers, one atomic pass at the end
+template <class Loader, bool kNeedDx>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows, int C,
+              const float* __restrict__ dres, long long lddres, float* __restrict__ dx, long long lddx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float4 red[LN_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 dg[LN_MAXV], db[LN_MAXV];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float invC = 1.0f / (float)C;
+  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[LN_MAXV], g[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < C) {
+        const float4 xv = ld.load(row, c);
+        const float4 d = *reinterpret_cast<const float4*>(dy + row * lddy + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        if (kNeedDx) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+          g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+          s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+          s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+        }
+      }
+    }
+    if (kNeedDx) {
+      s1 = warp_sum(s1) * invC;
+      s2 = warp_sum(s2) * invC;
+#pragma unroll
+      for (int i = 0; i < LN_MAXV; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < C) {
+          float4 o;
+          o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+          o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+          o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+          o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+          if (dres) {
+            const float4 r = *reinterpret_cast<const float4*>(dres + row * lddres + c);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          }
+          *reinterpret_cast<float4*>(dx + row * lddx + c) = o;
+        }
+      }
+    }
+  }
+  // cross-warp reduction of the parameter grads, then one atomicAdd per column per block
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c >= C) break;  // uniform across the warp's lanes only for full chunks; C % 128 == 0 is required
+    for (int pass = 0; pass < 2; ++pass) {
+      red[warp][lane] = pass == 0 ? dg[i] : db[i];
+      __syncthreads();
+      if (warp == 0) {
+        float4 a = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < LN_WARPS; ++w) {
+          a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
+        }
+        float* dst = (pass == 0 ? dgamma : dbeta) + c;
+        atomicAdd(dst + 0, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- ViT token assembly
+__global__ void vit_assemble_fwd_kernel(const float* __restrict__ e, int F, int N, int C, const float* __restrict__ cls,
+                                        const float* __restrict__ pos, Drop drop, uint32_t thresh, float scale,
+                                        float* __restrict__ x) {
+  const int n = N + 1, C4 = C / 4;
+  const long long total = (long long)F * n * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const long long ft = i / C4;
+    const int t = (int)(ft % n);
+    const long long f = ft / n;
+    const float4 a = (t == 0) ? __ldg(reinterpret_cast<const float4*>(cls + c))
+                              : *reinterpret_cast<const float4*>(e + (f * N + (t - 1)) * (long long)C + c);
+    const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)t * C + c));
+    float v[4] = {a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w};
+    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)ft * C + c);
+    *reinterpret_cast<float4*>(x + ft * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// grid: (ceil(n*C4/128), f-chunks); thread <-> (t, c4); loops over its f-chunk
+__global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, int F, int N, int C, Drop drop, uint32_t thresh,
+                                        float scale, float* __restrict__ de, float* __restrict__ dcls,
+                                        float* __restrict__ dpos, int f_per_block) {
+  const int n = N + 1, C4 = C / 4;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n * C4) return;
+  const int t = j / C4, c = (j % C4) * 4;
+  const int f0 = blockIdx.y * f_per_block;
+  const int f1 = min(F, f0 + f_per_block);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int f = f0; f < f1; ++f) {
+    const long long ft = (long long)f * n + t;
+    const float4 d = *reinterpret_cast<const float4*>(dx + ft * C + c);
+    float v[4] = {d.x, d.y, d.z, d.w};
+    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)ft * C + c);
+    if (t > 0) *reinterpret_cast<float4*>(de + ((long long)f * N + (t - 1)) * C + c) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += v[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    atomicAdd(dpos + (long long)t * C + c + i, acc[i]);
+    if (t == 0) atomicAdd(dcls + c + i, acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- act/dropout backward
+// grid: (ceil(N4/128), row chunks); thread <-> column quad; loops over rows of its chunk
+__global__ void act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M, int N, int act,
+                                       const float* __restrict__ aux, long long ldaux,
+                                       const __nv_bfloat16* __restrict__ aux_hi, long long ldaux_hi, Drop drop,
+                                       uint32_t thresh, float scale, float* __restrict__ g, long long ldg,
+                                       __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, long long ldgs,
+                                       float* __restrict__ colsum, int rows_per_block) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= N) return;
+  const int c = q * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = r0; r < r1; ++r) {
+    const float4 d = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+    float v[4] = {d.x, d.y, d.z, d.w};
+    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)r * N + c);
+    if (act == ACT_GELU) {
+      const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
+      v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
+    } else if (act == ACT_TANH) {
+      const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
+      v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
+    } else if (act == ACT_RELU) {
+      const uint2 a = *reinterpret_cast<const uint2*>(aux_hi + r * ldaux_hi + c);
+      if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
+      if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
+      if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
+      if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
+    }
+    if (g) *reinterpret_cast<float4*>(g + r * ldg + c) = make_float4(v[0], v[1], v[2], v[3]);
+    if (g_hi) {
+      uint2 h, l;
+      split4(v, h, l);
+      *reinterpret_cast<uint2*>(g_hi + r * ldgs + c) = h;
+      if (g_lo) *reinterpret_cast<uint2*>(g_lo + r * ldgs + c) = l;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += v[i];
+  }
+  if (colsum) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) atomicAdd(colsum + c + i, acc[i]);
+  }
+}
+
+__global__ void row_reduce_mod_kernel(const float* __restrict__ x, long long ldx, long long M, int N, int div, int mod,
+                                      float* __restrict__ out) {
+  const long long total = M * N;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N;
+    const int n = (int)(i % N);
+    atomicAdd(out + ((m / div) % mod) * N + n, x[m * ldx + n]);
+  }
+}
+
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, long long lds, long long M, int N, int div,
+                                      float* __restrict__ dst, long long ldd, __nv_bfloat16* __restrict__ d_hi,
+                                      __nv_bfloat16* __restrict__ d_lo, long long ldds) {
+  const int N4 = N / 4;
+  const long long total = M * N4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N4;
+    const int c = (int)(i % N4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(src + (m / div) * lds + c);
+    if (dst) *reinterpret_cast<float4*>(dst + m * ldd + c) = a;
+    if (d_hi) {
+      const float v[4] = {a.x, a.y, a.z, a.w};
+      uint2 h, l;
+      split4(v, h, l);
+      *reinterpret_cast<uint2*>(d_hi + m * ldds + c) = h;
+      if (d_lo) *reinterpret_cast<uint2*>(d_lo + m * ldds + c) = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------- embed_action (K = 7)
+__global__ void embed_action_fwd_kernel(const float* __restrict__ actions, long long R, int A, int H,
+                                        const float* __restrict__ W, const float* __restrict__ b,
+                                        const float* __restrict__ E, int T, float* __restrict__ y,
+                                        __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  const long long total = R * H;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / H;
+    const int h = (int)(i % H);
+    float acc = b[h];
+    for (int a = 0; a < A; ++a) acc += actions[r * A + a] * W[(long long)h * A + a];
+    if (E) acc += E[(r % T) * H + h];
+    const float v = tanhf(acc);
+    if (y) y[i] = v;
+    if (y_hi) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(v, hi, lo);
+      y_hi[i] = hi;
+      if (y_lo) y_lo[i] = lo;
+    }
+  }
+}
+
+// grid: (ceil(H/128), row chunks); thread <-> h
+__global__ void embed_action_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                        const float* __restrict__ actions, long long R, int A, int H, int T,
+                                        float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dE,
+                                        int rows_per_block) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float accW[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float accb = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float yv = y[r * H + h];
+    const float d = dy[r * H + h] * (1.f - yv * yv);
+    accb += d;
+    for (int a = 0; a < A && a < 8; ++a) accW[a] += d * actions[r * A + a];
+    if (dE) atomicAdd(dE + (r % T) * H + h, d);
+  }
+  atomicAdd(db + h, accb);
+  for (int a = 0; a < A && a < 8; ++a) atomicAdd(dW + (long long)h * A + a, accW[a]);
+}
+
+// ------------------------------------------------------------------------------------------- narrow head (N = 5)
+constexpr int HEAD_MAXC = 8;
+__global__ void head_small_fwd_kernel(const float* __restrict__ x, long long R, int H, const float* __restrict__ W,
+                                      const float* __restrict__ b, int C, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float acc[HEAD_MAXC];
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; ++c) acc[c] = 0.f;
+  for (int h = lane * 4; h < H; h += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * H + h);
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+      if (c < C) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long long)c * H + h));
+        acc[c] += xv.x * w.x + xv.y * w.y + xv.z * w.z + xv.w * w.w;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; ++c) {
+    if (c < C) {
+      const float s = warp_sum(acc[c]);
+      if (lane == 0) out[r * C + c] = s + b[c];
+    }
+  }
+}
+
+// grid: (ceil(H4/128), row chunks); thread <-> h quad
+__global__ void head_small_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, long long R, int H,
+                                      const float* __restrict__ W, int C, float* __restrict__ dx, int accumulate_dx,
+                                      float* __restrict__ dW, float* __restrict__ db, int rows_per_block) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q * 4 >= H) return;
+  const int h = q * 4;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(R, r0 + rows_per_block);
+  float4 w[HEAD_MAXC], aw[HEAD_MAXC];
+  float ab[HEAD_MAXC];
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; ++c) {
+    w[c] = (c < C) ? __ldg(reinterpret_cast<const float4*>(W + (long long)c * H + h)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    aw[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[c] = 0.f;
+  }
+  for (long long r = r0; r < r1; ++r) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * H + h);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < HEAD_MAXC; ++c) {
+      if (c < C) {
+        const float d = dout[r * C + c];
+        o.x += d * w[c].x; o.y += d * w[c].y; o.z += d * w[c].z; o.w += d * w[c].w;
+        aw[c].x += d * xv.x; aw[c].y += d * xv.y; aw[c].z += d * xv.z; aw[c].w += d * xv.w;
+        ab[c] += d;
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(dx + r * H + h);
+    if (accumulate_dx) {
+      const float4 p = *dst;
+      o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+    }
+    *dst = o;
+  }
+#pragma unroll
+  for (int c = 0; c < HEAD_MAXC; ++c) {
+    if (c < C) {
+      float* dst = dW + (long long)c * H + h;
+      atomicAdd(dst + 0, aw[c].x); atomicAdd(dst + 1, aw[c].y); atomicAdd(dst + 2, aw[c].z); atomicAdd(dst + 3, aw[c].w);
+      if (q == 0) atomicAdd(db + c, ab[c]);
+    }
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* b, float* out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
+__global__ void dropout_mask_kernel(Drop drop, uint32_t thresh, float scale, long long n, float* out) {
+  const long long n4 = (n + 3) / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const Philox4 w = dropout_words(drop.seed, drop.site, (unsigned long long)i);
+    for (int k = 0; k < 4; ++k)
+      if (i * 4 + k < n) out[i * 4 + k] = (w.v[k] >= thresh) ? scale : 0.f;
+  }
+}
+
+inline int ew_grid(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+inline float drop_scale(const Drop& d) { return d.p > 0.f ? 1.0f / (1.0f - d.p) : 1.0f; }
+
+}  // namespace
+
+// =================================================================================================== launchers
+int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t s) {
+  if (cols % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0) return set_error("split_f32: cols/ld must be multiples of 4");
+  if (rows <= 0 || cols <= 0) return 0;
+  split_kernel<<<ew_grid(rows * cols / 4, 256), 256, 0, cs(s)>>>(x, ldx, rows, cols / 4, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                reinterpret_cast<__nv_bfloat16*>(lo), ldo);
+  return check_launch("split_kernel");
+}
+
+int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  float* y, int64_t ldy, bf16_t* y_hi, bf16_t* y_lo, int64_t ldy_split, float* mean, float* rstd,
+                  stream_t s) {
+  if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_fwd: C must be a multiple of 128 and <= 1024");
+  if (rows <= 0) return 0;
+  RowLoader ld{x, ldx};
+  ln_fwd_kernel<RowLoader><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
+      ld, rows, C, gamma, beta, eps, y, ldy, reinterpret_cast<__nv_bfloat16*>(y_hi), reinterpret_cast<__nv_bfloat16*>(y_lo),
+      ldy_split, mean, rstd);
+  return check_launch("ln_fwd_kernel");
+}
+
+int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                  const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                  float* dgamma, float* dbeta, stream_t s) {
+  if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
+  if (rows <= 0) return 0;
+  RowLoader ld{x, ldx};
+  int grid = cdiv(rows, LN_WARPS * 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  ln_bwd_kernel<RowLoader, true><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, lddy, mean, rstd, gamma, rows, C, dres, lddres,
+                                                                    dx, lddx, dgamma, dbeta);
+  return check_launch("ln_bwd_kernel");
+}
+
+int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
+                        bf16_t* y_lo, float* mean, float* rstd, stream_t s) {
+  if (S % 32 != 0) return set_error("patch_layernorm_fwd: image size must be a multiple of 32");
+  const int wp = S / 32, N = wp * wp;
+  const long long rows = (long long)F * N;
+  if (rows <= 0) return 0;
+  PatchLoader ld{img, S, wp, N};
+  ln_fwd_kernel<PatchLoader><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
+      ld, rows, 1024, gamma, beta, eps, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(y_hi),
+      reinterpret_cast<__nv_bfloat16*>(y_lo), 1024, mean, rstd);
+  return check_launch("ln_fwd_kernel<patch>");
+}
+
+int patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
+                               float* dgamma, float* dbeta, stream_t s) {
+  if (S % 32 != 0) return set_error("patch_layernorm_bwd_params: image size must be a multiple of 32");
+  const int wp = S / 32, N = wp * wp;
+  const long long rows = (long long)F * N;
+  if (rows <= 0) return 0;
+  PatchLoader ld{img, S, wp, N};
+  int grid = cdiv(rows, LN_WARPS * 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  ln_bwd_kernel<PatchLoader, false><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, 1024, mean, rstd, nullptr, rows, 1024, nullptr,
+                                                                       0, nullptr, 0, dgamma, dbeta);
+  return check_launch("ln_bwd_kernel<patch>");
+}
+
+int vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, const float* pos, Drop drop, float* x,
+                     stream_t s) {
+  if (C % 4 != 0) return set_error("vit_assemble_fwd: C % 4 != 0");
+  const long long total = (long long)F * (N + 1) * (C / 4);
+  if (total <= 0) return 0;
+  vit_assemble_fwd_kernel<<<ew_grid(total, 256), 256, 0, cs(s)>>>(e, F, N, C, cls, pos, drop, dropout_threshold(drop.p),
+                                                                  drop_scale(drop), x);
+  return check_launch("vit_assemble_fwd_kernel");
+}
+
+int vit_assemble_bwd(const float* dx, int F, int N, int C, Drop drop, float* de, float* dcls, float* dpos, stream_t s) {
+  if (C % 4 != 0) return set_error("vit_assemble_bwd: C % 4 != 0");
+  if (F <= 0) return 0;
+  const int f_per_block = 8;
+  dim3 grid(cdiv((long long)(N + 1) * (C / 4), 128), cdiv(F, f_per_block));
+  vit_assemble_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dx, F, N, C, drop, dropout_threshold(drop.p), drop_scale(drop), de, dcls,
+                                                   dpos, f_per_block);
+  return check_launch("vit_assemble_bwd_kernel");
+}
+
+int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,
+                    const bf16_t* aux_hi, int64_t ldaux_hi, Drop drop, float* g, int64_t ldg, bf16_t* g_hi, bf16_t* g_lo,
+                    int64_t ldg_split, float* colsum, stream_t s) {
+  if (N % 4 != 0) return set_error("act_dropout_bwd: N % 4 != 0");
+  if ((act == VC_ACT_GELU || act == VC_ACT_TANH) && aux == nullptr) return set_error("act_dropout_bwd: aux required");
+  if (act == VC_ACT_RELU && aux_hi == nullptr) return set_error("act_dropout_bwd: aux_hi required for relu");
+  if (M <= 0) return 0;
+  const int rows_per_block = 32;
+  dim3 grid(cdiv(N / 4, 128), cdiv(M, rows_per_block));
+  act_dropout_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dy, lddy, M, N, act, aux, ldaux,
+                                                  reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldaux_hi, drop,
+                                                  dropout_threshold(drop.p), drop_scale(drop), g, ldg,
+                                                  reinterpret_cast<__nv_bfloat16*>(g_hi),
+                                                  reinterpret_cast<__nv_bfloat16*>(g_lo), ldg_split, colsum, rows_per_block);
+  return check_launch("act_dropout_bwd_kernel");
+}
+
+int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t s) {
+  if (M <= 0 || N <= 0) return 0;
+  if (div < 1 || mod < 1) return set_error("row_reduce_mod: div/mod must be >= 1");
+  row_reduce_mod_kernel<<<ew_grid(M * N, 256), 256, 0, cs(s)>>>(x, ldx, M, N, div, mod, out);
+  return check_launch("row_reduce_mod_kernel");
+}
+
+int broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, float* dst, int64_t ldd, bf16_t* d_hi,
+                   bf16_t* d_lo, int64_t ldd_split, stream_t s) {
+  if (N % 4 != 0) return set_error("broadcast_rows: N % 4 != 0");
+  if (M <= 0) return 0;
+  broadcast_rows_kernel<<<ew_grid(M * N / 4, 256), 256, 0, cs(s)>>>(src, lds, M, N, div, dst, ldd,
+                                                                   reinterpret_cast<__nv_bfloat16*>(d_hi),
+                                                                   reinterpret_cast<__nv_bfloat16*>(d_lo), ldd_split);
+  return check_launch("broadcast_rows_kernel");
+}
+
+int embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E, int T,
+                     float* y, bf16_t* y_hi, bf16_t* y_lo, stream_t s) {
+  if (R <= 0) return 0;
+  embed_action_fwd_kernel<<<ew_grid(R * H, 256), 256, 0, cs(s)>>>(actions, R, A, H, W, b, E, T, y,
+                                                                 reinterpret_cast<__nv_bfloat16*>(y_hi),
+                                                                 reinterpret_cast<__nv_bfloat16*>(y_lo));
+  return check_launch("embed_action_fwd_kernel");
+}
+
+int embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW,
+                     float* db, float* dE, stream_t s) {
+  if (A > 8) return set_error("embed_action_bwd: act_dim > 8 unsupported");
+  if (R <= 0) return 0;
+  const int rows_per_block = 16;
+  dim3 grid(cdiv(H, 128), cdiv(R, rows_per_block));
+  embed_action_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dy, y, actions, R, A, H, T, dW, db, dE, rows_per_block);
+  return check_launch("embed_action_bwd_kernel");
+}
+
+int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t s) {
+  if (C > HEAD_MAXC || H % 4 != 0) return set_error("head_small_fwd: C <= 8 and H % 4 == 0 required");
+  if (R <= 0) return 0;
+  head_small_fwd_kernel<<<cdiv(R, 4), 128, 0, cs(s)>>>(x, R, H, W, b, C, out);
+  return check_launch("head_small_fwd_kernel");
+}
+
+int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,
+                   float* dW, float* db, stream_t s) {
+  if (C > HEAD_MAXC || H % 4 != 0) return set_error("head_small_bwd: C <= 8 and H % 4 == 0 required");
+  if (R <= 0) return 0;
+  const int rows_per_block = 16;
+  dim3 grid(cdiv(H / 4, 128), cdiv(R, rows_per_block));
+  head_small_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dout, x, R, H, W, C, dx, accumulate_dx, dW, db, rows_per_block);
+  return check_launch("head_small_bwd_kernel");
+}
+
+int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s) {
+  if (n <= 0) return 0;
+  add_kernel<<<ew_grid(n, 256), 256, 0, cs(s)>>>(a, b, out, n);
+  return check_launch("add_kernel");
+}
+
+int zero_f32(float* x, int64_t n, stream_t s) {
+  if (n <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(x, 0, (size_t)n * sizeof(float), cs(s));
+  return e == cudaSuccess ? 0 : set_error(cudaGetErrorString(e));
+}
+
+int dropout_mask_debug(Drop drop, int64_t n, float* out, stream_t s) {
+  if (n <= 0) return 0;
+  dropout_mask_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, cs(s)>>>(drop, dropout_threshold(drop.p), drop_scale(drop), n, out);
+  return check_launch("dropout_mask_kernel");
+}
+
+}  // namespace vck
