@@ -112,6 +112,104 @@ int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stre
 int vc_zero_f32(float* x, int64_t n, void* stream);
 int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream);
 
+
+/* =====================================================================================================
+ * Model-level entry points: the drop-in path.  Three segments mirror the three autograd nodes of the
+ * host-side nn.Module (videocad_b200/model.py):
+ *   vc_vit_*   one vit_pytorch.ViT encoder (image_size 224, patch 32, dim 512, depth 6, heads 16 x 64,
+ *              mlp 512; reference call sites /root/reference/model/trajectory_model.py:52-67,90-100)
+ *   vc_seq_*   token construction + nn.TransformerDecoder (post-norm, ReLU) + the two action heads
+ *              (/root/reference/model/autoregressive_transformer.py:143-218)
+ * Weight structs carry, per parameter, the fp32 tensor, its split-bf16 copies (vc_split_f32 output,
+ * refreshed by the host whenever the fp32 tensor changes) and the gradient destination.
+ * Gradient buffers must be ZEROED by the caller before a backward call; backward accumulates into them.
+ * ===================================================================================================== */
+#define VC_VIT_DEPTH 6
+#define VC_VIT_DIM 512
+#define VC_VIT_HEADS 16
+#define VC_VIT_DHEAD 64
+#define VC_VIT_MLP 512
+#define VC_PATCH 32
+
+typedef struct vc_linear {      /* y = x W^T + b, W [out, in] row-major */
+  const float* w; const float* b;           /* b may be null (to_qkv has no bias) */
+  const vc_bf16* w_hi; const vc_bf16* w_lo; /* split copies of w */
+  float* dw; float* db;                     /* gradient destinations (null when not training) */
+} vc_linear;
+
+typedef struct vc_norm {        /* LayerNorm affine parameters */
+  const float* w; const float* b;
+  float* dw; float* db;
+} vc_norm;
+
+typedef struct vc_vit_layer {
+  vc_norm ln1; vc_linear qkv; vc_linear out;
+  vc_norm ln2; vc_linear fc1; vc_linear fc2;
+} vc_vit_layer;
+
+typedef struct vc_vit_weights {
+  const float* pos; const float* cls;   /* pos [>= n, 512] (leading rows used), cls [512] */
+  float* dpos; float* dcls;
+  vc_norm pe_ln1; vc_linear pe; vc_norm pe_ln2;
+  vc_vit_layer layer[VC_VIT_DEPTH];
+  vc_norm norm;
+} vc_vit_weights;
+
+typedef struct vc_vit_call {
+  const vc_vit_weights* w;
+  const float* img; int F; int S;       /* [F, 1, S, S], S multiple of 32, (S/32)^2 <= 49 */
+  float dropout_p; int training;        /* dropout applied only when training != 0 */
+  uint64_t seed; uint32_t site_base;
+  int passes;                           /* 3 = fp32-grade GEMMs (parity mode), 1 = bf16-grade */
+  void* ws; size_t ws_bytes;            /* activation workspace, >= vc_vit_workspace_bytes(F, S) */
+  float* cls_out;                       /* [F, 512] CLS embedding after the final LayerNorm */
+} vc_vit_call;
+
+size_t vc_vit_workspace_bytes(int F, int S);
+size_t vc_vit_scratch_bytes(int F, int S);
+int vc_vit_forward(const vc_vit_call* c, void* stream);
+/* needs the SAME call struct (and untouched workspace) as the forward; dcls [F,512] */
+int vc_vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, void* stream);
+
+typedef struct vc_dec_layer {
+  vc_linear sa_in; vc_linear sa_out;    /* self_attn.in_proj [3H,H], out_proj [H,H] */
+  vc_linear ca_in; vc_linear ca_out;    /* multihead_attn */
+  vc_linear lin1; vc_linear lin2;       /* [Ff,H], [H,Ff] */
+  vc_norm n1; vc_norm n2; vc_norm n3;
+} vc_dec_layer;
+
+typedef struct vc_seq_weights {
+  vc_linear embed_state; vc_linear embed_image; vc_linear image_proj; vc_linear head_params;
+  const float* embed_action_w; const float* embed_action_b; float* d_embed_action_w; float* d_embed_action_b;
+  const float* head_cmd_w; const float* head_cmd_b; float* d_head_cmd_w; float* d_head_cmd_b;
+  const float* timestep_emb; float* d_timestep_emb;     /* [max_ep_len, H] or null */
+  const vc_dec_layer* layers; int num_layers;
+} vc_seq_weights;
+
+typedef struct vc_seq_call {
+  const vc_seq_weights* w;
+  int B, T, H, nhead, Ff, window;
+  int past_actions, past_states;        /* the three branches of forward(), autoregressive_transformer.py:152-213 */
+  int act_dim, num_cmd, num_param_out;  /* 7, 5, 6000 */
+  const float* state_cls;               /* [B*T, 512] frame embeddings (unused unless past_states) */
+  const float* cad_cls;                 /* [B, 512] */
+  const float* actions;                 /* [B*T, act_dim] normalised actions */
+  float dropout_p; int training;
+  uint64_t seed; uint32_t site_base;
+  int passes;
+  void* ws; size_t ws_bytes;            /* >= vc_seq_workspace_bytes(...) */
+  float* cmds;                          /* [B*T, num_cmd] */
+  float* params;                        /* [B*T, num_param_out] */
+} vc_seq_call;
+
+size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out);
+size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out);
+int vc_seq_forward(const vc_seq_call* c, void* stream);
+/* dcmds [B*T,num_cmd], dparams [B*T,num_param_out]; d_state_cls [B*T,512] (may be null unless past_states),
+ * d_cad_cls [B,512] are OVERWRITTEN */
+int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
+                    void* scratch, size_t scratch_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

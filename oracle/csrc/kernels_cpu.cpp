@@ -1,0 +1,481 @@
+// TEST INFRASTRUCTURE ONLY -- plain C++ restatement of every kernel declared in videocad_b200/csrc/kernels.h,
+// operating on HOST pointers.  Linked with the product's host orchestration (model_vit.cpp, model_seq.cpp) into
+// oracle/_build/libvc_emu.so so that the orchestration (workspace layout, GEMM orientations, backward chain,
+// dropout-site bookkeeping) can be checked against the torch oracle on a machine without a GPU.
+// Never linked into, loaded by, or shipped with the product library.
+//
+// Each function follows the contract documented in kernels.h; arithmetic mirrors the CUDA kernels (same split-bf16
+// operand model, same Philox dropout masks) but accumulates in double.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "kernels.h"
+#include "host_util.h"
+#include "philox.h"
+
+namespace vck {
+
+namespace {
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);
+  const uint32_t r = 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)((u + r) >> 16);
+}
+inline float bf2f(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline void split1(float x, bf16_t& hi, bf16_t& lo) {
+  hi = f2bf(x);
+  lo = f2bf(x - bf2f(hi));
+}
+inline float keep_scale(const Drop& d, uint64_t idx) {
+  if (d.p <= 0.f) return 1.0f;
+  const Philox4 w = dropout_words(d.seed, d.site, idx >> 2);
+  return (w.v[idx & 3u] >= dropout_threshold(d.p)) ? 1.0f / (1.0f - d.p) : 0.0f;
+}
+inline double gelu_d(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }
+inline double gelu_grad_d(double x) {
+  return 0.5 * (1.0 + erf(x * 0.70710678118654752440)) + x * 0.39894228040143267794 * exp(-0.5 * x * x);
+}
+inline double act_d(double x, int act) {
+  switch (act) {
+    case VC_ACT_GELU: return gelu_d(x);
+    case VC_ACT_RELU: return x > 0 ? x : 0;
+    case VC_ACT_TANH: return tanh(x);
+    default: return x;
+  }
+}
+inline bool is_masked(int mask, int window, int i, int j) {
+  if (mask == VC_MASK_CAUSAL) return j > i;
+  if (mask == VC_MASK_WINDOW) return (j > i) || (j <= i - window);
+  return false;
+}
+
+}  // namespace
+
+void gemm_desc_init(GemmDesc* d) {
+  memset(d, 0, sizeof *d);
+  d->passes = 3;
+  d->splitk = 1;
+  d->rowadd_div = 1;
+  d->rowadd_mod = 1;
+}
+
+int gemm(const GemmDesc& d, stream_t) {
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error("gemm: empty problem");
+  if (d.N % 8 != 0) return set_error("gemm: N must be a multiple of 8");
+  if (d.lda % 8 != 0 || d.ldb % 8 != 0) return set_error("gemm: lda/ldb must be multiples of 8 elements");
+  if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
+  if (!d.a_hi || !d.b_hi) return set_error("gemm: null operand");
+  if (d.passes == 3 && (!d.a_lo || !d.b_lo)) return set_error("gemm: passes=3 needs lo operands");
+  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact))
+    return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");
+  if (!d.out_f32 && !d.out_hi) return set_error("gemm: no output");
+  const int num_kb = (d.K + 63) / 64;
+  int splitk = d.splitk < 1 ? 1 : d.splitk;
+  if (splitk > num_kb) splitk = num_kb;
+  const int kbps = (num_kb + splitk - 1) / splitk;
+  splitk = (num_kb + kbps - 1) / kbps;
+  // operands to float
+  std::vector<float> Ah((size_t)d.M * d.K), Al, Bh((size_t)d.N * d.K), Bl;
+  if (d.passes == 3) { Al.resize(Ah.size()); Bl.resize(Bh.size()); }
+  for (int m = 0; m < d.M; ++m)
+    for (int k = 0; k < d.K; ++k) {
+      const size_t src = d.a_mn_major ? (size_t)k * d.lda + m : (size_t)m * d.lda + k;
+      Ah[(size_t)m * d.K + k] = bf2f(d.a_hi[src]);
+      if (d.passes == 3) Al[(size_t)m * d.K + k] = bf2f(d.a_lo[src]);
+    }
+  for (int n = 0; n < d.N; ++n)
+    for (int k = 0; k < d.K; ++k) {
+      const size_t src = d.b_mn_major ? (size_t)k * d.ldb + n : (size_t)n * d.ldb + k;
+      Bh[(size_t)n * d.K + k] = bf2f(d.b_hi[src]);
+      if (d.passes == 3) Bl[(size_t)n * d.K + k] = bf2f(d.b_lo[src]);
+    }
+  const int rdiv = d.rowadd_div > 0 ? d.rowadd_div : 1, rmod = d.rowadd_mod > 0 ? d.rowadd_mod : 1;
+#pragma omp parallel for schedule(static)
+  for (int m = 0; m < d.M; ++m) {
+    for (int n = 0; n < d.N; ++n) {
+      const float* ah = &Ah[(size_t)m * d.K];
+      const float* bh = &Bh[(size_t)n * d.K];
+      double acc = 0.0;
+      if (d.passes == 3) {
+        const float* al = &Al[(size_t)m * d.K];
+        const float* bl = &Bl[(size_t)n * d.K];
+        for (int k = 0; k < d.K; ++k) acc += (double)ah[k] * bh[k] + (double)al[k] * bh[k] + (double)ah[k] * bl[k];
+      } else {
+        for (int k = 0; k < d.K; ++k) acc += (double)ah[k] * bh[k];
+      }
+      double v = acc;
+      if (d.bias) v += d.bias[n];
+      if (d.rowadd) v += d.rowadd[(size_t)((m / rdiv) % rmod) * d.ld_rowadd + n];
+      if (d.preact) d.preact[(size_t)m * d.ld_preact + n] = (float)v;
+      v = act_d(v, d.act);
+      v *= keep_scale(d.drop, (uint64_t)m * d.N + n);
+      if (d.residual) v += d.residual[(size_t)m * d.ld_res + n];
+      const float vf = (float)v;
+      if (d.out_f32) {
+        float* o = d.out_f32 + (size_t)m * d.ldo + n;
+        if (splitk > 1) *o += vf; else *o = vf;
+      }
+      if (d.out_hi) {
+        bf16_t hi, lo;
+        split1(vf, hi, lo);
+        d.out_hi[(size_t)m * d.ldo_split + n] = hi;
+        if (d.out_lo) d.out_lo[(size_t)m * d.ldo_split + n] = lo;
+      }
+    }
+  }
+  return 0;
+}
+
+int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t) {
+  if (cols % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0) return set_error("split_f32: cols/ld must be multiples of 4");
+  for (int64_t r = 0; r < rows; ++r)
+    for (int64_t c = 0; c < cols; ++c) split1(x[r * ldx + c], hi[r * ldo + c], lo[r * ldo + c]);
+  return 0;
+}
+
+namespace {
+template <class Load>
+void ln_fwd_rows(Load load, int64_t rows, int C, const float* gamma, const float* beta, float eps, float* y, int64_t ldy,
+                 bf16_t* y_hi, bf16_t* y_lo, int64_t ldys, float* mean, float* rstd) {
+  for (int64_t r = 0; r < rows; ++r) {
+    double s = 0;
+    for (int c = 0; c < C; ++c) s += load(r, c);
+    const double mu = s / C;
+    double q = 0;
+    for (int c = 0; c < C; ++c) { const double t = load(r, c) - mu; q += t * t; }
+    const double rs = 1.0 / sqrt(q / C + eps);
+    if (mean) mean[r] = (float)mu;
+    if (rstd) rstd[r] = (float)rs;
+    for (int c = 0; c < C; ++c) {
+      const float o = (float)((load(r, c) - mu) * rs * gamma[c] + beta[c]);
+      if (y) y[r * ldy + c] = o;
+      if (y_hi) {
+        bf16_t h, l;
+        split1(o, h, l);
+        y_hi[r * ldys + c] = h;
+        if (y_lo) y_lo[r * ldys + c] = l;
+      }
+    }
+  }
+}
+template <class Load>
+void ln_bwd_rows(Load load, const float* dy, int64_t lddy, const float* mean, const float* rstd, const float* gamma,
+                 int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx, float* dgamma,
+                 float* dbeta) {
+  std::vector<double> dg(C, 0.0), db(C, 0.0);
+  for (int64_t r = 0; r < rows; ++r) {
+    const double mu = mean[r], rs = rstd[r];
+    double s1 = 0, s2 = 0;
+    for (int c = 0; c < C; ++c) {
+      const double xh = (load(r, c) - mu) * rs, d = dy[r * lddy + c];
+      dg[c] += d * xh;
+      db[c] += d;
+      if (dx) { const double g = d * gamma[c]; s1 += g; s2 += g * xh; }
+    }
+    if (dx) {
+      s1 /= C; s2 /= C;
+      for (int c = 0; c < C; ++c) {
+        const double xh = (load(r, c) - mu) * rs, g = (double)dy[r * lddy + c] * gamma[c];
+        double o = rs * (g - s1 - xh * s2);
+        if (dres) o += dres[r * lddres + c];
+        dx[r * lddx + c] = (float)o;
+      }
+    }
+  }
+  for (int c = 0; c < C; ++c) { dgamma[c] += (float)dg[c]; dbeta[c] += (float)db[c]; }
+}
+struct PatchLoad {
+  const float* img; int S, wp, N;
+  double operator()(int64_t row, int c) const {
+    const int64_t f = row / N;
+    const int pidx = (int)(row % N), ph = pidx / wp, pw = pidx % wp, p1 = c >> 5, p2 = c & 31;
+    return img[(f * S + (ph * 32 + p1)) * (int64_t)S + pw * 32 + p2];
+  }
+};
+}  // namespace
+
+int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
+                  float* y, int64_t ldy, bf16_t* y_hi, bf16_t* y_lo, int64_t ldy_split, float* mean, float* rstd, stream_t) {
+  if (C % 128 != 0 || C > 1024) return set_error("layernorm_fwd: C must be a multiple of 128 and <= 1024");
+  ln_fwd_rows([&](int64_t r, int c) { return (double)x[r * ldx + c]; }, rows, C, gamma, beta, eps, y, ldy, y_hi, y_lo, ldy_split,
+              mean, rstd);
+  return 0;
+}
+int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                  const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                  float* dgamma, float* dbeta, stream_t) {
+  if (C % 128 != 0 || C > 1024) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
+  ln_bwd_rows([&](int64_t r, int c) { return (double)x[r * ldx + c]; }, dy, lddy, mean, rstd, gamma, rows, C, dres, lddres, dx, lddx,
+              dgamma, dbeta);
+  return 0;
+}
+int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
+                        bf16_t* y_lo, float* mean, float* rstd, stream_t) {
+  if (S % 32 != 0) return set_error("patch_layernorm_fwd: image size must be a multiple of 32");
+  const int wp = S / 32, N = wp * wp;
+  PatchLoad ld{img, S, wp, N};
+  ln_fwd_rows(ld, (int64_t)F * N, 1024, gamma, beta, eps, nullptr, 0, y_hi, y_lo, 1024, mean, rstd);
+  return 0;
+}
+int patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
+                               float* dgamma, float* dbeta, stream_t) {
+  if (S % 32 != 0) return set_error("patch_layernorm_bwd_params: image size must be a multiple of 32");
+  const int wp = S / 32, N = wp * wp;
+  PatchLoad ld{img, S, wp, N};
+  ln_bwd_rows(ld, dy, 1024, mean, rstd, nullptr, (int64_t)F * N, 1024, nullptr, 0, nullptr, 0, dgamma, dbeta);
+  return 0;
+}
+
+int vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, const float* pos, Drop drop, float* x, stream_t) {
+  const int n = N + 1;
+  for (int64_t f = 0; f < F; ++f)
+    for (int t = 0; t < n; ++t)
+      for (int c = 0; c < C; ++c) {
+        const int64_t idx = (f * n + t) * C + c;
+        const float v = (t == 0 ? cls[c] : e[(f * N + t - 1) * C + c]) + pos[(int64_t)t * C + c];
+        x[idx] = v * keep_scale(drop, (uint64_t)idx);
+      }
+  return 0;
+}
+int vit_assemble_bwd(const float* dx, int F, int N, int C, Drop drop, float* de, float* dcls, float* dpos, stream_t) {
+  const int n = N + 1;
+  for (int64_t f = 0; f < F; ++f)
+    for (int t = 0; t < n; ++t)
+      for (int c = 0; c < C; ++c) {
+        const int64_t idx = (f * n + t) * C + c;
+        const float g = dx[idx] * keep_scale(drop, (uint64_t)idx);
+        if (t > 0) de[(f * N + t - 1) * C + c] = g;
+        dpos[(int64_t)t * C + c] += g;
+        if (t == 0) dcls[c] += g;
+      }
+  return 0;
+}
+
+namespace {
+int attn_validate(const AttnDesc& a) {
+  if (a.d % 4 != 0 || a.d > 256 || a.d <= 0) return set_error("attention: head dim must be a multiple of 4 and <= 256");
+  if (a.mask != VC_MASK_NONE && a.Tq != a.Tk) return set_error("attention: masked attention needs Tq == Tk");
+  if (a.mask == VC_MASK_WINDOW && a.window < 1) return set_error("attention: window must be >= 1");
+  return 0;
+}
+}  // namespace
+
+int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t) {
+  if (int rc = attn_validate(a)) return rc;
+  const int d = a.d;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < a.B; ++b)
+    for (int h = 0; h < a.nh; ++h) {
+      std::vector<double> s(a.Tk), acc(d);
+      for (int i = 0; i < a.Tq; ++i) {
+        const float* q = a.q + ((int64_t)b * a.Tq + i) * a.ldq + (int64_t)h * d;
+        double m = -INFINITY;
+        for (int j = 0; j < a.Tk; ++j) {
+          if (is_masked(a.mask, a.window, i, j)) { s[j] = -INFINITY; continue; }
+          const float* k = a.k + ((int64_t)b * a.Tk + j) * a.ldk + (int64_t)h * d;
+          double t = 0;
+          for (int c = 0; c < d; ++c) t += (double)q[c] * k[c];
+          s[j] = t * a.scale;
+          if (s[j] > m) m = s[j];
+        }
+        double sum = 0;
+        for (int j = 0; j < a.Tk; ++j) sum += exp(s[j] - m);
+        const double l = m + log(sum);
+        lse[((int64_t)b * a.nh + h) * a.Tq + i] = (float)l;
+        for (int c = 0; c < d; ++c) acc[c] = 0;
+        for (int j = 0; j < a.Tk; ++j) {
+          if (s[j] == -INFINITY) continue;
+          const uint64_t idx = (((uint64_t)b * a.nh + h) * a.Tq + i) * (uint64_t)a.Tk + j;
+          const double pj = exp(s[j] - l) * keep_scale(a.drop, idx);
+          const float* v = a.v + ((int64_t)b * a.Tk + j) * a.ldv + (int64_t)h * d;
+          for (int c = 0; c < d; ++c) acc[c] += pj * v[c];
+        }
+        for (int c = 0; c < d; ++c) {
+          bf16_t hi, lo;
+          split1((float)acc[c], hi, lo);
+          const int64_t off = ((int64_t)b * a.Tq + i) * ldo + (int64_t)h * d + c;
+          o_hi[off] = hi;
+          if (o_lo) o_lo[off] = lo;
+        }
+      }
+    }
+  return 0;
+}
+
+int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse, const float* dout,
+                  int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, stream_t) {
+  if (int rc = attn_validate(a)) return rc;
+  const int d = a.d;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int b = 0; b < a.B; ++b)
+    for (int h = 0; h < a.nh; ++h) {
+      std::vector<double> dK((size_t)a.Tk * d, 0.0), dV((size_t)a.Tk * d, 0.0), dQ(d);
+      for (int i = 0; i < a.Tq; ++i) {
+        const int64_t ro = (int64_t)b * a.Tq + i;
+        const float* q = a.q + ro * a.ldq + (int64_t)h * d;
+        const float* dO = dout + ro * lddo + (int64_t)h * d;
+        double delta = 0;
+        for (int c = 0; c < d; ++c) {
+          const int64_t oo = ro * ldo + (int64_t)h * d + c;
+          delta += (double)dO[c] * (bf2f(o_hi[oo]) + (o_lo ? bf2f(o_lo[oo]) : 0.f));
+        }
+        const double l = lse[((int64_t)b * a.nh + h) * a.Tq + i];
+        for (int c = 0; c < d; ++c) dQ[c] = 0;
+        for (int j = 0; j < a.Tk; ++j) {
+          if (is_masked(a.mask, a.window, i, j)) continue;
+          const float* k = a.k + ((int64_t)b * a.Tk + j) * a.ldk + (int64_t)h * d;
+          const float* v = a.v + ((int64_t)b * a.Tk + j) * a.ldv + (int64_t)h * d;
+          double s = 0, dp = 0;
+          for (int c = 0; c < d; ++c) { s += (double)q[c] * k[c]; dp += (double)dO[c] * v[c]; }
+          const double pr = exp(s * a.scale - l);
+          const uint64_t idx = (((uint64_t)b * a.nh + h) * a.Tq + i) * (uint64_t)a.Tk + j;
+          const double m = keep_scale(a.drop, idx);
+          const double pt = pr * m, ds = pr * (dp * m - delta) * a.scale;
+          for (int c = 0; c < d; ++c) {
+            dV[(size_t)j * d + c] += pt * dO[c];
+            dK[(size_t)j * d + c] += ds * q[c];
+            dQ[c] += ds * k[c];
+          }
+        }
+        for (int c = 0; c < d; ++c) dq[ro * lddq + (int64_t)h * d + c] = (float)dQ[c];
+      }
+      for (int j = 0; j < a.Tk; ++j)
+        for (int c = 0; c < d; ++c) {
+          dk[((int64_t)b * a.Tk + j) * lddk + (int64_t)h * d + c] = (float)dK[(size_t)j * d + c];
+          dv[((int64_t)b * a.Tk + j) * lddv + (int64_t)h * d + c] = (float)dV[(size_t)j * d + c];
+        }
+    }
+  return 0;
+}
+
+int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,
+                    const bf16_t* aux_hi, int64_t ldaux_hi, Drop drop, float* g, int64_t ldg, bf16_t* g_hi, bf16_t* g_lo,
+                    int64_t ldg_split, float* colsum, stream_t) {
+  if (N % 4 != 0) return set_error("act_dropout_bwd: N % 4 != 0");
+  if ((act == VC_ACT_GELU || act == VC_ACT_TANH) && !aux) return set_error("act_dropout_bwd: aux required");
+  if (act == VC_ACT_RELU && !aux_hi) return set_error("act_dropout_bwd: aux_hi required for relu");
+  std::vector<double> cs(N, 0.0);
+  for (int64_t r = 0; r < M; ++r)
+    for (int c = 0; c < N; ++c) {
+      double v = (double)dy[r * lddy + c] * keep_scale(drop, (uint64_t)r * N + c);
+      if (act == VC_ACT_GELU) v *= gelu_grad_d(aux[r * ldaux + c]);
+      else if (act == VC_ACT_TANH) { const double t = aux[r * ldaux + c]; v *= 1.0 - t * t; }
+      else if (act == VC_ACT_RELU) { if ((aux_hi[r * ldaux_hi + c] & 0x7fffu) == 0) v = 0; }
+      const float vf = (float)v;
+      if (g) g[r * ldg + c] = vf;
+      if (g_hi) {
+        bf16_t hi, lo;
+        split1(vf, hi, lo);
+        g_hi[r * ldg_split + c] = hi;
+        if (g_lo) g_lo[r * ldg_split + c] = lo;
+      }
+      cs[c] += vf;
+    }
+  if (colsum) for (int c = 0; c < N; ++c) colsum[c] += (float)cs[c];
+  return 0;
+}
+
+int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t) {
+  if (div < 1 || mod < 1) return set_error("row_reduce_mod: div/mod must be >= 1");
+  for (int64_t m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) out[((m / div) % mod) * N + n] += x[m * ldx + n];
+  return 0;
+}
+
+int broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, float* dst, int64_t ldd, bf16_t* d_hi, bf16_t* d_lo,
+                   int64_t ldd_split, stream_t) {
+  for (int64_t m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      const float v = src[(m / div) * lds + n];
+      if (dst) dst[m * ldd + n] = v;
+      if (d_hi) {
+        bf16_t hi, lo;
+        split1(v, hi, lo);
+        d_hi[m * ldd_split + n] = hi;
+        if (d_lo) d_lo[m * ldd_split + n] = lo;
+      }
+    }
+  return 0;
+}
+
+int embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E, int T,
+                     float* y, bf16_t* y_hi, bf16_t* y_lo, stream_t) {
+  for (int64_t r = 0; r < R; ++r)
+    for (int h = 0; h < H; ++h) {
+      double acc = b[h];
+      for (int a = 0; a < A; ++a) acc += (double)actions[r * A + a] * W[(int64_t)h * A + a];
+      if (E) acc += E[(r % T) * H + h];
+      const float v = (float)tanh(acc);
+      if (y) y[r * H + h] = v;
+      if (y_hi) {
+        bf16_t hi, lo;
+        split1(v, hi, lo);
+        y_hi[r * H + h] = hi;
+        if (y_lo) y_lo[r * H + h] = lo;
+      }
+    }
+  return 0;
+}
+int embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW, float* db,
+                     float* dE, stream_t) {
+  if (A > 8) return set_error("embed_action_bwd: act_dim > 8 unsupported");
+  for (int64_t r = 0; r < R; ++r)
+    for (int h = 0; h < H; ++h) {
+      const float yv = y[r * H + h];
+      const float d = dy[r * H + h] * (1.f - yv * yv);
+      db[h] += d;
+      for (int a = 0; a < A; ++a) dW[(int64_t)h * A + a] += d * actions[r * A + a];
+      if (dE) dE[(r % T) * H + h] += d;
+    }
+  return 0;
+}
+
+int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t) {
+  if (C > 8 || H % 4 != 0) return set_error("head_small_fwd: C <= 8 and H % 4 == 0 required");
+  for (int64_t r = 0; r < R; ++r)
+    for (int c = 0; c < C; ++c) {
+      double acc = b[c];
+      for (int h = 0; h < H; ++h) acc += (double)x[r * H + h] * W[(int64_t)c * H + h];
+      out[r * C + c] = (float)acc;
+    }
+  return 0;
+}
+int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,
+                   float* dW, float* db, stream_t) {
+  if (C > 8 || H % 4 != 0) return set_error("head_small_bwd: C <= 8 and H % 4 == 0 required");
+  for (int64_t r = 0; r < R; ++r) {
+    for (int h = 0; h < H; ++h) {
+      double o = accumulate_dx ? dx[r * H + h] : 0.0;
+      for (int c = 0; c < C; ++c) o += (double)dout[r * C + c] * W[(int64_t)c * H + h];
+      dx[r * H + h] = (float)o;
+    }
+    for (int c = 0; c < C; ++c) {
+      db[c] += dout[r * C + c];
+      for (int h = 0; h < H; ++h) dW[(int64_t)c * H + h] += dout[r * C + c] * x[r * H + h];
+    }
+  }
+  return 0;
+}
+
+int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t) {
+  for (int64_t i = 0; i < n; ++i) out[i] = a[i] + b[i];
+  return 0;
+}
+int zero_f32(float* x, int64_t n, stream_t) {
+  if (n > 0) memset(x, 0, (size_t)n * sizeof(float));
+  return 0;
+}
+int dropout_mask_debug(Drop drop, int64_t n, float* out, stream_t) {
+  for (int64_t i = 0; i < n; ++i) out[i] = (drop.p > 0.f) ? keep_scale(drop, (uint64_t)i) : 1.0f;
+  return 0;
+}
+
+}  // namespace vck

@@ -69,14 +69,14 @@ def test_gemm_single_pass_is_bf16_grade():
 
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
 def test_gemm_epilogue(act):
-    M, N, K, T = 520, 264, 192, 8
-    A, B = _rand(M, K, seed=6, scale=0.5), _rand(N, K, seed=7, scale=0.2)
+    M, N, Kd, T = 520, 264, 192, 8
+    A, B = _rand(M, Kd, seed=6, scale=0.5), _rand(N, Kd, seed=7, scale=0.2)
     bias, rowadd, res = _rand(N, seed=8), _rand(T, N, seed=9), _rand(M, N, seed=10)
     drop = L.make_drop(0.1, 17, 1234)
     pre = torch.empty(M, N, device="cuda")
     out = torch.empty(M, N, device="cuda")
     outs = K.bf16_pair((M, N))
-    L.gemm(L.split(A), L.split(B), M, N, K, bias=bias, rowadd=rowadd, rowadd_div=1, rowadd_mod=T, preact=pre, act=act,
+    L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, rowadd=rowadd, rowadd_div=1, rowadd_mod=T, preact=pre, act=act,
            drop=drop, residual=res, out_f32=out, out_split=outs)
     mask = K.dropout_mask(drop, M * N).reshape(M, N)
     rows = torch.arange(M, device="cuda") % T
@@ -235,7 +235,8 @@ def test_attention_fwd_bwd(B, T, nh, d, mask, window, p):
     dq, dk, dv = K.attention_bwd(a, o, lse, dout, B, T, T, nh, d)
     for name, got, want in (("dq", dq, qd.grad), ("dk", dk, kd.grad), ("dv", dv, vd.grad)):
         assert torch.isfinite(got).all(), name
-        assert _relerr(got, want) < 1e-4, f"{name}: {_relerr(got, want):.3e}"
+        err = (got.double() - want).abs().max().item() / max(1.0, want.abs().max().item())
+        assert err < 1e-4, f"{name}: {err:.3e}"
 
 
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])

@@ -1,0 +1,465 @@
+// Host orchestration of the action-sequence transformer: token construction, nn.TransformerDecoder (post-norm,
+// ReLU, packed in_proj attention), the two action heads, and the full backward.
+//
+// Restates AutoRegressiveTransformer.forward after the image encoders
+// (/root/reference/model/autoregressive_transformer.py:143-218) with torch's TransformerDecoderLayer defaults
+// (norm_first=False, activation=relu, built at :54-62).  Math: SURVEY.md Appendix A.2 / A.3.
+// Rows are batch-first (r = b*T + t); the reference's seq-first permutes are views and do not change the math.
+//
+// Branches (autoregressive_transformer.py:152-213):
+//   past_actions            : tgt = tanh(embed_action(a)+E), causal self-attention;
+//                             memory = tanh(image_projection([ui ; cad])) if past_states else tanh(cad)
+//   past_states only        : tgt = ui = tanh(embed_state(vit(frames))+E), memory = tanh(cad), both masks banded
+//   neither                 : tgt = memory = tanh(cad), both masks banded
+// Dropout sites (site_base + 7*l + i): 0 self-attn probs, 1 dropout1, 2 cross-attn probs, 3 dropout2, 4 FFN hidden, 5 dropout3.
+#include <math.h>
+#include <vector>
+#include "model_common.h"
+
+namespace vck {
+
+namespace {
+
+constexpr int VD = VC_VIT_DIM;
+constexpr float LN_EPS = 1e-5f;
+
+struct Dims {
+  int B, T, R, H, Ff, L, nh, dh, NP, NC;
+  bool mem_has_ui, past_actions, past_states;
+};
+
+Dims dims_of(const vc_seq_call* c) {
+  Dims d;
+  d.B = c->B; d.T = c->T; d.R = c->B * c->T; d.H = c->H; d.Ff = c->Ff; d.L = c->w ? c->w->num_layers : 0;
+  d.nh = c->nhead; d.dh = c->nhead > 0 ? c->H / c->nhead : 0; d.NP = c->num_param_out; d.NC = c->num_cmd;
+  d.past_actions = c->past_actions != 0;
+  d.past_states = c->past_states != 0;
+  d.mem_has_ui = d.past_actions && d.past_states;
+  return d;
+}
+
+struct SeqWs {
+  Split scls, ccls;
+  float* cad_tok;
+  float* cat; Split catS;   // [R,2H]  (mem_has_ui): left = ui, right = cad token broadcast over T
+  float* ui; Split uiS;     // [R,H]   (past_states && !mem_has_ui)
+  float* mem; Split memS;   // [R,H]
+  float* act; Split actS;   // [R,H]   action tokens (past_actions)
+  struct Layer {
+    float* qkv; float* sa_lse; Split a; float* y1; float *m1, *r1; float* x1; Split x1S;
+    float* q2; float* kv2; float* ca_lse; Split c; float* y2; float *m2, *r2; float* x2; Split x2S;
+    Split f; float* y3; float *m3, *r3; float* x3; Split x3S;
+  };
+  std::vector<Layer> l;
+};
+
+void seq_carve(Arena& a, int B, int T, int H, int Ff, int L, int nh, SeqWs& w) {
+  const size_t R = (size_t)B * T;
+  w.scls = a.alloc_split(R, VD);
+  w.ccls = a.alloc_split(B, VD);
+  w.cad_tok = a.alloc<float>((size_t)B * H);
+  w.cat = a.alloc<float>(R * 2 * H); w.catS = a.alloc_split(R, 2 * H);
+  w.ui = a.alloc<float>(R * H); w.uiS = a.alloc_split(R, H);
+  w.mem = a.alloc<float>(R * H); w.memS = a.alloc_split(R, H);
+  w.act = a.alloc<float>(R * H); w.actS = a.alloc_split(R, H);
+  w.l.resize(L);
+  for (int i = 0; i < L; ++i) {
+    SeqWs::Layer& Y = w.l[i];
+    Y.qkv = a.alloc<float>(R * 3 * H); Y.sa_lse = a.alloc<float>((size_t)B * nh * T); Y.a = a.alloc_split(R, H);
+    Y.y1 = a.alloc<float>(R * H); Y.m1 = a.alloc<float>(R); Y.r1 = a.alloc<float>(R);
+    Y.x1 = a.alloc<float>(R * H); Y.x1S = a.alloc_split(R, H);
+    Y.q2 = a.alloc<float>(R * H); Y.kv2 = a.alloc<float>(R * 2 * H); Y.ca_lse = a.alloc<float>((size_t)B * nh * T);
+    Y.c = a.alloc_split(R, H);
+    Y.y2 = a.alloc<float>(R * H); Y.m2 = a.alloc<float>(R); Y.r2 = a.alloc<float>(R);
+    Y.x2 = a.alloc<float>(R * H); Y.x2S = a.alloc_split(R, H);
+    Y.f = a.alloc_split(R, Ff);
+    Y.y3 = a.alloc<float>(R * H); Y.m3 = a.alloc<float>(R); Y.r3 = a.alloc<float>(R);
+    Y.x3 = a.alloc<float>(R * H); Y.x3S = a.alloc_split(R, H);
+  }
+}
+
+struct SeqScratch {
+  float *A, *Bf, *Y, *dF, *dAtt, *dqkv, *dmem, *dcat, *dcadtok;
+  Split gH, dpreF, dqkvS, dparS, gB;
+};
+
+void seq_scratch_carve(Arena& a, int B, int T, int H, int Ff, int NP, SeqScratch& s) {
+  const size_t R = (size_t)B * T;
+  s.A = a.alloc<float>(R * H); s.Bf = a.alloc<float>(R * H); s.Y = a.alloc<float>(R * H);
+  s.dF = a.alloc<float>(R * Ff); s.dAtt = a.alloc<float>(R * H);
+  s.dqkv = a.alloc<float>(R * 3 * H); s.dmem = a.alloc<float>(R * H);
+  s.dcat = a.alloc<float>(R * 2 * H); s.dcadtok = a.alloc<float>((size_t)B * H);
+  s.gH = a.alloc_split(R, H); s.dpreF = a.alloc_split(R, Ff); s.dqkvS = a.alloc_split(R, 3 * H);
+  s.dparS = a.alloc_split(R, NP); s.gB = a.alloc_split(B, H);
+}
+
+int check_call(const vc_seq_call* c) {
+  if (!c || !c->w || !c->cad_cls || !c->ws || !c->cmds || !c->params) return set_error("seq: null argument");
+  if (c->B <= 0 || c->T <= 0) return set_error("seq: B and T must be positive");
+  if (c->H % 128 != 0 || c->H > 1024) return set_error("seq: hidden_size must be a multiple of 128 and <= 1024");
+  if (c->Ff % 8 != 0) return set_error("seq: dim_feedforward must be a multiple of 8");
+  if (c->nhead <= 0 || c->H % c->nhead != 0) return set_error("seq: hidden_size must be divisible by nhead");
+  if ((c->H / c->nhead) % 4 != 0 || c->H / c->nhead > 256) return set_error("seq: head dim must be a multiple of 4 and <= 256");
+  if (c->window < 1) return set_error("seq: window_size must be > 0");
+  if (c->num_param_out % 8 != 0) return set_error("seq: parameter head width must be a multiple of 8");
+  if (c->num_cmd > 8) return set_error("seq: more than 8 command classes unsupported");
+  if (c->past_states && !c->state_cls) return set_error("seq: past_states needs state_cls");
+  if (c->past_actions && !c->actions) return set_error("seq: past_actions needs actions");
+  if (c->passes != 1 && c->passes != 3) return set_error("seq: passes must be 1 or 3");
+  if (c->w->num_layers < 1 || !c->w->layers) return set_error("seq: need at least one decoder layer");
+  return 0;
+}
+
+AttnDesc self_attn_desc(const vc_seq_call* c, const Dims& d, const SeqWs::Layer& Y, Drop drop) {
+  AttnDesc a;
+  a.q = Y.qkv; a.k = Y.qkv + d.H; a.v = Y.qkv + 2 * d.H;
+  a.ldq = a.ldk = a.ldv = 3 * d.H;
+  a.B = d.B; a.Tq = d.T; a.Tk = d.T; a.nh = d.nh; a.d = d.dh;
+  a.mask = d.past_actions ? VC_MASK_CAUSAL : VC_MASK_WINDOW;
+  a.window = c->window;
+  a.scale = 1.0f / sqrtf((float)d.dh);
+  a.drop = drop;
+  return a;
+}
+AttnDesc cross_attn_desc(const vc_seq_call* c, const Dims& d, const SeqWs::Layer& Y, Drop drop) {
+  AttnDesc a;
+  a.q = Y.q2; a.k = Y.kv2; a.v = Y.kv2 + d.H;
+  a.ldq = d.H; a.ldk = a.ldv = 2 * d.H;
+  a.B = d.B; a.Tq = d.T; a.Tk = d.T; a.nh = d.nh; a.d = d.dh;
+  a.mask = VC_MASK_WINDOW;
+  a.window = c->window;
+  a.scale = 1.0f / sqrtf((float)d.dh);
+  a.drop = drop;
+  return a;
+}
+
+static inline Split cols(const Split& s, int64_t col0) { return mk_split(s.hi + col0, s.lo + col0, s.ld); }
+
+}  // namespace
+
+size_t seq_workspace_bytes(int B, int T, int H, int Ff, int L, int nh) {
+  Arena a(nullptr, 0);
+  SeqWs w;
+  seq_carve(a, B, T, H, Ff, L, nh, w);
+  return a.used();
+}
+size_t seq_scratch_bytes(int B, int T, int H, int Ff, int NP) {
+  Arena a(nullptr, 0);
+  SeqScratch s;
+  seq_scratch_carve(a, B, T, H, Ff, NP, s);
+  return a.used();
+}
+
+int seq_forward(const vc_seq_call* c, stream_t st) {
+  VC_TRY(check_call(c));
+  const vc_seq_weights& W = *c->w;
+  const Dims d = dims_of(c);
+  const int B = d.B, T = d.T, R = d.R, H = d.H, Ff = d.Ff, P = c->passes;
+  Arena arena(c->ws, c->ws_bytes);
+  SeqWs w;
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, w);
+  if (!arena.ok()) return set_error("seq_forward: workspace too small");
+  const float p = c->dropout_p;
+  const float* E = W.timestep_emb;  // rows 0..T-1 are the positions arange(T)
+
+  // ---- frame tokens: ui = tanh(embed_state(cls) + E[t])
+  float* ui = nullptr; Split uiS = mk_split(nullptr, nullptr, 0); int64_t ld_ui = 0;
+  if (d.past_states) {
+    VC_TRY(split_f32(c->state_cls, VD, R, VD, w.scls.hi, w.scls.lo, VD, st));
+    if (d.mem_has_ui) { ui = w.cat; uiS = w.catS; ld_ui = 2 * H; } else { ui = w.ui; uiS = w.uiS; ld_ui = H; }
+    GemmDesc g;
+    gemm_linear_fwd(g, w.scls, wsplit(W.embed_state, VD), R, H, VD, P);
+    g.bias = W.embed_state.b;
+    if (E) { g.rowadd = E; g.ld_rowadd = H; g.rowadd_div = 1; g.rowadd_mod = T; }
+    g.act = VC_ACT_TANH;
+    g.out_f32 = ui; g.ldo = ld_ui; g.out_hi = uiS.hi; g.out_lo = uiS.lo; g.ldo_split = uiS.ld;
+    VC_TRY(gemm(g, st));
+  }
+  // ---- CAD token (static over T)
+  VC_TRY(split_f32(c->cad_cls, VD, B, VD, w.ccls.hi, w.ccls.lo, VD, st));
+  {
+    GemmDesc g;
+    gemm_linear_fwd(g, w.ccls, wsplit(W.embed_image, VD), B, H, VD, P);
+    g.bias = W.embed_image.b;
+    g.act = d.mem_has_ui ? VC_ACT_NONE : VC_ACT_TANH;
+    g.out_f32 = w.cad_tok; g.ldo = H;
+    VC_TRY(gemm(g, st));
+  }
+  if (d.mem_has_ui) {
+    VC_TRY(broadcast_rows(w.cad_tok, H, R, H, T, w.cat + H, 2 * H, w.catS.hi + H, w.catS.lo + H, 2 * H, st));
+    GemmDesc g;
+    gemm_linear_fwd(g, w.catS, wsplit(W.image_proj, 2 * H), R, H, 2 * H, P);
+    g.bias = W.image_proj.b; g.act = VC_ACT_TANH;
+    g.out_f32 = w.mem; g.ldo = H; g.out_hi = w.memS.hi; g.out_lo = w.memS.lo; g.ldo_split = H;
+    VC_TRY(gemm(g, st));
+  } else {
+    VC_TRY(broadcast_rows(w.cad_tok, H, R, H, T, w.mem, H, w.memS.hi, w.memS.lo, H, st));
+  }
+  // ---- target tokens
+  const float* x_in; Split x_inS; int64_t ld_x;
+  if (d.past_actions) {
+    VC_TRY(embed_action_fwd(c->actions, R, c->act_dim, H, W.embed_action_w, W.embed_action_b, E, T, w.act, w.actS.hi, w.actS.lo, st));
+    x_in = w.act; x_inS = w.actS; ld_x = H;
+  } else if (d.past_states) {
+    x_in = ui; x_inS = uiS; ld_x = ld_ui;
+  } else {
+    x_in = w.mem; x_inS = w.memS; ld_x = H;
+  }
+
+  for (int l = 0; l < d.L; ++l) {
+    const vc_dec_layer& LW = W.layers[l];
+    SeqWs::Layer& Y = w.l[l];
+    const uint32_t s0 = c->site_base + 7 * l;
+    // self-attention block: x1 = LN1(x + drop(out_proj(SA(x))))
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, x_inS, wsplit(LW.sa_in, H), R, 3 * H, H, P);
+      g.bias = LW.sa_in.b; g.out_f32 = Y.qkv; g.ldo = 3 * H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(attention_fwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0)), Y.a.hi, Y.a.lo, H, Y.sa_lse, st));
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, Y.a, wsplit(LW.sa_out, H), R, H, H, P);
+      g.bias = LW.sa_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 1);
+      g.residual = x_in; g.ld_res = ld_x; g.out_f32 = Y.y1; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(layernorm_fwd(Y.y1, H, R, H, LW.n1.w, LW.n1.b, LN_EPS, Y.x1, H, Y.x1S.hi, Y.x1S.lo, H, Y.m1, Y.r1, st));
+    // cross-attention block: x2 = LN2(x1 + drop(out_proj(CA(x1, mem))))
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, Y.x1S, wsplit(LW.ca_in, H, 0), R, H, H, P);
+      g.bias = LW.ca_in.b; g.out_f32 = Y.q2; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, w.memS, wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
+      g.bias = LW.ca_in.b ? LW.ca_in.b + H : nullptr; g.out_f32 = Y.kv2; g.ldo = 2 * H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(attention_fwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2)), Y.c.hi, Y.c.lo, H, Y.ca_lse, st));
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, Y.c, wsplit(LW.ca_out, H), R, H, H, P);
+      g.bias = LW.ca_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 3);
+      g.residual = Y.x1; g.ld_res = H; g.out_f32 = Y.y2; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(layernorm_fwd(Y.y2, H, R, H, LW.n2.w, LW.n2.b, LN_EPS, Y.x2, H, Y.x2S.hi, Y.x2S.lo, H, Y.m2, Y.r2, st));
+    // feed-forward block: x3 = LN3(x2 + drop(linear2(drop(relu(linear1(x2))))))
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, Y.x2S, wsplit(LW.lin1, H), R, Ff, H, P);
+      g.bias = LW.lin1.b; g.act = VC_ACT_RELU; g.drop = site_drop(p, c->training, c->seed, s0 + 4);
+      g.out_hi = Y.f.hi; g.out_lo = Y.f.lo; g.ldo_split = Ff;
+      VC_TRY(gemm(g, st));
+    }
+    {
+      GemmDesc g;
+      gemm_linear_fwd(g, Y.f, wsplit(LW.lin2, Ff), R, H, Ff, P);
+      g.bias = LW.lin2.b; g.drop = site_drop(p, c->training, c->seed, s0 + 5);
+      g.residual = Y.x2; g.ld_res = H; g.out_f32 = Y.y3; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(layernorm_fwd(Y.y3, H, R, H, LW.n3.w, LW.n3.b, LN_EPS, Y.x3, H, Y.x3S.hi, Y.x3S.lo, H, Y.m3, Y.r3, st));
+    x_in = Y.x3; x_inS = Y.x3S; ld_x = H;
+  }
+  // ---- heads
+  VC_TRY(head_small_fwd(x_in, R, H, W.head_cmd_w, W.head_cmd_b, d.NC, c->cmds, st));
+  {
+    GemmDesc g;
+    gemm_linear_fwd(g, x_inS, wsplit(W.head_params, H), R, d.NP, H, P);
+    g.bias = W.head_params.b; g.out_f32 = c->params; g.ldo = d.NP;
+    VC_TRY(gemm(g, st));
+  }
+  return 0;
+}
+
+int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
+                 void* scratch, size_t scratch_bytes, stream_t st) {
+  VC_TRY(check_call(c));
+  if (!dcmds || !dparams || !d_cad_cls || !scratch) return set_error("seq_backward: null argument");
+  const vc_seq_weights& W = *c->w;
+  const Dims d = dims_of(c);
+  if (d.past_states && !d_state_cls) return set_error("seq_backward: past_states needs d_state_cls");
+  const int B = d.B, T = d.T, R = d.R, H = d.H, Ff = d.Ff, P = c->passes;
+  Arena arena(c->ws, c->ws_bytes);
+  SeqWs w;
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, w);
+  if (!arena.ok()) return set_error("seq_backward: workspace too small");
+  Arena sa(scratch, scratch_bytes);
+  SeqScratch s;
+  seq_scratch_carve(sa, B, T, H, Ff, d.NP, s);
+  if (!sa.ok()) return set_error("seq_backward: scratch too small");
+  const float p = c->dropout_p;
+
+  float* ui = nullptr; int64_t ld_ui = 0;
+  if (d.past_states) { if (d.mem_has_ui) { ui = w.cat; ld_ui = 2 * H; } else { ui = w.ui; ld_ui = H; } }
+  const SeqWs::Layer& last = w.l[d.L - 1];
+
+  // ---- heads: A = d x_last
+  VC_TRY(act_dropout_bwd(dparams, d.NP, R, d.NP, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dparS.hi, s.dparS.lo,
+                         d.NP, W.head_params.db, st));
+  VC_TRY(linear_wgrad(s.dparS, last.x3S, R, d.NP, H, W.head_params.dw, P, st));
+  {
+    GemmDesc g;
+    gemm_linear_dgrad(g, s.dparS, wsplit(W.head_params, H), R, d.NP, H, P);
+    g.out_f32 = s.A; g.ldo = H;
+    VC_TRY(gemm(g, st));
+  }
+  VC_TRY(head_small_bwd(dcmds, last.x3, R, H, W.head_cmd_w, d.NC, s.A, 1, W.d_head_cmd_w, W.d_head_cmd_b, st));
+
+  bool dmem_init = false;
+  for (int l = d.L - 1; l >= 0; --l) {
+    const vc_dec_layer& LW = W.layers[l];
+    const SeqWs::Layer& Y = w.l[l];
+    const uint32_t s0 = c->site_base + 7 * l;
+    const Split x_inS = (l > 0) ? w.l[l - 1].x3S
+                                : (d.past_actions ? w.actS : (d.past_states ? (d.mem_has_ui ? w.catS : w.uiS) : w.memS));
+    // ---- feed-forward block
+    VC_TRY(layernorm_bwd(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db, st));
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5), nullptr, 0,
+                           s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
+    VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gH, wsplit(LW.lin2, Ff), R, H, Ff, P);
+      g.out_f32 = s.dF; g.ldo = Ff;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(act_dropout_bwd(s.dF, Ff, R, Ff, VC_ACT_RELU, nullptr, 0, Y.f.hi, Ff, site_drop(p, c->training, c->seed, s0 + 4), nullptr, 0,
+                           s.dpreF.hi, s.dpreF.lo, Ff, LW.lin1.db, st));
+    VC_TRY(linear_wgrad(s.dpreF, Y.x2S, R, Ff, H, LW.lin1.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.dpreF, wsplit(LW.lin1, H), R, Ff, H, P);
+      g.residual = s.Y; g.ld_res = H; g.out_f32 = s.Bf; g.ldo = H;  // d x2 = d y3 + dpre W1
+      VC_TRY(gemm(g, st));
+    }
+    // ---- cross-attention block
+    VC_TRY(layernorm_bwd(s.Bf, H, Y.y2, H, Y.m2, Y.r2, LW.n2.w, R, H, nullptr, 0, s.Y, H, LW.n2.dw, LW.n2.db, st));
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3), nullptr, 0,
+                           s.gH.hi, s.gH.lo, H, LW.ca_out.db, st));
+    VC_TRY(linear_wgrad(s.gH, Y.c, R, H, H, LW.ca_out.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gH, wsplit(LW.ca_out, H), R, H, H, P);
+      g.out_f32 = s.dAtt; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(attention_bwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2)), Y.c.hi, Y.c.lo, H, Y.ca_lse, s.dAtt, H,
+                         s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
+    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
+                           3 * H, LW.ca_in.db, st));
+    VC_TRY(linear_wgrad(cols(s.dqkvS, 0), Y.x1S, R, H, H, LW.ca_in.dw, P, st));
+    VC_TRY(linear_wgrad(cols(s.dqkvS, H), w.memS, R, 2 * H, H, LW.ca_in.dw + (size_t)H * H, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, cols(s.dqkvS, 0), wsplit(LW.ca_in, H, 0), R, H, H, P);
+      g.residual = s.Y; g.ld_res = H; g.out_f32 = s.A; g.ldo = H;  // d x1 = d y2 + dq Wq
+      VC_TRY(gemm(g, st));
+    }
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, cols(s.dqkvS, H), wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
+      if (dmem_init) { g.residual = s.dmem; g.ld_res = H; }
+      g.out_f32 = s.dmem; g.ldo = H;  // d mem accumulates over the layers
+      VC_TRY(gemm(g, st));
+      dmem_init = true;
+    }
+    // ---- self-attention block
+    VC_TRY(layernorm_bwd(s.A, H, Y.y1, H, Y.m1, Y.r1, LW.n1.w, R, H, nullptr, 0, s.Y, H, LW.n1.dw, LW.n1.db, st));
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1), nullptr, 0,
+                           s.gH.hi, s.gH.lo, H, LW.sa_out.db, st));
+    VC_TRY(linear_wgrad(s.gH, Y.a, R, H, H, LW.sa_out.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gH, wsplit(LW.sa_out, H), R, H, H, P);
+      g.out_f32 = s.dAtt; g.ldo = H;
+      VC_TRY(gemm(g, st));
+    }
+    VC_TRY(attention_bwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0)), Y.a.hi, Y.a.lo, H, Y.sa_lse, s.dAtt, H,
+                         s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
+    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
+                           3 * H, LW.sa_in.db, st));
+    VC_TRY(linear_wgrad(s.dqkvS, x_inS, R, 3 * H, H, LW.sa_in.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.dqkvS, wsplit(LW.sa_in, H), R, 3 * H, H, P);
+      g.residual = s.Y; g.ld_res = H; g.out_f32 = s.A; g.ldo = H;  // d x_in = d y1 + dqkv W_in
+      VC_TRY(gemm(g, st));
+    }
+  }
+
+  // ---- token construction backward: s.A = d tgt, s.dmem = d memory
+  float* dE = W.d_timestep_emb;  // may be null
+  const float* dui = nullptr; int64_t ld_dui = 0;
+  if (d.past_actions) {
+    VC_TRY(embed_action_bwd(s.A, w.act, c->actions, R, c->act_dim, H, T, W.d_embed_action_w, W.d_embed_action_b,
+                            W.timestep_emb ? dE : nullptr, st));
+  } else if (d.past_states) {
+    dui = s.A; ld_dui = H;
+  } else {
+    VC_TRY(add_f32(s.dmem, s.A, s.dmem, (int64_t)R * H, st));
+  }
+  VC_TRY(zero_f32(s.dcadtok, (int64_t)B * H, st));
+  if (d.mem_has_ui) {
+    // mem = tanh(image_projection([ui ; cad]))
+    VC_TRY(act_dropout_bwd(s.dmem, H, R, H, VC_ACT_TANH, w.mem, H, nullptr, 0, no_drop(), nullptr, 0, s.gH.hi, s.gH.lo, H,
+                           W.image_proj.db, st));
+    VC_TRY(linear_wgrad(s.gH, w.catS, R, H, 2 * H, W.image_proj.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gH, wsplit(W.image_proj, 2 * H), R, H, 2 * H, P);
+      g.out_f32 = s.dcat; g.ldo = 2 * H;
+      VC_TRY(gemm(g, st));
+    }
+    dui = s.dcat; ld_dui = 2 * H;
+    VC_TRY(row_reduce_mod(s.dcat + H, 2 * H, R, H, T, B, s.dcadtok, st));
+  } else {
+    VC_TRY(row_reduce_mod(s.dmem, H, R, H, T, B, s.dcadtok, st));
+  }
+  if (d.past_states) {
+    // ui = tanh(embed_state(cls) + E[t])
+    VC_TRY(act_dropout_bwd(dui, ld_dui, R, H, VC_ACT_TANH, ui, ld_ui, nullptr, 0, no_drop(), s.Y, H, s.gH.hi, s.gH.lo, H,
+                           W.embed_state.db, st));
+    if (W.timestep_emb && dE) VC_TRY(row_reduce_mod(s.Y, H, R, H, 1, T, dE, st));
+    VC_TRY(linear_wgrad(s.gH, w.scls, R, H, VD, W.embed_state.dw, P, st));
+    {
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gH, wsplit(W.embed_state, VD), R, H, VD, P);
+      g.out_f32 = d_state_cls; g.ldo = VD;
+      VC_TRY(gemm(g, st));
+    }
+  }
+  // cad token: embed_image (with tanh folded in when there is no projection)
+  VC_TRY(act_dropout_bwd(s.dcadtok, H, B, H, d.mem_has_ui ? VC_ACT_NONE : VC_ACT_TANH, w.cad_tok, H, nullptr, 0, no_drop(), nullptr, 0,
+                         s.gB.hi, s.gB.lo, H, W.embed_image.db, st));
+  VC_TRY(linear_wgrad(s.gB, w.ccls, B, H, VD, W.embed_image.dw, P, st));
+  {
+    GemmDesc g;
+    gemm_linear_dgrad(g, s.gB, wsplit(W.embed_image, VD), B, H, VD, P);
+    g.out_f32 = d_cad_cls; g.ldo = VD;
+    VC_TRY(gemm(g, st));
+  }
+  return 0;
+}
+
+}  // namespace vck
+
+extern "C" {
+size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out) {
+  (void)num_param_out;
+  return vck::seq_workspace_bytes(B, T, H, Ff, num_layers, nhead);
+}
+size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out) {
+  return vck::seq_scratch_bytes(B, T, H, Ff, num_param_out);
+}
+int vc_seq_forward(const vc_seq_call* c, void* stream) { return vck::seq_forward(c, stream); }
+int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
+                    void* scratch, size_t scratch_bytes, void* stream) {
+  return vck::seq_backward(c, dcmds, dparams, d_state_cls, d_cad_cls, scratch, scratch_bytes, stream);
+}
+}
