@@ -73,6 +73,16 @@ int vc_version(void);
 /* 1 if this library was built from the CUDA sources (product), 0 for the CPU emulation used by host-logic tests */
 int vc_is_cuda_build(void);
 
+/* ---- instrumentation (bench.py): number of kernels launched by this library, and CUDA-event timing of every
+ * tensor-core GEMM launch (events recorded on the launching stream around each launch while enabled) ---- */
+long long vc_launch_count(void);
+void vc_launch_count_reset(void);
+void vc_gemm_profile(int enable);                  /* enable/disable + clear the event pool */
+int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches); /* synchronises the events */
+/* sizeof() of the ABI structs, for binding self-checks: 0 vc_drop, 1 vc_gemm_desc, 2 vc_attn_desc, 3 vc_linear,
+ * 4 vc_norm, 5 vc_vit_weights, 6 vc_vit_call, 7 vc_dec_layer, 8 vc_seq_weights, 9 vc_seq_call */
+size_t vc_abi_sizeof(int which);
+
 /* ---- per-kernel entry points (unit parity tests call these; the model-level calls below chain them) ---- */
 void vc_gemm_desc_init(vc_gemm_desc* d);
 int vc_gemm(const vc_gemm_desc* d, void* stream);

@@ -1,0 +1,197 @@
+"""Parity of the full CUDA path (through the drop-in nn.Module and the C ABI) against the oracle and the committed
+golden fixtures produced by the unmodified reference.  Run on the B200 box: python -m pytest tests -m gpu"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import torch_oracle as to  # noqa: E402
+from videocad_b200 import AutoRegressiveTransformer  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small"]
+
+# fp tolerance of the parity mode (3-pass split-bf16 GEMMs, fp32 everything else) against the reference's fp32
+# forward: BASELINE.json asks for 1e-3 max-abs on the logits; measured ~2e-5, asserted at 2e-4.
+LOGIT_TOL = 2e-4
+GRAD_REL_TOL = 2e-3
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    norms = json.loads(bytes(z["grad_norms_json"]).decode())
+    return z, meta, norms
+
+
+def build(cfg, device="cuda", dropout=0.1, seed=0, **kw):
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, encoder="vit", **cfg, **kw)
+    sd = to.seeded_state_dict(cfg, seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    return m.to(device), sd
+
+
+def loss_weights(cs, ps, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(cs, generator=g), torch.randn(ps, generator=g) * 0.05
+
+
+def cuda_inputs(B, T, S, seed=1234):
+    batch = to.synthetic_batch(B, T + 1, S, seed=seed)
+    inp = to.model_inputs_from_batch(batch)
+    return {k: v.cuda() for k, v in inp.items()}, batch
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_forward_backward_vs_reference_golden(name):
+    z, meta, norms = load_case(name)
+    m, sd = build(meta["cfg"])
+    m.eval()
+    inp, _ = cuda_inputs(meta["B"], meta["T"], meta["S"], meta["batch_seed"])
+    cmds, params = m(inp)
+    dc = (cmds.cpu() - torch.from_numpy(z["cmds"])).abs().max().item()
+    dp = (params.cpu() - torch.from_numpy(z["params"])).abs().max().item()
+    assert dc < LOGIT_TOL and dp < LOGIT_TOL, f"{name}: max|d| cmds {dc:.3e} params {dp:.3e}"
+    wc, wp = loss_weights(cmds.shape, params.shape, meta["loss_seed"])
+    loss = (cmds * wc.cuda()).sum() + (params * wp.cuda()).sum()
+    assert abs(loss.item() - float(z["loss"])) < 5e-3
+    loss.backward()
+    worst = 0.0
+    for k, p in m.named_parameters():
+        if k not in norms:
+            assert p.grad is None or p.grad.abs().max().item() == 0.0, f"{k} should be unused"
+            continue
+        assert p.grad is not None, k
+        n = p.grad.double().norm().item()
+        rel = abs(n - norms[k]) / (norms[k] + 1e-6)
+        assert rel < GRAD_REL_TOL, f"{name} {k}: grad norm {n:.6e} vs reference {norms[k]:.6e}"
+        if ("grad::" + k) in z.files:
+            ref = torch.from_numpy(z["grad::" + k])
+            err = (p.grad.cpu() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+            worst = max(worst, err)
+            assert err < GRAD_REL_TOL, f"{name} {k}: grad max rel err {err:.3e}"
+    print(f"{name}: logits {dc:.2e}/{dp:.2e}, worst full-grad rel err {worst:.2e}")
+
+
+def test_c1_shape_vs_oracle_fp64():
+    """BASELINE config C1 model (H=512, 8 layers, window 10) at a reduced batch, against the fp64 oracle on the GPU."""
+    cfg = dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build(cfg)
+    m.eval()
+    inp, _ = cuda_inputs(3, 8, 224)
+    with torch.no_grad():
+        cmds, params = m(inp)
+        sdd = {k: v.double().cuda() for k, v in sd.items()}
+        oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
+    dc, dp = (cmds.double() - oc).abs().max().item(), (params.double() - op).abs().max().item()
+    print(f"C1-shape logits max|d|: cmds {dc:.3e} params {dp:.3e}")
+    assert dc < LOGIT_TOL and dp < LOGIT_TOL
+
+
+def test_bf16_single_pass_mode_is_looser_but_close():
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=3,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build(cfg, precision="bf16")
+    m.eval()
+    inp, _ = cuda_inputs(2, 4, 224)
+    with torch.no_grad():
+        cmds, params = m(inp)
+        oc, op = to.forward({k: v.cuda() for k, v in sd.items()}, cfg, inp)
+    d = max((cmds - oc).abs().max().item(), (params - op).abs().max().item())
+    assert 1e-4 < d < 0.1, d
+
+
+def test_prefix_invariance_and_rollout():
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=2,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build(cfg)
+    m.eval()
+    B, T, S = 2, 6, 64
+    inp, _ = cuda_inputs(B, T, S)
+    with torch.no_grad():
+        full_c, full_p = m(inp)
+        k = 4
+        pre = {"frames": inp["frames"][:, :k], "actions": inp["actions"][:, :k], "cad_image": inp["cad_image"]}
+        pc, pp = m(pre)
+        assert (pc - full_c[:, :k]).abs().max() < 1e-5 and (pp - full_p[:, :k]).abs().max() < 1e-5
+        # rollout without feedback == one forward with zero actions
+        rc, rp = m.sequential_inference(inp["frames"], inp["cad_image"], action=False)
+        zc, zp = m({"frames": inp["frames"], "actions": torch.zeros_like(inp["actions"]), "cad_image": inp["cad_image"]})
+        assert (rc - zc).abs().max() < 1e-6 and (rp - zp).abs().max() < 1e-6
+        # rollout with action feedback against the oracle's O(T^2) recompute
+        ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
+        oc, op = to.rollout(sd, cfg, inp["frames"].cpu(), inp["cad_image"].cpu(), action=True)
+        assert (ac.cpu().argmax(-1) == oc.argmax(-1)).all()
+        assert (ac.cpu() - oc).abs().max() < LOGIT_TOL and (ap.cpu() - op).abs().max() < LOGIT_TOL
+
+
+def test_training_mode_dropout_is_reproducible_and_trains():
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=3,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    from videocad_b200.loss import compute_loss
+
+    m, sd = build(cfg, dropout=0.1)
+    m.train()
+    inp, batch = cuda_inputs(4, 4, 64)
+    tgt = batch["actions"][:, 1:].cuda()
+    torch.manual_seed(7)
+    c1, p1 = m(inp)
+    torch.manual_seed(7)
+    c2, p2 = m(inp)
+    assert torch.equal(c1, c2) and torch.equal(p1, p2), "same torch seed -> same dropout masks"
+    c3, _ = m(inp)
+    assert not torch.equal(c1, c3), "a new seed is drawn on every forward"
+    m.eval()
+    ce, _ = m(inp)
+    assert 1e-3 < (ce - c1).abs().max().item() < 5.0
+    # a few Adam steps on one batch must reduce the reference loss
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(12):
+        opt.zero_grad()
+        loss = compute_loss(m(inp), tgt)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        losses.append(loss.item())
+    assert all(np.isfinite(losses))
+    assert np.mean(losses[-3:]) < np.mean(losses[:3]), losses
+
+
+def test_full_size_c1_batch_properties():
+    """BASELINE C1 at full size (B=32, T=8, 224x224, H=512): size-independent properties."""
+    cfg = dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, _ = build(cfg)
+    m.eval()
+    inp, _ = cuda_inputs(32, 8, 224)
+    with torch.no_grad():
+        c, p = m(inp)
+        assert c.shape == (32, 8, 5) and p.shape == (32, 8, 6, 1000)
+        assert torch.isfinite(c).all() and torch.isfinite(p).all()
+        # batch independence: any sub-batch gives the same rows
+        sub = {k: v[5:9] for k, v in inp.items()}
+        sc, sp = m(sub)
+        assert (sc - c[5:9]).abs().max() < 1e-5 and (sp - p[5:9]).abs().max() < 1e-5
+        # prefix invariance at full size
+        pre = {"frames": inp["frames"][:, :3], "actions": inp["actions"][:, :3], "cad_image": inp["cad_image"]}
+        pc, pp = m(pre)
+        assert (pc - c[:, :3]).abs().max() < 1e-5 and (pp - p[:, :3]).abs().max() < 1e-5
+
+
+def test_errors_match_reference_behaviour():
+    with pytest.raises(ValueError):
+        AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=256, encoder="resnet")
+    with pytest.raises(AssertionError):
+        AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=256, window_size=0)
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=256, enable_past_actions=True, enable_past_states=True).cuda()
+    bad = {"frames": torch.zeros(1, 2, 1, 256, 256).cuda(), "actions": torch.zeros(1, 2, 7).cuda(), "cad_image": torch.zeros(1, 1, 64, 64).cuda()}
+    with pytest.raises(ValueError):
+        m(bad)  # > 224x224 exceeds the positional table (the reference raises a shape error here too)

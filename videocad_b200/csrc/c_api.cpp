@@ -13,6 +13,27 @@ extern "C" {
 const char* vc_last_error(void) { return vck::last_error(); }
 int vc_version(void) { return 100; }
 int vc_is_cuda_build(void) { return VC_CUDA_BUILD; }
+long long vc_launch_count(void) { return vck::launch_count(); }
+void vc_launch_count_reset(void) { vck::launch_count_reset(); }
+void vc_gemm_profile(int enable) { vck::gemm_profile_enable(enable); }
+int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  return vck::gemm_profile_read(total_ms, total_flops, launches);
+}
+size_t vc_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(vc_drop);
+    case 1: return sizeof(vc_gemm_desc);
+    case 2: return sizeof(vc_attn_desc);
+    case 3: return sizeof(vc_linear);
+    case 4: return sizeof(vc_norm);
+    case 5: return sizeof(vc_vit_weights);
+    case 6: return sizeof(vc_vit_call);
+    case 7: return sizeof(vc_dec_layer);
+    case 8: return sizeof(vc_seq_weights);
+    case 9: return sizeof(vc_seq_call);
+    default: return 0;
+  }
+}
 
 void vc_gemm_desc_init(vc_gemm_desc* d) { vck::gemm_desc_init(d); }
 int vc_gemm(const vc_gemm_desc* d, void* stream) {

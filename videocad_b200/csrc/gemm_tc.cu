@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "host_util.h"
+#include "gemm_profile.h"
 
 namespace vck {
 
@@ -414,7 +415,10 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   const int num_m = (d.M + BM - 1) / BM, num_n = (d.N + BN - 1) / BN;
   const long long tiles = (long long)num_m * num_n * p.splitk;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  int slot = -1;
+  const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot);
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_kernel");
 }
 

@@ -1,5 +1,9 @@
 #include "host_util.h"
 #include <string.h>
+#include <atomic>
+#ifndef VC_CUDA_BUILD
+#define VC_CUDA_BUILD 0
+#endif
 
 namespace vck {
 
@@ -12,5 +16,20 @@ int set_error(const char* msg) {
 }
 
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+void launch_count_reset() { g_launches.store(0); }
+
+#if !VC_CUDA_BUILD
+void gemm_profile_enable(int) {}
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  if (total_ms) *total_ms = 0;
+  if (total_flops) *total_flops = 0;
+  if (launches) *launches = 0;
+  return 0;
+}
+#endif
 
 }  // namespace vck

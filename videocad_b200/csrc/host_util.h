@@ -7,6 +7,12 @@ namespace vck {
 // stores msg as the calling thread's last error and returns a non-zero status
 int set_error(const char* msg);
 const char* last_error();
+void count_launch();
+long long launch_count();
+void launch_count_reset();
+// GEMM profiling hooks (CUDA build: event pairs around each launch; emulation build: no-ops)
+void gemm_profile_enable(int enable);
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
 
 #if defined(__CUDACC__)
 // checks cudaGetLastError() after a launch; returns 0 or sets the error

@@ -54,6 +54,11 @@ class AttnDesc(C.Structure):
 _PROTOS = {
     "vc_version": ([], i32),
     "vc_is_cuda_build": ([], i32),
+    "vc_launch_count": ([], C.c_longlong),
+    "vc_launch_count_reset": ([], None),
+    "vc_gemm_profile": ([i32], None),
+    "vc_gemm_profile_read": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], i32),
+    "vc_abi_sizeof": ([i32], C.c_size_t),
     "vc_gemm_desc_init": ([C.POINTER(GemmDesc)], None),
     "vc_gemm": ([C.POINTER(GemmDesc), vp], i32),
     "vc_split_f32": ([vp, i64, i64, i64, vp, vp, i64, vp], i32),
@@ -92,6 +97,8 @@ def load(path: Optional[str] = None, require_cuda_build: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    from . import model_abi  # noqa: F401  (registers the model-level prototypes in EXTRA_PROTOS)
+
     p = path or LIB_PATH
     if not os.path.exists(p):
         raise RuntimeError(
