@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- train frames/sec of the VideoCAD behaviour-cloning hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--config c1|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+A "step" is one optimiser step of the reference trainer (trainer.py:480-496: zero_grad -> model forward in training
+mode (dropout 0.1) -> compute_loss -> backward -> clip_grad_norm_(1.0) -> Adam(lr=1e-5).step) over one synthetic batch of
+the named shape; frames = B*T model frames per step, summed over ranks (weak scaling: B per GPU is fixed).
+
+  value      whole-job frames/s with inputs already resident in HBM when the timed region starts (CUDA events, barrier +
+             synchronize on both sides, max over ranks)
+  e2e        the same metric through the public API with HOST (pinned) inputs: H2D copy of frames/actions/cad and a
+             D2H read of the loss inside the timed region, every step
+  roofline   the tcgen05 GEMM kernel (dominant kernel): algorithmic FLOPs (2*M*N*K per launch, counted by the library)
+             / summed CUDA-event launch durations recorded around every launch on the launching stream during the timed
+             region, against the measured bf16 tensor peak in MEASURED_PEAKS.json
+  cpu_baseline  the oracle's CPU port of the same training step on the host cores (bounded sample)
+
+--impl reference times the CPU port only (rank 0), printing the same JSON line with "impl": "reference".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1]: 1xB200, 8-frame context, 224x224, d_model=512, batch=32
+    "c1": dict(model=dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,
+                          enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
+               B=32, T=8, S=224, cpu_B=2),
+    # BASELINE.json configs[3]: DDP, 32-frame context, H=1024, 32 samples per GPU
+    "c3": dict(model=dict(hidden_size=1024, nhead=4, num_decoder_layers=8, dim_feedforward=1024, window_size=10,
+                          enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
+               B=32, T=32, S=224, cpu_B=1),
+}
+NUM_BATCHES = 4  # distinct synthetic batches rotated through the timed region (4 x 58 MB of frames at c1 > 126 MB L2)
+
+
+def fwd_flops_per_sample(cfg, T, S):
+    """SURVEY.md 8(d) / BASELINE.md section 3: algorithmic forward FLOPs per sample."""
+    H, Ff, L = cfg["hidden_size"], cfg["dim_feedforward"], cfg["num_decoder_layers"]
+    N = (S // 32) ** 2
+    n = N + 1
+    f_vit = 2 * N * 1024 * 512 + 6 * (2 * n * 512 * 3072 + 4 * n * n * 1024 + 2 * n * 1024 * 512 + 4 * n * 512 * 512)
+    glue = 2 * T * 512 * H + 2 * 512 * H + 2 * T * 2 * H * H + 2 * T * 7 * H
+    dec = L * (16 * T * H * H + 4 * T * H * Ff + 8 * T * T * H)
+    head = 2 * T * H * 6005
+    return T * f_vit + f_vit + glue + dec + head
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, source="fallback (B200_PROFILING.md sustained figure)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+
+def make_batches(B, T, S, rank, device=None, pinned=False):
+    from videocad_b200.synthetic import synthetic_batch
+
+    out = []
+    for i in range(NUM_BATCHES):
+        b = synthetic_batch(B, T + 1, S, seed=1234 + 1000 * rank + i)
+        if device is not None:
+            b = {k: v.to(device) for k, v in b.items()}
+        elif pinned:
+            b = {k: v.pin_memory() for k, v in b.items()}
+        out.append(b)
+    return out
+
+
+def run_reference(args, cfg):
+    """The reference arm: the CPU implementation of the path (oracle port) on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.train_port import CpuTrainStep
+    from oracle import torch_oracle as to
+
+    B, T, S = cfg["cpu_B"], cfg["T"], cfg["S"]
+    runner = CpuTrainStep(cfg["model"])
+    batches = [to.synthetic_batch(B, T + 1, S, seed=100 + i) for i in range(2)]
+    for i in range(args.warmup):
+        runner.step(batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        runner.step(batches[i % 2])
+    dt = time.perf_counter() - t0
+    fps = B * T * args.steps / dt
+    line = dict(metric="train frames/sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload=f"{args.config}: CPU port of trainer._process_batch, batch {B} x T={T} x {S}x{S}, "
+                            f"H={cfg['model']['hidden_size']} (bounded sample of the {cfg['B']}-sample GPU batch)"),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=torch.get_num_threads(), kind="port",
+                                  sample=f"{args.steps} steps at batch {B}, host_cpus={os.cpu_count()}"),
+                e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import torch.distributed as dist
+    from videocad_b200 import AutoRegressiveTransformer
+    from videocad_b200 import lib as L
+    from videocad_b200.loss import compute_loss
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} needs a {args.gpus}-rank launch (torch.distributed.run --nproc-per-node {args.gpus}); "
+                         f"WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl")
+    lib = L.load()
+
+    torch.manual_seed(0)
+    model = AutoRegressiveTransformer(state_dim=1644, act_dim=7, encoder="vit", precision=args.precision, **cfg["model"]).to(dev)
+    model.train()
+    net = model
+    if world > 1:
+        # the wrapper the reference builds (experiment.py:104-109)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
+                                                        find_unused_parameters=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    B, T, S = cfg["B"], cfg["T"], cfg["S"]
+
+    def train_step(batch):
+        opt.zero_grad()
+        acts = batch["actions"]
+        inputs = {"frames": batch["frames"][:, :-1], "actions": model.normalize_actions(acts[:, :-1].clone()),
+                  "cad_image": batch["cad_image"]}
+        loss = compute_loss(net(inputs), acts[:, 1:])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(run_step, steps, profile_gemm=False):
+        barrier()
+        if profile_gemm:
+            lib.vc_gemm_profile(1)
+        lib.vc_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            run_step(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), lib.vc_launch_count()
+
+    # ---------------- value: inputs resident in HBM
+    dev_batches = make_batches(B, T, S, rank, device=dev)
+    for i in range(args.warmup):
+        train_step(dev_batches[i % NUM_BATCHES])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps, profile_gemm=True)
+    clocks = sampler.stop() if rank == 0 else None
+    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
+    lib.vc_gemm_profile_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
+    lib.vc_gemm_profile(0)
+    frames_per_step = world * B * T
+    value = frames_per_step * args.steps / (ms / 1000.0)
+
+    # ---------------- e2e: host (pinned) inputs, H2D + loss read-back inside the timed region
+    del dev_batches
+    host_batches = make_batches(B, T, S, rank, pinned=True)
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+
+    def e2e_step(i):
+        hb = host_batches[i % NUM_BATCHES]
+        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return float(train_step(batch).item())
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    e2e_value = frames_per_step * args.steps / (ms_e2e / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak = measured_peaks()
+    f_fwd = fwd_flops_per_sample(cfg["model"], T, S)
+    gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
+    step_tflops = value / world * 3.0 * f_fwd / T / 1e12  # per GPU, whole step (fwd + 2x bwd) algorithmic
+    passes = 3 if args.precision == "fp32x3" else 1
+    roofline = dict(bound="tensor", kernel="gemm_tc_kernel<128> (tcgen05, split-bf16)", achieved=gemm_tflops, peak=peak["tflops"],
+                    unit="TFLOP/s", frac=gemm_tflops / peak["tflops"], traffic=None, peak_source=peak["source"],
+                    mma_passes_per_flop=passes, mma_issue_frac=passes * gemm_tflops / peak["tflops"],
+                    gemm_launches_per_step=g_n.value / args.steps, gemm_ms_per_step=g_ms.value / args.steps,
+                    gemm_share_of_step=(g_ms.value / args.steps) / (ms / args.steps),
+                    whole_step_algorithmic_tflops_per_gpu=step_tflops, whole_step_frac=step_tflops / peak["tflops"])
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.train_port import time_cpu_train
+
+        cpu_baseline = time_cpu_train(cfg["model"], cfg["cpu_B"], T, S, steps=6, warmup=1)
+    line = dict(metric="train frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32 (3-pass split-bf16 tensor-core GEMMs, fp32 accumulate)" if passes == 3 else "bf16",
+                data="synthetic", impl="native",
+                config=dict(workload=f"{args.config}: {world} x (batch {B}, T={T}, {S}x{S} frames), H={cfg['model']['hidden_size']}, "
+                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0",
+                            global_batch=world * B, parallelism=f"dp{world}" if world > 1 else "single",
+                            l2="inputs rotate over 4 distinct batches (232 MB of frames at c1 > 126 MB L2); activations (>5 GB/step) stream through HBM",
+                            fwd_gflop_per_sample=f_fwd / 1e9),
+                clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                                        ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu_baseline)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

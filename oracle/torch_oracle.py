@@ -149,29 +149,7 @@ def seeded_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str
     return sd
 
 
-def synthetic_batch(B: int, L: int, S: int, seed: int = 1234):
-    """Synthetic loader batch as SURVEY.md 8(d): frames/cad in [-1,1], raw action rows with a valid
-    command/parameter structure, first row all-zero.  L = T + 1 loaded steps."""
-    g = torch.Generator().manual_seed(seed)
-    frames = torch.randn(B, L, 1, S, S, generator=g).clamp_(-1, 1)
-    cad = torch.randn(B, 1, S, S, generator=g).clamp_(-1, 1)
-    actions = -torch.ones(B, L, 7)
-    cmd = torch.randint(0, 5, (B, L), generator=g)
-    actions[..., 0] = cmd.float()
-    xy = torch.randint(0, 1000, (B, L, 2), generator=g).float()
-    key = (torch.randint(0, 20, (B, L), generator=g) * 50).float()
-    times = torch.tensor([-1.0, 0.0, 200.0, 400.0])[torch.randint(0, 4, (B, L), generator=g)]
-    scroll = (torch.randint(0, 2, (B, L), generator=g) * 500).float()
-    typed = torch.randint(0, 1000, (B, L), generator=g).float()
-    m0, m1, m2, m3 = (cmd == 0), (cmd == 1), (cmd == 2), (cmd == 3)
-    actions[..., 1] = torch.where(m0, xy[..., 0], actions[..., 1])
-    actions[..., 2] = torch.where(m0, xy[..., 1], actions[..., 2])
-    actions[..., 3] = torch.where(m1, key, actions[..., 3])
-    actions[..., 4] = torch.where(m1, times, actions[..., 4])
-    actions[..., 5] = torch.where(m2, scroll, actions[..., 5])
-    actions[..., 6] = torch.where(m3, typed, actions[..., 6])
-    actions[:, 0, :] = 0.0
-    return {"frames": frames, "actions": actions, "cad_image": cad}
+from videocad_b200.synthetic import synthetic_batch  # noqa: E402,F401  (shared synthetic-input generator)
 
 
 def normalize_actions(actions: torch.Tensor) -> torch.Tensor:
@@ -206,8 +184,13 @@ def patchify(img: torch.Tensor) -> torch.Tensor:
     return x.reshape(b, h * w, PATCH * PATCH * c)
 
 
-def vit_forward(sd: dict, prefix: str, img: torch.Tensor, inter: Optional[dict] = None) -> torch.Tensor:
-    """[F,1,S,S] -> CLS embedding [F,512].  SURVEY.md App. A.1."""
+def _drop(x, p):
+    return F.dropout(x, p, training=True) if p > 0 else x
+
+
+def vit_forward(sd: dict, prefix: str, img: torch.Tensor, inter: Optional[dict] = None, dropout_p: float = 0.0) -> torch.Tensor:
+    """[F,1,S,S] -> CLS embedding [F,512].  SURVEY.md App. A.1.  dropout_p > 0 = training mode (statistical only)."""
+    dp = dropout_p
     x = patchify(img)
     x = _ln(x, sd, prefix + "to_patch_embedding.1.")
     x = x @ sd[prefix + "to_patch_embedding.2.weight"].T + sd[prefix + "to_patch_embedding.2.bias"]
@@ -215,7 +198,7 @@ def vit_forward(sd: dict, prefix: str, img: torch.Tensor, inter: Optional[dict] 
     b, n, _ = x.shape
     cls = sd[prefix + "cls_token"].reshape(1, 1, VIT_DIM).expand(b, 1, VIT_DIM)
     pos = sd[prefix + "pos_embedding"].reshape(-1, VIT_DIM)
-    x = torch.cat([cls, x], dim=1) + pos[: n + 1]
+    x = _drop(torch.cat([cls, x], dim=1) + pos[: n + 1], dp)
     if inter is not None:
         inter[prefix + "tokens"] = x
     for l in range(VIT_DEPTH):
@@ -224,12 +207,12 @@ def vit_forward(sd: dict, prefix: str, img: torch.Tensor, inter: Optional[dict] 
         qkv = h @ sd[p + "0.to_qkv.weight"].T
         q, k, v = qkv.chunk(3, dim=-1)
         q, k, v = (t.reshape(b, n + 1, VIT_HEADS, VIT_DHEAD).permute(0, 2, 1, 3) for t in (q, k, v))
-        a = torch.softmax((q @ k.transpose(-1, -2)) * (VIT_DHEAD ** -0.5), dim=-1)
+        a = _drop(torch.softmax((q @ k.transpose(-1, -2)) * (VIT_DHEAD ** -0.5), dim=-1), dp)
         o = (a @ v).permute(0, 2, 1, 3).reshape(b, n + 1, VIT_HEADS * VIT_DHEAD)
-        x = o @ sd[p + "0.to_out.0.weight"].T + sd[p + "0.to_out.0.bias"] + x
+        x = _drop(o @ sd[p + "0.to_out.0.weight"].T + sd[p + "0.to_out.0.bias"], dp) + x
         h = _ln(x, sd, p + "1.net.0.")
-        u = F.gelu(h @ sd[p + "1.net.1.weight"].T + sd[p + "1.net.1.bias"])
-        x = u @ sd[p + "1.net.4.weight"].T + sd[p + "1.net.4.bias"] + x
+        u = _drop(F.gelu(h @ sd[p + "1.net.1.weight"].T + sd[p + "1.net.1.bias"]), dp)
+        x = _drop(u @ sd[p + "1.net.4.weight"].T + sd[p + "1.net.4.bias"], dp) + x
         if inter is not None:
             inter[f"{prefix}layer{l}"] = x
     x = _ln(x, sd, prefix + "transformer.norm.")
@@ -250,7 +233,7 @@ def build_masks(T: int, W: int, dtype, device=None):
     return causal, window
 
 
-def _mha(xq, xkv, sd, prefix, nh, mask):
+def _mha(xq, xkv, sd, prefix, nh, mask, dp=0.0):
     """nn.MultiheadAttention (packed in_proj), batch-first restatement: [B,T,H]."""
     B, Tq, H = xq.shape
     Tk = xkv.shape[1]
@@ -263,25 +246,28 @@ def _mha(xq, xkv, sd, prefix, nh, mask):
     k = k.reshape(B, Tk, nh, d).permute(0, 2, 1, 3)
     v = v.reshape(B, Tk, nh, d).permute(0, 2, 1, 3)
     s = (q @ k.transpose(-1, -2)) / math.sqrt(d) + mask
-    a = torch.softmax(s, dim=-1)
+    a = _drop(torch.softmax(s, dim=-1), dp)
     o = (a @ v).permute(0, 2, 1, 3).reshape(B, Tq, H)
     return o @ sd[prefix + "out_proj.weight"].T + sd[prefix + "out_proj.bias"]
 
 
-def decoder_layer(sd, prefix, x, mem, nh, tgt_mask, mem_mask):
-    x = _ln(x + _mha(x, x, sd, prefix + "self_attn.", nh, tgt_mask), sd, prefix + "norm1.")
-    x = _ln(x + _mha(x, mem, sd, prefix + "multihead_attn.", nh, mem_mask), sd, prefix + "norm2.")
-    ff = torch.relu(x @ sd[prefix + "linear1.weight"].T + sd[prefix + "linear1.bias"])
-    ff = ff @ sd[prefix + "linear2.weight"].T + sd[prefix + "linear2.bias"]
+def decoder_layer(sd, prefix, x, mem, nh, tgt_mask, mem_mask, dp=0.0):
+    x = _ln(x + _drop(_mha(x, x, sd, prefix + "self_attn.", nh, tgt_mask, dp), dp), sd, prefix + "norm1.")
+    x = _ln(x + _drop(_mha(x, mem, sd, prefix + "multihead_attn.", nh, mem_mask, dp), dp), sd, prefix + "norm2.")
+    ff = _drop(torch.relu(x @ sd[prefix + "linear1.weight"].T + sd[prefix + "linear1.bias"]), dp)
+    ff = _drop(ff @ sd[prefix + "linear2.weight"].T + sd[prefix + "linear2.bias"], dp)
     return _ln(x + ff, sd, prefix + "norm3.")
 
 
 # --------------------------------------------------------------------------------------------
 # full forward
 # --------------------------------------------------------------------------------------------
-def forward(sd: dict, cfg: dict, inputs: dict, inter: Optional[dict] = None):
-    """AutoRegressiveTransformer.forward (eval mode).  Returns (cmds [B,T,5], params [B,T,6,1000])."""
+def forward(sd: dict, cfg: dict, inputs: dict, inter: Optional[dict] = None, dropout_p: float = 0.0):
+    """AutoRegressiveTransformer.forward.  Returns (cmds [B,T,5], params [B,T,6,1000]).
+    dropout_p = 0 is eval mode (bit-level parity runs); > 0 applies dropout at the reference's call sites (used only
+    by the timed CPU port of the training step)."""
     c = full_cfg(cfg)
+    dp = dropout_p
     H, nh, L, W = c["hidden_size"], c["nhead"], c["num_decoder_layers"], c["window_size"]
     frames, actions, cad = inputs["frames"], inputs["actions"], inputs["cad_image"]
     B, T = actions.shape[0], actions.shape[1]
@@ -294,13 +280,13 @@ def forward(sd: dict, cfg: dict, inputs: dict, inter: Optional[dict] = None):
     images = []
     ui = None
     if c["enable_past_states"]:
-        emb = vit_forward(sd, "state_embedding_model.", frames.reshape(-1, *frames.shape[2:]), inter)
+        emb = vit_forward(sd, "state_embedding_model.", frames.reshape(-1, *frames.shape[2:]), inter, dp)
         if inter is not None:
             inter["state_cls"] = emb
         ui = torch.tanh((emb @ sd["embed_state.weight"].T + sd["embed_state.bias"]).reshape(B, T, H) + E)
         if c["enable_past_actions"]:
             images.append(ui)
-    cad_emb = vit_forward(sd, "cad_embedding_model.", cad, inter)
+    cad_emb = vit_forward(sd, "cad_embedding_model.", cad, inter, dp)
     if inter is not None:
         inter["cad_cls"] = cad_emb
     cad_tok = (cad_emb @ sd["embed_image.weight"].T + sd["embed_image.bias"]).unsqueeze(1).expand(B, T, H)
@@ -308,7 +294,7 @@ def forward(sd: dict, cfg: dict, inputs: dict, inter: Optional[dict] = None):
     mv = inputs.get("multiview_images", None)
     if mv is not None and c["num_views"] > 0:
         nv = mv.shape[1]
-        mv_emb = vit_forward(sd, "cad_embedding_model.", mv.reshape(-1, *mv.shape[2:]), None).reshape(B, nv * VIT_DIM)
+        mv_emb = vit_forward(sd, "cad_embedding_model.", mv.reshape(-1, *mv.shape[2:]), None, dp).reshape(B, nv * VIT_DIM)
         mv_tok = mv_emb @ sd["embed_multiview.weight"].T + sd["embed_multiview.bias"]
         images.append(mv_tok.unsqueeze(1).expand(B, T, H))
     mem = torch.cat(images, dim=-1)
@@ -326,7 +312,7 @@ def forward(sd: dict, cfg: dict, inputs: dict, inter: Optional[dict] = None):
     if inter is not None:
         inter["tgt"], inter["memory"] = x, mem
     for l in range(L):
-        x = decoder_layer(sd, f"transformer_decoder.layers.{l}.", x, mem, nh, tgt_mask, window)
+        x = decoder_layer(sd, f"transformer_decoder.layers.{l}.", x, mem, nh, tgt_mask, window, dp)
         if inter is not None:
             inter[f"dec{l}"] = x
     cmds = x @ sd["predict_action_class_0_4.weight"].T + sd["predict_action_class_0_4.bias"]
