@@ -1,0 +1,185 @@
+"""CPU tests of the host side: the C ABI surface, the ctypes binding, the drop-in module's contract, and the host
+orchestration (model_vit.cpp / model_seq.cpp) executed against the CPU emulation of the kernels
+(oracle/_build/libvc_emu.so -- test infrastructure, never loaded by the product path)."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import build_emu
+from oracle import torch_oracle as to
+from videocad_b200 import AutoRegressiveTransformer, ModelFactory, ModelType
+from videocad_b200 import lib as L
+from videocad_b200 import model_abi as A
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return L.load(build_emu.build(), require_cuda_build=False)
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "videocad_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_are_bound_and_exported(emu):
+    syms = header_symbols()
+    assert len(syms) >= 35
+    assert set(syms) == set(L.exported_symbols()), set(syms) ^ set(L.exported_symbols())
+    for s in syms:
+        assert hasattr(emu, s), s
+    native = os.path.join(ROOT, "videocad_b200", "libvideocad_b200.so")
+    if not os.path.exists(native):
+        from videocad_b200.build import build
+
+        build()
+    out = subprocess.run(["nm", "-D", "--defined-only", native], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vc_[a-z0-9_]+)", out))
+    assert set(syms) <= exported, set(syms) - exported
+
+
+def test_ctypes_struct_layout_matches_c(emu):
+    for which, struct in enumerate([L.Drop, L.GemmDesc, L.AttnDesc, A.Linear, A.Norm, A.VitWeights, A.VitCall, A.DecLayer,
+                                    A.SeqWeights, A.SeqCall]):
+        assert emu.vc_abi_sizeof(which) == C.sizeof(struct), (which, struct.__name__)
+
+
+def test_product_loader_refuses_non_cuda_library():
+    with pytest.raises(RuntimeError):
+        L.load(build_emu.build(), require_cuda_build=True)
+    with pytest.raises(RuntimeError):
+        L.load("/nonexistent/libvideocad_b200.so")
+
+
+def test_module_contract_and_errors():
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, enable_past_actions=True,
+               enable_past_states=True, enable_timestep_embedding=True, model_name="autoregressive", normalize=True,
+               network_layers=[1, 2], enable_random=True)  # unknown keys must be tolerated, as in the reference
+    m, mt = ModelFactory().create_model("whatever", dict(cfg, state_dim=1644, act_dim=7, encoder="vit"), "cpu")
+    assert mt == ModelType.MULTI_CLASSES
+    shapes = to.param_shapes(cfg)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == shapes
+    # checkpoints saved from DDP / torch.compile wrappers load through the factory
+    sd = {"module._orig_mod." + k: v for k, v in to.seeded_state_dict(cfg, 2).items()}
+    sd["transformer.wte.weight"] = torch.zeros(1, 128)  # dead GPT-2 key of a reference checkpoint: ignored (strict=False)
+    m2, _ = ModelFactory().create_model("x", dict(cfg, state_dim=1644, act_dim=7, encoder="vit"), "cpu", state_dict=sd)
+    assert torch.equal(m2.embed_action.weight, sd["module._orig_mod.embed_action.weight"])
+    assert list(m.cad_embedding_model.parameters()) and list(m.state_embedding_model.parameters())
+    with pytest.raises(ValueError):
+        AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=128, encoder="resnet")
+    with pytest.raises(AssertionError):
+        AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=128, window_size=0)
+    inp = to.model_inputs_from_batch(to.synthetic_batch(1, 3, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(inp)  # CPU tensors and no injected test library: the product path refuses
+
+
+def build_emu_model(emu, cfg, seed=0, dropout=0.1):
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, encoder="vit", **cfg)
+    sd = to.seeded_state_dict(cfg, seed)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    m._use_library_for_tests(emu)
+    return m, sd
+
+
+MODES = [dict(enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
+         dict(enable_past_actions=False, enable_past_states=True, enable_timestep_embedding=True),
+         dict(enable_past_actions=False, enable_past_states=False),
+         dict(enable_past_actions=True, enable_past_states=False, enable_timestep_embedding=True)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_orchestration_forward_backward_vs_fp64_oracle(emu, mode):
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=2, **mode)
+    m, sd = build_emu_model(emu, cfg)
+    m.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 4, 64))
+    cmds, params = m(inp)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
+    assert (cmds.double() - oc).abs().max() < 1e-4 and (params.double() - op).abs().max() < 1e-4
+    g = torch.Generator().manual_seed(5)
+    wc, wp = torch.randn(cmds.shape, generator=g), torch.randn(params.shape, generator=g) * 0.05
+    ((cmds * wc).sum() + (params * wp).sum()).backward()
+    ((oc * wc.double()).sum() + (op * wp.double()).sum()).backward()
+    for name, p in m.named_parameters():
+        ref = sdd[name].grad
+        if p.grad is None:
+            assert ref is None or ref.abs().max() == 0, f"{name}: missing gradient"
+            continue
+        ref = ref if ref is not None else torch.zeros_like(p.grad, dtype=torch.double)
+        err = (p.grad.double() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        assert err < 2e-4, f"{name}: rel grad err {err:.3e}"
+
+
+def test_orchestration_matches_reference_golden(emu):
+    z = np.load(os.path.join(GOLDEN, "c0_states_actions.npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    m, _ = build_emu_model(emu, meta["cfg"])
+    m.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(meta["B"], meta["T"] + 1, meta["S"], seed=meta["batch_seed"]))
+    with torch.no_grad():
+        cmds, params = m(inp)
+    assert (cmds - torch.from_numpy(z["cmds"])).abs().max() < 2e-4
+    assert (params - torch.from_numpy(z["params"])).abs().max() < 2e-4
+
+
+def test_training_mode_dropout_bookkeeping(emu):
+    """Forward and backward regenerate identical Philox masks: with dropout on, the analytic gradient must match a
+    finite difference of the (fixed-seed) stochastic forward."""
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, _ = build_emu_model(emu, cfg, dropout=0.2)
+    m.train()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(1, 3, 64))
+    m._draw_seed = lambda: 4242  # same masks on every call
+    c1, p1 = m(inp)
+    c2, p2 = m(inp)
+    assert torch.equal(c1, c2) and torch.equal(p1, p2)
+    m.eval()
+    ce, _ = m(inp)
+    assert (ce - c1).abs().max() > 1e-3  # dropout really is active in training mode
+    m.train()
+    g = torch.Generator().manual_seed(1)
+    wc = torch.randn(c1.shape, generator=g)
+    (c1 * wc).sum().backward()
+    for prm, idx in ((m.embed_action.bias, 5), (m.state_embedding_model.transformer.layers[3][1].net[1].bias, 17),
+                     (m.transformer_decoder.layers[0].norm2.weight, 3), (m.cad_embedding_model.cls_token.view(-1), 100)):
+        base = prm.view(-1) if prm.dim() else prm
+        analytic = (prm.grad if prm.grad is not None else m.cad_embedding_model.cls_token.grad.view(-1))[idx].item() \
+            if prm.is_leaf else m.cad_embedding_model.cls_token.grad.view(-1)[idx].item()
+        eps = 1e-2
+        with torch.no_grad():
+            old = base[idx].item()
+            base[idx] = old + eps
+            lp = (m(inp)[0] * wc).sum().item()
+            base[idx] = old - eps
+            lm = (m(inp)[0] * wc).sum().item()
+            base[idx] = old
+        fd = (lp - lm) / (2 * eps)
+        assert abs(fd - analytic) < 2e-2 * max(1.0, abs(analytic)), (fd, analytic)
+
+
+def test_sequential_inference_matches_oracle(emu):
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build_emu_model(emu, cfg)
+    m.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 5, 64))
+    ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
+    oc, op = to.rollout(sd, cfg, inp["frames"], inp["cad_image"], action=True)
+    assert (ac - oc).abs().max() < 2e-4 and (ap - op).abs().max() < 2e-4
+    zc, zp = m.sequential_inference(inp["frames"], inp["cad_image"], action=False)
+    fc, fp = m(dict(inp, actions=torch.zeros_like(inp["actions"])))
+    assert torch.equal(zc, fc.detach()) and torch.equal(zp, fp.detach())

@@ -1,0 +1,147 @@
+"""CPU tests of the oracle: pinned against the golden fixtures (outputs of the unmodified reference) and, where
+/root/reference exists (the build container), against the reference itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_oracle as to
+from oracle import reference_model as rm
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small"]
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    norms = json.loads(bytes(z["grad_norms_json"]).decode())
+    return z, meta, norms
+
+
+def loss_weights(cs, ps, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(cs, generator=g), torch.randn(ps, generator=g) * 0.05
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_golden(name):
+    z, meta, norms = load_case(name)
+    cfg = meta["cfg"]
+    sd = {k: v.requires_grad_(True) for k, v in to.seeded_state_dict(cfg, meta["weight_seed"]).items()}
+    chk = sum(v.detach().double().abs().sum().item() for v in sd.values())
+    assert abs(chk - float(z["weight_checksum"])) < 1e-6 * chk, "seeded weights are not reproducible on this machine"
+    batch = to.synthetic_batch(meta["B"], meta["T"] + 1, meta["S"], seed=meta["batch_seed"])
+    cmds, params = to.forward(sd, cfg, to.model_inputs_from_batch(batch))
+    assert (cmds.detach() - torch.from_numpy(z["cmds"])).abs().max() < 2e-5
+    assert (params.detach() - torch.from_numpy(z["params"])).abs().max() < 2e-5
+    wc, wp = loss_weights(cmds.shape, params.shape, meta["loss_seed"])
+    ((cmds * wc).sum() + (params * wp).sum()).backward()
+    for k, ref_norm in norms.items():
+        g = sd[k].grad
+        assert g is not None, k
+        assert abs(g.double().norm().item() - ref_norm) < 1e-3 * ref_norm + 1e-7, k
+        if ("grad::" + k) in z.files:
+            ref = torch.from_numpy(z["grad::" + k])
+            assert (g - ref).abs().max() < 2e-4 * ref.abs().max() + 1e-7, k
+    unused = [k for k in sd if k not in norms]
+    for k in unused:
+        assert sd[k].grad is None or sd[k].grad.abs().max() == 0
+
+
+@pytest.mark.skipif(not rm.available(), reason="/root/reference not present on this machine")
+@pytest.mark.parametrize("mode", [(True, True), (False, True), (False, False), (True, False)])
+def test_oracle_vs_live_reference(mode):
+    pa, ps = mode
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2, encoder="vit",
+               enable_past_actions=pa, enable_past_states=ps, enable_timestep_embedding=pa or ps)
+    model, _ = rm.build_reference_model(cfg)
+    sd = to.seeded_state_dict(cfg, 3)
+    model.load_state_dict(sd, strict=False)
+    model.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 5, 64, seed=9))
+    with torch.no_grad():
+        rc, rp = model(dict(inp, timesteps=torch.zeros(2, 1)))
+        oc, op = to.forward(sd, cfg, inp)
+    assert (rc - oc).abs().max() < 5e-6 and (rp - op).abs().max() < 5e-6
+
+
+def test_state_dict_schema_matches_reference_or_appendix_b():
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, enable_past_actions=True,
+               enable_past_states=True, enable_timestep_embedding=True)
+    shapes = to.param_shapes(cfg)
+    if rm.available():
+        model, _ = rm.build_reference_model(dict(cfg, encoder="vit"))
+        ref = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        dead = ("transformer.", "embed_timestep", "embed_ln", "predict_action.")
+        live = {k: v for k, v in ref.items() if not k.startswith(dead)}
+        assert live == shapes
+    assert shapes["transformer_decoder.layers.1.multihead_attn.in_proj_weight"] == (384, 128)
+    assert shapes["cad_embedding_model.transformer.layers.5.0.to_qkv.weight"] == (3072, 512)
+
+
+def test_prefix_invariance_and_rollout_semantics():
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    sd = to.seeded_state_dict(cfg, 1)
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 6, 64, seed=4))
+    with torch.no_grad():
+        c, p = to.forward(sd, cfg, inp)
+        k = 3
+        pc, pp = to.forward(sd, cfg, {"frames": inp["frames"][:, :k], "actions": inp["actions"][:, :k], "cad_image": inp["cad_image"]})
+        assert (pc - c[:, :k]).abs().max() < 1e-5 and (pp - p[:, :k]).abs().max() < 1e-5
+        rc, rp = to.rollout(sd, cfg, inp["frames"], inp["cad_image"], action=False)
+        zc, zp = to.forward(sd, cfg, dict(inp, actions=torch.zeros_like(inp["actions"])))
+        assert (rc - zc).abs().max() < 1e-5 and (rp - zp).abs().max() < 1e-5
+
+
+def test_action_mask_rules():
+    cmd = torch.tensor([[0, 1, 1, 2, 3, 4]])
+    par = torch.tensor([[[5, 6, 7, 8, 9, 10], [5, 6, 210, 8, 9, 10], [5, 6, 300, 8, 9, 10], [5, 6, 7, 8, 9, 10],
+                         [5, 6, 7, 8, 9, 10], [5, 6, 7, 8, 9, 10]]])
+    out = to.apply_action_mask(cmd, par)
+    assert out[0, 0].tolist() == [5, 6, -1, -1, -1, -1]
+    assert out[0, 1].tolist() == [-1, -1, 210, 8, -1, -1]      # param[3] kept only if 200 <= param[2] < 250
+    assert out[0, 2].tolist() == [-1, -1, 300, -1, -1, -1]
+    assert out[0, 3].tolist() == [-1, -1, -1, -1, 9, -1]
+    assert out[0, 4].tolist() == [-1, -1, -1, -1, -1, 10]
+    assert out[0, 5].tolist() == [-1] * 6
+
+
+@pytest.mark.skipif(not rm.available(), reason="/root/reference not present on this machine")
+def test_loss_port_matches_reference_trainer(tmp_path, monkeypatch):
+    import shutil
+
+    from videocad_b200.loss import compute_loss
+
+    shutil.copy(os.path.join(rm.REFERENCE_ROOT, "class_weights.json"), tmp_path / "class_weights.json")
+    monkeypatch.chdir(tmp_path)
+    tr = rm.import_trainer()
+
+    class Dummy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+    pk = {"loader": [], "sampler": None}
+    t = tr.MultiClassesTrainer(pk, pk, pk, Dummy(), {"lr": 1e-5, "use_mse": True, "experiment_name": "x"}, "cpu", 0)
+    torch.manual_seed(0)
+    B, T = 3, 7
+    tgt = to.synthetic_batch(B, T + 1, 32)["actions"][:, 1:]
+    cmds = torch.randn(B, T, 5, requires_grad=True)
+    params = torch.randn(B, T, 6, 1000, requires_grad=True)
+    with torch.no_grad():  # make some predictions land inside the tolerance window (those rows are dropped)
+        for b in range(B):
+            for tt in range(0, T, 2):
+                for i in range(6):
+                    v = int(tgt[b, tt, 1 + i].item())
+                    if v >= 0:
+                        params[b, tt, i, min(v + 1, 999)] += 20
+    lr, _ = t.compute_loss((cmds, params), tgt)
+    lm = compute_loss((cmds, params), tgt)
+    assert abs(lr.item() - lm.item()) < 1e-5 * abs(lr.item())
+    gr = torch.autograd.grad(lr, [cmds, params])
+    gm = torch.autograd.grad(lm, [cmds, params])
+    assert (gr[0] - gm[0]).abs().max() < 1e-6 and (gr[1] - gm[1]).abs().max() < 1e-6
