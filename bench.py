@@ -238,6 +238,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
     lib.vc_gemm_profile_read(C.byref(g_ms), C.byref(g_fl), C.byref(g_n))
+    if os.environ.get("VC_GEMM_DUMP"):
+        lib.vc_gemm_profile_dump(os.environ["VC_GEMM_DUMP"].encode())
     lib.vc_gemm_profile(0)
     frames_per_step = world * B * T
     value = frames_per_step * args.steps / (ms / 1000.0)

@@ -2,6 +2,6 @@
 #pragma once
 #include <cuda_runtime.h>
 namespace vck {
-bool gemm_profile_begin(cudaStream_t st, double flops, int* slot);
+bool gemm_profile_begin(cudaStream_t st, double flops, int* slot, const char* tag = nullptr);
 void gemm_profile_end(cudaStream_t st, int slot);
 }  // namespace vck

@@ -416,7 +416,10 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   const long long tiles = (long long)num_m * num_n * p.splitk;
   const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
   int slot = -1;
-  const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot);
+  char tag[64];
+  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
+           d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
+  const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_kernel");
