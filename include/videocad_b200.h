@@ -30,11 +30,14 @@ typedef uint16_t vc_bf16;
 enum { VC_ACT_NONE = 0, VC_ACT_GELU = 1, VC_ACT_RELU = 2, VC_ACT_TANH = 3 };
 enum { VC_MASK_NONE = 0, VC_MASK_CAUSAL = 1, VC_MASK_WINDOW = 2 };
 
-/* one dropout call site: keep-mask is a pure function of (seed, site, element index); p == 0 disables */
+/* one dropout call site: keep-mask is a pure function of (seed, site, element index); p == 0 disables.
+ * If seed_ptr != NULL the kernels read the seed from that DEVICE location instead of `seed` (lets a captured CUDA graph
+ * be replayed with a fresh seed). */
 typedef struct vc_drop {
   float p;
   uint32_t site;
   uint64_t seed;
+  const uint64_t* seed_ptr;
 } vc_drop;
 
 /* Tensor-core GEMM  acc[m,n] = sum_k A[m,k] * B[n,k]  with fused epilogue.
@@ -94,6 +97,15 @@ int vc_layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const flo
 int vc_layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                      const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
                      float* dgamma, float* dbeta, void* stream);
+/* layernorm_bwd + fused second output g = dx * dropout_mask (split-bf16) and its column sums (see csrc/kernels.h) */
+int vc_layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                           const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                           float* dgamma, float* dbeta, vc_drop gdrop, vc_bf16* g_hi, vc_bf16* g_lo, int64_t ldg,
+                           float* g_colsum, void* stream);
+/* attention backward delivering dq/dk/dv as split-bf16 GEMM operands (scratch: 3*B*T*nh*d floats, may be unused) */
+int vc_attention_bwd_split(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
+                           const float* dout, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
+                           vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, void* stream);
 int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
                            vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream);
 int vc_patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,
@@ -171,6 +183,7 @@ typedef struct vc_vit_call {
   const float* img; int F; int S;       /* [F, 1, S, S], S multiple of 32, (S/32)^2 <= 49 */
   float dropout_p; int training;        /* dropout applied only when training != 0 */
   uint64_t seed; uint32_t site_base;
+  const uint64_t* seed_dev;             /* optional device-resident seed (overrides `seed`; for CUDA-graph replay) */
   int passes;                           /* 3 = fp32-grade GEMMs (parity mode), 1 = bf16-grade */
   void* ws; size_t ws_bytes;            /* activation workspace, >= vc_vit_workspace_bytes(F, S) */
   float* cls_out;                       /* [F, 512] CLS embedding after the final LayerNorm */
@@ -207,6 +220,7 @@ typedef struct vc_seq_call {
   const float* actions;                 /* [B*T, act_dim] normalised actions */
   float dropout_p; int training;
   uint64_t seed; uint32_t site_base;
+  const uint64_t* seed_dev;             /* optional device-resident seed (overrides `seed`) */
   int passes;
   void* ws; size_t ws_bytes;            /* >= vc_seq_workspace_bytes(...) */
   float* cmds;                          /* [B*T, num_cmd] */

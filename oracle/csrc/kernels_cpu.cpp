@@ -36,7 +36,7 @@ inline void split1(float x, bf16_t& hi, bf16_t& lo) {
 }
 inline float keep_scale(const Drop& d, uint64_t idx) {
   if (d.p <= 0.f) return 1.0f;
-  const Philox4 w = dropout_words(d.seed, d.site, idx >> 2);
+  const Philox4 w = dropout_words(drop_seed(d), d.site, idx >> 2);
   return (w.v[idx & 3u] >= dropout_threshold(d.p)) ? 1.0f / (1.0f - d.p) : 0.0f;
 }
 inline double gelu_d(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }
@@ -217,6 +217,22 @@ int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, co
               dgamma, dbeta);
   return 0;
 }
+int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                        const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, Drop gdrop, bf16_t* g_hi, bf16_t* g_lo, int64_t ldg, float* g_colsum,
+                        stream_t st) {
+  if (int rc = layernorm_bwd(dy, lddy, x, ldx, mean, rstd, gamma, rows, C, dres, lddres, dx, lddx, dgamma, dbeta, st)) return rc;
+  if (g_hi) {
+    for (int64_t r = 0; r < rows; ++r)
+      for (int c = 0; c < C; ++c) {
+        const float v = dx[r * lddx + c] * keep_scale(gdrop, (uint64_t)r * C + c);
+        split1(v, g_hi[r * ldg + c], g_lo[r * ldg + c]);
+        if (g_colsum) g_colsum[c] += v;
+      }
+  }
+  return 0;
+}
+
 int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
                         bf16_t* y_lo, float* mean, float* rstd, stream_t) {
   if (S % 32 != 0) return set_error("patch_layernorm_fwd: image size must be a multiple of 32");
@@ -354,6 +370,20 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
         }
     }
   return 0;
+}
+
+int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                        bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t st) {
+  if (!scratch) return set_error("attention_bwd_split: scratch required");
+  const int64_t W = (int64_t)a.nh * a.d, Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  float* dq = scratch;
+  float* dk = dq + Rq * W;
+  float* dv = dk + Rk * W;
+  if (int rc = attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, W, dk, W, dv, W, st)) return rc;
+  if (int rc = split_f32(dq, W, Rq, W, dq_hi, dq_lo, ld_split, st)) return rc;
+  if (int rc = split_f32(dk, W, Rk, W, dk_hi, dk_lo, ld_split, st)) return rc;
+  return split_f32(dv, W, Rk, W, dv_hi, dv_lo, ld_split, st);
 }
 
 int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, const float* aux, int64_t ldaux,

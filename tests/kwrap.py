@@ -43,6 +43,19 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dres=None):
     return dx, dg, db
 
 
+def layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres, drop):
+    rows, Cc = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(Cc, device=x.device)
+    db = torch.zeros(Cc, device=x.device)
+    gs = bf16_pair(x.shape)
+    cs = torch.zeros(Cc, device=x.device)
+    L.check(L.load().vc_layernorm_bwd_fused(L.ptr(dy), dy.stride(0), L.ptr(x), x.stride(0), L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+                                           rows, Cc, L.ptr(dres), Cc, L.ptr(dx), Cc, L.ptr(dg), L.ptr(db), drop, L.ptr(gs[0]),
+                                           L.ptr(gs[1]), Cc, L.ptr(cs), L.cur_stream()))
+    return dx, dg, db, gs, cs
+
+
 def patch_layernorm_fwd(img, gamma, beta, eps=1e-5):
     F, _, S, _ = img.shape
     N = (S // 32) ** 2

@@ -146,6 +146,23 @@ def test_layernorm_fwd_bwd(rows, C):
     assert _relerr(db, bd.grad) < 2e-5
 
 
+@pytest.mark.parametrize("rows,C", [(77, 256), (1000, 512), (40, 1024)])
+def test_layernorm_bwd_fused_second_output(rows, C):
+    x = _rand(rows, C, seed=25)
+    gamma, beta = 1 + 0.1 * _rand(C, seed=26), 0.1 * _rand(C, seed=27)
+    _, _, mean, rstd = K.layernorm_fwd(x, gamma, beta)
+    dy, dres = _rand(rows, C, seed=28), _rand(rows, C, seed=29)
+    drop = L.make_drop(0.1, 21, 31337)
+    dx_ref, dg_ref, db_ref = K.layernorm_bwd(dy, x, mean, rstd, gamma, dres)
+    dx, dg, db, gs, cs = K.layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres, drop)
+    assert torch.equal(dx, dx_ref)
+    assert _relerr(dg, dg_ref) < 1e-5 and _relerr(db, db_ref) < 1e-5
+    mask = K.dropout_mask(drop, rows * C).reshape(rows, C)
+    g = dx * mask
+    assert (K.join(gs) - g).abs().max() <= g.abs().max() * 2.0 ** -15
+    assert _relerr(cs, g.double().sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("F,S", [(3, 64), (5, 224)])
 def test_patch_layernorm(F, S):
     img = _rand(F, 1, S, S, seed=30).clamp(-1, 1)

@@ -165,6 +165,39 @@ def test_training_mode_dropout_is_reproducible_and_trains():
     assert np.mean(losses[-3:]) < np.mean(losses[:3]), losses
 
 
+def test_cuda_graph_replay_matches_eager():
+    """2nd use of a shape captures the native call sequence into a CUDA graph, later uses replay it: outputs and
+    gradients must be identical to the eager launches, in eval mode and (same seed) in training mode."""
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=3,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, _ = build(cfg, dropout=0.1)
+    inp, _ = cuda_inputs(3, 4, 64)
+    wc, wp = loss_weights((3, 4, 5), (3, 4, 6, 1000))
+    for mode in ("eval", "train"):
+        m.train(mode == "train")
+        m._draw_seed = lambda: 987654321
+        outs, grads = [], []
+        for it in range(4):  # eager, capture, replay, replay
+            m.zero_grad(set_to_none=True)
+            c, p = m(inp)
+            ((c * wc.cuda()).sum() + (p * wp.cuda()).sum()).backward()
+            outs.append((c.detach().clone(), p.detach().clone()))
+            grads.append({k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+        for it in range(1, 4):
+            assert torch.equal(outs[it][0], outs[0][0]) and torch.equal(outs[it][1], outs[0][1]), (mode, it)
+            for k in grads[0]:
+                d = (grads[it][k] - grads[0][k]).abs().max().item()
+                assert d <= 1e-5 * grads[0][k].abs().max().item() + 1e-9, (mode, it, k, d)  # split-K atomics reorder sums
+    # weights changed by an optimizer step must be picked up by the replayed graph
+    m.eval()
+    with torch.no_grad():
+        before, _ = m(inp)
+        m.embed_action.weight.add_(0.05)
+        m.cad_embedding_model.transformer.layers[0][1].net[1].weight.mul_(1.1)
+        after, _ = m(inp)
+    assert (after - before).abs().max() > 1e-4
+
+
 def test_full_size_c1_batch_properties():
     """BASELINE C1 at full size (B=32, T=8, 224x224, H=512): size-independent properties."""
     cfg = dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "host_util.h"
+#include "attention_vit.h"
 
 namespace vck {
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ bool tile_masked(int mask, int window, int q0, int nq
 }
 __device__ __forceinline__ float drop_factor(const AttnP& p, unsigned long long idx) {
   if (p.drop.p <= 0.f) return 1.0f;
-  const Philox4 w = dropout_words(p.drop.seed, p.drop.site, idx >> 2);
+  const Philox4 w = dropout_words(drop_seed(p.drop), p.drop.site, idx >> 2);
   return (w.v[idx & 3ull] >= p.thresh) ? p.dscale : 0.0f;
 }
 
@@ -345,9 +346,14 @@ int launch_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_
 
 }  // namespace
 
+// tests can force the generic SIMT kernels for shapes the tensor-core specialisation would take
+static bool g_force_simt = false;
+void attention_force_simt(int on) { g_force_simt = on != 0; }
+
 int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s) {
   if (int rc = validate(a, "attention_fwd")) return rc;
   if (a.B <= 0 || a.Tq <= 0) return 0;
+  if (vit_attention_eligible(a) && !g_force_simt) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_fwd<64>(a, o_hi, o_lo, ldo, lse, st);
   if (a.d <= 128) return launch_fwd<128>(a, o_hi, o_lo, ldo, lse, st);
@@ -360,10 +366,31 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
   if (int rc = validate(a, "attention_bwd")) return rc;
   if (lddo % 4 != 0) return set_error("attention_bwd: dout stride must be a multiple of 4");
   if (a.B <= 0 || a.Tq <= 0) return 0;
+  if (vit_attention_eligible(a) && !g_force_simt)
+    return vit_attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_bwd<64>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
   if (a.d <= 128) return launch_bwd<128>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
   return launch_bwd<256>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
+}
+
+int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                        bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s) {
+  if (int rc = validate(a, "attention_bwd_split")) return rc;
+  if (a.B <= 0 || a.Tq <= 0) return 0;
+  if (vit_attention_eligible(a) && !g_force_simt)
+    return vit_attention_bwd_split(a, o_hi, o_lo, ldo, lse, dout, lddo, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo, ld_split, s);
+  if (!scratch) return set_error("attention_bwd_split: scratch required");
+  const int64_t W = (int64_t)a.nh * a.d;
+  const int64_t Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  float* dq = scratch;
+  float* dk = dq + Rq * W;
+  float* dv = dk + Rk * W;
+  if (int rc = attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, W, dk, W, dv, W, s)) return rc;
+  if (int rc = split_f32(dq, W, Rq, W, dq_hi, dq_lo, ld_split, s)) return rc;
+  if (int rc = split_f32(dk, W, Rk, W, dk_hi, dk_lo, ld_split, s)) return rc;
+  return split_f32(dv, W, Rk, W, dv_hi, dv_lo, ld_split, s);
 }
 
 }  // namespace vck

@@ -18,6 +18,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <mutex>
+#include <unordered_map>
+#include <functional>
 #include "common.cuh"
 #include "kernels.h"
 #include "host_util.h"
@@ -31,6 +33,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 192;
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+constexpr int STG_LD = 36;  // floats per staged epilogue row (144 B): 16-byte aligned, conflict-free for 128-bit accesses
 
 struct GemmParams {
   int M, N, K, passes, splitk, kb_per_split, num_kb;
@@ -39,7 +42,7 @@ struct GemmParams {
   const float* rowadd; long long ld_rowadd; int rowadd_div, rowadd_mod;
   float* preact; long long ld_preact;
   int act;
-  float drop_scale; uint32_t drop_thresh; uint32_t drop_site; uint64_t drop_seed; int drop_on;
+  float drop_scale; uint32_t drop_thresh; uint32_t drop_site; uint64_t drop_seed; const uint64_t* drop_seed_ptr; int drop_on;
   const float* residual; long long ld_res;
   float* out_f32; long long ldo;
   __nv_bfloat16 *out_hi, *out_lo; long long ldo_split;
@@ -51,7 +54,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
   static constexpr int STAGES = (BN <= 128) ? 3 : 2;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int STG_BYTES = 4 * 32 * STG_LD * 4;  // per-warp 32x32 fp32 transpose buffers of the epilogue
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STG_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
 };
 
@@ -69,57 +73,49 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int mn_major)
   return d;
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row, int col0,
-                                               bool add_bias) {
+// Epilogue math on 4 consecutive columns of one output row, in the COALESCED layout (8 lanes cover 128 B of a row).
+__device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias) {
+  if (p.bias != nullptr && add_bias) {
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (p.rowadd != nullptr && add_bias) {
+    const long long rr = (row / p.rowadd_div) % p.rowadd_mod;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowadd + rr * p.ld_rowadd + col));
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (p.preact != nullptr) {
+    *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (p.act != ACT_NONE) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int col = col0 + 4 * q;
-    if (col >= p.N) break;
-    float v[4];
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+  }
+  if (p.drop_on) {
+    const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
+    const uint64_t seed = p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
+    const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * q + i]);
-    if (p.bias != nullptr && add_bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (p.rowadd != nullptr && add_bias) {
-      const long long rr = (row / p.rowadd_div) % p.rowadd_mod;
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowadd + rr * p.ld_rowadd + col));
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (p.preact != nullptr) {
-      *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    if (p.act != ACT_NONE) {
+    for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+  }
+  if (p.residual != nullptr) {
+    const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
+    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+  }
+  if (p.out_f32 != nullptr) {
+    float* o = p.out_f32 + row * p.ldo + col;
+    if (p.splitk > 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+      for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     }
-    if (p.drop_on) {
-      const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
-      const Philox4 w = dropout_words(p.drop_seed, p.drop_site, idx >> 2);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
-    }
-    if (p.residual != nullptr) {
-      const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
-      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-    }
-    if (p.out_f32 != nullptr) {
-      float* o = p.out_f32 + row * p.ldo + col;
-      if (p.splitk > 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
-      } else {
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      }
-    }
-    if (p.out_hi != nullptr) {
-      uint2 hi, lo;
-      split4(v, hi, lo);
-      *reinterpret_cast<uint2*>(p.out_hi + row * p.ldo_split + col) = hi;
-      if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
-    }
+  }
+  if (p.out_hi != nullptr) {
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    *reinterpret_cast<uint2*>(p.out_hi + row * p.ldo_split + col) = hi;
+    if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
   }
 }
 
@@ -280,7 +276,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t aph = (acc_it >> 1) & 1u;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      const long long row = (long long)m0 + g * 32 + lane;
+      // Each thread owns one accumulator ROW in TMEM; storing rows directly would scatter every 128-bit store over 32
+      // different lines.  Stage 32x32 chunks through shared memory so that 8 lanes write 128 contiguous bytes of a row.
+      float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -288,7 +286,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) epilogue_chunk<BN>(p, r, row, col0, split == 0);
+        if (col0 < p.N) {  // warp-uniform
+          float* myrow = stg + lane * STG_LD;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(myrow + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          __syncwarp();
+          const int q = lane & 7;
+          const int col = col0 + 4 * q;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const long long row = (long long)m0 + g * 32 + rr;
+            if (row < p.M && col < p.N) {
+              const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
+              float v[4] = {t4.x, t4.y, t4.z, t4.w};
+              epilogue_quad(p, v, row, col, split == 0);
+            }
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -324,8 +342,43 @@ PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs a few microseconds of host time; the same (buffer, shape) pairs recur every training step
+// (weights, persistent workspaces), so encoded maps are cached.
+struct TmapKey {
+  const void* base; int64_t rows, cols, ld; int box_cols, box_rows;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.base);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix((size_t)k.rows); mix((size_t)k.cols); mix((size_t)k.ld); mix((size_t)k.box_cols * 1024 + (size_t)k.box_rows);
+    return h;
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+
+int make_tmap_uncached(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows);
+
 // bf16 matrix stored [rows, cols] row-major with leading dimension ld; box = {box_cols (inner), box_rows}
 int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  TmapKey key{base, rows, cols, ld, box_cols, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *tm = it->second; return 0; }
+  }
+  if (int rc = make_tmap_uncached(tm, base, rows, cols, ld, box_cols, box_rows)) return rc;
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *tm);
+  return 0;
+}
+
+int make_tmap_uncached(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -380,6 +433,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.drop_thresh = dropout_threshold(d.drop.p);
   p.drop_site = d.drop.site;
   p.drop_seed = d.drop.seed;
+  p.drop_seed_ptr = d.drop.seed_ptr;
   p.residual = d.residual; p.ld_res = d.ld_res;
   p.out_f32 = d.out_f32; p.ldo = d.ldo;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);

@@ -21,8 +21,10 @@ namespace vck {
 typedef void* stream_t;
 typedef vc_bf16 bf16_t;  // raw bfloat16 bits
 typedef vc_drop Drop;    // dropout call site; p == 0 disables
-static inline Drop no_drop() { Drop d; d.p = 0.f; d.site = 0; d.seed = 0; return d; }
-static inline Drop make_drop(float p, uint32_t site, uint64_t seed) { Drop d; d.p = p; d.site = site; d.seed = seed; return d; }
+static inline Drop no_drop() { Drop d; d.p = 0.f; d.site = 0; d.seed = 0; d.seed_ptr = nullptr; return d; }
+static inline Drop make_drop(float p, uint32_t site, uint64_t seed, const uint64_t* seed_ptr = nullptr) {
+  Drop d; d.p = p; d.site = site; d.seed = seed; d.seed_ptr = seed_ptr; return d;
+}
 
 // -------------------------------------------------------------------------------------------------
 // tensor-core GEMM (tcgen05 / TMEM / TMA):   acc[m,n] = sum_k A[m,k] * B[n,k]
@@ -52,6 +54,13 @@ int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, co
                   const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
                   float* dgamma, float* dbeta, stream_t s);
 
+// same, with a fused second output for the next backward GEMMs: g = dx * dropout_mask(gdrop; element index row*C + c)
+// written as split-bf16 (g_hi, g_lo) and, if g_colsum != null, g_colsum[c] += sum_rows g (atomic, pre-zeroed).
+int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                        const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, Drop gdrop, bf16_t* g_hi, bf16_t* g_lo, int64_t ldg, float* g_colsum,
+                        stream_t s);
+
 // ViT front end: 'f 1 (h 32) (w 32) -> (f h w) 1024' gather + LayerNorm(1024) -> split operand of the patch GEMM
 int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
                         bf16_t* y_lo, float* mean, float* rstd, stream_t s);
@@ -76,6 +85,13 @@ int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, fl
 int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
                   const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                   int64_t lddv, stream_t s);
+
+// same backward, but dq/dk/dv are delivered as split-bf16 operands for the following dgrad/wgrad GEMMs (columns
+// [0,nh*d) of three [B*T, ld_split] matrices).  `scratch` is an fp32 workspace of 3*B*T*nh*d floats that an
+// implementation may use for an fp32 intermediate (the tensor-core ViT kernel writes split directly and ignores it).
+int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                        bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s);
 
 // backward of "v = dropout(act(pre))":  g = dy * mask*scale * act'(.)
 //   act GELU: aux = pre-activation fp32; TANH: aux = forward output fp32; RELU: aux_hi = forward output hi (bf16) != 0

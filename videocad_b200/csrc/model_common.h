@@ -92,8 +92,8 @@ static inline int linear_wgrad(const Split& g, const Split& x, int M, int out_f,
   return gemm(d, st);
 }
 
-static inline Drop site_drop(float p, int training, uint64_t seed, uint32_t site) {
-  return make_drop(training ? p : 0.f, site, seed);
+static inline Drop site_drop(float p, int training, uint64_t seed, uint32_t site, const uint64_t* seed_dev = nullptr) {
+  return make_drop(training ? p : 0.f, site, seed, seed_dev);
 }
 
 }  // namespace vck

@@ -217,11 +217,11 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
       g.bias = LW.sa_in.b; g.out_f32 = Y.qkv; g.ldo = 3 * H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_fwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0)), Y.a.hi, Y.a.lo, H, Y.sa_lse, st));
+    VC_TRY(attention_fwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev)), Y.a.hi, Y.a.lo, H, Y.sa_lse, st));
     {
       GemmDesc g;
       gemm_linear_fwd(g, Y.a, wsplit(LW.sa_out, H), R, H, H, P);
-      g.bias = LW.sa_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 1);
+      g.bias = LW.sa_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev);
       g.residual = x_in; g.ld_res = ld_x; g.out_f32 = Y.y1; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
@@ -239,11 +239,11 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
       g.bias = LW.ca_in.b ? LW.ca_in.b + H : nullptr; g.out_f32 = Y.kv2; g.ldo = 2 * H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_fwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2)), Y.c.hi, Y.c.lo, H, Y.ca_lse, st));
+    VC_TRY(attention_fwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev)), Y.c.hi, Y.c.lo, H, Y.ca_lse, st));
     {
       GemmDesc g;
       gemm_linear_fwd(g, Y.c, wsplit(LW.ca_out, H), R, H, H, P);
-      g.bias = LW.ca_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 3);
+      g.bias = LW.ca_out.b; g.drop = site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev);
       g.residual = Y.x1; g.ld_res = H; g.out_f32 = Y.y2; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
@@ -252,14 +252,14 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
     {
       GemmDesc g;
       gemm_linear_fwd(g, Y.x2S, wsplit(LW.lin1, H), R, Ff, H, P);
-      g.bias = LW.lin1.b; g.act = VC_ACT_RELU; g.drop = site_drop(p, c->training, c->seed, s0 + 4);
+      g.bias = LW.lin1.b; g.act = VC_ACT_RELU; g.drop = site_drop(p, c->training, c->seed, s0 + 4, c->seed_dev);
       g.out_hi = Y.f.hi; g.out_lo = Y.f.lo; g.ldo_split = Ff;
       VC_TRY(gemm(g, st));
     }
     {
       GemmDesc g;
       gemm_linear_fwd(g, Y.f, wsplit(LW.lin2, Ff), R, H, Ff, P);
-      g.bias = LW.lin2.b; g.drop = site_drop(p, c->training, c->seed, s0 + 5);
+      g.bias = LW.lin2.b; g.drop = site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev);
       g.residual = Y.x2; g.ld_res = H; g.out_f32 = Y.y3; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
@@ -320,7 +320,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
                                 : (d.past_actions ? w.actS : (d.past_states ? (d.mem_has_ui ? w.catS : w.uiS) : w.memS));
     // ---- feed-forward block
     VC_TRY(layernorm_bwd(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5), nullptr, 0,
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev), nullptr, 0,
                            s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
     VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, st));
     {
@@ -329,7 +329,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_f32 = s.dF; g.ldo = Ff;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(act_dropout_bwd(s.dF, Ff, R, Ff, VC_ACT_RELU, nullptr, 0, Y.f.hi, Ff, site_drop(p, c->training, c->seed, s0 + 4), nullptr, 0,
+    VC_TRY(act_dropout_bwd(s.dF, Ff, R, Ff, VC_ACT_RELU, nullptr, 0, Y.f.hi, Ff, site_drop(p, c->training, c->seed, s0 + 4, c->seed_dev), nullptr, 0,
                            s.dpreF.hi, s.dpreF.lo, Ff, LW.lin1.db, st));
     VC_TRY(linear_wgrad(s.dpreF, Y.x2S, R, Ff, H, LW.lin1.dw, P, st));
     {
@@ -340,7 +340,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     }
     // ---- cross-attention block
     VC_TRY(layernorm_bwd(s.Bf, H, Y.y2, H, Y.m2, Y.r2, LW.n2.w, R, H, nullptr, 0, s.Y, H, LW.n2.dw, LW.n2.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3), nullptr, 0,
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev), nullptr, 0,
                            s.gH.hi, s.gH.lo, H, LW.ca_out.db, st));
     VC_TRY(linear_wgrad(s.gH, Y.c, R, H, H, LW.ca_out.dw, P, st));
     {
@@ -349,7 +349,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_bwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2)), Y.c.hi, Y.c.lo, H, Y.ca_lse, s.dAtt, H,
+    VC_TRY(attention_bwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev)), Y.c.hi, Y.c.lo, H, Y.ca_lse, s.dAtt, H,
                          s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
     VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
                            3 * H, LW.ca_in.db, st));
@@ -371,7 +371,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     }
     // ---- self-attention block
     VC_TRY(layernorm_bwd(s.A, H, Y.y1, H, Y.m1, Y.r1, LW.n1.w, R, H, nullptr, 0, s.Y, H, LW.n1.dw, LW.n1.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1), nullptr, 0,
+    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), nullptr, 0,
                            s.gH.hi, s.gH.lo, H, LW.sa_out.db, st));
     VC_TRY(linear_wgrad(s.gH, Y.a, R, H, H, LW.sa_out.dw, P, st));
     {
@@ -380,7 +380,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_bwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0)), Y.a.hi, Y.a.lo, H, Y.sa_lse, s.dAtt, H,
+    VC_TRY(attention_bwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev)), Y.a.hi, Y.a.lo, H, Y.sa_lse, s.dAtt, H,
                          s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
     VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
                            3 * H, LW.sa_in.db, st));

@@ -134,7 +134,7 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
     VC_TRY(gemm(d, st));
   }
   VC_TRY(layernorm_fwd(w.e0, D, Mp, D, W.pe_ln2.w, W.pe_ln2.b, LN_EPS, w.e1, D, nullptr, nullptr, 0, w.emean, w.erstd, st));
-  VC_TRY(vit_assemble_fwd(w.e1, F, N, D, W.cls, W.pos, site_drop(p, c->training, c->seed, sb + 0), w.x[0], st));
+  VC_TRY(vit_assemble_fwd(w.e1, F, N, D, W.cls, W.pos, site_drop(p, c->training, c->seed, sb + 0, c->seed_dev), w.x[0], st));
 
   for (int l = 0; l < VC_VIT_DEPTH; ++l) {
     const vc_vit_layer& LW = W.layer[l];
@@ -149,13 +149,13 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
       VC_TRY(gemm(d, st));
     }
     {
-      AttnDesc a = vit_attn_desc(L, F, n, site_drop(p, c->training, c->seed, s0 + 0));
+      AttnDesc a = vit_attn_desc(L, F, n, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev));
       VC_TRY(attention_fwd(a, L.o.hi, L.o.lo, DI, L.lse, st));
     }
     {
       GemmDesc d;
       gemm_linear_fwd(d, L.o, wsplit(LW.out, DI), M, D, DI, P);
-      d.bias = LW.out.b; d.drop = site_drop(p, c->training, c->seed, s0 + 1);
+      d.bias = LW.out.b; d.drop = site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev);
       d.residual = w.x[l]; d.ld_res = D; d.out_f32 = L.x2; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
@@ -165,14 +165,14 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
       GemmDesc d;
       gemm_linear_fwd(d, L.h2, wsplit(LW.fc1, D), M, VC_VIT_MLP, D, P);
       d.bias = LW.fc1.b; d.preact = L.pre1; d.ld_preact = VC_VIT_MLP; d.act = VC_ACT_GELU;
-      d.drop = site_drop(p, c->training, c->seed, s0 + 2);
+      d.drop = site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev);
       d.out_hi = L.ud.hi; d.out_lo = L.ud.lo; d.ldo_split = VC_VIT_MLP;
       VC_TRY(gemm(d, st));
     }
     {
       GemmDesc d;
       gemm_linear_fwd(d, L.ud, wsplit(LW.fc2, VC_VIT_MLP), M, D, VC_VIT_MLP, P);
-      d.bias = LW.fc2.b; d.drop = site_drop(p, c->training, c->seed, s0 + 3);
+      d.bias = LW.fc2.b; d.drop = site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev);
       d.residual = L.x2; d.ld_res = D; d.out_f32 = w.x[l + 1]; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
@@ -210,9 +210,11 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
     const vc_vit_layer& LW = W.layer[l];
     VitWs::Layer& L = w.l[l];
     const uint32_t s0 = sb + 1 + 4 * l;
-    // ---- MLP block
-    VC_TRY(act_dropout_bwd(cur, D, M, D, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3), nullptr,
-                           0, s.g.hi, s.g.lo, D, LW.fc2.db, st));
+    // ---- MLP block.  s.g = split(d x[l+1] * mask(fc2 site)): for l < depth-1 it was produced, together with the fc2 bias
+    // gradient, by the fused LayerNorm backward at the end of the previous iteration.
+    if (l == VC_VIT_DEPTH - 1)
+      VC_TRY(act_dropout_bwd(cur, D, M, D, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev), nullptr,
+                             0, s.g.hi, s.g.lo, D, LW.fc2.db, st));
     VC_TRY(linear_wgrad(s.g, L.ud, M, D, VC_VIT_MLP, LW.fc2.dw, P, st));
     {
       GemmDesc d;
@@ -221,7 +223,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       VC_TRY(gemm(d, st));
     }
     VC_TRY(act_dropout_bwd(s.dud, VC_VIT_MLP, M, VC_VIT_MLP, VC_ACT_GELU, L.pre1, VC_VIT_MLP, nullptr, 0,
-                           site_drop(p, c->training, c->seed, s0 + 2), nullptr, 0, s.dpre.hi, s.dpre.lo, VC_VIT_MLP, LW.fc1.db,
+                           site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev), nullptr, 0, s.dpre.hi, s.dpre.lo, VC_VIT_MLP, LW.fc1.db,
                            st));
     VC_TRY(linear_wgrad(s.dpre, L.h2, M, VC_VIT_MLP, D, LW.fc1.dw, P, st));
     {
@@ -230,10 +232,10 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       d.out_f32 = s.dh; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(layernorm_bwd(s.dh, D, L.x2, D, L.m2, L.r2, LW.ln2.w, M, D, cur, D, other, D, LW.ln2.dw, LW.ln2.db, st));
+    // d x2 = d x3 + LN2_bwd(dh); fused: s.g = split(d x2 * mask(to_out site)), to_out bias gradient
+    VC_TRY(layernorm_bwd_fused(s.dh, D, L.x2, D, L.m2, L.r2, LW.ln2.w, M, D, cur, D, other, D, LW.ln2.dw, LW.ln2.db,
+                               site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), s.g.hi, s.g.lo, D, LW.out.db, st));
     // ---- attention block (other = d x2)
-    VC_TRY(act_dropout_bwd(other, D, M, D, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1),
-                           nullptr, 0, s.g.hi, s.g.lo, D, LW.out.db, st));
     VC_TRY(linear_wgrad(s.g, L.o, M, D, DI, LW.out.dw, P, st));
     {
       GemmDesc d;
@@ -242,11 +244,10 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       VC_TRY(gemm(d, st));
     }
     {
-      AttnDesc a = vit_attn_desc(L, F, n, site_drop(p, c->training, c->seed, s0 + 0));
-      VC_TRY(attention_bwd(a, L.o.hi, L.o.lo, DI, L.lse, s.dO, DI, s.dqkv, 3 * DI, s.dqkv + DI, 3 * DI, s.dqkv + 2 * DI, 3 * DI,
-                           st));
+      AttnDesc a = vit_attn_desc(L, F, n, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev));
+      VC_TRY(attention_bwd_split(a, L.o.hi, L.o.lo, DI, L.lse, s.dO, DI, s.dqkv, s.dqkvS.hi, s.dqkvS.lo, s.dqkvS.hi + DI,
+                                 s.dqkvS.lo + DI, s.dqkvS.hi + 2 * DI, s.dqkvS.lo + 2 * DI, 3 * DI, st));
     }
-    VC_TRY(split_f32(s.dqkv, 3 * DI, M, 3 * DI, s.dqkvS.hi, s.dqkvS.lo, 3 * DI, st));
     VC_TRY(linear_wgrad(s.dqkvS, L.h1, M, 3 * DI, D, LW.qkv.dw, P, st));
     {
       GemmDesc d;
@@ -254,13 +255,20 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       d.out_f32 = s.dh; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(layernorm_bwd(s.dh, D, w.x[l], D, L.m1, L.r1, LW.ln1.w, M, D, other, D, cur, D, LW.ln1.dw, LW.ln1.db, st));
+    if (l > 0) {
+      // d x[l] = d x2 + LN1_bwd(dh); fused: s.g = split(d x[l] * mask(fc2 site of layer l-1)), fc2 bias gradient of layer l-1
+      VC_TRY(layernorm_bwd_fused(s.dh, D, w.x[l], D, L.m1, L.r1, LW.ln1.w, M, D, other, D, cur, D, LW.ln1.dw, LW.ln1.db,
+                                 site_drop(p, c->training, c->seed, sb + 1 + 4 * (l - 1) + 3, c->seed_dev), s.g.hi, s.g.lo, D,
+                                 W.layer[l - 1].fc2.db, st));
+    } else {
+      VC_TRY(layernorm_bwd(s.dh, D, w.x[l], D, L.m1, L.r1, LW.ln1.w, M, D, other, D, cur, D, LW.ln1.dw, LW.ln1.db, st));
+    }
   }
   // ---- token assembly + patch embedding (cur = d x[0]); buffers reused: dh -> d e1, dud -> d e0, dO -> d pl
   float* de1 = s.dh;
   float* de0 = s.dud;
   float* dpl = s.dO;
-  VC_TRY(vit_assemble_bwd(cur, F, N, D, site_drop(p, c->training, c->seed, sb + 0), de1, W.dcls, W.dpos, st));
+  VC_TRY(vit_assemble_bwd(cur, F, N, D, site_drop(p, c->training, c->seed, sb + 0, c->seed_dev), de1, W.dcls, W.dpos, st));
   if (Mp > 0) {
     VC_TRY(layernorm_bwd(de1, D, w.e0, D, w.emean, w.erstd, W.pe_ln2.w, Mp, D, nullptr, 0, de0, D, W.pe_ln2.dw, W.pe_ln2.db, st));
     VC_TRY(act_dropout_bwd(de0, D, Mp, D, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.g.hi, s.g.lo, D, W.pe.db,

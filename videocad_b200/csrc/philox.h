@@ -49,6 +49,12 @@ VC_HD Philox4 dropout_words(uint64_t seed, uint32_t site, uint64_t q) {
   return philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), site, 0x5eedu, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
 
+// seed of a dropout site: the device-resident value if a pointer was given (CUDA-graph replay), else the by-value seed
+template <class DropT>
+VC_HD uint64_t drop_seed(const DropT& d) {
+  return d.seed_ptr != nullptr ? *d.seed_ptr : d.seed;
+}
+
 // keep-probability threshold: keep iff word >= thresh, thresh = round(p * 2^32)
 VC_HD uint32_t dropout_threshold(float p) {
   double t = (double)p * 4294967296.0;

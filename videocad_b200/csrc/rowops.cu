@@ -16,7 +16,7 @@ inline cudaStream_t cs(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 __device__ __forceinline__ void drop4(float (&v)[4], const Drop& d, uint32_t thresh, float scale, unsigned long long idx) {
-  const Philox4 w = dropout_words(d.seed, d.site, idx >> 2);
+  const Philox4 w = dropout_words(drop_seed(d), d.site, idx >> 2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= thresh) ? v[i] * scale : 0.0f;
 }
@@ -57,12 +57,12 @@ struct PatchLoader {  // 'f 1 (h 32) (w 32) -> (f h w) (32 32)' gather; C = 1024
   }
 };
 
-template <class Loader>
-__device__ __forceinline__ void ln_load_stats(const Loader& ld, long long row, int C, int lane, float4 (&v)[LN_MAXV],
+template <class Loader, int NV>
+__device__ __forceinline__ void ln_load_stats(const Loader& ld, long long row, int C, int lane, float4 (&v)[NV],
                                               float& mean, float& rstd, float eps) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < C) {
       v[i] = ld.load(row, c);
@@ -72,7 +72,7 @@ __device__ __forceinline__ void ln_load_stats(const Loader& ld, long long row, i
   mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < C) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -82,7 +82,7 @@ __device__ __forceinline__ void ln_load_stats(const Loader& ld, long long row, i
   rstd = rsqrtf(warp_sum(q) / (float)C + eps);
 }
 
-template <class Loader>
+template <class Loader, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(Loader ld, long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               float* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
@@ -90,15 +90,15 @@ ln_fwd_kernel(Loader ld, long long rows, int C, const float* __restrict__ gamma,
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
-  float4 v[LN_MAXV];
+  float4 v[NV];
   float mean, rstd;
-  ln_load_stats(ld, row, C, lane, v, mean, rstd, eps);
+  ln_load_stats<Loader, NV>(ld, row, C, lane, v, mean, rstd, eps);
   if (lane == 0) {
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < C) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -120,24 +120,32 @@ ln_fwd_kernel(Loader ld, long long rows, int C, const float* __restrict__ gamma,
 }
 
 // backward: block loops over rows (grid-stride by warps); dgamma/dbeta partials in registers, one atomic pass at the end
-template <class Loader, bool kNeedDx>
+struct LnFuse {  // optional second output: g = dx * dropout_mask -> split-bf16 (+ column sums), see layernorm_bwd_fused
+  Drop drop; uint32_t thresh; float scale;
+  __nv_bfloat16 *g_hi, *g_lo; long long ldg;
+  float* colsum;
+};
+
+template <class Loader, bool kNeedDx, bool kFuse, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows, int C,
               const float* __restrict__ dres, long long lddres, float* __restrict__ dx, long long lddx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+              float* __restrict__ dgamma, float* __restrict__ dbeta, const LnFuse fuse) {
   __shared__ float4 red[LN_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 dg[LN_MAXV], db[LN_MAXV];
+  float4 dg[NV], db[NV], cs[kFuse ? NV : 1];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) dg[i] = db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (kFuse ? NV : 1); ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / (float)C;
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[LN_MAXV], g[LN_MAXV];
+    float4 xh[NV], g[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < C) {
         const float4 xv = ld.load(row, c);
@@ -157,7 +165,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
       s1 = warp_sum(s1) * invC;
       s2 = warp_sum(s2) * invC;
 #pragma unroll
-      for (int i = 0; i < LN_MAXV; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const int c = lane * 4 + i * 128;
         if (c < C) {
           float4 o;
@@ -170,17 +178,27 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
           }
           *reinterpret_cast<float4*>(dx + row * lddx + c) = o;
+          if (kFuse) {
+            float v[4] = {o.x, o.y, o.z, o.w};
+            if (fuse.drop.p > 0.f) drop4(v, fuse.drop, fuse.thresh, fuse.scale, (unsigned long long)row * C + c);
+            uint2 h, l;
+            split4(v, h, l);
+            *reinterpret_cast<uint2*>(fuse.g_hi + row * fuse.ldg + c) = h;
+            *reinterpret_cast<uint2*>(fuse.g_lo + row * fuse.ldg + c) = l;
+            cs[i].x += v[0]; cs[i].y += v[1]; cs[i].z += v[2]; cs[i].w += v[3];
+          }
         }
       }
     }
   }
   // cross-warp reduction of the parameter grads, then one atomicAdd per column per block
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int c = lane * 4 + i * 128;
     if (c >= C) break;  // uniform across the warp's lanes only for full chunks; C % 128 == 0 is required
-    for (int pass = 0; pass < 2; ++pass) {
-      red[warp][lane] = pass == 0 ? dg[i] : db[i];
+    for (int pass = 0; pass < (kFuse ? 3 : 2); ++pass) {
+      if (pass == 2 && fuse.colsum == nullptr) break;  // uniform
+      red[warp][lane] = pass == 0 ? dg[i] : (pass == 1 ? db[i] : cs[kFuse ? i : 0]);
       __syncthreads();
       if (warp == 0) {
         float4 a = red[0][lane];
@@ -188,7 +206,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
         for (int w = 1; w < LN_WARPS; ++w) {
           a.x += red[w][lane].x; a.y += red[w][lane].y; a.z += red[w][lane].z; a.w += red[w][lane].w;
         }
-        float* dst = (pass == 0 ? dgamma : dbeta) + c;
+        float* dst = (pass == 0 ? dgamma : (pass == 1 ? dbeta : fuse.colsum)) + c;
         atomicAdd(dst + 0, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
       }
       __syncthreads();
@@ -244,49 +262,64 @@ __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, int F, int
 }
 
 // ------------------------------------------------------------------------------------------- act/dropout backward
-// grid: (ceil(N4/128), row chunks); thread <-> column quad; loops over rows of its chunk
-__global__ void act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M, int N, int act,
-                                       const float* __restrict__ aux, long long ldaux,
-                                       const __nv_bfloat16* __restrict__ aux_hi, long long ldaux_hi, Drop drop,
-                                       uint32_t thresh, float scale, float* __restrict__ g, long long ldg,
-                                       __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, long long ldgs,
-                                       float* __restrict__ colsum, int rows_per_block) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q * 4 >= N) return;
+// block = (128 column quads) x (ADB_RG row groups); grid = (ceil(N4/128), row chunks).  Each thread walks the rows
+// r0 + ty, r0 + ty + ADB_RG, ... of its chunk; the ADB_RG partial column sums are combined through shared memory so that
+// every block issues ONE atomicAdd per column (bias gradient).
+constexpr int ADB_RG = 4;
+__global__ void __launch_bounds__(128 * ADB_RG)
+act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M, int N, int act,
+                       const float* __restrict__ aux, long long ldaux, const __nv_bfloat16* __restrict__ aux_hi,
+                       long long ldaux_hi, Drop drop, uint32_t thresh, float scale, float* __restrict__ g, long long ldg,
+                       __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, long long ldgs,
+                       float* __restrict__ colsum, int rows_per_block) {
+  __shared__ float4 red[ADB_RG][128];
+  const int q = blockIdx.x * 128 + threadIdx.x;
+  const bool active = q * 4 < N;
   const int c = q * 4;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (long long r = r0; r < r1; ++r) {
-    const float4 d = *reinterpret_cast<const float4*>(dy + r * lddy + c);
-    float v[4] = {d.x, d.y, d.z, d.w};
-    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)r * N + c);
-    if (act == ACT_GELU) {
-      const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
-      v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
-    } else if (act == ACT_TANH) {
-      const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
-      v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
-    } else if (act == ACT_RELU) {
-      const uint2 a = *reinterpret_cast<const uint2*>(aux_hi + r * ldaux_hi + c);
-      if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
-      if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
-      if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
-      if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
-    }
-    if (g) *reinterpret_cast<float4*>(g + r * ldg + c) = make_float4(v[0], v[1], v[2], v[3]);
-    if (g_hi) {
-      uint2 h, l;
-      split4(v, h, l);
-      *reinterpret_cast<uint2*>(g_hi + r * ldgs + c) = h;
-      if (g_lo) *reinterpret_cast<uint2*>(g_lo + r * ldgs + c) = l;
-    }
+  if (active) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += ADB_RG) {
+      const float4 d = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+      float v[4] = {d.x, d.y, d.z, d.w};
+      if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)r * N + c);
+      if (act == ACT_GELU) {
+        const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
+        v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
+      } else if (act == ACT_TANH) {
+        const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
+        v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
+      } else if (act == ACT_RELU) {
+        const uint2 a = *reinterpret_cast<const uint2*>(aux_hi + r * ldaux_hi + c);
+        if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
+        if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
+        if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
+        if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
+      }
+      if (g) *reinterpret_cast<float4*>(g + r * ldg + c) = make_float4(v[0], v[1], v[2], v[3]);
+      if (g_hi) {
+        uint2 h, l;
+        split4(v, h, l);
+        *reinterpret_cast<uint2*>(g_hi + r * ldgs + c) = h;
+        if (g_lo) *reinterpret_cast<uint2*>(g_lo + r * ldgs + c) = l;
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[i] += v[i];
+      for (int i = 0; i < 4; ++i) acc[i] += v[i];
+    }
   }
   if (colsum) {
+    red[threadIdx.y][threadIdx.x] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    __syncthreads();
+    if (threadIdx.y == 0 && active) {
+      float4 a = red[0][threadIdx.x];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) atomicAdd(colsum + c + i, acc[i]);
+      for (int k = 1; k < ADB_RG; ++k) {
+        const float4 b = red[k][threadIdx.x];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      atomicAdd(colsum + c + 0, a.x); atomicAdd(colsum + c + 1, a.y); atomicAdd(colsum + c + 2, a.z); atomicAdd(colsum + c + 3, a.w);
+    }
   }
 }
 
@@ -448,7 +481,7 @@ __global__ void add_kernel(const float* __restrict__ a, const float* b, float* o
 __global__ void dropout_mask_kernel(Drop drop, uint32_t thresh, float scale, long long n, float* out) {
   const long long n4 = (n + 3) / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const Philox4 w = dropout_words(drop.seed, drop.site, (unsigned long long)i);
+    const Philox4 w = dropout_words(drop_seed(drop), drop.site, (unsigned long long)i);
     for (int k = 0; k < 4; ++k)
       if (i * 4 + k < n) out[i * 4 + k] = (w.v[k] >= thresh) ? scale : 0.f;
   }
@@ -480,23 +513,46 @@ int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float*
   if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_fwd: C must be a multiple of 128 and <= 1024");
   if (rows <= 0) return 0;
   RowLoader ld{x, ldx};
-  ln_fwd_kernel<RowLoader><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
-      ld, rows, C, gamma, beta, eps, y, ldy, reinterpret_cast<__nv_bfloat16*>(y_hi), reinterpret_cast<__nv_bfloat16*>(y_lo),
-      ldy_split, mean, rstd);
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_hi);
+  __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(y_lo);
+  const int grid = cdiv(rows, LN_WARPS);
+  if (C <= 256) ln_fwd_kernel<RowLoader, 2><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
+  else if (C <= 512) ln_fwd_kernel<RowLoader, 4><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
+  else ln_fwd_kernel<RowLoader, 8><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
   return check_launch("ln_fwd_kernel");
+}
+
+int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
+                        const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
+                        float* dgamma, float* dbeta, Drop gdrop, bf16_t* g_hi, bf16_t* g_lo, int64_t ldg, float* g_colsum,
+                        stream_t s) {
+  if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
+  if (rows <= 0) return 0;
+  RowLoader ld{x, ldx};
+  int grid = cdiv(rows, LN_WARPS * 4);
+  if (grid > 148 * 8) grid = 148 * 8;
+  LnFuse f;
+  f.drop = gdrop; f.thresh = dropout_threshold(gdrop.p); f.scale = drop_scale(gdrop);
+  f.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); f.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo); f.ldg = ldg;
+  f.colsum = g_colsum;
+#define VC_LN_BWD(FUSE, NVV)                                                                                              \
+  ln_bwd_kernel<RowLoader, true, FUSE, NVV><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, lddy, mean, rstd, gamma, rows, C, dres, \
+                                                                               lddres, dx, lddx, dgamma, dbeta, f)
+  if (g_hi != nullptr) {
+    if (g_lo == nullptr) return set_error("layernorm_bwd_fused: g_lo required with g_hi");
+    if (C <= 256) VC_LN_BWD(true, 2); else if (C <= 512) VC_LN_BWD(true, 4); else VC_LN_BWD(true, 8);
+  } else {
+    if (C <= 256) VC_LN_BWD(false, 2); else if (C <= 512) VC_LN_BWD(false, 4); else VC_LN_BWD(false, 8);
+  }
+#undef VC_LN_BWD
+  return check_launch("ln_bwd_kernel");
 }
 
 int layernorm_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* mean, const float* rstd,
                   const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
                   float* dgamma, float* dbeta, stream_t s) {
-  if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
-  if (rows <= 0) return 0;
-  RowLoader ld{x, ldx};
-  int grid = cdiv(rows, LN_WARPS * 8);
-  if (grid > 148 * 4) grid = 148 * 4;
-  ln_bwd_kernel<RowLoader, true><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, lddy, mean, rstd, gamma, rows, C, dres, lddres,
-                                                                    dx, lddx, dgamma, dbeta);
-  return check_launch("ln_bwd_kernel");
+  return layernorm_bwd_fused(dy, lddy, x, ldx, mean, rstd, gamma, rows, C, dres, lddres, dx, lddx, dgamma, dbeta, no_drop(),
+                             nullptr, nullptr, 0, nullptr, s);
 }
 
 int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps, bf16_t* y_hi,
@@ -506,7 +562,7 @@ int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, cons
   const long long rows = (long long)F * N;
   if (rows <= 0) return 0;
   PatchLoader ld{img, S, wp, N};
-  ln_fwd_kernel<PatchLoader><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
+  ln_fwd_kernel<PatchLoader, 8><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
       ld, rows, 1024, gamma, beta, eps, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(y_hi),
       reinterpret_cast<__nv_bfloat16*>(y_lo), 1024, mean, rstd);
   return check_launch("ln_fwd_kernel<patch>");
@@ -521,8 +577,10 @@ int patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean
   PatchLoader ld{img, S, wp, N};
   int grid = cdiv(rows, LN_WARPS * 8);
   if (grid > 148 * 4) grid = 148 * 4;
-  ln_bwd_kernel<PatchLoader, false><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, 1024, mean, rstd, nullptr, rows, 1024, nullptr,
-                                                                       0, nullptr, 0, dgamma, dbeta);
+  LnFuse f;
+  f.drop = no_drop(); f.thresh = 0; f.scale = 1.f; f.g_hi = f.g_lo = nullptr; f.ldg = 0; f.colsum = nullptr;
+  ln_bwd_kernel<PatchLoader, false, false, 8><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, 1024, mean, rstd, nullptr, rows, 1024,
+                                                                              nullptr, 0, nullptr, 0, dgamma, dbeta, f);
   return check_launch("ln_bwd_kernel<patch>");
 }
 
@@ -555,7 +613,7 @@ int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, co
   if (M <= 0) return 0;
   const int rows_per_block = 32;
   dim3 grid(cdiv(N / 4, 128), cdiv(M, rows_per_block));
-  act_dropout_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dy, lddy, M, N, act, aux, ldaux,
+  act_dropout_bwd_kernel<<<grid, dim3(128, ADB_RG), 0, cs(s)>>>(dy, lddy, M, N, act, aux, ldaux,
                                                   reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldaux_hi, drop,
                                                   dropout_threshold(drop.p), drop_scale(drop), g, ldg,
                                                   reinterpret_cast<__nv_bfloat16*>(g_hi),

@@ -22,7 +22,7 @@ vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
 
 
 class Drop(C.Structure):
-    _fields_ = [("p", C.c_float), ("site", C.c_uint32), ("seed", C.c_uint64)]
+    _fields_ = [("p", C.c_float), ("site", C.c_uint32), ("seed", C.c_uint64), ("seed_ptr", C.c_void_p)]
 
 
 class GemmDesc(C.Structure):
@@ -65,6 +65,8 @@ _PROTOS = {
     "vc_split_f32": ([vp, i64, i64, i64, vp, vp, i64, vp], i32),
     "vc_layernorm_fwd": ([vp, i64, i64, i32, vp, vp, f32, vp, i64, vp, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, vp], i32),
+    "vc_layernorm_bwd_fused": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, Drop, vp, vp, i64, vp, vp], i32),
+    "vc_attention_bwd_split": ([C.POINTER(AttnDesc), vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp], i32),
     "vc_patch_layernorm_fwd": ([vp, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp], i32),
     "vc_patch_layernorm_bwd_params": ([vp, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "vc_vit_assemble_fwd": ([vp, i32, i32, i32, vp, vp, Drop, vp, vp], i32),
@@ -133,8 +135,8 @@ def cur_stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def make_drop(p: float = 0.0, site: int = 0, seed: int = 0) -> Drop:
-    return Drop(float(p), int(site) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFFFFFFFFFF)
+def make_drop(p: float = 0.0, site: int = 0, seed: int = 0, seed_ptr=None) -> Drop:
+    return Drop(float(p), int(site) & 0xFFFFFFFF, int(seed) & 0xFFFFFFFFFFFFFFFF, seed_ptr)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -25,6 +25,10 @@ import torch.nn as nn
 from . import lib as L
 from . import model_abi as A
 
+# CUDA-graph replay of the native call sequences (one graph per segment, direction and problem shape); "0" disables
+_GRAPHS = os.environ.get("VIDEOCAD_B200_GRAPHS", "1") != "0"
+_MAX_SLOTS = 3
+
 _SITE_STATE_VIT = 0x100
 _SITE_CAD_VIT = 0x200
 _SITE_SEQ = 0x300
@@ -87,11 +91,86 @@ class ViTParams(_NoForward):
 # =====================================================================================================
 # runners: own the C structs, the split-bf16 weight cache and the flat gradient arena of one segment
 # =====================================================================================================
+class _Slot:
+    """Persistent buffers, call structs and captured CUDA graphs of one segment for one problem shape."""
+
+    def __init__(self):
+        self.graphs, self.uses, self.busy = {}, {}, False
+
+
+class _Lease:
+    """Marks a slot busy between a forward that needs gradients and its backward (or the death of the autograd node)."""
+
+    def __init__(self, slot):
+        self.slot = slot
+        slot.busy = True
+
+    def release(self):
+        if self.slot is not None:
+            self.slot.busy = False
+            self.slot = None
+
+    def __del__(self):
+        self.release()
+
+
 class _Segment:
     def __init__(self):
         self.params: List[nn.Parameter] = []
+        self._mats: List[nn.Parameter] = []
         self._split = {}
+        self._slots = {}
+        self._sig = None
         self._lib = None  # tests may inject the CPU emulation library; the product path loads the CUDA build
+
+    def graphs_enabled(self, t: torch.Tensor) -> bool:
+        return _GRAPHS and t.is_cuda and self._lib is None
+
+    def _check_storage(self):
+        """Persistent structs and graphs bake parameter addresses: drop them if a parameter's storage moved (.to(), ...)."""
+        sig = tuple(p.data_ptr() for p in self.params)
+        if sig != self._sig:
+            self._sig, self._slots, self._split = sig, {}, {}
+
+    def _slot_for(self, key, make):
+        slot = self._slots.get(key)
+        if slot is None:
+            if len(self._slots) >= _MAX_SLOTS:
+                for k in list(self._slots):
+                    if not self._slots[k].busy:
+                        del self._slots[k]
+                        break
+            if len(self._slots) >= _MAX_SLOTS:
+                return None
+            slot = make()
+            self._slots[key] = slot
+        return slot
+
+    def resplit_all(self, stream):
+        """Unconditional refresh of every split-bf16 weight copy (body of the captured forward graph)."""
+        lib = self.lib()
+        for p in self._mats:
+            ent = self._split[id(p)]
+            rows, cols = p.shape[0], p.numel() // p.shape[0]
+            L.check(lib.vc_split_f32(p.data_ptr(), cols, rows, cols, ent[2].data_ptr(), ent[3].data_ptr(), cols, stream), lib)
+            self._split[id(p)] = (p._version, p.data_ptr(), ent[2], ent[3])
+
+    @staticmethod
+    def _launch(slot, name, body):
+        """Run `body` eagerly on first use, capture it into a CUDA graph on the second, replay afterwards."""
+        g = slot.graphs.get(name)
+        if g is not None:
+            g.replay()
+            return
+        if slot.uses.get(name, 0) >= 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                body()
+            slot.graphs[name] = g
+            g.replay()
+        else:
+            body()
+            slot.uses[name] = slot.uses.get(name, 0) + 1
 
     def lib(self):
         return self._lib if self._lib is not None else L.load()
@@ -114,8 +193,11 @@ class _Segment:
         if ent is None or ent[0] != p._version or ent[1] != p.data_ptr():
             w = p.detach()
             rows, cols = w.shape[0], w.numel() // w.shape[0]
-            hi = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-            lo = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+            if ent is not None and ent[2].shape == w.shape and ent[2].device == w.device:
+                hi, lo = ent[2], ent[3]  # refresh in place: captured graphs and cached structs keep these addresses
+            else:
+                hi = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+                lo = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
             lib = self.lib()
             L.check(lib.vc_split_f32(w.data_ptr(), cols, rows, cols, hi.data_ptr(), lo.data_ptr(), cols, stream), lib)
             ent = (p._version, p.data_ptr(), hi, lo)
@@ -123,6 +205,8 @@ class _Segment:
         return ent[2], ent[3]
 
     def _fill_linear(self, s: A.Linear, w: nn.Parameter, b: Optional[nn.Parameter], stream, flat, offs, idx_w, idx_b):
+        if not any(w is m for m in self._mats):
+            self._mats.append(w)
         hi, lo = self.split_of(w, stream)
         s.w, s.w_hi, s.w_lo = w.data_ptr(), hi.data_ptr(), lo.data_ptr()
         s.b = b.data_ptr() if b is not None else None
@@ -187,7 +271,31 @@ class _VitRunner(_Segment):
         self._fill_norm(W.norm, v.transformer.norm, flat, o, self.i_norm[0], self.i_norm[1])
         return W
 
-    def forward(self, img: torch.Tensor, training: bool, p: float, seed: int, passes: int):
+    def _make_slot(self, F_, S, dev, training, p, passes):
+        lib = self.lib()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        sl = _Slot()
+        sl.img = torch.empty(F_, 1, S, S, dtype=torch.float32, device=dev)
+        sl.ws_bytes = lib.vc_vit_workspace_bytes(F_, S)
+        sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
+        sl.out = torch.empty(F_, A.VIT_DIM, dtype=torch.float32, device=dev)
+        sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        sl.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        sl.dcls = torch.empty(F_, A.VIT_DIM, dtype=torch.float32, device=dev)
+        sl.sc_bytes = lib.vc_vit_scratch_bytes(F_, S)
+        sl.scratch = None  # allocated at the first backward
+        sl.W, sl.Wg = self._weights(stream), self._weights(stream, sl.flat)
+        for name, W in (("call", sl.W), ("call_b", sl.Wg)):
+            c = A.VitCall()
+            c.w = C.pointer(W)
+            c.img, c.F, c.S = sl.img.data_ptr(), F_, S
+            c.dropout_p, c.training = float(p), int(bool(training))
+            c.seed, c.site_base, c.seed_dev, c.passes = 0, self.site_base, sl.seed_t.data_ptr(), passes
+            c.ws, c.ws_bytes, c.cls_out = sl.ws.data_ptr(), sl.ws_bytes, sl.out.data_ptr()
+            setattr(sl, name, c)
+        return sl
+
+    def forward(self, img: torch.Tensor, training: bool, p: float, seed: int, passes: int, need_grad: bool = True):
         lib = self.lib()
         img = img.contiguous().float()
         if img.dim() != 4 or img.shape[1] != 1 or img.shape[2] != img.shape[3]:
@@ -195,6 +303,22 @@ class _VitRunner(_Segment):
         F_, S = img.shape[0], img.shape[2]
         if S % A.PATCH != 0 or (S // A.PATCH) ** 2 > 49:
             raise ValueError(f"image size {S} unsupported: need a multiple of 32 and at most 224 (positional table has 50 rows)")
+        if self.graphs_enabled(img):
+            self._check_storage()
+            key = (F_, S, img.device, bool(training), float(p), passes)
+            sl = self._slot_for(key, lambda: self._make_slot(F_, S, img.device, training, p, passes))
+            if sl is not None and not sl.busy:
+                sl.img.copy_(img)
+                sl.seed_t.fill_(seed)
+
+                def body():
+                    st = torch.cuda.current_stream(img.device).cuda_stream
+                    self.resplit_all(st)
+                    L.check(lib.vc_vit_forward(C.byref(sl.call), st), lib)
+
+                self._launch(sl, "fwd", body)
+                lease = _Lease(sl) if need_grad else None
+                return sl.out.clone(), ("slot", sl, lease)
         stream = _stream_of(img)
         ws_bytes = lib.vc_vit_workspace_bytes(F_, S)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
@@ -211,6 +335,23 @@ class _VitRunner(_Segment):
 
     def backward(self, saved, dcls: torch.Tensor):
         lib = self.lib()
+        if saved[0] == "slot":
+            _, sl, lease = saved
+            dev = sl.img.device
+            if sl.scratch is None:
+                sl.scratch = torch.empty(sl.sc_bytes, dtype=torch.uint8, device=dev)
+            sl.dcls.copy_(dcls)
+
+            def body():
+                st = torch.cuda.current_stream(dev).cuda_stream
+                sl.flat.zero_()
+                L.check(lib.vc_vit_backward(C.byref(sl.call_b), sl.dcls.data_ptr(), sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
+
+            self._launch(sl, "bwd", body)
+            grads = self.grad_views(sl.flat.clone(), self.offs)
+            if lease is not None:
+                lease.release()
+            return grads
         call, W, ws, img = saved
         stream = _stream_of(img)
         flat = torch.zeros(self.total, dtype=torch.float32, device=img.device)
@@ -299,7 +440,44 @@ class _SeqRunner(_Segment):
         W.num_layers = nl
         return W, arr
 
-    def forward(self, state_cls, cad_cls, actions, B, T, training, p, seed, passes):
+    def _make_slot(self, B, T, dev, training, p, passes, has_state):
+        lib, m = self.lib(), self.model
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, len(m.transformer_decoder.layers), m.nhead
+        NP, NC = m.num_params * m.num_params_values, m.num_classes
+        R = B * T
+        sl = _Slot()
+        f32 = dict(dtype=torch.float32, device=dev)
+        sl.state = torch.empty(R, A.VIT_DIM, **f32) if has_state else None
+        sl.cad = torch.empty(B, A.VIT_DIM, **f32)
+        sl.actions = torch.empty(R, m.act_dim, **f32)
+        sl.ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP)
+        sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
+        sl.cmds, sl.params = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
+        sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        sl.flat = torch.zeros(self.total, **f32)
+        sl.dcmds, sl.dparams = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
+        sl.d_state = torch.empty(R, A.VIT_DIM, **f32) if (has_state and m.enable_past_states) else None
+        sl.d_cad = torch.empty(B, A.VIT_DIM, **f32)
+        sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP)
+        sl.scratch = None
+        (sl.W, sl.arr), (sl.Wg, sl.arrg) = self._weights(stream), self._weights(stream, sl.flat)
+        for name, W in (("call", sl.W), ("call_b", sl.Wg)):
+            c = A.SeqCall()
+            c.w = C.pointer(W)
+            c.B, c.T, c.H, c.nhead, c.Ff, c.window = B, T, H, nh, Ff, m.window_size
+            c.past_actions, c.past_states = int(m.enable_past_actions), int(m.enable_past_states)
+            c.act_dim, c.num_cmd, c.num_param_out = m.act_dim, NC, NP
+            c.state_cls = sl.state.data_ptr() if sl.state is not None else None
+            c.cad_cls, c.actions = sl.cad.data_ptr(), sl.actions.data_ptr()
+            c.dropout_p, c.training, c.seed, c.site_base = float(p), int(bool(training)), 0, _SITE_SEQ
+            c.seed_dev, c.passes = sl.seed_t.data_ptr(), passes
+            c.ws, c.ws_bytes, c.cmds, c.params = sl.ws.data_ptr(), sl.ws_bytes, sl.cmds.data_ptr(), sl.params.data_ptr()
+            setattr(sl, name, c)
+        return sl
+
+    def forward(self, state_cls, cad_cls, actions, B, T, training, p, seed, passes, need_grad: bool = True,
+                allow_graph: bool = True):
         lib, m = self.lib(), self.model
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
@@ -309,6 +487,25 @@ class _SeqRunner(_Segment):
         actions = actions.contiguous().float().reshape(B * T, -1)
         if state_cls is not None:
             state_cls = state_cls.contiguous().float()
+        if allow_graph and self.graphs_enabled(cad_cls):
+            self._check_storage()
+            key = (B, T, dev, bool(training), float(p), passes, state_cls is not None)
+            sl = self._slot_for(key, lambda: self._make_slot(B, T, dev, training, p, passes, state_cls is not None))
+            if sl is not None and not sl.busy:
+                if sl.state is not None:
+                    sl.state.copy_(state_cls)
+                sl.cad.copy_(cad_cls)
+                sl.actions.copy_(actions)
+                sl.seed_t.fill_(seed)
+
+                def body():
+                    st = torch.cuda.current_stream(dev).cuda_stream
+                    self.resplit_all(st)
+                    L.check(lib.vc_seq_forward(C.byref(sl.call), st), lib)
+
+                self._launch(sl, "fwd", body)
+                lease = _Lease(sl) if need_grad else None
+                return sl.cmds.clone(), sl.params.clone(), ("slot", sl, lease)
         ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         cmds = torch.empty(B * T, NC, dtype=torch.float32, device=dev)
@@ -328,6 +525,28 @@ class _SeqRunner(_Segment):
 
     def backward(self, saved, dcmds, dparams):
         lib, m = self.lib(), self.model
+        if saved[0] == "slot":
+            _, sl, lease = saved
+            dev = sl.cad.device
+            if sl.scratch is None:
+                sl.scratch = torch.empty(sl.sc_bytes, dtype=torch.uint8, device=dev)
+            sl.dcmds.copy_(dcmds.reshape(sl.dcmds.shape))
+            sl.dparams.copy_(dparams.reshape(sl.dparams.shape))
+
+            def body():
+                st = torch.cuda.current_stream(dev).cuda_stream
+                sl.flat.zero_()
+                L.check(lib.vc_seq_backward(C.byref(sl.call_b), sl.dcmds.data_ptr(), sl.dparams.data_ptr(),
+                                           sl.d_state.data_ptr() if sl.d_state is not None else None, sl.d_cad.data_ptr(),
+                                           sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
+
+            self._launch(sl, "bwd", body)
+            grads = self.grad_views(sl.flat.clone(), self.offs, self.used_mask())
+            d_state = sl.d_state.clone() if sl.d_state is not None else None
+            d_cad = sl.d_cad.clone()
+            if lease is not None:
+                lease.release()
+            return d_state, d_cad, grads
         c, W, arr, ws, state_cls, cad_cls, actions = saved
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
@@ -349,7 +568,7 @@ class _SeqRunner(_Segment):
 class _VitFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, training, p, seed, passes, img, *params):
-        out, saved = runner.forward(img, training, p, seed, passes)
+        out, saved = runner.forward(img, training, p, seed, passes, need_grad=any(ctx.needs_input_grad))
         ctx.runner, ctx.saved = runner, saved
         return out
 
@@ -363,7 +582,8 @@ class _VitFn(torch.autograd.Function):
 class _SeqFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, training, p, seed, passes, B, T, state_cls, cad_cls, actions, *params):
-        cmds, pars, saved = runner.forward(state_cls, cad_cls, actions, B, T, training, p, seed, passes)
+        cmds, pars, saved = runner.forward(state_cls, cad_cls, actions, B, T, training, p, seed, passes,
+                                           need_grad=any(ctx.needs_input_grad))
         ctx.runner, ctx.saved = runner, saved
         return cmds, pars
 
@@ -509,19 +729,20 @@ class AutoRegressiveTransformer(nn.Module):
         dev, passes = ui_images.device, self._passes
         state_cls = None
         if self.enable_past_states:
-            state_cls, _ = st_r.forward(ui_images.reshape(-1, *ui_images.shape[2:]), False, 0.0, 0, passes)
+            state_cls, _ = st_r.forward(ui_images.reshape(-1, *ui_images.shape[2:]), False, 0.0, 0, passes, need_grad=False)
             state_cls = state_cls.view(B, T, -1)
-        cad_cls, _ = cad_r.forward(cad_image, False, 0.0, 0, passes)
+        cad_cls, _ = cad_r.forward(cad_image, False, 0.0, 0, passes, need_grad=False)
         if not action:
             zeros = torch.zeros(B, T, self.act_dim, device=dev)
             cmds, params, _ = seq_r.forward(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, zeros, B, T,
-                                            False, 0.0, 0, passes)
+                                            False, 0.0, 0, passes, need_grad=False)
             return cmds.view(B, T, -1), params.view(B, T, self.num_params, self.num_params_values)
         actions = torch.zeros(B, 1, self.act_dim, device=dev)
         out_c, out_p = [], []
         for t in range(T):
             sc = state_cls[:, : t + 1].reshape(B * (t + 1), -1) if state_cls is not None else None
-            cmds, params, _ = seq_r.forward(sc, cad_cls, actions, B, t + 1, False, 0.0, 0, passes)
+            cmds, params, _ = seq_r.forward(sc, cad_cls, actions, B, t + 1, False, 0.0, 0, passes, need_grad=False,
+                                            allow_graph=False)  # T grows every step: no point capturing
             cmd = cmds.view(B, t + 1, -1)[:, -1]
             par = params.view(B, t + 1, self.num_params, self.num_params_values)[:, -1]
             out_c.append(cmd)

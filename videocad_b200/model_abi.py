@@ -34,7 +34,7 @@ class VitWeights(C.Structure):
 
 class VitCall(C.Structure):
     _fields_ = [("w", C.POINTER(VitWeights)), ("img", vp), ("F", i32), ("S", i32), ("dropout_p", f32), ("training", i32),
-                ("seed", u64), ("site_base", u32), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cls_out", vp)]
+                ("seed", u64), ("site_base", u32), ("seed_dev", vp), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cls_out", vp)]
 
 
 class DecLayer(C.Structure):
@@ -54,7 +54,7 @@ class SeqCall(C.Structure):
     _fields_ = [("w", C.POINTER(SeqWeights)), ("B", i32), ("T", i32), ("H", i32), ("nhead", i32), ("Ff", i32), ("window", i32),
                 ("past_actions", i32), ("past_states", i32), ("act_dim", i32), ("num_cmd", i32), ("num_param_out", i32),
                 ("state_cls", vp), ("cad_cls", vp), ("actions", vp), ("dropout_p", f32), ("training", i32), ("seed", u64),
-                ("site_base", u32), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cmds", vp), ("params", vp)]
+                ("site_base", u32), ("seed_dev", vp), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cmds", vp), ("params", vp)]
 
 
 L.EXTRA_PROTOS.update({
