@@ -46,7 +46,10 @@ typedef struct vc_drop {
  *   B: b_mn_major == 0 -> stored [N,K] (ldb >= K);  == 1 -> stored [K,N] (ldb >= N)
  *   passes: 3 = hi*hi + lo*hi + hi*lo (fp32-grade), 1 = hi*hi (bf16-grade)
  * epilogue order: +bias[n], +rowadd[(m/rowadd_div)%rowadd_mod, n], store preact, act, dropout, +residual,
- *   store out_f32 (atomicAdd when splitk > 1) and/or split (out_hi, out_lo). */
+ *   store out_f32 (atomicAdd when splitk > 1) and/or split (out_hi, out_lo).
+ * backward-activation mode (act_backward != 0; used by dgrad GEMMs): instead of "act, dropout" the epilogue applies
+ *   v = dropout_mask(v) * act'(.)  with act' taken from act_aux (GELU: pre-activation fp32; TANH: forward output fp32) or
+ *   act_aux_hi (RELU: forward output hi != 0), and colsum[n] += sum_m v[m,n] (atomic, caller-zeroed) if colsum != NULL. */
 typedef struct vc_gemm_desc {
   const vc_bf16 *a_hi, *a_lo; int64_t lda; int a_mn_major;
   const vc_bf16 *b_hi, *b_lo; int64_t ldb; int b_mn_major;
@@ -59,6 +62,10 @@ typedef struct vc_gemm_desc {
   const float* residual; int64_t ld_res;
   float* out_f32; int64_t ldo;
   vc_bf16 *out_hi, *out_lo; int64_t ldo_split;
+  int act_backward;
+  const float* act_aux; int64_t ld_act_aux;
+  const vc_bf16* act_aux_hi; int64_t ld_act_aux_hi;
+  float* colsum;
 } vc_gemm_desc;
 
 /* Multi-head attention core (replaces the bmm/softmax/dropout/bmm chain of vit_pytorch Attention and of

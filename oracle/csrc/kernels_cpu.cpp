@@ -74,9 +74,13 @@ int gemm(const GemmDesc& d, stream_t) {
   if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
   if (!d.a_hi || !d.b_hi) return set_error("gemm: null operand");
   if (d.passes == 3 && (!d.a_lo || !d.b_lo)) return set_error("gemm: passes=3 needs lo operands");
-  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact))
+  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH) && !d.act_aux)) return set_error("gemm: act_aux required");
+  if (d.act_backward && d.act == VC_ACT_RELU && !d.act_aux_hi) return set_error("gemm: act_aux_hi required");
+  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact || d.colsum))
     return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");
   if (!d.out_f32 && !d.out_hi) return set_error("gemm: no output");
+  std::vector<double> colsum_acc(d.colsum ? d.N : 0, 0.0);
+  std::vector<float> vals(d.colsum ? (size_t)d.M * d.N : 0);
   const int num_kb = (d.K + 63) / 64;
   int splitk = d.splitk < 1 ? 1 : d.splitk;
   if (splitk > num_kb) splitk = num_kb;
@@ -115,10 +119,16 @@ int gemm(const GemmDesc& d, stream_t) {
       if (d.bias) v += d.bias[n];
       if (d.rowadd) v += d.rowadd[(size_t)((m / rdiv) % rmod) * d.ld_rowadd + n];
       if (d.preact) d.preact[(size_t)m * d.ld_preact + n] = (float)v;
-      v = act_d(v, d.act);
+      if (!d.act_backward) v = act_d(v, d.act);
       v *= keep_scale(d.drop, (uint64_t)m * d.N + n);
+      if (d.act_backward) {
+        if (d.act == VC_ACT_GELU) v *= gelu_grad_d(d.act_aux[(size_t)m * d.ld_act_aux + n]);
+        else if (d.act == VC_ACT_TANH) { const double t = d.act_aux[(size_t)m * d.ld_act_aux + n]; v *= 1.0 - t * t; }
+        else if (d.act == VC_ACT_RELU) { if ((d.act_aux_hi[(size_t)m * d.ld_act_aux_hi + n] & 0x7fffu) == 0) v = 0; }
+      }
       if (d.residual) v += d.residual[(size_t)m * d.ld_res + n];
       const float vf = (float)v;
+      if (d.colsum) vals[(size_t)m * d.N + n] = vf;
       if (d.out_f32) {
         float* o = d.out_f32 + (size_t)m * d.ldo + n;
         if (splitk > 1) *o += vf; else *o = vf;
@@ -130,6 +140,11 @@ int gemm(const GemmDesc& d, stream_t) {
         if (d.out_lo) d.out_lo[(size_t)m * d.ldo_split + n] = lo;
       }
     }
+  }
+  if (d.colsum) {
+    for (int m = 0; m < d.M; ++m)
+      for (int n = 0; n < d.N; ++n) colsum_acc[n] += vals[(size_t)m * d.N + n];
+    for (int n = 0; n < d.N; ++n) d.colsum[n] += (float)colsum_acc[n];
   }
   return 0;
 }

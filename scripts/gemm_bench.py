@@ -33,9 +33,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default="", help="comma-separated substrings selecting shapes")
     args = ap.parse_args()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    only = [t for t in args.only.split(",") if t]
     for name, M, N, K, a_mn, b_mn, sk, out in SHAPES:
+        if only and not any(t in name for t in only):
+            continue
         A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
         B = torch.randn((K, N) if b_mn else (N, K), device="cuda")
         a, b = L.split(A), L.split(B)

@@ -91,6 +91,35 @@ def test_gemm_epilogue(act):
     assert abs(keep - 0.9) < 0.01
 
 
+@pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
+def test_gemm_backward_activation_epilogue(act):
+    """dgrad GEMM with the fused activation/dropout backward and bias-gradient column sums."""
+    M, N, Kd = 700, 264, 320
+    G, W = _rand(M, Kd, seed=70, scale=0.5), _rand(Kd, N, seed=71, scale=0.2)  # dX[M,N] = G[M,Kd] W[Kd,N]
+    pre = _rand(M, N, seed=72)
+    drop = L.make_drop(0.1, 33, 4321)
+    mask = K.dropout_mask(drop, M * N).reshape(M, N)
+    aux, aux_hi, deriv = None, None, torch.ones_like(pre)
+    if act == L.ACT_GELU:
+        aux = pre
+        t = pre.double().requires_grad_(True)
+        torch.nn.functional.gelu(t).sum().backward()
+        deriv = t.grad.float()
+    elif act == L.ACT_TANH:
+        aux = torch.tanh(pre)
+        deriv = 1 - aux * aux
+    elif act == L.ACT_RELU:
+        aux_hi = (torch.relu(pre) * mask).to(torch.bfloat16)
+        deriv = (pre > 0).float()
+    outs = K.bf16_pair((M, N))
+    cs = torch.zeros(N, device="cuda")
+    L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=act, act_backward=True, act_aux=aux, act_aux_hi=aux_hi, drop=drop,
+           out_split=outs, colsum=cs)
+    ref = (G.double() @ W.double()) * mask.double() * deriv.double()
+    assert _relerr(K.join(outs), ref) < 3e-5
+    assert _relerr(cs, ref.sum(0)) < 3e-5
+
+
 def test_gemm_rowadd_div():
     M, N, K, T = 64, 128, 64, 8
     A, B = _rand(M, K, seed=11), _rand(N, K, seed=12)

@@ -187,7 +187,7 @@ def test_cuda_graph_replay_matches_eager():
             assert torch.equal(outs[it][0], outs[0][0]) and torch.equal(outs[it][1], outs[0][1]), (mode, it)
             for k in grads[0]:
                 d = (grads[it][k] - grads[0][k]).abs().max().item()
-                assert d <= 1e-5 * grads[0][k].abs().max().item() + 1e-9, (mode, it, k, d)  # split-K atomics reorder sums
+                assert d <= 1e-4 * grads[0][k].abs().max().item() + 1e-9, (mode, it, k, d)  # split-K atomics reorder sums
     # weights changed by an optimizer step must be picked up by the replayed graph
     m.eval()
     with torch.no_grad():

@@ -16,6 +16,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <unordered_map>
@@ -46,6 +47,11 @@ struct GemmParams {
   const float* residual; long long ld_res;
   float* out_f32; long long ldo;
   __nv_bfloat16 *out_hi, *out_lo; long long ldo_split;
+  int act_backward;
+  const float* act_aux; long long ld_act_aux;
+  const __nv_bfloat16* act_aux_hi; long long ld_act_aux_hi;
+  float* colsum;
+  int debug;  // VC_GEMM_DEBUG (profiling experiments only): 1 = no global stores, 2 = TMEM loads only, 4 = no TMEM loads
 };
 
 template <int BN>
@@ -87,7 +93,7 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   if (p.preact != nullptr) {
     *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  if (p.act != ACT_NONE) {
+  if (p.act != ACT_NONE && !p.act_backward) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
   }
@@ -97,6 +103,21 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
     const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+  }
+  if (p.act_backward) {
+    if (p.act == ACT_GELU) {
+      const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+      v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
+    } else if (p.act == ACT_TANH) {
+      const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+      v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
+    } else if (p.act == ACT_RELU) {
+      const uint2 a = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
+      if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
+      if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
+      if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
+      if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
+    }
   }
   if (p.residual != nullptr) {
     const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
@@ -283,9 +304,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32;
+        if (p.debug & 4) continue;
         tmem_ld_32x32(taddr, r);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        if (p.debug & 2) {
+          if (r[0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the load alive
+          continue;
+        }
         if (col0 < p.N) {  // warp-uniform
           float* myrow = stg + lane * STG_LD;
 #pragma unroll
@@ -295,6 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __syncwarp();
           const int q = lane & 7;
           const int col = col0 + 4 * q;
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + (lane >> 3);
@@ -302,7 +329,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (row < p.M && col < p.N) {
               const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
               float v[4] = {t4.x, t4.y, t4.z, t4.w};
-              epilogue_quad(p, v, row, col, split == 0);
+              if (p.debug & 1) {
+                if (v[0] == 123.456f) p.out_f32[0] = v[1];
+              } else {
+                epilogue_quad(p, v, row, col, split == 0);
+              }
+              cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
+            }
+          }
+          if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+            }
+            if (lane < 8 && col < p.N) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
             }
           }
           __syncwarp();
@@ -439,6 +482,15 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(d.out_lo);
   p.ldo_split = d.ldo_split;
+  p.act_backward = d.act_backward ? 1 : 0;
+  p.act_aux = d.act_aux; p.ld_act_aux = d.ld_act_aux;
+  p.act_aux_hi = reinterpret_cast<const __nv_bfloat16*>(d.act_aux_hi); p.ld_act_aux_hi = d.ld_act_aux_hi;
+  p.colsum = d.colsum;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("VC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
 
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   int rc = 0;
@@ -496,7 +548,9 @@ int gemm(const GemmDesc& d, stream_t stream) {
   if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
   if (d.a_hi == nullptr || d.b_hi == nullptr) return set_error("gemm: null operand");
   if (d.passes == 3 && (d.a_lo == nullptr || d.b_lo == nullptr)) return set_error("gemm: passes=3 needs lo operands");
-  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact))
+  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH) && !d.act_aux)) return set_error("gemm: act_aux required");
+  if (d.act_backward && d.act == VC_ACT_RELU && !d.act_aux_hi) return set_error("gemm: act_aux_hi required");
+  if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact || d.colsum))
     return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");
   if (d.out_f32 == nullptr && d.out_hi == nullptr) return set_error("gemm: no output");
   if ((d.out_f32 && d.ldo % 4 != 0) || (d.out_hi && d.ldo_split % 4 != 0) || (d.residual && d.ld_res % 4 != 0) ||

@@ -324,13 +324,14 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
                            s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
     VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, st));
     {
+      // d pre = (g W2) * mask(FFN hidden site) * relu'(f): fused activation backward + linear1 bias gradient
       GemmDesc g;
       gemm_linear_dgrad(g, s.gH, wsplit(LW.lin2, Ff), R, H, Ff, P);
-      g.out_f32 = s.dF; g.ldo = Ff;
+      g.act_backward = 1; g.act = VC_ACT_RELU; g.act_aux_hi = Y.f.hi; g.ld_act_aux_hi = Ff;
+      g.drop = site_drop(p, c->training, c->seed, s0 + 4, c->seed_dev);
+      g.out_hi = s.dpreF.hi; g.out_lo = s.dpreF.lo; g.ldo_split = Ff; g.colsum = LW.lin1.db;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(act_dropout_bwd(s.dF, Ff, R, Ff, VC_ACT_RELU, nullptr, 0, Y.f.hi, Ff, site_drop(p, c->training, c->seed, s0 + 4, c->seed_dev), nullptr, 0,
-                           s.dpreF.hi, s.dpreF.lo, Ff, LW.lin1.db, st));
     VC_TRY(linear_wgrad(s.dpreF, Y.x2S, R, Ff, H, LW.lin1.dw, P, st));
     {
       GemmDesc g;

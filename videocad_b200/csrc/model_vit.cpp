@@ -217,14 +217,14 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
                              0, s.g.hi, s.g.lo, D, LW.fc2.db, st));
     VC_TRY(linear_wgrad(s.g, L.ud, M, D, VC_VIT_MLP, LW.fc2.dw, P, st));
     {
+      // d pre1 = (g W2) * mask(MLP hidden site) * gelu'(pre1): activation backward + fc1 bias gradient fused in the epilogue
       GemmDesc d;
       gemm_linear_dgrad(d, s.g, wsplit(LW.fc2, VC_VIT_MLP), M, D, VC_VIT_MLP, P);
-      d.out_f32 = s.dud; d.ldo = VC_VIT_MLP;
+      d.act_backward = 1; d.act = VC_ACT_GELU; d.act_aux = L.pre1; d.ld_act_aux = VC_VIT_MLP;
+      d.drop = site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev);
+      d.out_hi = s.dpre.hi; d.out_lo = s.dpre.lo; d.ldo_split = VC_VIT_MLP; d.colsum = LW.fc1.db;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(act_dropout_bwd(s.dud, VC_VIT_MLP, M, VC_VIT_MLP, VC_ACT_GELU, L.pre1, VC_VIT_MLP, nullptr, 0,
-                           site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev), nullptr, 0, s.dpre.hi, s.dpre.lo, VC_VIT_MLP, LW.fc1.db,
-                           st));
     VC_TRY(linear_wgrad(s.dpre, L.h2, M, VC_VIT_MLP, D, LW.fc1.dw, P, st));
     {
       GemmDesc d;

@@ -38,6 +38,7 @@ class GemmDesc(C.Structure):
         ("residual", vp), ("ld_res", i64),
         ("out_f32", vp), ("ldo", i64),
         ("out_hi", vp), ("out_lo", vp), ("ldo_split", i64),
+        ("act_backward", i32), ("act_aux", vp), ("ld_act_aux", i64), ("act_aux_hi", vp), ("ld_act_aux_hi", i64), ("colsum", vp),
     ]
 
 
@@ -152,7 +153,8 @@ def split(x: torch.Tensor):
 
 
 def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, passes=3, splitk=1, bias=None, rowadd=None, rowadd_div=1,
-         rowadd_mod=1, preact=None, act=ACT_NONE, drop=None, residual=None, out_f32=None, out_split=None):
+         rowadd_mod=1, preact=None, act=ACT_NONE, drop=None, residual=None, out_f32=None, out_split=None, act_backward=False,
+         act_aux=None, act_aux_hi=None, colsum=None):
     """a, b: (hi, lo) tuples of contiguous bf16 matrices.  See vc_gemm_desc."""
     lib = load()
     d = GemmDesc()
@@ -173,4 +175,10 @@ def gemm(a, b, M, N, K, *, a_mn=False, b_mn=False, passes=3, splitk=1, bias=None
         d.out_f32, d.ldo = ptr(out_f32), out_f32.stride(0)
     if out_split is not None:
         d.out_hi, d.out_lo, d.ldo_split = ptr(out_split[0]), ptr(out_split[1]), out_split[0].stride(0)
+    d.act_backward = int(act_backward)
+    if act_aux is not None:
+        d.act_aux, d.ld_act_aux = ptr(act_aux), act_aux.stride(0)
+    if act_aux_hi is not None:
+        d.act_aux_hi, d.ld_act_aux_hi = ptr(act_aux_hi), act_aux_hi.stride(0)
+    d.colsum = ptr(colsum)
     check(lib.vc_gemm(C.byref(d), cur_stream()), lib)
