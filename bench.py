@@ -25,7 +25,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -69,34 +68,32 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region (one looping nvidia-smi process)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
-
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self.gpu, self.proc = gpu_index, None
 
     def start(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._t:
-            self._t.join(timeout=6)
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.strip()]
+            except Exception:
+                pass
         sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))

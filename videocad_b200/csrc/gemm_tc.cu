@@ -140,11 +140,47 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   }
 }
 
+// Store phase of one staged 32x32 chunk (coalesced: 8 lanes cover 128 B of a row).  Deliberately NOT inlined and not
+// unrolled: one compact copy of the generic epilogue keeps the kernel inside the instruction cache (an unrolled version
+// left the epilogue warps in stall_no_inst).
+__device__ __noinline__ void epilogue_store_chunk(const GemmParams& p, const float* stg, int lane, long long row_base, int col0,
+                                                  bool add_bias) {
+  const int q = lane & 7;
+  const int col = col0 + 4 * q;
+  float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {
+    const int rr = it * 4 + (lane >> 3);
+    const long long row = row_base + rr;
+    if (row < p.M && col < p.N) {
+      const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
+      float v[4] = {t4.x, t4.y, t4.z, t4.w};
+      if (p.debug & 1) {
+        if (v[0] == 123.456f) p.out_f32[0] = v[1];
+      } else {
+        epilogue_quad(p, v, row, col, add_bias);
+      }
+      cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
+    }
+  }
+  if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+    }
+    if (lane < 8 && col < p.N) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const GemmParams p) {
+               const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -297,63 +333,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t aph = (acc_it >> 1) & 1u;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      // Each thread owns one accumulator ROW in TMEM; storing rows directly would scatter every 128-bit store over 32
-      // different lines.  Stage 32x32 chunks through shared memory so that 8 lanes write 128 contiguous bytes of a row.
-      float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32;
-        if (p.debug & 4) continue;
-        tmem_ld_32x32(taddr, r);
+      // Each thread owns one accumulator ROW in TMEM.  Pull the whole 128 x BN tile into registers with back-to-back
+      // tcgen05.ld (one wait), hand the TMEM stage back to the MMA issuer immediately, and only then run the store
+      // phase -- it overlaps with the next tile's MMAs instead of holding the accumulator.
+      uint32_t r[BN / 32][32];
+      if (!(p.debug & 4)) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c)
+          tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32, r[c]);
         tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (p.debug & 2) {
-          if (r[0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the load alive
-          continue;
-        }
-        if (col0 < p.N) {  // warp-uniform
-          float* myrow = stg + lane * STG_LD;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(myrow + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-          __syncwarp();
-          const int q = lane & 7;
-          const int col = col0 + 4 * q;
-          float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3);
-            const long long row = (long long)m0 + g * 32 + rr;
-            if (row < p.M && col < p.N) {
-              const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
-              float v[4] = {t4.x, t4.y, t4.z, t4.w};
-              if (p.debug & 1) {
-                if (v[0] == 123.456f) p.out_f32[0] = v[1];
-              } else {
-                epilogue_quad(p, v, row, col, split == 0);
-              }
-              cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
-            }
-          }
-          if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
-              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
-            }
-            if (lane < 8 && col < p.N) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
-            }
-          }
-          __syncwarp();
-        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      if (p.debug & 6) {
+        if ((p.debug & 2) && r[0][0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the loads alive
+        continue;
+      }
+      // Storing rows directly would scatter every 128-bit store over 32 different lines: stage 32x32 chunks through
+      // shared memory so that 8 lanes write 128 contiguous bytes of a row.
+      float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {  // unrolled (register array indexing); the body below is kept small
+        const int col0 = n0 + c * 32;
+        if (col0 < p.N) {  // warp-uniform
+          float* myrow = stg + lane * STG_LD;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(myrow + 4 * q) =
+                make_float4(__uint_as_float(r[c][4 * q]), __uint_as_float(r[c][4 * q + 1]), __uint_as_float(r[c][4 * q + 2]),
+                            __uint_as_float(r[c][4 * q + 3]));
+          __syncwarp();
+          epilogue_store_chunk(p, stg, lane, (long long)m0 + g * 32, col0, split == 0);
+          __syncwarp();
+        }
+      }
     }
   }
 
