@@ -79,108 +79,113 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int mn_major)
   return d;
 }
 
+// Epilogue feature bits: the kernel is instantiated for a handful of feature sets so that each instance carries only the
+// code it needs (the all-features body, unrolled, overflowed the instruction cache: ncu showed the epilogue warps in
+// stall_no_inst).  A variant may be used for any launch whose required features are a SUBSET of its mask (each feature
+// still checks its runtime pointer/flag).
+enum : uint32_t {
+  EF_BIAS = 1u << 0,     // per-column bias
+  EF_PREACT = 1u << 1,
+  EF_ACT = 1u << 2,      // forward activation
+  EF_DROP = 1u << 3,
+  EF_ACTBWD = 1u << 4,   // backward activation (act_backward)
+  EF_RES = 1u << 5,
+  EF_F32 = 1u << 6,      // fp32 output (plain store)
+  EF_ATOMIC = 1u << 7,   // fp32 output accumulated with atomics (split-K)
+  EF_SPLIT = 1u << 8,    // split-bf16 output
+  EF_COLSUM = 1u << 9,
+  EF_ROWADD = 1u << 10,  // row-broadcast add (timestep embedding rows)
+  EF_ALL = (1u << 11) - 1
+};
+
 // Epilogue math on 4 consecutive columns of one output row, in the COALESCED layout (8 lanes cover 128 B of a row).
+template <uint32_t F>
 __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias) {
-  if (p.bias != nullptr && add_bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  if (p.rowadd != nullptr && add_bias) {
-    const long long rr = (row / p.rowadd_div) % p.rowadd_mod;
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowadd + rr * p.ld_rowadd + col));
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  if (p.preact != nullptr) {
-    *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  if (p.act != ACT_NONE && !p.act_backward) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
-  }
-  if (p.drop_on) {
-    const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
-    const uint64_t seed = p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
-    const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
-  }
-  if (p.act_backward) {
-    if (p.act == ACT_GELU) {
-      const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
-      v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
-    } else if (p.act == ACT_TANH) {
-      const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
-      v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
-    } else if (p.act == ACT_RELU) {
-      const uint2 a = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
-      if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
-      if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
-      if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
-      if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
+  if constexpr ((F & EF_BIAS) != 0) {
+    if (p.bias != nullptr && add_bias) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
   }
-  if (p.residual != nullptr) {
-    const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
-    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-  }
-  if (p.out_f32 != nullptr) {
-    float* o = p.out_f32 + row * p.ldo + col;
-    if (p.splitk > 1) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
-    } else {
-      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+  if constexpr ((F & EF_ROWADD) != 0) {
+    if (p.rowadd != nullptr && add_bias) {
+      const int rr = ((int)row / p.rowadd_div) % p.rowadd_mod;
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.rowadd + (long long)rr * p.ld_rowadd + col));
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
   }
-  if (p.out_hi != nullptr) {
-    uint2 hi, lo;
-    split4(v, hi, lo);
-    *reinterpret_cast<uint2*>(p.out_hi + row * p.ldo_split + col) = hi;
-    if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
+  if constexpr ((F & EF_PREACT) != 0) {
+    if (p.preact != nullptr)
+      *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
   }
-}
-
-// Store phase of one staged 32x32 chunk (coalesced: 8 lanes cover 128 B of a row).  Deliberately NOT inlined and not
-// unrolled: one compact copy of the generic epilogue keeps the kernel inside the instruction cache (an unrolled version
-// left the epilogue warps in stall_no_inst).
-__device__ __noinline__ void epilogue_store_chunk(const GemmParams& p, const float* stg, int lane, long long row_base, int col0,
-                                                  bool add_bias) {
-  const int q = lane & 7;
-  const int col = col0 + 4 * q;
-  float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int it = 0; it < 8; ++it) {
-    const int rr = it * 4 + (lane >> 3);
-    const long long row = row_base + rr;
-    if (row < p.M && col < p.N) {
-      const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
-      float v[4] = {t4.x, t4.y, t4.z, t4.w};
-      if (p.debug & 1) {
-        if (v[0] == 123.456f) p.out_f32[0] = v[1];
-      } else {
-        epilogue_quad(p, v, row, col, add_bias);
+  if constexpr ((F & EF_ACT) != 0) {
+    if (p.act != ACT_NONE && !p.act_backward) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+    }
+  }
+  if constexpr ((F & EF_DROP) != 0) {
+    if (p.drop_on) {
+      const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
+      const uint64_t seed = p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
+      const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+    }
+  }
+  if constexpr ((F & EF_ACTBWD) != 0) {
+    if (p.act_backward) {
+      if (p.act == ACT_GELU) {
+        const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+        v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
+      } else if (p.act == ACT_TANH) {
+        const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+        v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
+      } else if (p.act == ACT_RELU) {
+        const uint2 a = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
+        if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
+        if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
+        if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
+        if ((a.y & 0x7fff0000u) == 0u) v[3] = 0.f;
       }
-      cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3];
     }
   }
-  if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
-      cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+  if constexpr ((F & EF_RES) != 0) {
+    if (p.residual != nullptr) {
+      const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
+      v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
-    if (lane < 8 && col < p.N) {
+  }
+  if constexpr ((F & (EF_F32 | EF_ATOMIC)) != 0) {
+    if (p.out_f32 != nullptr) {
+      float* o = p.out_f32 + row * p.ldo + col;
+      if constexpr ((F & EF_ATOMIC) != 0) {
+        if (p.splitk > 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+          for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      } else {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  if constexpr ((F & EF_SPLIT) != 0) {
+    if (p.out_hi != nullptr) {
+      uint2 hi, lo;
+      split4(v, hi, lo);
+      *reinterpret_cast<uint2*>(p.out_hi + row * p.ldo_split + col) = hi;
+      if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
     }
   }
 }
 
-template <int BN>
+template <int BN, uint32_t F>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-               const __grid_constant__ GemmParams p) {
+               const GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -333,38 +338,67 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const uint32_t aph = (acc_it >> 1) & 1u;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      // Each thread owns one accumulator ROW in TMEM.  Pull the whole 128 x BN tile into registers with back-to-back
-      // tcgen05.ld (one wait), hand the TMEM stage back to the MMA issuer immediately, and only then run the store
-      // phase -- it overlaps with the next tile's MMAs instead of holding the accumulator.
-      uint32_t r[BN / 32][32];
-      if (!(p.debug & 4)) {
-#pragma unroll
-        for (int c = 0; c < BN / 32; ++c)
-          tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32, r[c]);
-        tmem_ld_wait();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[a]);
-      if (p.debug & 6) {
-        if ((p.debug & 2) && r[0][0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the loads alive
-        continue;
-      }
-      // Storing rows directly would scatter every 128-bit store over 32 different lines: stage 32x32 chunks through
-      // shared memory so that 8 lanes write 128 contiguous bytes of a row.
+      // Each thread owns one accumulator ROW in TMEM (tcgen05.ld 32x32b).  Storing rows directly would scatter every
+      // 128-bit store over 32 different lines: stage 32x32 chunks through shared memory so that 8 lanes write 128
+      // contiguous bytes of a row.  The TMEM stage is handed back to the MMA issuer as soon as the last chunk has been
+      // read, before that chunk's store phase.
       float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {  // unrolled (register array indexing); the body below is kept small
+      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? 2 : 8;  // bound the code size
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        if (!(p.debug & 4)) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + a * BN + c * 32, r);
+          tmem_ld_wait();
+        }
+        if (c == BN / 32 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[a]);
+        }
+        if (p.debug & 6) {
+          if ((p.debug & 2) && r[0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the loads alive
+          continue;
+        }
         const int col0 = n0 + c * 32;
         if (col0 < p.N) {  // warp-uniform
           float* myrow = stg + lane * STG_LD;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(myrow + 4 * q) =
-                make_float4(__uint_as_float(r[c][4 * q]), __uint_as_float(r[c][4 * q + 1]), __uint_as_float(r[c][4 * q + 2]),
-                            __uint_as_float(r[c][4 * q + 3]));
+            *reinterpret_cast<float4*>(myrow + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                    __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
           __syncwarp();
-          epilogue_store_chunk(p, stg, lane, (long long)m0 + g * 32, col0, split == 0);
+          const int q = lane & 7;
+          const int col = col0 + 4 * q;
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll kUnrollIt
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3);
+            const long long row = (long long)m0 + g * 32 + rr;
+            if (row < p.M && col < p.N) {
+              const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + 4 * q);
+              float v[4] = {t4.x, t4.y, t4.z, t4.w};
+              if (p.debug & 1) {
+                if (v[0] == 123.456f) p.out_f32[0] = v[1];
+              } else {
+                epilogue_quad<F>(p, v, row, col, split == 0);
+              }
+              if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
+            }
+          }
+          if constexpr ((F & EF_COLSUM) != 0) {
+            if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+                cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+              }
+              if (lane < 8 && col < p.N) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+              }
+            }
+          }
           __syncwarp();
         }
       }
@@ -465,8 +499,50 @@ int num_sms() {
   return n;
 }
 
+uint32_t required_features(const GemmDesc& d) {
+  uint32_t f = 0;
+  if (d.bias) f |= EF_BIAS;
+  if (d.rowadd) f |= EF_ROWADD;
+  if (d.preact) f |= EF_PREACT;
+  if (d.act != VC_ACT_NONE && !d.act_backward) f |= EF_ACT;
+  if (d.drop.p > 0.f) f |= EF_DROP;
+  if (d.act_backward && d.act != VC_ACT_NONE) f |= EF_ACTBWD;
+  if (d.residual) f |= EF_RES;
+  if (d.out_f32) f |= (d.splitk > 1 ? EF_ATOMIC : EF_F32);
+  if (d.out_hi) f |= EF_SPLIT;
+  if (d.colsum) f |= EF_COLSUM;
+  return f;
+}
+
+template <int BN, uint32_t F>
+int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream);
+
+// variants, most specific first; the first whose mask covers the required features is used
+constexpr uint32_t V_F32 = EF_F32;
+constexpr uint32_t V_F32_BIAS = EF_F32 | EF_BIAS;
+constexpr uint32_t V_F32_RES = EF_F32 | EF_RES | EF_BIAS;
+constexpr uint32_t V_F32_DROP_RES = EF_F32 | EF_BIAS | EF_DROP | EF_RES;
+constexpr uint32_t V_SPLIT_ACT = EF_SPLIT | EF_BIAS | EF_ACT | EF_DROP | EF_PREACT;
+constexpr uint32_t V_SPLIT_BWD = EF_SPLIT | EF_ACTBWD | EF_DROP | EF_COLSUM;
+constexpr uint32_t V_ATOMIC = EF_ATOMIC | EF_BIAS;
+
 template <int BN>
 int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
+  const uint32_t req = required_features(d);
+#define VC_TRY_VARIANT(V) if ((req & ~(V)) == 0) return launch_gemm_variant<BN, (V)>(d, stream);
+  VC_TRY_VARIANT(V_F32)
+  VC_TRY_VARIANT(V_F32_BIAS)
+  VC_TRY_VARIANT(V_ATOMIC)
+  VC_TRY_VARIANT(V_F32_RES)
+  VC_TRY_VARIANT(V_F32_DROP_RES)
+  VC_TRY_VARIANT(V_SPLIT_ACT)
+  VC_TRY_VARIANT(V_SPLIT_BWD)
+#undef VC_TRY_VARIANT
+  return launch_gemm_variant<BN, EF_ALL>(d, stream);
+}
+
+template <int BN, uint32_t F>
+int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream) {
   using C = Cfg<BN>;
   GemmParams p;
   memset(&p, 0, sizeof p);
@@ -528,7 +604,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     attr_set = true;
   }
@@ -540,7 +616,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  gemm_tc_kernel<BN, F><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_kernel");
 }
