@@ -226,11 +226,11 @@ def main():
 
     # ---------------- value: inputs resident in HBM
     dev_batches = make_batches(B, T, S, rank, device=dev)
-    for i in range(args.warmup):
-        train_step(dev_batches[i % NUM_BATCHES])
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up
+    for i in range(args.warmup):
+        train_step(dev_batches[i % NUM_BATCHES])
     ms, launches = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     frames_per_step = world * B * T

@@ -263,9 +263,10 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16 *Qh = base, *Ql = Qh + NT * LDH, *Kh = Ql + NT * LDH, *Kl = Kh + NT * LDH, *Vh = Kl + NT * LDH, *Vl = Vh + NT * LDH,
-                *Dh = Vl + NT * LDH, *Dl = Dh + NT * LDH, *Ph = Dl + NT * LDH, *Pl = Ph + NT * LDH, *Sh = Pl + NT * LDH,
-                *Sl = Sh + NT * LDH;
-  float* delta = reinterpret_cast<float*>(Sl + NT * LDH);  // [64]
+                *Dh = Vl + NT * LDH, *Dl = Dh + NT * LDH;
+  // P~ and dS (phase 2 operands) reuse the K / V tiles, which are dead once every warp has finished phase 1
+  __nv_bfloat16 *Ph = Kh, *Pl = Kl, *Sh = Vh, *Sl = Vl;
+  float* delta = reinterpret_cast<float*>(Dl + NT * LDH);  // [64]
   const int h = blockIdx.x % p.nh, b = blockIdx.x / p.nh;
   const int n = p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
@@ -339,13 +340,6 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
         s[j][rr * 2 + 1] = p1 * f1;
         dp[j][rr * 2] = p0 * (dp[j][rr * 2] * f0 - dl) * p.scale;
         dp[j][rr * 2 + 1] = p1 * (dp[j][rr * 2 + 1] * f1 - dl) * p.scale;
-        uint32_t hi, lo;
-        split2(s[j][rr * 2], s[j][rr * 2 + 1], hi, lo);
-        *reinterpret_cast<uint32_t*>(Ph + row * LDH + col) = hi;
-        *reinterpret_cast<uint32_t*>(Pl + row * LDH + col) = lo;
-        split2(dp[j][rr * 2], dp[j][rr * 2 + 1], hi, lo);
-        *reinterpret_cast<uint32_t*>(Sh + row * LDH + col) = hi;
-        *reinterpret_cast<uint32_t*>(Sl + row * LDH + col) = lo;
       }
     }
     // dQ = dS K   (contract over keys; K read transposed)
@@ -360,6 +354,22 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
       if (row < n) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) store_pair(out, 0, rowbase + row, h * HD + 8 * j + 2 * t, acc[j][rr * 2], acc[j][rr * 2 + 1]);
+      }
+    }
+    __syncthreads();  // every warp is done reading K and V: their tiles become the P~ / dS tiles
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = warp * 16 + g + rr * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = 8 * j + 2 * t;
+        uint32_t hi, lo;
+        split2(s[j][rr * 2], s[j][rr * 2 + 1], hi, lo);
+        *reinterpret_cast<uint32_t*>(Ph + row * LDH + col) = hi;
+        *reinterpret_cast<uint32_t*>(Pl + row * LDH + col) = lo;
+        split2(dp[j][rr * 2], dp[j][rr * 2 + 1], hi, lo);
+        *reinterpret_cast<uint32_t*>(Sh + row * LDH + col) = hi;
+        *reinterpret_cast<uint32_t*>(Sl + row * LDH + col) = lo;
       }
     }
   }
@@ -409,7 +419,7 @@ VitAttnP make_p(const AttnDesc& a) {
 }
 
 constexpr size_t FWD_SMEM = (size_t)4 * NT * LDH * 2;
-constexpr size_t BWD_SMEM = (size_t)12 * NT * LDH * 2 + NT * sizeof(float);
+constexpr size_t BWD_SMEM = (size_t)8 * NT * LDH * 2 + NT * sizeof(float);
 
 }  // namespace
 
