@@ -72,6 +72,9 @@ typedef struct vc_gemm_desc {
  * F.multi_head_attention_forward).  Rows are (b*T + t); head h owns columns [h*d, (h+1)*d). */
 typedef struct vc_attn_desc {
   const float *q, *k, *v; int64_t ldq, ldk, ldv;
+  /* optional split-bf16 inputs (as written by a GEMM epilogue): when q_hi != NULL they replace q/k/v and ldq/ldk/ldv are
+   * the leading dimensions of the bf16 arrays */
+  const vc_bf16 *q_hi, *q_lo, *k_hi, *k_lo, *v_hi, *v_lo;
   int B, Tq, Tk, nh, d;
   int mask, window;
   float scale;
@@ -109,9 +112,10 @@ int vc_layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_
                            const float* gamma, int64_t rows, int C, const float* dres, int64_t lddres, float* dx, int64_t lddx,
                            float* dgamma, float* dbeta, vc_drop gdrop, vc_bf16* g_hi, vc_bf16* g_lo, int64_t ldg,
                            float* g_colsum, void* stream);
-/* attention backward delivering dq/dk/dv as split-bf16 GEMM operands (scratch: 3*B*T*nh*d floats, may be unused) */
+/* attention backward delivering dq/dk/dv as split-bf16 GEMM operands (scratch: 3*B*T*nh*d floats, may be unused);
+ * the upstream gradient is either fp32 (dout) or split-bf16 (dout_hi/dout_lo, when dout == NULL), leading dimension lddo */
 int vc_attention_bwd_split(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
-                           const float* dout, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
+                           const float* dout, const vc_bf16* dout_hi, const vc_bf16* dout_lo, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
                            vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, void* stream);
 int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
                            vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream);

@@ -299,7 +299,34 @@ int attn_validate(const AttnDesc& a) {
 }
 }  // namespace
 
-int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t) {
+namespace {
+// split-bf16 q/k/v -> temporary fp32 copies (the emulation always computes from fp32)
+struct JoinedQKV {
+  std::vector<float> q, k, v;
+  AttnDesc d;
+};
+void join_inputs(const AttnDesc& a, JoinedQKV& j) {
+  j.d = a;
+  if (a.q_hi == nullptr) return;
+  const int64_t W = (int64_t)a.nh * a.d, Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  j.q.resize(Rq * W); j.k.resize(Rk * W); j.v.resize(Rk * W);
+  for (int64_t r = 0; r < Rq; ++r)
+    for (int64_t c = 0; c < W; ++c) j.q[r * W + c] = bf2f(a.q_hi[r * a.ldq + c]) + bf2f(a.q_lo[r * a.ldq + c]);
+  for (int64_t r = 0; r < Rk; ++r)
+    for (int64_t c = 0; c < W; ++c) {
+      j.k[r * W + c] = bf2f(a.k_hi[r * a.ldk + c]) + bf2f(a.k_lo[r * a.ldk + c]);
+      j.v[r * W + c] = bf2f(a.v_hi[r * a.ldv + c]) + bf2f(a.v_lo[r * a.ldv + c]);
+    }
+  j.d.q = j.q.data(); j.d.k = j.k.data(); j.d.v = j.v.data();
+  j.d.ldq = j.d.ldk = j.d.ldv = W;
+  j.d.q_hi = j.d.q_lo = j.d.k_hi = j.d.k_lo = j.d.v_hi = j.d.v_lo = nullptr;
+}
+}  // namespace
+
+int attention_fwd(const AttnDesc& a_in, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t) {
+  JoinedQKV joined;
+  join_inputs(a_in, joined);
+  const AttnDesc& a = joined.d;
   if (int rc = attn_validate(a)) return rc;
   const int d = a.d;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -341,8 +368,11 @@ int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, fl
   return 0;
 }
 
-int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse, const float* dout,
+int attention_bwd(const AttnDesc& a_in, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse, const float* dout,
                   int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv, stream_t) {
+  JoinedQKV joined;
+  join_inputs(a_in, joined);
+  const AttnDesc& a = joined.d;
   if (int rc = attn_validate(a)) return rc;
   const int d = a.d;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -388,10 +418,19 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
 }
 
 int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
-                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
-                        bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t st) {
+                        const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, float* scratch, bf16_t* dq_hi,
+                        bf16_t* dq_lo, bf16_t* dk_hi, bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t st) {
   if (!scratch) return set_error("attention_bwd_split: scratch required");
   const int64_t W = (int64_t)a.nh * a.d, Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  std::vector<float> dout_joined;
+  if (dout == nullptr) {
+    if (!dout_hi || !dout_lo) return set_error("attention_bwd_split: no upstream gradient");
+    dout_joined.resize(Rq * W);
+    for (int64_t r = 0; r < Rq; ++r)
+      for (int64_t c = 0; c < W; ++c) dout_joined[r * W + c] = bf2f(dout_hi[r * lddo + c]) + bf2f(dout_lo[r * lddo + c]);
+    dout = dout_joined.data();
+    lddo = W;
+  }
   float* dq = scratch;
   float* dk = dq + Rq * W;
   float* dv = dk + Rk * W;

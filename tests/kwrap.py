@@ -123,6 +123,28 @@ def attention_bwd(a, o, lse, dout, B, Tq, Tk, nh, d):
     return dq, dk, dv
 
 
+def attn_desc_split(qs, ks, vs, B, T, nh, d, scale=None, drop=None):
+    """q/k/v given as (hi, lo) pairs of bf16 views with a common row stride"""
+    a = L.AttnDesc()
+    a.q_hi, a.q_lo, a.k_hi, a.k_lo, a.v_hi, a.v_lo = (L.ptr(t) for t in (qs[0], qs[1], ks[0], ks[1], vs[0], vs[1]))
+    a.ldq, a.ldk, a.ldv = qs[0].stride(0), ks[0].stride(0), vs[0].stride(0)
+    a.B, a.Tq, a.Tk, a.nh, a.d = B, T, T, nh, d
+    a.mask, a.window = L.MASK_NONE, 1
+    a.scale = scale if scale is not None else 1.0 / math.sqrt(d)
+    a.drop = drop if drop is not None else L.make_drop()
+    return a
+
+
+def attention_bwd_split(a, o, lse, dout_split, B, T, nh, d):
+    W = nh * d
+    dq, dk, dv = bf16_pair((B * T, W)), bf16_pair((B * T, W)), bf16_pair((B * T, W))
+    scratch = torch.empty(3 * B * T * W, device="cuda")
+    L.check(L.load().vc_attention_bwd_split(C.byref(a), L.ptr(o[0]), L.ptr(o[1]), W, L.ptr(lse), None, L.ptr(dout_split[0]),
+                                           L.ptr(dout_split[1]), dout_split[0].stride(0), L.ptr(scratch), L.ptr(dq[0]), L.ptr(dq[1]),
+                                           L.ptr(dk[0]), L.ptr(dk[1]), L.ptr(dv[0]), L.ptr(dv[1]), W, L.cur_stream()))
+    return dq, dk, dv
+
+
 def act_dropout_bwd(dy, act, aux=None, aux_hi=None, drop=None, want_colsum=True):
     M, N = dy.shape
     g = torch.empty_like(dy)

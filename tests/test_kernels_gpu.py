@@ -285,6 +285,34 @@ def test_attention_fwd_bwd(B, T, nh, d, mask, window, p):
         assert err < 1e-4, f"{name}: {err:.3e}"
 
 
+@pytest.mark.parametrize("B,T,p", [(5, 50, 0.0), (5, 50, 0.1), (3, 5, 0.1), (2, 64, 0.0)])
+def test_vit_attention_split_inputs(B, T, p):
+    """The tensor-core ViT kernels fed with split-bf16 q/k/v/dO (as the GEMM epilogues write them) and delivering
+    split-bf16 dq/dk/dv: same answers as the fp64 reference."""
+    nh, d = 16, 64
+    H = nh * d
+    qkv = _rand(B * T, 3 * H, seed=52)
+    hi, lo = L.split(qkv)
+    drop = L.make_drop(p, 6, 78)
+    a = K.attn_desc_split((hi[:, :H], lo[:, :H]), (hi[:, H:2 * H], lo[:, H:2 * H]), (hi[:, 2 * H:], lo[:, 2 * H:]), B, T, nh, d, drop=drop)
+    o, lse = K.attention_fwd(a, B, T, nh, d)
+    joined = (hi.float() + lo.float()).double()
+    qd = joined[:, :H].contiguous().requires_grad_(True)
+    kd = joined[:, H:2 * H].contiguous().requires_grad_(True)
+    vd = joined[:, 2 * H:].contiguous().requires_grad_(True)
+    pmask = K.dropout_mask(drop, B * nh * T * T).reshape(B, nh, T, T).double() if p > 0 else None
+    ref, ref_lse = _attn_ref(qd, kd, vd, B, T, T, nh, d, L.MASK_NONE, 1, pmask)
+    assert (K.join(o).double() - ref).abs().max() < 5e-5
+    assert (lse.double() - ref_lse).abs().max() < 1e-4
+    dout = _rand(B * T, H, seed=53)
+    dsplit = L.split(dout)
+    ref.backward((dsplit[0].float() + dsplit[1].float()).double())
+    dq, dk, dv = K.attention_bwd_split(a, o, lse, dsplit, B, T, nh, d)
+    for name, got, want in (("dq", dq, qd.grad), ("dk", dk, kd.grad), ("dv", dv, vd.grad)):
+        err = (K.join(got).double() - want).abs().max().item() / max(1.0, want.abs().max().item())
+        assert err < 1e-4, f"{name}: {err:.3e}"
+
+
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
 def test_act_dropout_bwd(act):
     M, N = 777, 512

@@ -301,6 +301,8 @@ inline AttnP make_params(const AttnDesc& a) {
 }
 
 int validate(const AttnDesc& a, const char* who) {
+  if (a.q_hi != nullptr && !(vit_attention_eligible(a)))
+    return set_error("attention: split-bf16 inputs are supported by the tensor-core ViT kernel only (n <= 64, d = 64, no mask)");
   if (a.d % 4 != 0 || a.d > 256 || a.d <= 0) return set_error("attention: head dim must be a multiple of 4 and <= 256");
   if (a.ldq % 4 != 0 || a.ldk % 4 != 0 || a.ldv % 4 != 0) return set_error("attention: q/k/v strides must be multiples of 4");
   if (a.mask != VC_MASK_NONE && a.Tq != a.Tk) return set_error("attention: masked attention needs Tq == Tk");
@@ -353,7 +355,7 @@ void attention_force_simt(int on) { g_force_simt = on != 0; }
 int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s) {
   if (int rc = validate(a, "attention_fwd")) return rc;
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && !g_force_simt) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
+  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_fwd<64>(a, o_hi, o_lo, ldo, lse, st);
   if (a.d <= 128) return launch_fwd<128>(a, o_hi, o_lo, ldo, lse, st);
@@ -366,7 +368,7 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
   if (int rc = validate(a, "attention_bwd")) return rc;
   if (lddo % 4 != 0) return set_error("attention_bwd: dout stride must be a multiple of 4");
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && !g_force_simt)
+  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr))
     return vit_attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_bwd<64>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
@@ -375,12 +377,14 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
 }
 
 int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
-                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                        const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
                         bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s) {
   if (int rc = validate(a, "attention_bwd_split")) return rc;
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && !g_force_simt)
-    return vit_attention_bwd_split(a, o_hi, o_lo, ldo, lse, dout, lddo, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo, ld_split, s);
+  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr || dout == nullptr))
+    return vit_attention_bwd_split(a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo,
+                                   ld_split, s);
+  if (!dout) return set_error("attention_bwd_split: the generic kernel needs an fp32 upstream gradient");
   if (!scratch) return set_error("attention_bwd_split: scratch required");
   const int64_t W = (int64_t)a.nh * a.d;
   const int64_t Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;

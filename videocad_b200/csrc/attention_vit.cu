@@ -29,6 +29,7 @@ struct VitBwdOut {  // fp32 outputs (dq/dk/dv) or, when s_hi[0] != nullptr, spli
 
 struct VitAttnP {
   const float *q, *k, *v; long long ldq, ldk, ldv;
+  const __nv_bfloat16 *qh, *ql, *kh, *kl, *vh, *vl;  // split-bf16 inputs (used when qh != nullptr)
   int n, nh;
   float scale;
   Drop drop; uint32_t thresh; float dscale;
@@ -81,6 +82,43 @@ __device__ __forceinline__ void stage_split(const float* src, long long ld, int 
     split4(vv, h, l);
     *reinterpret_cast<uint2*>(hi + r * LDH + c) = h;
     *reinterpret_cast<uint2*>(lo + r * LDH + c) = l;
+  }
+}
+
+// same staging when the source already is split-bf16: plain 16-byte copies, no conversion
+__device__ __forceinline__ void stage_copy(const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, long long ld, int n,
+                                           __nv_bfloat16* hi, __nv_bfloat16* lo) {
+  for (int idx = threadIdx.x; idx < NT * (HD / 8); idx += VA_THREADS) {
+    const int r = idx / (HD / 8), c = (idx % (HD / 8)) * 8;
+    uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
+    if (r < n) {
+      h = *reinterpret_cast<const uint4*>(src_hi + (long long)r * ld + c);
+      l = *reinterpret_cast<const uint4*>(src_lo + (long long)r * ld + c);
+    }
+    *reinterpret_cast<uint4*>(hi + r * LDH + c) = h;
+    *reinterpret_cast<uint4*>(lo + r * LDH + c) = l;
+  }
+}
+
+// A fragments of this warp's 16 rows straight from global split-bf16
+__device__ __forceinline__ void load_a_global_split(const __nv_bfloat16* bh, const __nv_bfloat16* bl, long long ld, int row0, int n,
+                                                    int g, int t, uint32_t (&ah)[4][4], uint32_t (&al)[4][4]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int row = row0 + g + rr * 8, col = kk * 16 + 2 * t + half * 8;
+        uint32_t h = 0u, l = 0u;
+        if (row < n) {
+          h = *reinterpret_cast<const uint32_t*>(bh + (long long)row * ld + col);
+          l = *reinterpret_cast<const uint32_t*>(bl + (long long)row * ld + col);
+        }
+        ah[kk][half * 2 + rr] = h;
+        al[kk][half * 2 + rr] = l;
+      }
+    }
   }
 }
 
@@ -167,10 +205,17 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
   const int n = p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const long long rowbase = (long long)b * n;
-  stage_split(p.k + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
-  stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
   uint32_t qh[4][4], ql[4][4];
-  load_a_global(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, warp * 16, n, g, t, qh, ql);
+  if (p.qh != nullptr) {
+    stage_copy(p.kh + rowbase * p.ldk + (long long)h * HD, p.kl + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    stage_copy(p.vh + rowbase * p.ldv + (long long)h * HD, p.vl + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
+    load_a_global_split(p.qh + rowbase * p.ldq + (long long)h * HD, p.ql + rowbase * p.ldq + (long long)h * HD, p.ldq, warp * 16, n,
+                        g, t, qh, ql);
+  } else {
+    stage_split(p.k + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
+    load_a_global(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, warp * 16, n, g, t, qh, ql);
+  }
   __syncthreads();
 
   float s[8][4];
@@ -258,7 +303,8 @@ __device__ __forceinline__ void store_pair(const VitBwdOut& out, int which, long
 
 __global__ void __launch_bounds__(VA_THREADS)
 vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
-                        long long ldo, const float* __restrict__ lse, const float* __restrict__ dout, long long lddo,
+                        long long ldo, const float* __restrict__ lse, const float* __restrict__ dout,
+                        const __nv_bfloat16* __restrict__ dout_hi, const __nv_bfloat16* __restrict__ dout_lo, long long lddo,
                         const VitBwdOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -272,17 +318,35 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const long long rowbase = (long long)b * n;
 
-  stage_split(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, n, Qh, Ql);
-  stage_split(p.k + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
-  stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
-  stage_split(dout + rowbase * lddo + (long long)h * HD, lddo, n, Dh, Dl);
+  if (p.qh != nullptr) {
+    stage_copy(p.qh + rowbase * p.ldq + (long long)h * HD, p.ql + rowbase * p.ldq + (long long)h * HD, p.ldq, n, Qh, Ql);
+    stage_copy(p.kh + rowbase * p.ldk + (long long)h * HD, p.kl + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    stage_copy(p.vh + rowbase * p.ldv + (long long)h * HD, p.vl + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
+  } else {
+    stage_split(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, n, Qh, Ql);
+    stage_split(p.k + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
+  }
+  if (dout != nullptr) {
+    stage_split(dout + rowbase * lddo + (long long)h * HD, lddo, n, Dh, Dl);
+  } else {
+    stage_copy(dout_hi + rowbase * lddo + (long long)h * HD, dout_lo + rowbase * lddo + (long long)h * HD, lddo, n, Dh, Dl);
+  }
   // delta_i = dO_i . O_i  (warp w: rows 16w .. 16w+15, two columns per lane)
   for (int r = 0; r < 16; ++r) {
     const int row = warp * 16 + r;
     float sacc = 0.f;
     if (row < n) {
       const long long oo = (rowbase + row) * ldo + (long long)h * HD + 2 * lane;
-      const float2 d2 = *reinterpret_cast<const float2*>(dout + (rowbase + row) * lddo + (long long)h * HD + 2 * lane);
+      float2 d2;
+      if (dout != nullptr) {
+        d2 = *reinterpret_cast<const float2*>(dout + (rowbase + row) * lddo + (long long)h * HD + 2 * lane);
+      } else {
+        const long long doff = (rowbase + row) * lddo + (long long)h * HD + 2 * lane;
+        const __nv_bfloat162 dh2 = *reinterpret_cast<const __nv_bfloat162*>(dout_hi + doff);
+        const __nv_bfloat162 dl2 = *reinterpret_cast<const __nv_bfloat162*>(dout_lo + doff);
+        d2 = make_float2(__bfloat162float(dh2.x) + __bfloat162float(dl2.x), __bfloat162float(dh2.y) + __bfloat162float(dl2.y));
+      }
       const __nv_bfloat162 oh = *reinterpret_cast<const __nv_bfloat162*>(o_hi + oo);
       float ox = __bfloat162float(oh.x), oy = __bfloat162float(oh.y);
       if (o_lo) {
@@ -411,6 +475,9 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
 VitAttnP make_p(const AttnDesc& a) {
   VitAttnP p;
   p.q = a.q; p.k = a.k; p.v = a.v; p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv;
+  p.qh = reinterpret_cast<const __nv_bfloat16*>(a.q_hi); p.ql = reinterpret_cast<const __nv_bfloat16*>(a.q_lo);
+  p.kh = reinterpret_cast<const __nv_bfloat16*>(a.k_hi); p.kl = reinterpret_cast<const __nv_bfloat16*>(a.k_lo);
+  p.vh = reinterpret_cast<const __nv_bfloat16*>(a.v_hi); p.vl = reinterpret_cast<const __nv_bfloat16*>(a.v_lo);
   p.n = a.Tq; p.nh = a.nh; p.scale = a.scale;
   p.drop = a.drop;
   p.thresh = dropout_threshold(a.drop.p);
@@ -424,7 +491,9 @@ constexpr size_t BWD_SMEM = (size_t)8 * NT * LDH * 2 + NT * sizeof(float);
 }  // namespace
 
 bool vit_attention_eligible(const AttnDesc& a) {
-  return a.mask == VC_MASK_NONE && a.d == HD && a.Tq == a.Tk && a.Tq <= NT && a.ldq % 4 == 0 && a.ldk % 4 == 0 && a.ldv % 4 == 0;
+  const int al = a.q_hi != nullptr ? 8 : 4;  // 16-byte rows for the bf16 copies, float4 for the fp32 conversion
+  if (a.q_hi != nullptr && !(a.q_lo && a.k_hi && a.k_lo && a.v_hi && a.v_lo)) return false;
+  return a.mask == VC_MASK_NONE && a.d == HD && a.Tq == a.Tk && a.Tq <= NT && a.ldq % al == 0 && a.ldk % al == 0 && a.ldv % al == 0;
 }
 
 int vit_attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s) {
@@ -441,8 +510,10 @@ int vit_attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo
 }
 
 static int launch_vit_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
-                          const float* dout, int64_t lddo, const VitBwdOut& out, stream_t s) {
-  if (ldo % 2 != 0 || lddo % 4 != 0) return set_error("vit_attention_bwd: unsupported strides");
+                          const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, const VitBwdOut& out,
+                          stream_t s) {
+  if (ldo % 2 != 0 || lddo % (dout ? 4 : 8) != 0) return set_error("vit_attention_bwd: unsupported strides");
+  if (!dout && !(dout_hi && dout_lo)) return set_error("vit_attention_bwd: no upstream gradient");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(vit_attn_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
@@ -450,8 +521,8 @@ static int launch_vit_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o
     configured = true;
   }
   vit_attn_bwd_mma_kernel<<<a.B * a.nh, VA_THREADS, BWD_SMEM, reinterpret_cast<cudaStream_t>(s)>>>(
-      make_p(a), reinterpret_cast<const __nv_bfloat16*>(o_hi), reinterpret_cast<const __nv_bfloat16*>(o_lo), ldo, lse, dout, lddo,
-      out);
+      make_p(a), reinterpret_cast<const __nv_bfloat16*>(o_hi), reinterpret_cast<const __nv_bfloat16*>(o_lo), ldo, lse, dout,
+      reinterpret_cast<const __nv_bfloat16*>(dout_hi), reinterpret_cast<const __nv_bfloat16*>(dout_lo), lddo, out);
   return check_launch("vit_attn_bwd_mma_kernel");
 }
 
@@ -463,11 +534,11 @@ int vit_attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo,
   out.ldd[0] = lddq; out.ldd[1] = lddk; out.ldd[2] = lddv;
   for (int i = 0; i < 3; ++i) out.s_hi[i] = out.s_lo[i] = nullptr;
   out.lds = 0;
-  return launch_vit_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, out, s);
+  return launch_vit_bwd(a, o_hi, o_lo, ldo, lse, dout, nullptr, nullptr, lddo, out, s);
 }
 
 int vit_attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
-                            const float* dout, int64_t lddo, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi, bf16_t* dk_lo,
+                            const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi, bf16_t* dk_lo,
                             bf16_t* dv_hi, bf16_t* dv_lo, int64_t lds, stream_t s) {
   if (lds % 2 != 0) return set_error("vit_attention_bwd_split: unsupported stride");
   VitBwdOut out;
@@ -476,7 +547,7 @@ int vit_attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t*
   out.s_hi[1] = reinterpret_cast<__nv_bfloat16*>(dk_hi); out.s_lo[1] = reinterpret_cast<__nv_bfloat16*>(dk_lo);
   out.s_hi[2] = reinterpret_cast<__nv_bfloat16*>(dv_hi); out.s_lo[2] = reinterpret_cast<__nv_bfloat16*>(dv_lo);
   out.lds = lds;
-  return launch_vit_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, out, s);
+  return launch_vit_bwd(a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, out, s);
 }
 
 }  // namespace vck

@@ -62,11 +62,12 @@ int vc_layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_
                                   g_lo, ldg, g_colsum, stream);
 }
 int vc_attention_bwd_split(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
-                           const float* dout, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
-                           vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, void* stream) {
+                           const float* dout, const vc_bf16* dout_hi, const vc_bf16* dout_lo, int64_t lddo, float* scratch,
+                           vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi, vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo,
+                           int64_t ld_split, void* stream) {
   if (!a) return vck::set_error("vc_attention_bwd_split: null descriptor");
-  return vck::attention_bwd_split(*a, o_hi, o_lo, ldo, lse, dout, lddo, scratch, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo, ld_split,
-                                  stream);
+  return vck::attention_bwd_split(*a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, scratch, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi,
+                                  dv_lo, ld_split, stream);
 }
 int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
                            vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream) {

@@ -343,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // contiguous bytes of a row.  The TMEM stage is handed back to the MMA issuer as soon as the last chunk has been
       // read, before that chunk's store phase.
       float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
-      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? 2 : 8;  // bound the code size
+      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? ((F & EF_ROWADD) ? 2 : 4) : 8;  // bound the code size
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -522,6 +522,7 @@ constexpr uint32_t V_F32 = EF_F32;
 constexpr uint32_t V_F32_BIAS = EF_F32 | EF_BIAS;
 constexpr uint32_t V_F32_RES = EF_F32 | EF_RES | EF_BIAS;
 constexpr uint32_t V_F32_DROP_RES = EF_F32 | EF_BIAS | EF_DROP | EF_RES;
+constexpr uint32_t V_SPLIT = EF_SPLIT | EF_BIAS;
 constexpr uint32_t V_SPLIT_ACT = EF_SPLIT | EF_BIAS | EF_ACT | EF_DROP | EF_PREACT;
 constexpr uint32_t V_SPLIT_BWD = EF_SPLIT | EF_ACTBWD | EF_DROP | EF_COLSUM;
 constexpr uint32_t V_ATOMIC = EF_ATOMIC | EF_BIAS;
@@ -535,6 +536,7 @@ int launch_gemm(const GemmDesc& d, cudaStream_t stream) {
   VC_TRY_VARIANT(V_ATOMIC)
   VC_TRY_VARIANT(V_F32_RES)
   VC_TRY_VARIANT(V_F32_DROP_RES)
+  VC_TRY_VARIANT(V_SPLIT)
   VC_TRY_VARIANT(V_SPLIT_ACT)
   VC_TRY_VARIANT(V_SPLIT_BWD)
 #undef VC_TRY_VARIANT

@@ -86,11 +86,13 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
                   const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                   int64_t lddv, stream_t s);
 
+// (q/k/v may alternatively be given as split-bf16 arrays through AttnDesc::q_hi..v_lo; the generic SIMT kernels accept
+//  fp32 inputs only, the tensor-core ViT kernel and the CPU emulation accept both)
 // same backward, but dq/dk/dv are delivered as split-bf16 operands for the following dgrad/wgrad GEMMs (columns
 // [0,nh*d) of three [B*T, ld_split] matrices).  `scratch` is an fp32 workspace of 3*B*T*nh*d floats that an
 // implementation may use for an fp32 intermediate (the tensor-core ViT kernel writes split directly and ignores it).
 int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
-                        const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                        const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
                         bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s);
 
 // backward of "v = dropout(act(pre))":  g = dy * mask*scale * act'(.)

@@ -111,7 +111,7 @@ int check_call(const vc_seq_call* c) {
 }
 
 AttnDesc self_attn_desc(const vc_seq_call* c, const Dims& d, const SeqWs::Layer& Y, Drop drop) {
-  AttnDesc a;
+  AttnDesc a = {};
   a.q = Y.qkv; a.k = Y.qkv + d.H; a.v = Y.qkv + 2 * d.H;
   a.ldq = a.ldk = a.ldv = 3 * d.H;
   a.B = d.B; a.Tq = d.T; a.Tk = d.T; a.nh = d.nh; a.d = d.dh;
@@ -122,7 +122,7 @@ AttnDesc self_attn_desc(const vc_seq_call* c, const Dims& d, const SeqWs::Layer&
   return a;
 }
 AttnDesc cross_attn_desc(const vc_seq_call* c, const Dims& d, const SeqWs::Layer& Y, Drop drop) {
-  AttnDesc a;
+  AttnDesc a = {};
   a.q = Y.q2; a.k = Y.kv2; a.v = Y.kv2 + d.H;
   a.ldq = d.H; a.ldk = a.ldv = 2 * d.H;
   a.B = d.B; a.Tq = d.T; a.Tk = d.T; a.nh = d.nh; a.d = d.dh;

@@ -8,7 +8,7 @@
 // HBM layout (all row-major, M = F*(N+1) token rows, Mp = F*N patch rows):
 //   residual stream x[0..6]  fp32 [M,512]           (kept for the LayerNorm backward)
 //   GEMM A-operands           split-bf16 [M,K]        (written directly by the producing LN / epilogue / attention)
-//   qkv                       fp32 [M,3072]           (consumed by the SIMT attention kernels)
+//   qkv                       split-bf16 [M,3072]     (written by the to_qkv GEMM epilogue, read by the attention kernels)
 // Dropout sites (site_base + i): 0 embedding; layer l: 1+4l attention probs, 2+4l to_out, 3+4l MLP hidden, 4+4l MLP out.
 #include "model_common.h"
 
@@ -26,7 +26,7 @@ struct VitWs {
   float* e0; float *emean, *erstd; float* e1;
   float* x[VC_VIT_DEPTH + 1];
   struct Layer {
-    float *m1, *r1; Split h1; float* qkv; float* lse; Split o;
+    float *m1, *r1; Split h1; Split qkv; float* lse; Split o;
     float* x2; float *m2, *r2; Split h2; float* pre1; Split ud;
   } l[VC_VIT_DEPTH];
   float *fmean, *frstd;
@@ -45,7 +45,7 @@ void vit_carve(Arena& a, int F, int S, VitWs& w) {
     VitWs::Layer& L = w.l[l];
     L.m1 = a.alloc<float>(M); L.r1 = a.alloc<float>(M);
     L.h1 = a.alloc_split(M, D);
-    L.qkv = a.alloc<float>(M * 3 * DI);
+    L.qkv = a.alloc_split(M, 3 * DI);
     L.lse = a.alloc<float>((size_t)F * VC_VIT_HEADS * n);
     L.o = a.alloc_split(M, DI);
     L.x2 = a.alloc<float>(M * D);
@@ -59,7 +59,7 @@ void vit_carve(Arena& a, int F, int S, VitWs& w) {
 
 struct VitScratch {
   float *dxa, *dxb, *dh, *dud, *dO, *dqkv;
-  Split g, dpre, dqkvS;
+  Split g, dpre, dqkvS, dOS;
 };
 
 void vit_scratch_carve(Arena& a, int F, int S, VitScratch& s) {
@@ -74,6 +74,7 @@ void vit_scratch_carve(Arena& a, int F, int S, VitScratch& s) {
   s.g = a.alloc_split(M, D);
   s.dpre = a.alloc_split(M, VC_VIT_MLP);
   s.dqkvS = a.alloc_split(M, 3 * DI);
+  s.dOS = a.alloc_split(M, DI);
 }
 
 int check_call(const vc_vit_call* c) {
@@ -87,8 +88,11 @@ int check_call(const vc_vit_call* c) {
 }
 
 AttnDesc vit_attn_desc(const VitWs::Layer& L, int F, int n, Drop drop) {
-  AttnDesc a;
-  a.q = L.qkv; a.k = L.qkv + DI; a.v = L.qkv + 2 * DI;
+  AttnDesc a = {};
+  a.q = a.k = a.v = nullptr;  // q/k/v come as split-bf16, straight from the to_qkv GEMM epilogue
+  a.q_hi = L.qkv.hi; a.q_lo = L.qkv.lo;
+  a.k_hi = L.qkv.hi + DI; a.k_lo = L.qkv.lo + DI;
+  a.v_hi = L.qkv.hi + 2 * DI; a.v_lo = L.qkv.lo + 2 * DI;
   a.ldq = a.ldk = a.ldv = 3 * DI;
   a.B = F; a.Tq = n; a.Tk = n; a.nh = VC_VIT_HEADS; a.d = VC_VIT_DHEAD;
   a.mask = VC_MASK_NONE; a.window = 1;
@@ -145,7 +149,7 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
     {
       GemmDesc d;
       gemm_linear_fwd(d, L.h1, wsplit(LW.qkv, D), M, 3 * DI, D, P);
-      d.out_f32 = L.qkv; d.ldo = 3 * DI;
+      d.out_hi = L.qkv.hi; d.out_lo = L.qkv.lo; d.ldo_split = 3 * DI;
       VC_TRY(gemm(d, st));
     }
     {
@@ -240,12 +244,12 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
     {
       GemmDesc d;
       gemm_linear_dgrad(d, s.g, wsplit(LW.out, DI), M, D, DI, P);
-      d.out_f32 = s.dO; d.ldo = DI;
+      d.out_hi = s.dOS.hi; d.out_lo = s.dOS.lo; d.ldo_split = DI;  // d(attention output), consumed as split-bf16
       VC_TRY(gemm(d, st));
     }
     {
       AttnDesc a = vit_attn_desc(L, F, n, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev));
-      VC_TRY(attention_bwd_split(a, L.o.hi, L.o.lo, DI, L.lse, s.dO, DI, s.dqkv, s.dqkvS.hi, s.dqkvS.lo, s.dqkvS.hi + DI,
+      VC_TRY(attention_bwd_split(a, L.o.hi, L.o.lo, DI, L.lse, nullptr, s.dOS.hi, s.dOS.lo, DI, s.dqkv, s.dqkvS.hi, s.dqkvS.lo, s.dqkvS.hi + DI,
                                  s.dqkvS.lo + DI, s.dqkvS.hi + 2 * DI, s.dqkvS.lo + 2 * DI, 3 * DI, st));
     }
     VC_TRY(linear_wgrad(s.dqkvS, L.h1, M, 3 * DI, D, LW.qkv.dw, P, st));

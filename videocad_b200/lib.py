@@ -45,6 +45,7 @@ class GemmDesc(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [
         ("q", vp), ("k", vp), ("v", vp), ("ldq", i64), ("ldk", i64), ("ldv", i64),
+        ("q_hi", vp), ("q_lo", vp), ("k_hi", vp), ("k_lo", vp), ("v_hi", vp), ("v_lo", vp),
         ("B", i32), ("Tq", i32), ("Tk", i32), ("nh", i32), ("d", i32),
         ("mask", i32), ("window", i32),
         ("scale", C.c_float),
@@ -67,7 +68,7 @@ _PROTOS = {
     "vc_layernorm_fwd": ([vp, i64, i64, i32, vp, vp, f32, vp, i64, vp, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd_fused": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, Drop, vp, vp, i64, vp, vp], i32),
-    "vc_attention_bwd_split": ([C.POINTER(AttnDesc), vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp], i32),
+    "vc_attention_bwd_split": ([C.POINTER(AttnDesc), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp], i32),
     "vc_patch_layernorm_fwd": ([vp, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp], i32),
     "vc_patch_layernorm_bwd_params": ([vp, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "vc_vit_assemble_fwd": ([vp, i32, i32, i32, vp, vp, Drop, vp, vp], i32),
