@@ -92,6 +92,7 @@ long long vc_launch_count(void);
 void vc_launch_count_reset(void);
 void vc_gemm_profile(int enable);                  /* enable/disable + clear the event pool */
 int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches); /* synchronises the events */
+int vc_gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches); /* only launches >= min_flops */
 int vc_gemm_profile_dump(const char* path);       /* per-launch CSV: tag (shape/majors/split/epilogue), flops, ms */
 /* sizeof() of the ABI structs, for binding self-checks: 0 vc_drop, 1 vc_gemm_desc, 2 vc_attn_desc, 3 vc_linear,
  * 4 vc_norm, 5 vc_vit_weights, 6 vc_vit_call, 7 vc_dec_layer, 8 vc_seq_weights, 9 vc_seq_call */

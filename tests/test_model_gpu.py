@@ -94,6 +94,31 @@ def test_c1_shape_vs_oracle_fp64():
     assert dc < LOGIT_TOL and dp < LOGIT_TOL
 
 
+def test_c3_width_small_batch_forward_backward_vs_oracle():
+    """BASELINE config C3 model width (H = Ff = 1024, head dim 256) at a small batch: logits and a few gradients against
+    the fp64 oracle (covers the d = 256 attention kernels, the 64-wide GEMM tiles and the auxiliary-stream fork/join)."""
+    cfg = dict(hidden_size=1024, nhead=4, num_decoder_layers=3, dim_feedforward=1024, window_size=10,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build(cfg, dropout=0.0)
+    m.train()  # dropout p = 0: training path without randomness
+    inp, _ = cuda_inputs(2, 12, 64)
+    wc, wp = loss_weights((2, 12, 5), (2, 12, 6, 1000))
+    for it in range(3):  # eager, graph capture, graph replay
+        m.zero_grad(set_to_none=True)
+        cmds, params = m(inp)
+        ((cmds * wc.cuda()).sum() + (params * wp.cuda()).sum()).backward()
+    sdd = {k: v.double().cuda().requires_grad_(True) for k, v in sd.items()}
+    oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
+    ((oc * wc.cuda().double()).sum() + (op * wp.cuda().double()).sum()).backward()
+    assert (cmds.double() - oc).abs().max() < LOGIT_TOL and (params.double() - op).abs().max() < LOGIT_TOL
+    for k, p in m.named_parameters():
+        ref = sdd[k].grad
+        if ref is None:
+            continue
+        err = (p.grad.double() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        assert err < GRAD_REL_TOL, f"{k}: {err:.3e}"
+
+
 def test_bf16_single_pass_mode_is_looser_but_close():
     cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=3,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)

@@ -19,6 +19,9 @@ void vc_gemm_profile(int enable) { vck::gemm_profile_enable(enable); }
 int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
   return vck::gemm_profile_read(total_ms, total_flops, launches);
 }
+int vc_gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches) {
+  return vck::gemm_profile_read_min(min_flops, total_ms, total_flops, launches);
+}
 int vc_gemm_profile_dump(const char* path) { return vck::gemm_profile_dump(path); }
 size_t vc_abi_sizeof(int which) {
   switch (which) {

@@ -648,6 +648,10 @@ int gemm(const GemmDesc& d, stream_t stream) {
   if ((d.out_f32 && d.ldo % 4 != 0) || (d.out_hi && d.ldo_split % 4 != 0) || (d.residual && d.ld_res % 4 != 0) ||
       (d.preact && d.ld_preact % 4 != 0) || (d.rowadd && d.ld_rowadd % 4 != 0))
     return set_error("gemm: epilogue leading dimensions must be multiples of 4");
+  // decoder-sized problems fill only a few SMs with 128x128 tiles: halve the tile width so that twice as many CTAs each
+  // run half the MMA work
+  const long long tiles128 = (long long)((d.M + BM - 1) / BM) * ((d.N + 127) / 128) * (d.splitk > 1 ? d.splitk : 1);
+  if (tiles128 <= 48 && d.N >= 64) return launch_gemm<64>(d, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<128>(d, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -25,6 +25,7 @@ void launch_count_reset() { g_launches.store(0); }
 #if !VC_CUDA_BUILD
 void gemm_profile_enable(int) {}
 int gemm_profile_dump(const char*) { return 0; }
+int gemm_profile_read_min(double, double* a, double* b, long long* c) { return gemm_profile_read(a, b, c); }
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
   if (total_ms) *total_ms = 0;
   if (total_flops) *total_flops = 0;

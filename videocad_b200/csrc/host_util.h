@@ -13,6 +13,7 @@ void launch_count_reset();
 // GEMM profiling hooks (CUDA build: event pairs around each launch; emulation build: no-ops)
 void gemm_profile_enable(int enable);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
+int gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches);
 int gemm_profile_dump(const char* path);  // per-launch CSV (tag,flops,ms)
 
 #if defined(__CUDACC__)

@@ -49,18 +49,68 @@ void gemm_profile_end(cudaStream_t st, int slot) {
   if (slot >= 0 && slot < (int)g_recs.size()) cudaEventRecord(g_recs[slot].b, st);
 }
 
-int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+int gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches) {
   std::lock_guard<std::mutex> lk(g_mu);
   double ms = 0, fl = 0;
+  long long n = 0;
   for (auto& r : g_recs) {
+    if (r.flops < min_flops) continue;
     cudaEventSynchronize(r.b);
     float t = 0;
     if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) ms += t;
     fl += r.flops;
+    ++n;
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
-  if (launches) *launches = (long long)g_recs.size();
+  if (launches) *launches = n;
+  return 0;
+}
+
+int gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
+  return gemm_profile_read_min(0.0, total_ms, total_flops, launches);
+}
+
+namespace {
+constexpr int kSide = 2, kEvents = 64;
+cudaStream_t g_side[kSide] = {nullptr, nullptr};
+cudaEvent_t g_ev[kEvents];
+bool g_side_init = false;
+int g_ev_next = 0;
+int side_init() {
+  if (g_side_init) return 0;
+  for (int i = 0; i < kSide; ++i)
+    if (cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking) != cudaSuccess) return set_error("cudaStreamCreate failed");
+  for (int i = 0; i < kEvents; ++i)
+    if (cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming) != cudaSuccess) return set_error("cudaEventCreate failed");
+  g_side_init = true;
+  return 0;
+}
+cudaEvent_t next_event() {
+  cudaEvent_t e = g_ev[g_ev_next];
+  g_ev_next = (g_ev_next + 1) % kEvents;
+  return e;
+}
+}  // namespace
+
+int stream_fork(void* main_s, int i, void** side) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (i < 0 || i >= kSide) return set_error("stream_fork: bad index");
+  if (int rc = side_init()) return rc;
+  cudaEvent_t e = next_event();
+  if (cudaEventRecord(e, reinterpret_cast<cudaStream_t>(main_s)) != cudaSuccess) return set_error("stream_fork: event record failed");
+  if (cudaStreamWaitEvent(g_side[i], e, 0) != cudaSuccess) return set_error("stream_fork: wait failed");
+  *side = g_side[i];
+  return 0;
+}
+
+int stream_join(void* main_s, int i) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (i < 0 || i >= kSide) return set_error("stream_join: bad index");
+  if (int rc = side_init()) return rc;
+  cudaEvent_t e = next_event();
+  if (cudaEventRecord(e, g_side[i]) != cudaSuccess) return set_error("stream_join: event record failed");
+  if (cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(main_s), e, 0) != cudaSuccess) return set_error("stream_join: wait failed");
   return 0;
 }
 

@@ -121,6 +121,14 @@ int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float
 int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,
                    float* dW, float* db, stream_t s);
 
+// fork/join onto auxiliary streams, so that small independent kernels (decoder-sized wgrad GEMMs, K/V projections)
+// can run next to the critical chain instead of serialising behind it.  Works under CUDA-graph capture (event edges).
+//   stream_fork: auxiliary stream `i` (0..1) first waits for everything enqueued so far on `main`; returned in *side
+//   stream_join: `main` waits for everything enqueued so far on auxiliary stream `i`
+// The CPU emulation returns `main` itself (everything is serial there).
+int stream_fork(stream_t main, int i, stream_t* side);
+int stream_join(stream_t main, int i);
+
 // misc
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s);  // out = a + b (b may alias out)
 int zero_f32(float* x, int64_t n, stream_t s);

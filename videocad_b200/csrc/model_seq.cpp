@@ -81,6 +81,7 @@ void seq_carve(Arena& a, int B, int T, int H, int Ff, int L, int nh, SeqWs& w) {
 struct SeqScratch {
   float *A, *Bf, *Y, *dF, *dAtt, *dqkv, *dmem, *dcat, *dcadtok;
   Split gH, dpreF, dqkvS, dparS, gB;
+  Split gH_ca, gH_sa, dqkvS_sa;  // separate buffers per use: the weight-gradient GEMMs read them on an auxiliary stream
 };
 
 void seq_scratch_carve(Arena& a, int B, int T, int H, int Ff, int NP, SeqScratch& s) {
@@ -91,6 +92,7 @@ void seq_scratch_carve(Arena& a, int B, int T, int H, int Ff, int NP, SeqScratch
   s.dcat = a.alloc<float>(R * 2 * H); s.dcadtok = a.alloc<float>((size_t)B * H);
   s.gH = a.alloc_split(R, H); s.dpreF = a.alloc_split(R, Ff); s.dqkvS = a.alloc_split(R, 3 * H);
   s.dparS = a.alloc_split(R, NP); s.gB = a.alloc_split(B, H);
+  s.gH_ca = a.alloc_split(R, H); s.gH_sa = a.alloc_split(R, H); s.dqkvS_sa = a.alloc_split(R, 3 * H);
 }
 
 int check_call(const vc_seq_call* c) {
@@ -206,6 +208,19 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
     x_in = w.mem; x_inS = w.memS; ld_x = H;
   }
 
+  // The cross-attention K/V projections of ALL layers depend only on the memory tokens: issue them on an auxiliary stream,
+  // next to the first self-attention block, instead of inside the per-layer chain.
+  {
+    stream_t side;
+    VC_TRY(stream_fork(st, 0, &side));
+    for (int l = 0; l < d.L; ++l) {
+      const vc_dec_layer& LW = W.layers[l];
+      GemmDesc g;
+      gemm_linear_fwd(g, w.memS, wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
+      g.bias = LW.ca_in.b ? LW.ca_in.b + H : nullptr; g.out_f32 = w.l[l].kv2; g.ldo = 2 * H;
+      VC_TRY(gemm(g, side));
+    }
+  }
   for (int l = 0; l < d.L; ++l) {
     const vc_dec_layer& LW = W.layers[l];
     SeqWs::Layer& Y = w.l[l];
@@ -233,12 +248,7 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
       g.bias = LW.ca_in.b; g.out_f32 = Y.q2; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
-    {
-      GemmDesc g;
-      gemm_linear_fwd(g, w.memS, wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
-      g.bias = LW.ca_in.b ? LW.ca_in.b + H : nullptr; g.out_f32 = Y.kv2; g.ldo = 2 * H;
-      VC_TRY(gemm(g, st));
-    }
+    if (l == 0) VC_TRY(stream_join(st, 0));  // K/V projections of all layers are complete from here on
     VC_TRY(attention_fwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev)), Y.c.hi, Y.c.lo, H, Y.ca_lse, st));
     {
       GemmDesc g;
@@ -267,13 +277,18 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
     x_in = Y.x3; x_inS = Y.x3S; ld_x = H;
   }
   // ---- heads
-  VC_TRY(head_small_fwd(x_in, R, H, W.head_cmd_w, W.head_cmd_b, d.NC, c->cmds, st));
+  {
+    stream_t side;
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(head_small_fwd(x_in, R, H, W.head_cmd_w, W.head_cmd_b, d.NC, c->cmds, side));
+  }
   {
     GemmDesc g;
     gemm_linear_fwd(g, x_inS, wsplit(W.head_params, H), R, d.NP, H, P);
     g.bias = W.head_params.b; g.out_f32 = c->params; g.ldo = d.NP;
     VC_TRY(gemm(g, st));
   }
+  VC_TRY(stream_join(st, 0));
   return 0;
 }
 
@@ -302,7 +317,10 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
   // ---- heads: A = d x_last
   VC_TRY(act_dropout_bwd(dparams, d.NP, R, d.NP, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dparS.hi, s.dparS.lo,
                          d.NP, W.head_params.db, st));
-  VC_TRY(linear_wgrad(s.dparS, last.x3S, R, d.NP, H, W.head_params.dw, P, st));
+  // weight gradients never feed the activation-gradient chain: they go to an auxiliary stream (joined once per layer)
+  stream_t side;
+  VC_TRY(stream_fork(st, 0, &side));
+  VC_TRY(linear_wgrad(s.dparS, last.x3S, R, d.NP, H, W.head_params.dw, P, side));
   {
     GemmDesc g;
     gemm_linear_dgrad(g, s.dparS, wsplit(W.head_params, H), R, d.NP, H, P);
@@ -322,7 +340,8 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     VC_TRY(layernorm_bwd(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db, st));
     VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev), nullptr, 0,
                            s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
-    VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, side));
     {
       // d pre = (g W2) * mask(FFN hidden site) * relu'(f): fused activation backward + linear1 bias gradient
       GemmDesc g;
@@ -332,7 +351,8 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_hi = s.dpreF.hi; g.out_lo = s.dpreF.lo; g.ldo_split = Ff; g.colsum = LW.lin1.db;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(linear_wgrad(s.dpreF, Y.x2S, R, Ff, H, LW.lin1.dw, P, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(s.dpreF, Y.x2S, R, Ff, H, LW.lin1.dw, P, side));
     {
       GemmDesc g;
       gemm_linear_dgrad(g, s.dpreF, wsplit(LW.lin1, H), R, Ff, H, P);
@@ -342,11 +362,12 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     // ---- cross-attention block
     VC_TRY(layernorm_bwd(s.Bf, H, Y.y2, H, Y.m2, Y.r2, LW.n2.w, R, H, nullptr, 0, s.Y, H, LW.n2.dw, LW.n2.db, st));
     VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev), nullptr, 0,
-                           s.gH.hi, s.gH.lo, H, LW.ca_out.db, st));
-    VC_TRY(linear_wgrad(s.gH, Y.c, R, H, H, LW.ca_out.dw, P, st));
+                           s.gH_ca.hi, s.gH_ca.lo, H, LW.ca_out.db, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(s.gH_ca, Y.c, R, H, H, LW.ca_out.dw, P, side));
     {
       GemmDesc g;
-      gemm_linear_dgrad(g, s.gH, wsplit(LW.ca_out, H), R, H, H, P);
+      gemm_linear_dgrad(g, s.gH_ca, wsplit(LW.ca_out, H), R, H, H, P);
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
@@ -354,44 +375,48 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
                          s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
     VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
                            3 * H, LW.ca_in.db, st));
-    VC_TRY(linear_wgrad(cols(s.dqkvS, 0), Y.x1S, R, H, H, LW.ca_in.dw, P, st));
-    VC_TRY(linear_wgrad(cols(s.dqkvS, H), w.memS, R, 2 * H, H, LW.ca_in.dw + (size_t)H * H, P, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(cols(s.dqkvS, 0), Y.x1S, R, H, H, LW.ca_in.dw, P, side));
+    VC_TRY(linear_wgrad(cols(s.dqkvS, H), w.memS, R, 2 * H, H, LW.ca_in.dw + (size_t)H * H, P, side));
+    {
+      GemmDesc g;  // d mem accumulates over the layers; only needed after the last layer -> auxiliary stream as well
+      gemm_linear_dgrad(g, cols(s.dqkvS, H), wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
+      if (dmem_init) { g.residual = s.dmem; g.ld_res = H; }
+      g.out_f32 = s.dmem; g.ldo = H;
+      VC_TRY(gemm(g, side));
+      dmem_init = true;
+    }
     {
       GemmDesc g;
       gemm_linear_dgrad(g, cols(s.dqkvS, 0), wsplit(LW.ca_in, H, 0), R, H, H, P);
       g.residual = s.Y; g.ld_res = H; g.out_f32 = s.A; g.ldo = H;  // d x1 = d y2 + dq Wq
       VC_TRY(gemm(g, st));
     }
-    {
-      GemmDesc g;
-      gemm_linear_dgrad(g, cols(s.dqkvS, H), wsplit(LW.ca_in, H, H), R, 2 * H, H, P);
-      if (dmem_init) { g.residual = s.dmem; g.ld_res = H; }
-      g.out_f32 = s.dmem; g.ldo = H;  // d mem accumulates over the layers
-      VC_TRY(gemm(g, st));
-      dmem_init = true;
-    }
     // ---- self-attention block
     VC_TRY(layernorm_bwd(s.A, H, Y.y1, H, Y.m1, Y.r1, LW.n1.w, R, H, nullptr, 0, s.Y, H, LW.n1.dw, LW.n1.db, st));
     VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), nullptr, 0,
-                           s.gH.hi, s.gH.lo, H, LW.sa_out.db, st));
-    VC_TRY(linear_wgrad(s.gH, Y.a, R, H, H, LW.sa_out.dw, P, st));
+                           s.gH_sa.hi, s.gH_sa.lo, H, LW.sa_out.db, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(s.gH_sa, Y.a, R, H, H, LW.sa_out.dw, P, side));
     {
       GemmDesc g;
-      gemm_linear_dgrad(g, s.gH, wsplit(LW.sa_out, H), R, H, H, P);
+      gemm_linear_dgrad(g, s.gH_sa, wsplit(LW.sa_out, H), R, H, H, P);
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
     VC_TRY(attention_bwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev)), Y.a.hi, Y.a.lo, H, Y.sa_lse, s.dAtt, H,
                          s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
-    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
+    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS_sa.hi, s.dqkvS_sa.lo,
                            3 * H, LW.sa_in.db, st));
-    VC_TRY(linear_wgrad(s.dqkvS, x_inS, R, 3 * H, H, LW.sa_in.dw, P, st));
+    VC_TRY(stream_fork(st, 0, &side));
+    VC_TRY(linear_wgrad(s.dqkvS_sa, x_inS, R, 3 * H, H, LW.sa_in.dw, P, side));
     {
       GemmDesc g;
-      gemm_linear_dgrad(g, s.dqkvS, wsplit(LW.sa_in, H), R, 3 * H, H, P);
+      gemm_linear_dgrad(g, s.dqkvS_sa, wsplit(LW.sa_in, H), R, 3 * H, H, P);
       g.residual = s.Y; g.ld_res = H; g.out_f32 = s.A; g.ldo = H;  // d x_in = d y1 + dqkv W_in
       VC_TRY(gemm(g, st));
     }
+    VC_TRY(stream_join(st, 0));  // the scratch operands of this layer's weight-gradient GEMMs may be overwritten from here on
   }
 
   // ---- token construction backward: s.A = d tgt, s.dmem = d memory

@@ -60,6 +60,7 @@ _PROTOS = {
     "vc_launch_count_reset": ([], None),
     "vc_gemm_profile": ([i32], None),
     "vc_gemm_profile_read": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], i32),
+    "vc_gemm_profile_read_min": ([C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], i32),
     "vc_gemm_profile_dump": ([C.c_char_p], i32),
     "vc_abi_sizeof": ([i32], C.c_size_t),
     "vc_gemm_desc_init": ([C.POINTER(GemmDesc)], None),
