@@ -102,6 +102,13 @@ size_t vc_abi_sizeof(int which);
 void vc_gemm_desc_init(vc_gemm_desc* d);
 int vc_gemm(const vc_gemm_desc* d, void* stream);
 int vc_split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, vc_bf16* hi, vc_bf16* lo, int64_t ldo, void* stream);
+/* many fp32 -> split conversions in ONE launch (all weight matrices of a segment after an optimizer step).
+ * `items` is a DEVICE array; item i converts n4 float4 groups and owns blocks [block_start, block_start + ceil(n4/1024)). */
+typedef struct vc_split_item {
+  const float* src; vc_bf16* hi; vc_bf16* lo;
+  int64_t n4; int64_t block_start;
+} vc_split_item;
+int vc_split_many(const vc_split_item* items, int n_items, int64_t total_blocks, void* stream);
 int vc_layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                      float* y, int64_t ldy, vc_bf16* y_hi, vc_bf16* y_lo, int64_t ldy_split, float* mean, float* rstd,
                      void* stream);

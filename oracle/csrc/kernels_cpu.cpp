@@ -156,6 +156,12 @@ int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* h
   return 0;
 }
 
+int split_many(const vc_split_item* items, int n_items, int64_t, stream_t) {
+  for (int k = 0; k < n_items; ++k)
+    for (int64_t i = 0; i < items[k].n4 * 4; ++i) split1(items[k].src[i], items[k].hi[i], items[k].lo[i]);
+  return 0;
+}
+
 namespace {
 template <class Load>
 void ln_fwd_rows(Load load, int64_t rows, int C, const float* gamma, const float* beta, float eps, float* y, int64_t ldy,

@@ -85,18 +85,23 @@ __device__ __forceinline__ void stage_split(const float* src, long long ld, int 
   }
 }
 
-// same staging when the source already is split-bf16: plain 16-byte copies, no conversion
+// same staging when the source already is split-bf16: asynchronous 16-byte copies (cp.async, zero-fill for the padding
+// rows), no conversion and no registers; the caller waits once (cp_async_wait_all + __syncthreads) for all tiles
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void stage_copy(const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, long long ld, int n,
                                            __nv_bfloat16* hi, __nv_bfloat16* lo) {
-  for (int idx = threadIdx.x; idx < NT * (HD / 8); idx += VA_THREADS) {
+#pragma unroll
+  for (int it = 0; it < NT * (HD / 8) / VA_THREADS; ++it) {
+    const int idx = threadIdx.x + it * VA_THREADS;
     const int r = idx / (HD / 8), c = (idx % (HD / 8)) * 8;
-    uint4 h = make_uint4(0u, 0u, 0u, 0u), l = make_uint4(0u, 0u, 0u, 0u);
-    if (r < n) {
-      h = *reinterpret_cast<const uint4*>(src_hi + (long long)r * ld + c);
-      l = *reinterpret_cast<const uint4*>(src_lo + (long long)r * ld + c);
-    }
-    *reinterpret_cast<uint4*>(hi + r * LDH + c) = h;
-    *reinterpret_cast<uint4*>(lo + r * LDH + c) = l;
+    const int ok = r < n ? 16 : 0;
+    const long long off = (long long)(r < n ? r : 0) * ld + c;
+    cp_async16(hi + r * LDH + c, src_hi + off, ok);
+    cp_async16(lo + r * LDH + c, src_lo + off, ok);
   }
 }
 
@@ -216,6 +221,7 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
     stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
     load_a_global(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, warp * 16, n, g, t, qh, ql);
   }
+  cp_async_wait_all();
   __syncthreads();
 
   float s[8][4];
@@ -291,13 +297,18 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
 }
 
 __device__ __forceinline__ void store_pair(const VitBwdOut& out, int which, long long row, int col, float x, float y) {
+  // explicit selects instead of dynamic indexing into the kernel-parameter arrays (that forced a local-memory copy)
   if (out.s_hi[0] != nullptr) {
+    __nv_bfloat16* ph = which == 0 ? out.s_hi[0] : (which == 1 ? out.s_hi[1] : out.s_hi[2]);
+    __nv_bfloat16* pl = which == 0 ? out.s_lo[0] : (which == 1 ? out.s_lo[1] : out.s_lo[2]);
     uint32_t hi, lo;
     split2(x, y, hi, lo);
-    *reinterpret_cast<uint32_t*>(out.s_hi[which] + row * out.lds + col) = hi;
-    *reinterpret_cast<uint32_t*>(out.s_lo[which] + row * out.lds + col) = lo;
+    *reinterpret_cast<uint32_t*>(ph + row * out.lds + col) = hi;
+    *reinterpret_cast<uint32_t*>(pl + row * out.lds + col) = lo;
   } else {
-    *reinterpret_cast<float2*>(out.d[which] + row * out.ldd[which] + col) = make_float2(x, y);
+    float* pd = which == 0 ? out.d[0] : (which == 1 ? out.d[1] : out.d[2]);
+    const long long ldd = which == 0 ? out.ldd[0] : (which == 1 ? out.ldd[1] : out.ldd[2]);
+    *reinterpret_cast<float2*>(pd + row * ldd + col) = make_float2(x, y);
   }
 }
 
@@ -332,33 +343,41 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
   } else {
     stage_copy(dout_hi + rowbase * lddo + (long long)h * HD, dout_lo + rowbase * lddo + (long long)h * HD, lddo, n, Dh, Dl);
   }
-  // delta_i = dO_i . O_i  (warp w: rows 16w .. 16w+15, two columns per lane)
-  for (int r = 0; r < 16; ++r) {
-    const int row = warp * 16 + r;
-    float sacc = 0.f;
-    if (row < n) {
-      const long long oo = (rowbase + row) * ldo + (long long)h * HD + 2 * lane;
-      float2 d2;
-      if (dout != nullptr) {
-        d2 = *reinterpret_cast<const float2*>(dout + (rowbase + row) * lddo + (long long)h * HD + 2 * lane);
-      } else {
-        const long long doff = (rowbase + row) * lddo + (long long)h * HD + 2 * lane;
-        const __nv_bfloat162 dh2 = *reinterpret_cast<const __nv_bfloat162*>(dout_hi + doff);
-        const __nv_bfloat162 dl2 = *reinterpret_cast<const __nv_bfloat162*>(dout_lo + doff);
-        d2 = make_float2(__bfloat162float(dh2.x) + __bfloat162float(dl2.x), __bfloat162float(dh2.y) + __bfloat162float(dl2.y));
+  // delta_i = dO_i . O_i  (warp w: rows 16w .. 16w+15, two columns per lane; the 16 rows' loads are all in flight together)
+  {
+    float part[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int row = warp * 16 + r;
+      part[r] = 0.f;
+      if (row < n) {
+        const long long oo = (rowbase + row) * ldo + (long long)h * HD + 2 * lane;
+        float2 d2;
+        if (dout != nullptr) {
+          d2 = *reinterpret_cast<const float2*>(dout + (rowbase + row) * lddo + (long long)h * HD + 2 * lane);
+        } else {
+          const long long doff = (rowbase + row) * lddo + (long long)h * HD + 2 * lane;
+          const __nv_bfloat162 dh2 = *reinterpret_cast<const __nv_bfloat162*>(dout_hi + doff);
+          const __nv_bfloat162 dl2 = *reinterpret_cast<const __nv_bfloat162*>(dout_lo + doff);
+          d2 = make_float2(__bfloat162float(dh2.x) + __bfloat162float(dl2.x), __bfloat162float(dh2.y) + __bfloat162float(dl2.y));
+        }
+        const __nv_bfloat162 oh = *reinterpret_cast<const __nv_bfloat162*>(o_hi + oo);
+        float ox = __bfloat162float(oh.x), oy = __bfloat162float(oh.y);
+        if (o_lo) {
+          const __nv_bfloat162 ol = *reinterpret_cast<const __nv_bfloat162*>(o_lo + oo);
+          ox += __bfloat162float(ol.x);
+          oy += __bfloat162float(ol.y);
+        }
+        part[r] = d2.x * ox + d2.y * oy;
       }
-      const __nv_bfloat162 oh = *reinterpret_cast<const __nv_bfloat162*>(o_hi + oo);
-      float ox = __bfloat162float(oh.x), oy = __bfloat162float(oh.y);
-      if (o_lo) {
-        const __nv_bfloat162 ol = *reinterpret_cast<const __nv_bfloat162*>(o_lo + oo);
-        ox += __bfloat162float(ol.x);
-        oy += __bfloat162float(ol.y);
-      }
-      sacc = d2.x * ox + d2.y * oy;
     }
-    sacc = warp_sum(sacc);
-    if (lane == 0) delta[row] = sacc;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float sacc = warp_sum(part[r]);
+      if (lane == 0) delta[warp * 16 + r] = sacc;
+    }
   }
+  cp_async_wait_all();
   __syncthreads();
 
   // ---------------- phase 1: this warp's 16 query rows

@@ -47,6 +47,9 @@ int vc_gemm(const vc_gemm_desc* d, void* stream) {
 int vc_split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, vc_bf16* hi, vc_bf16* lo, int64_t ldo, void* stream) {
   return vck::split_f32(x, ldx, rows, cols, hi, lo, ldo, stream);
 }
+int vc_split_many(const vc_split_item* items, int n_items, int64_t total_blocks, void* stream) {
+  return vck::split_many(items, n_items, total_blocks, stream);
+}
 int vc_layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                      float* y, int64_t ldy, vc_bf16* y_hi, vc_bf16* y_lo, int64_t ldy_split, float* mean, float* rstd,
                      void* stream) {

@@ -45,6 +45,9 @@ int gemm(const GemmDesc& d, stream_t stream);
 // x[rows, cols] fp32 -> (hi, lo)
 int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t s);
 
+// many contiguous fp32 -> split conversions in one launch; `items` lives in device memory (see vc_split_item)
+int split_many(const vc_split_item* items, int n_items, int64_t total_blocks, stream_t s);
+
 // LayerNorm over the last dim (biased variance, eps inside sqrt).  Outputs optional (may be null).
 int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,
                   float* y, int64_t ldy, bf16_t* y_hi, bf16_t* y_lo, int64_t ldy_split, float* mean, float* rstd,

@@ -36,6 +36,30 @@ __global__ void split_kernel(const float* __restrict__ x, long long ldx, long lo
   }
 }
 
+// one launch for all weight matrices: block -> item by binary search over block_start (n_items is small)
+__global__ void __launch_bounds__(256) split_many_kernel(const vc_split_item* __restrict__ items, int n_items) {
+  int lo = 0, hi = n_items - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].block_start <= b) lo = mid; else hi = mid - 1;
+  }
+  const vc_split_item it = items[lo];
+  const long long base = (b - it.block_start) * 1024;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long i = base + k * 256 + threadIdx.x;
+    if (i < it.n4) {
+      const float4 v4 = *reinterpret_cast<const float4*>(it.src + i * 4);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      uint2 h, l;
+      split4(v, h, l);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(it.hi) + i * 4) = h;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(it.lo) + i * 4) = l;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------- LayerNorm
 constexpr int LN_MAXV = 8;  // float4 chunks per lane -> C <= 1024
 constexpr int LN_WARPS = 4;
@@ -505,6 +529,12 @@ int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* h
   split_kernel<<<ew_grid(rows * cols / 4, 256), 256, 0, cs(s)>>>(x, ldx, rows, cols / 4, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                 reinterpret_cast<__nv_bfloat16*>(lo), ldo);
   return check_launch("split_kernel");
+}
+
+int split_many(const vc_split_item* items, int n_items, int64_t total_blocks, stream_t s) {
+  if (n_items <= 0 || total_blocks <= 0) return 0;
+  split_many_kernel<<<(unsigned)total_blocks, 256, 0, cs(s)>>>(items, n_items);
+  return check_launch("split_many_kernel");
 }
 
 int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float* gamma, const float* beta, float eps,

@@ -66,6 +66,7 @@ _PROTOS = {
     "vc_gemm_desc_init": ([C.POINTER(GemmDesc)], None),
     "vc_gemm": ([C.POINTER(GemmDesc), vp], i32),
     "vc_split_f32": ([vp, i64, i64, i64, vp, vp, i64, vp], i32),
+    "vc_split_many": ([vp, i32, i64, vp], i32),
     "vc_layernorm_fwd": ([vp, i64, i64, i32, vp, vp, f32, vp, i64, vp, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd_fused": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, Drop, vp, vp, i64, vp, vp], i32),

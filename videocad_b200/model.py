@@ -130,7 +130,7 @@ class _Segment:
         """Persistent structs and graphs bake parameter addresses: drop them if a parameter's storage moved (.to(), ...)."""
         sig = tuple(p.data_ptr() for p in self.params)
         if sig != self._sig:
-            self._sig, self._slots, self._split = sig, {}, {}
+            self._sig, self._slots, self._split, self._split_table = sig, {}, {}, None
 
     def _slot_for(self, key, make):
         slot = self._slots.get(key)
@@ -147,8 +147,22 @@ class _Segment:
         return slot
 
     def resplit_all(self, stream):
-        """Unconditional refresh of every split-bf16 weight copy (body of the captured forward graph)."""
+        """Unconditional refresh of every split-bf16 weight copy (body of the captured forward graph): one multi-tensor
+        launch driven by a device-resident pointer table (rebuilt whenever parameter storage moves, see _check_storage)."""
         lib = self.lib()
+        tab = getattr(self, "_split_table", None)
+        if tab is None and self._mats and self._mats[0].is_cuda and all(p.numel() % 4 == 0 for p in self._mats):
+            rows, start = [], 0
+            for p in self._mats:
+                ent = self._split[id(p)]
+                n4 = p.numel() // 4
+                rows.append([p.data_ptr(), ent[2].data_ptr(), ent[3].data_ptr(), n4, start])
+                start += (n4 + 1023) // 1024
+            tab = (torch.tensor(rows, dtype=torch.int64).to(self._mats[0].device), len(rows), start)
+            self._split_table = tab
+        if tab is not None:
+            L.check(lib.vc_split_many(tab[0].data_ptr(), tab[1], tab[2], stream), lib)
+            return
         for p in self._mats:
             ent = self._split[id(p)]
             rows, cols = p.shape[0], p.numel() // p.shape[0]
