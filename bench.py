@@ -260,14 +260,35 @@ def main():
     host_batches = make_batches(B, T, S, rank, pinned=True)
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
 
-    def e2e_step(i):
+    # Input pipeline of the e2e arm: pinned host batches, H2D copy of batch i+1 issued on a copy stream while step i
+    # computes (what a DataLoader(pin_memory=True) + non_blocking .to() gives a trainer); every step still moves its own
+    # h2d bytes inside the timed region and reads the loss back.
+    copy_stream = torch.cuda.Stream(device=dev)
+    pending = {}
+
+    def prefetch(i):
         hb = host_batches[i % NUM_BATCHES]
-        batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        with torch.cuda.stream(copy_stream):
+            batch = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        pending[i] = (batch, ev)
+
+    def e2e_step(i):
+        if i not in pending:
+            prefetch(i)
+        batch, ev = pending.pop(i)
+        torch.cuda.current_stream().wait_event(ev)
+        for v in batch.values():
+            v.record_stream(torch.cuda.current_stream())
+        prefetch(i + 1)
         return float(train_step(batch).item())
 
     for i in range(2):
         e2e_step(i)
+    pending.clear()
     ms_e2e, _ = timed(e2e_step, args.steps)
+    pending.clear()
     e2e_value = frames_per_step * args.steps / (ms_e2e / 1000.0)
 
     if rank != 0:
