@@ -223,6 +223,7 @@ typedef struct vc_dec_layer {
 
 typedef struct vc_seq_weights {
   vc_linear embed_state; vc_linear embed_image; vc_linear image_proj; vc_linear head_params;
+  vc_linear embed_multiview;            /* [H, 512*num_views]; all-null when num_views == 0 */
   const float* embed_action_w; const float* embed_action_b; float* d_embed_action_w; float* d_embed_action_b;
   const float* head_cmd_w; const float* head_cmd_b; float* d_head_cmd_w; float* d_head_cmd_b;
   const float* timestep_emb; float* d_timestep_emb;     /* [max_ep_len, H] or null */
@@ -237,6 +238,7 @@ typedef struct vc_seq_call {
   const float* state_cls;               /* [B*T, 512] frame embeddings (unused unless past_states) */
   const float* cad_cls;                 /* [B, 512] */
   const float* actions;                 /* [B*T, act_dim] normalised actions */
+  int num_views; const float* mv_cls;   /* multiview conditioning: CAD-encoder embeddings of the views, [B*num_views, 512] */
   float dropout_p; int training;
   uint64_t seed; uint32_t site_base;
   const uint64_t* seed_dev;             /* optional device-resident seed (overrides `seed`) */
@@ -246,13 +248,13 @@ typedef struct vc_seq_call {
   float* params;                        /* [B*T, num_param_out] */
 } vc_seq_call;
 
-size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out);
-size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out);
+size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out, int num_views);
+size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out, int num_views);
 int vc_seq_forward(const vc_seq_call* c, void* stream);
 /* dcmds [B*T,num_cmd], dparams [B*T,num_param_out]; d_state_cls [B*T,512] (may be null unless past_states),
- * d_cad_cls [B,512] are OVERWRITTEN */
+ * d_cad_cls [B,512] and d_mv_cls [B*num_views,512] (may be null when num_views == 0) are OVERWRITTEN */
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
-                    void* scratch, size_t scratch_bytes, void* stream);
+                    float* d_mv_cls, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

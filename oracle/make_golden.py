@@ -42,6 +42,10 @@ CASES = {
     "fullres_small": dict(cfg=dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=512, window_size=10,
                                    enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
                           B=1, T=3, S=224),
+    # multiview conditioning: two extra views through the CAD encoder, embed_multiview, 3-source image_projection
+    "multiview": dict(cfg=dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2, num_views=2,
+                               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
+                      B=2, T=3, S=64),
 }
 
 FULL_GRADS = [
@@ -51,7 +55,7 @@ FULL_GRADS = [
     "embed_action.weight", "embed_state.bias", "embed_image.bias", "image_projection.bias",
     "transformer_decoder.layers.0.self_attn.in_proj_bias", "transformer_decoder.layers.1.multihead_attn.in_proj_bias",
     "transformer_decoder.layers.1.norm2.weight", "transformer_decoder.layers.0.linear1.bias",
-    "predict_action_class_0_4.weight", "predict_action_class_0_4.bias",
+    "predict_action_class_0_4.weight", "predict_action_class_0_4.bias", "embed_multiview.bias",
 ]
 
 
@@ -73,6 +77,9 @@ def run_case(name, case):
     batch = to.synthetic_batch(case["B"], case["T"] + 1, case["S"], seed=1234)
     inp = to.model_inputs_from_batch(batch)
     inp["timesteps"] = torch.zeros(case["B"], 1, dtype=torch.long)
+    nv = cfg.get("num_views", 0)
+    if nv > 0:
+        inp["multiview_images"] = to.synthetic_views(case["B"], nv, case["S"], seed=4321)
     cmds, params = model(inp)
     wc, wp = loss_weights(cmds.shape, params.shape)
     loss = (cmds * wc).sum() + (params * wp).sum()

@@ -152,6 +152,12 @@ def seeded_state_dict(cfg: dict, seed: int = 0, dtype=torch.float32) -> Dict[str
 from videocad_b200.synthetic import synthetic_batch  # noqa: E402,F401  (shared synthetic-input generator)
 
 
+def synthetic_views(B: int, num_views: int, S: int, seed: int = 4321) -> torch.Tensor:
+    """Synthetic multiview CAD renderings [B, num_views, 1, S, S] in [-1, 1]."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, num_views, 1, S, S, generator=g).clamp_(-1, 1)
+
+
 def normalize_actions(actions: torch.Tensor) -> torch.Tensor:
     """autoregressive_transformer.py:115-118 (out-of-place here)."""
     out = actions.clone()

@@ -123,6 +123,31 @@ def test_orchestration_forward_backward_vs_fp64_oracle(emu, mode):
         assert err < 2e-4, f"{name}: rel grad err {err:.3e}"
 
 
+@pytest.mark.parametrize("mode", [MODES[0], MODES[2], MODES[3]])
+def test_orchestration_multiview_vs_fp64_oracle(emu, mode):
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2, num_views=2, **mode)
+    m, sd = build_emu_model(emu, cfg, dropout=0.0)
+    m.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 4, 64))
+    inp["multiview_images"] = to.synthetic_views(2, 2, 64)
+    cmds, params = m(inp)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
+    assert (cmds.double() - oc).abs().max() < 1e-4 and (params.double() - op).abs().max() < 1e-4
+    (cmds.sum() + params.sum() * 0.01).backward()
+    (oc.sum() + op.sum() * 0.01).backward()
+    for name, p in m.named_parameters():
+        ref = sdd[name].grad
+        if p.grad is None:
+            assert ref is None or ref.abs().max() == 0, name
+            continue
+        assert (p.grad.double() - ref).abs().max() < 2e-4 * ref.abs().max() + 1e-9, name
+    with pytest.raises(ValueError):
+        m({k: v for k, v in inp.items() if k != "multiview_images"})
+    with pytest.raises(ValueError):
+        AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=128, num_views=2, enable_past_states=True)
+
+
 def test_orchestration_matches_reference_golden(emu):
     z = np.load(os.path.join(GOLDEN, "c0_states_actions.npz"))
     meta = json.loads(bytes(z["meta_json"]).decode())

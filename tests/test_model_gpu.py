@@ -13,7 +13,7 @@ from oracle import torch_oracle as to  # noqa: E402
 from videocad_b200 import AutoRegressiveTransformer  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small"]
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview"]
 
 # fp tolerance of the parity mode (3-pass split-bf16 GEMMs, fp32 everything else) against the reference's fp32
 # forward: BASELINE.json asks for 1e-3 max-abs on the logits; measured ~2e-5, asserted at 2e-4.
@@ -53,6 +53,8 @@ def test_forward_backward_vs_reference_golden(name):
     m, sd = build(meta["cfg"])
     m.eval()
     inp, _ = cuda_inputs(meta["B"], meta["T"], meta["S"], meta["batch_seed"])
+    if meta["cfg"].get("num_views", 0) > 0:
+        inp["multiview_images"] = to.synthetic_views(meta["B"], meta["cfg"]["num_views"], meta["S"], seed=4321).cuda()
     cmds, params = m(inp)
     dc = (cmds.cpu() - torch.from_numpy(z["cmds"])).abs().max().item()
     dp = (params.cpu() - torch.from_numpy(z["params"])).abs().max().item()

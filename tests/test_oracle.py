@@ -11,7 +11,7 @@ from oracle import torch_oracle as to
 from oracle import reference_model as rm
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small"]
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview"]
 
 
 def load_case(name):
@@ -34,7 +34,10 @@ def test_oracle_matches_reference_golden(name):
     chk = sum(v.detach().double().abs().sum().item() for v in sd.values())
     assert abs(chk - float(z["weight_checksum"])) < 1e-6 * chk, "seeded weights are not reproducible on this machine"
     batch = to.synthetic_batch(meta["B"], meta["T"] + 1, meta["S"], seed=meta["batch_seed"])
-    cmds, params = to.forward(sd, cfg, to.model_inputs_from_batch(batch))
+    inp = to.model_inputs_from_batch(batch)
+    if cfg.get("num_views", 0) > 0:
+        inp["multiview_images"] = to.synthetic_views(meta["B"], cfg["num_views"], meta["S"], seed=4321)
+    cmds, params = to.forward(sd, cfg, inp)
     assert (cmds.detach() - torch.from_numpy(z["cmds"])).abs().max() < 2e-5
     assert (params.detach() - torch.from_numpy(z["params"])).abs().max() < 2e-5
     wc, wp = loss_weights(cmds.shape, params.shape, meta["loss_seed"])
@@ -52,16 +55,18 @@ def test_oracle_matches_reference_golden(name):
 
 
 @pytest.mark.skipif(not rm.available(), reason="/root/reference not present on this machine")
-@pytest.mark.parametrize("mode", [(True, True), (False, True), (False, False), (True, False)])
+@pytest.mark.parametrize("mode", [(True, True, 0), (False, True, 0), (False, False, 0), (True, False, 0), (True, True, 2), (False, False, 3)])
 def test_oracle_vs_live_reference(mode):
-    pa, ps = mode
-    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2, encoder="vit",
+    pa, ps, nv = mode
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2, encoder="vit", num_views=nv,
                enable_past_actions=pa, enable_past_states=ps, enable_timestep_embedding=pa or ps)
     model, _ = rm.build_reference_model(cfg)
     sd = to.seeded_state_dict(cfg, 3)
     model.load_state_dict(sd, strict=False)
     model.eval()
     inp = to.model_inputs_from_batch(to.synthetic_batch(2, 5, 64, seed=9))
+    if nv > 0:
+        inp["multiview_images"] = to.synthetic_views(2, nv, 64)
     with torch.no_grad():
         rc, rp = model(dict(inp, timesteps=torch.zeros(2, 1)))
         oc, op = to.forward(sd, cfg, inp)

@@ -24,8 +24,10 @@ constexpr int VD = VC_VIT_DIM;
 constexpr float LN_EPS = 1e-5f;
 
 struct Dims {
-  int B, T, R, H, Ff, L, nh, dh, NP, NC;
+  int B, T, R, H, Ff, L, nh, dh, NP, NC, nv;
   bool mem_has_ui, past_actions, past_states;
+  // memory sources concatenated before image_projection: [ui][cad][multiview]; offsets in units of H
+  int nsrc, cad_off, mv_off;
 };
 
 Dims dims_of(const vc_seq_call* c) {
@@ -35,13 +37,18 @@ Dims dims_of(const vc_seq_call* c) {
   d.past_actions = c->past_actions != 0;
   d.past_states = c->past_states != 0;
   d.mem_has_ui = d.past_actions && d.past_states;
+  d.nv = c->num_views > 0 ? c->num_views : 0;
+  d.nsrc = (d.mem_has_ui ? 1 : 0) + 1 + (d.nv > 0 ? 1 : 0);
+  d.cad_off = d.mem_has_ui ? 1 : 0;
+  d.mv_off = d.cad_off + 1;
   return d;
 }
 
 struct SeqWs {
   Split scls, ccls;
   float* cad_tok;
-  float* cat; Split catS;   // [R,2H]  (mem_has_ui): left = ui, right = cad token broadcast over T
+  float* cat; Split catS;   // [R,3H]  sources of image_projection: [ui][cad token][multiview token], the latter two broadcast over T
+  Split mvS; float* mv_tok; // multiview: split copy of the view embeddings [B, nv*512], token [B,H]
   float* ui; Split uiS;     // [R,H]   (past_states && !mem_has_ui)
   float* mem; Split memS;   // [R,H]
   float* act; Split actS;   // [R,H]   action tokens (past_actions)
@@ -53,12 +60,13 @@ struct SeqWs {
   std::vector<Layer> l;
 };
 
-void seq_carve(Arena& a, int B, int T, int H, int Ff, int L, int nh, SeqWs& w) {
+void seq_carve(Arena& a, int B, int T, int H, int Ff, int L, int nh, int nv, SeqWs& w) {
   const size_t R = (size_t)B * T;
   w.scls = a.alloc_split(R, VD);
   w.ccls = a.alloc_split(B, VD);
   w.cad_tok = a.alloc<float>((size_t)B * H);
-  w.cat = a.alloc<float>(R * 2 * H); w.catS = a.alloc_split(R, 2 * H);
+  w.cat = a.alloc<float>(R * 3 * H); w.catS = a.alloc_split(R, 3 * H);
+  w.mvS = a.alloc_split(B, (int64_t)(nv > 0 ? nv : 1) * VD); w.mv_tok = a.alloc<float>((size_t)B * H);
   w.ui = a.alloc<float>(R * H); w.uiS = a.alloc_split(R, H);
   w.mem = a.alloc<float>(R * H); w.memS = a.alloc_split(R, H);
   w.act = a.alloc<float>(R * H); w.actS = a.alloc_split(R, H);
@@ -79,17 +87,20 @@ void seq_carve(Arena& a, int B, int T, int H, int Ff, int L, int nh, SeqWs& w) {
 }
 
 struct SeqScratch {
-  float *A, *Bf, *Y, *dF, *dAtt, *dqkv, *dmem, *dcat, *dcadtok;
+  float *A, *Bf, *Y, *dF, *dAtt, *dqkv, *dmem, *dcat, *dcadtok, *dmvtok;
+  Split gB2;
   Split gH, dpreF, dqkvS, dparS, gB;
   Split gH_ca, gH_sa, dqkvS_sa;  // separate buffers per use: the weight-gradient GEMMs read them on an auxiliary stream
 };
 
-void seq_scratch_carve(Arena& a, int B, int T, int H, int Ff, int NP, SeqScratch& s) {
+void seq_scratch_carve(Arena& a, int B, int T, int H, int Ff, int NP, int nv, SeqScratch& s) {
+  (void)nv;
   const size_t R = (size_t)B * T;
   s.A = a.alloc<float>(R * H); s.Bf = a.alloc<float>(R * H); s.Y = a.alloc<float>(R * H);
   s.dF = a.alloc<float>(R * Ff); s.dAtt = a.alloc<float>(R * H);
   s.dqkv = a.alloc<float>(R * 3 * H); s.dmem = a.alloc<float>(R * H);
-  s.dcat = a.alloc<float>(R * 2 * H); s.dcadtok = a.alloc<float>((size_t)B * H);
+  s.dcat = a.alloc<float>(R * 3 * H); s.dcadtok = a.alloc<float>((size_t)B * H); s.dmvtok = a.alloc<float>((size_t)B * H);
+  s.gB2 = a.alloc_split(B, H);
   s.gH = a.alloc_split(R, H); s.dpreF = a.alloc_split(R, Ff); s.dqkvS = a.alloc_split(R, 3 * H);
   s.dparS = a.alloc_split(R, NP); s.gB = a.alloc_split(B, H);
   s.gH_ca = a.alloc_split(R, H); s.gH_sa = a.alloc_split(R, H); s.dqkvS_sa = a.alloc_split(R, 3 * H);
@@ -109,6 +120,9 @@ int check_call(const vc_seq_call* c) {
   if (c->past_actions && !c->actions) return set_error("seq: past_actions needs actions");
   if (c->passes != 1 && c->passes != 3) return set_error("seq: passes must be 1 or 3");
   if (c->w->num_layers < 1 || !c->w->layers) return set_error("seq: need at least one decoder layer");
+  if (c->num_views > 0 && (!c->mv_cls || !c->w->embed_multiview.w)) return set_error("seq: num_views > 0 needs mv_cls and embed_multiview");
+  if (c->num_views > 0 && c->past_states && !c->past_actions)
+    return set_error("seq: multiview with past_states only is shape-inconsistent in the reference as well (image_projection width)");
   return 0;
 }
 
@@ -139,16 +153,16 @@ static inline Split cols(const Split& s, int64_t col0) { return mk_split(s.hi + 
 
 }  // namespace
 
-size_t seq_workspace_bytes(int B, int T, int H, int Ff, int L, int nh) {
+size_t seq_workspace_bytes(int B, int T, int H, int Ff, int L, int nh, int nv) {
   Arena a(nullptr, 0);
   SeqWs w;
-  seq_carve(a, B, T, H, Ff, L, nh, w);
+  seq_carve(a, B, T, H, Ff, L, nh, nv, w);
   return a.used();
 }
-size_t seq_scratch_bytes(int B, int T, int H, int Ff, int NP) {
+size_t seq_scratch_bytes(int B, int T, int H, int Ff, int NP, int nv) {
   Arena a(nullptr, 0);
   SeqScratch s;
-  seq_scratch_carve(a, B, T, H, Ff, NP, s);
+  seq_scratch_carve(a, B, T, H, Ff, NP, nv, s);
   return a.used();
 }
 
@@ -159,7 +173,7 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
   const int B = d.B, T = d.T, R = d.R, H = d.H, Ff = d.Ff, P = c->passes;
   Arena arena(c->ws, c->ws_bytes);
   SeqWs w;
-  seq_carve(arena, B, T, H, Ff, d.L, d.nh, w);
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, d.nv, w);
   if (!arena.ok()) return set_error("seq_forward: workspace too small");
   const float p = c->dropout_p;
   const float* E = W.timestep_emb;  // rows 0..T-1 are the positions arange(T)
@@ -168,7 +182,7 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
   float* ui = nullptr; Split uiS = mk_split(nullptr, nullptr, 0); int64_t ld_ui = 0;
   if (d.past_states) {
     VC_TRY(split_f32(c->state_cls, VD, R, VD, w.scls.hi, w.scls.lo, VD, st));
-    if (d.mem_has_ui) { ui = w.cat; uiS = w.catS; ld_ui = 2 * H; } else { ui = w.ui; uiS = w.uiS; ld_ui = H; }
+    if (d.mem_has_ui) { ld_ui = (int64_t)d.nsrc * H; ui = w.cat; uiS = mk_split(w.catS.hi, w.catS.lo, ld_ui); } else { ui = w.ui; uiS = w.uiS; ld_ui = H; }
     GemmDesc g;
     gemm_linear_fwd(g, w.scls, wsplit(W.embed_state, VD), R, H, VD, P);
     g.bias = W.embed_state.b;
@@ -183,14 +197,28 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
     GemmDesc g;
     gemm_linear_fwd(g, w.ccls, wsplit(W.embed_image, VD), B, H, VD, P);
     g.bias = W.embed_image.b;
-    g.act = d.mem_has_ui ? VC_ACT_NONE : VC_ACT_TANH;
+    g.act = d.nsrc > 1 ? VC_ACT_NONE : VC_ACT_TANH;
     g.out_f32 = w.cad_tok; g.ldo = H;
     VC_TRY(gemm(g, st));
   }
-  if (d.mem_has_ui) {
-    VC_TRY(broadcast_rows(w.cad_tok, H, R, H, T, w.cat + H, 2 * H, w.catS.hi + H, w.catS.lo + H, 2 * H, st));
+  const int64_t ldc = (int64_t)d.nsrc * H;
+  if (d.nv > 0) {
+    // multiview token (trajectory_model.py:77-87, autoregressive_transformer.py:167-170): Linear over the concatenated view
+    // embeddings, identical for every time step
+    const int Kmv = d.nv * VD;
+    VC_TRY(split_f32(c->mv_cls, Kmv, B, Kmv, w.mvS.hi, w.mvS.lo, Kmv, st));
     GemmDesc g;
-    gemm_linear_fwd(g, w.catS, wsplit(W.image_proj, 2 * H), R, H, 2 * H, P);
+    gemm_linear_fwd(g, w.mvS, wsplit(W.embed_multiview, Kmv), B, H, Kmv, P);
+    g.bias = W.embed_multiview.b; g.out_f32 = w.mv_tok; g.ldo = H;
+    VC_TRY(gemm(g, st));
+    VC_TRY(broadcast_rows(w.mv_tok, H, R, H, T, w.cat + (int64_t)d.mv_off * H, ldc, w.catS.hi + (int64_t)d.mv_off * H,
+                          w.catS.lo + (int64_t)d.mv_off * H, ldc, st));
+  }
+  if (d.nsrc > 1) {
+    VC_TRY(broadcast_rows(w.cad_tok, H, R, H, T, w.cat + (int64_t)d.cad_off * H, ldc, w.catS.hi + (int64_t)d.cad_off * H,
+                          w.catS.lo + (int64_t)d.cad_off * H, ldc, st));
+    GemmDesc g;
+    gemm_linear_fwd(g, mk_split(w.catS.hi, w.catS.lo, ldc), wsplit(W.image_proj, ldc), R, H, (int)ldc, P);
     g.bias = W.image_proj.b; g.act = VC_ACT_TANH;
     g.out_f32 = w.mem; g.ldo = H; g.out_hi = w.memS.hi; g.out_lo = w.memS.lo; g.ldo_split = H;
     VC_TRY(gemm(g, st));
@@ -293,25 +321,27 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
 }
 
 int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
-                 void* scratch, size_t scratch_bytes, stream_t st) {
+                 float* d_mv_cls, void* scratch, size_t scratch_bytes, stream_t st) {
   VC_TRY(check_call(c));
   if (!dcmds || !dparams || !d_cad_cls || !scratch) return set_error("seq_backward: null argument");
   const vc_seq_weights& W = *c->w;
   const Dims d = dims_of(c);
   if (d.past_states && !d_state_cls) return set_error("seq_backward: past_states needs d_state_cls");
+  if (d.nv > 0 && !d_mv_cls) return set_error("seq_backward: num_views > 0 needs d_mv_cls");
+  const int64_t ldc = (int64_t)d.nsrc * d.H;
   const int B = d.B, T = d.T, R = d.R, H = d.H, Ff = d.Ff, P = c->passes;
   Arena arena(c->ws, c->ws_bytes);
   SeqWs w;
-  seq_carve(arena, B, T, H, Ff, d.L, d.nh, w);
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, d.nv, w);
   if (!arena.ok()) return set_error("seq_backward: workspace too small");
   Arena sa(scratch, scratch_bytes);
   SeqScratch s;
-  seq_scratch_carve(sa, B, T, H, Ff, d.NP, s);
+  seq_scratch_carve(sa, B, T, H, Ff, d.NP, d.nv, s);
   if (!sa.ok()) return set_error("seq_backward: scratch too small");
   const float p = c->dropout_p;
 
   float* ui = nullptr; int64_t ld_ui = 0;
-  if (d.past_states) { if (d.mem_has_ui) { ui = w.cat; ld_ui = 2 * H; } else { ui = w.ui; ld_ui = H; } }
+  if (d.past_states) { if (d.mem_has_ui) { ui = w.cat; ld_ui = ldc; } else { ui = w.ui; ld_ui = H; } }
   const SeqWs::Layer& last = w.l[d.L - 1];
 
   // ---- heads: A = d x_last
@@ -335,7 +365,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     const SeqWs::Layer& Y = w.l[l];
     const uint32_t s0 = c->site_base + 7 * l;
     const Split x_inS = (l > 0) ? w.l[l - 1].x3S
-                                : (d.past_actions ? w.actS : (d.past_states ? (d.mem_has_ui ? w.catS : w.uiS) : w.memS));
+                                : (d.past_actions ? w.actS : (d.past_states ? (d.mem_has_ui ? mk_split(w.catS.hi, w.catS.lo, ldc) : w.uiS) : w.memS));
     // ---- feed-forward block
     VC_TRY(layernorm_bwd(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db, st));
     VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev), nullptr, 0,
@@ -431,19 +461,31 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     VC_TRY(add_f32(s.dmem, s.A, s.dmem, (int64_t)R * H, st));
   }
   VC_TRY(zero_f32(s.dcadtok, (int64_t)B * H, st));
-  if (d.mem_has_ui) {
-    // mem = tanh(image_projection([ui ; cad]))
+  if (d.nsrc > 1) {
+    // mem = tanh(image_projection([ui ; cad ; multiview]))
     VC_TRY(act_dropout_bwd(s.dmem, H, R, H, VC_ACT_TANH, w.mem, H, nullptr, 0, no_drop(), nullptr, 0, s.gH.hi, s.gH.lo, H,
                            W.image_proj.db, st));
-    VC_TRY(linear_wgrad(s.gH, w.catS, R, H, 2 * H, W.image_proj.dw, P, st));
+    VC_TRY(linear_wgrad(s.gH, mk_split(w.catS.hi, w.catS.lo, ldc), R, H, (int)ldc, W.image_proj.dw, P, st));
     {
       GemmDesc g;
-      gemm_linear_dgrad(g, s.gH, wsplit(W.image_proj, 2 * H), R, H, 2 * H, P);
-      g.out_f32 = s.dcat; g.ldo = 2 * H;
+      gemm_linear_dgrad(g, s.gH, wsplit(W.image_proj, ldc), R, H, (int)ldc, P);
+      g.out_f32 = s.dcat; g.ldo = ldc;
       VC_TRY(gemm(g, st));
     }
-    dui = s.dcat; ld_dui = 2 * H;
-    VC_TRY(row_reduce_mod(s.dcat + H, 2 * H, R, H, T, B, s.dcadtok, st));
+    if (d.mem_has_ui) { dui = s.dcat; ld_dui = ldc; }
+    VC_TRY(row_reduce_mod(s.dcat + (int64_t)d.cad_off * H, ldc, R, H, T, B, s.dcadtok, st));
+    if (d.nv > 0) {
+      const int Kmv = d.nv * VD;
+      VC_TRY(zero_f32(s.dmvtok, (int64_t)B * H, st));
+      VC_TRY(row_reduce_mod(s.dcat + (int64_t)d.mv_off * H, ldc, R, H, T, B, s.dmvtok, st));
+      VC_TRY(act_dropout_bwd(s.dmvtok, H, B, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.gB2.hi, s.gB2.lo, H,
+                             W.embed_multiview.db, st));
+      VC_TRY(linear_wgrad(s.gB2, w.mvS, B, H, Kmv, W.embed_multiview.dw, P, st));
+      GemmDesc g;
+      gemm_linear_dgrad(g, s.gB2, wsplit(W.embed_multiview, Kmv), B, H, Kmv, P);
+      g.out_f32 = d_mv_cls; g.ldo = Kmv;
+      VC_TRY(gemm(g, st));
+    }
   } else {
     VC_TRY(row_reduce_mod(s.dmem, H, R, H, T, B, s.dcadtok, st));
   }
@@ -461,7 +503,7 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     }
   }
   // cad token: embed_image (with tanh folded in when there is no projection)
-  VC_TRY(act_dropout_bwd(s.dcadtok, H, B, H, d.mem_has_ui ? VC_ACT_NONE : VC_ACT_TANH, w.cad_tok, H, nullptr, 0, no_drop(), nullptr, 0,
+  VC_TRY(act_dropout_bwd(s.dcadtok, H, B, H, d.nsrc > 1 ? VC_ACT_NONE : VC_ACT_TANH, w.cad_tok, H, nullptr, 0, no_drop(), nullptr, 0,
                          s.gB.hi, s.gB.lo, H, W.embed_image.db, st));
   VC_TRY(linear_wgrad(s.gB, w.ccls, B, H, VD, W.embed_image.dw, P, st));
   {
@@ -476,16 +518,16 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
 }  // namespace vck
 
 extern "C" {
-size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out) {
+size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out, int num_views) {
   (void)num_param_out;
-  return vck::seq_workspace_bytes(B, T, H, Ff, num_layers, nhead);
+  return vck::seq_workspace_bytes(B, T, H, Ff, num_layers, nhead, num_views);
 }
-size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out) {
-  return vck::seq_scratch_bytes(B, T, H, Ff, num_param_out);
+size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out, int num_views) {
+  return vck::seq_scratch_bytes(B, T, H, Ff, num_param_out, num_views);
 }
 int vc_seq_forward(const vc_seq_call* c, void* stream) { return vck::seq_forward(c, stream); }
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
-                    void* scratch, size_t scratch_bytes, void* stream) {
-  return vck::seq_backward(c, dcmds, dparams, d_state_cls, d_cad_cls, scratch, scratch_bytes, stream);
+                    float* d_mv_cls, void* scratch, size_t scratch_bytes, void* stream) {
+  return vck::seq_backward(c, dcmds, dparams, d_state_cls, d_cad_cls, d_mv_cls, scratch, scratch_bytes, stream);
 }
 }

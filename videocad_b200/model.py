@@ -388,6 +388,7 @@ class _SeqRunner(_Segment):
         self.i_ip = [r(m.image_projection.weight), r(m.image_projection.bias)]
         self.i_ea = [r(m.embed_action.weight), r(m.embed_action.bias)]
         self.i_ts = r(m.timestep_embedding.weight) if m.enable_timestep_embedding else None
+        self.i_mv = [r(m.embed_multiview.weight), r(m.embed_multiview.bias)] if m.num_views > 0 else None
         self.i_layers = []
         for layer in m.transformer_decoder.layers:
             sa, ca = layer.self_attn, layer.multihead_attn
@@ -405,10 +406,11 @@ class _SeqRunner(_Segment):
         m = self.model
         used = [True] * len(self.params)
         mem_has_ui = m.enable_past_actions and m.enable_past_states
+        nsrc = (1 if mem_has_ui else 0) + 1 + (1 if m.num_views > 0 else 0)
         if not m.enable_past_states:
             for i in self.i_es:
                 used[i] = False
-        if not mem_has_ui:
+        if nsrc == 1:
             for i in self.i_ip:
                 used[i] = False
         if not m.enable_past_actions:
@@ -426,6 +428,8 @@ class _SeqRunner(_Segment):
         fl(W.embed_image, m.embed_image.weight, m.embed_image.bias, stream, flat, o, *self.i_ei)
         fl(W.image_proj, m.image_projection.weight, m.image_projection.bias, stream, flat, o, *self.i_ip)
         fl(W.head_params, m.predict_action_class_0_999.weight, m.predict_action_class_0_999.bias, stream, flat, o, *self.i_hp)
+        if self.i_mv is not None:
+            fl(W.embed_multiview, m.embed_multiview.weight, m.embed_multiview.bias, stream, flat, o, *self.i_mv)
         W.embed_action_w, W.embed_action_b = m.embed_action.weight.data_ptr(), m.embed_action.bias.data_ptr()
         W.head_cmd_w, W.head_cmd_b = m.predict_action_class_0_4.weight.data_ptr(), m.predict_action_class_0_4.bias.data_ptr()
         if self.i_ts is not None:
@@ -456,6 +460,7 @@ class _SeqRunner(_Segment):
 
     def _make_slot(self, B, T, dev, training, p, passes, has_state):
         lib, m = self.lib(), self.model
+        nv = m.num_views
         stream = torch.cuda.current_stream(dev).cuda_stream
         H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, len(m.transformer_decoder.layers), m.nhead
         NP, NC = m.num_params * m.num_params_values, m.num_classes
@@ -465,7 +470,9 @@ class _SeqRunner(_Segment):
         sl.state = torch.empty(R, A.VIT_DIM, **f32) if has_state else None
         sl.cad = torch.empty(B, A.VIT_DIM, **f32)
         sl.actions = torch.empty(R, m.act_dim, **f32)
-        sl.ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP)
+        sl.mv = torch.empty(B * nv, A.VIT_DIM, **f32) if nv > 0 else None
+        sl.d_mv = torch.empty(B * nv, A.VIT_DIM, **f32) if nv > 0 else None
+        sl.ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP, nv)
         sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
         sl.cmds, sl.params = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
         sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
@@ -473,7 +480,7 @@ class _SeqRunner(_Segment):
         sl.dcmds, sl.dparams = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
         sl.d_state = torch.empty(R, A.VIT_DIM, **f32) if (has_state and m.enable_past_states) else None
         sl.d_cad = torch.empty(B, A.VIT_DIM, **f32)
-        sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP)
+        sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP, nv)
         sl.scratch = None
         (sl.W, sl.arr), (sl.Wg, sl.arrg) = self._weights(stream), self._weights(stream, sl.flat)
         for name, W in (("call", sl.W), ("call_b", sl.Wg)):
@@ -484,6 +491,7 @@ class _SeqRunner(_Segment):
             c.act_dim, c.num_cmd, c.num_param_out = m.act_dim, NC, NP
             c.state_cls = sl.state.data_ptr() if sl.state is not None else None
             c.cad_cls, c.actions = sl.cad.data_ptr(), sl.actions.data_ptr()
+            c.num_views, c.mv_cls = nv, (sl.mv.data_ptr() if sl.mv is not None else None)
             c.dropout_p, c.training, c.seed, c.site_base = float(p), int(bool(training)), 0, _SITE_SEQ
             c.seed_dev, c.passes = sl.seed_t.data_ptr(), passes
             c.ws, c.ws_bytes, c.cmds, c.params = sl.ws.data_ptr(), sl.ws_bytes, sl.cmds.data_ptr(), sl.params.data_ptr()
@@ -491,7 +499,7 @@ class _SeqRunner(_Segment):
         return sl
 
     def forward(self, state_cls, cad_cls, actions, B, T, training, p, seed, passes, need_grad: bool = True,
-                allow_graph: bool = True):
+                allow_graph: bool = True, mv_cls=None):
         lib, m = self.lib(), self.model
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
@@ -501,6 +509,11 @@ class _SeqRunner(_Segment):
         actions = actions.contiguous().float().reshape(B * T, -1)
         if state_cls is not None:
             state_cls = state_cls.contiguous().float()
+        nv = m.num_views
+        if nv > 0:
+            if mv_cls is None:
+                raise ValueError("num_views > 0: inputs['multiview_images'] is required")
+            mv_cls = mv_cls.contiguous().float()
         if allow_graph and self.graphs_enabled(cad_cls):
             self._check_storage()
             key = (B, T, dev, bool(training), float(p), passes, state_cls is not None)
@@ -510,6 +523,8 @@ class _SeqRunner(_Segment):
                     sl.state.copy_(state_cls)
                 sl.cad.copy_(cad_cls)
                 sl.actions.copy_(actions)
+                if sl.mv is not None:
+                    sl.mv.copy_(mv_cls)
                 sl.seed_t.fill_(seed)
 
                 def body():
@@ -520,7 +535,7 @@ class _SeqRunner(_Segment):
                 self._launch(sl, "fwd", body)
                 lease = _Lease(sl) if need_grad else None
                 return sl.cmds.clone(), sl.params.clone(), ("slot", sl, lease)
-        ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP)
+        ws_bytes = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP, nv)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         cmds = torch.empty(B * T, NC, dtype=torch.float32, device=dev)
         params = torch.empty(B * T, NP, dtype=torch.float32, device=dev)
@@ -532,10 +547,11 @@ class _SeqRunner(_Segment):
         c.act_dim, c.num_cmd, c.num_param_out = m.act_dim, NC, NP
         c.state_cls = state_cls.data_ptr() if state_cls is not None else None
         c.cad_cls, c.actions = cad_cls.data_ptr(), actions.data_ptr()
+        c.num_views, c.mv_cls = nv, (mv_cls.data_ptr() if nv > 0 else None)
         c.dropout_p, c.training, c.seed, c.site_base, c.passes = float(p), int(bool(training)), seed, _SITE_SEQ, passes
         c.ws, c.ws_bytes, c.cmds, c.params = ws.data_ptr(), ws_bytes, cmds.data_ptr(), params.data_ptr()
         L.check(lib.vc_seq_forward(C.byref(c), stream), lib)
-        return cmds, params, (c, W, arr, ws, state_cls, cad_cls, actions)
+        return cmds, params, (c, W, arr, ws, state_cls, cad_cls, actions, mv_cls)
 
     def backward(self, saved, dcmds, dparams):
         lib, m = self.lib(), self.model
@@ -552,16 +568,18 @@ class _SeqRunner(_Segment):
                 sl.flat.zero_()
                 L.check(lib.vc_seq_backward(C.byref(sl.call_b), sl.dcmds.data_ptr(), sl.dparams.data_ptr(),
                                            sl.d_state.data_ptr() if sl.d_state is not None else None, sl.d_cad.data_ptr(),
+                                           sl.d_mv.data_ptr() if sl.d_mv is not None else None,
                                            sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
 
             self._launch(sl, "bwd", body)
             grads = self.grad_views(sl.flat.clone(), self.offs, self.used_mask())
             d_state = sl.d_state.clone() if sl.d_state is not None else None
             d_cad = sl.d_cad.clone()
+            d_mv = sl.d_mv.clone() if sl.d_mv is not None else None
             if lease is not None:
                 lease.release()
-            return d_state, d_cad, grads
-        c, W, arr, ws, state_cls, cad_cls, actions = saved
+            return d_state, d_cad, d_mv, grads
+        c, W, arr, ws, state_cls, cad_cls, actions, mv_cls = saved
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
         flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
@@ -570,13 +588,14 @@ class _SeqRunner(_Segment):
         R = c.B * c.T
         d_state = torch.empty(R, A.VIT_DIM, dtype=torch.float32, device=dev) if state_cls is not None and m.enable_past_states else None
         d_cad = torch.empty(c.B, A.VIT_DIM, dtype=torch.float32, device=dev)
-        sc_bytes = lib.vc_seq_scratch_bytes(c.B, c.T, c.H, c.Ff, c.num_param_out)
+        d_mv = torch.empty(c.B * c.num_views, A.VIT_DIM, dtype=torch.float32, device=dev) if c.num_views > 0 else None
+        sc_bytes = lib.vc_seq_scratch_bytes(c.B, c.T, c.H, c.Ff, c.num_param_out, c.num_views)
         scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=dev)
         dcmds, dparams = dcmds.contiguous().float(), dparams.contiguous().float()
         L.check(lib.vc_seq_backward(C.byref(c), dcmds.data_ptr(), dparams.data_ptr(),
                                    d_state.data_ptr() if d_state is not None else None, d_cad.data_ptr(),
-                                   scratch.data_ptr(), sc_bytes, stream), lib)
-        return d_state, d_cad, self.grad_views(flat, self.offs, self.used_mask())
+                                   d_mv.data_ptr() if d_mv is not None else None, scratch.data_ptr(), sc_bytes, stream), lib)
+        return d_state, d_cad, d_mv, self.grad_views(flat, self.offs, self.used_mask())
 
 
 class _VitFn(torch.autograd.Function):
@@ -595,17 +614,17 @@ class _VitFn(torch.autograd.Function):
 
 class _SeqFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, training, p, seed, passes, B, T, state_cls, cad_cls, actions, *params):
+    def forward(ctx, runner, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, *params):
         cmds, pars, saved = runner.forward(state_cls, cad_cls, actions, B, T, training, p, seed, passes,
-                                           need_grad=any(ctx.needs_input_grad))
+                                           need_grad=any(ctx.needs_input_grad), mv_cls=mv_cls)
         ctx.runner, ctx.saved = runner, saved
         return cmds, pars
 
     @staticmethod
     def backward(ctx, dcmds, dparams):
-        d_state, d_cad, grads = ctx.runner.backward(ctx.saved, dcmds, dparams)
+        d_state, d_cad, d_mv, grads = ctx.runner.backward(ctx.saved, dcmds, dparams)
         ctx.saved = None
-        return (None, None, None, None, None, None, None, d_state, d_cad, None, *grads)
+        return (None, None, None, None, None, None, None, d_state, d_cad, d_mv, None, *grads)
 
 
 # =====================================================================================================
@@ -624,8 +643,10 @@ class AutoRegressiveTransformer(nn.Module):
         if use_pretrained_cad_model:
             raise ValueError("Model type gencad not supported")  # same error the reference raises (trajectory_model.py:39,74)
         assert window_size > 0, "Window size must be greater than 0"
-        if num_views and num_views > 0:
-            raise NotImplementedError("videocad_b200: multiview conditioning (num_views > 0) is not implemented yet")
+        num_views = int(num_views or 0)
+        if num_views > 0 and enable_past_states and not enable_past_actions:
+            # the reference builds image_projection for 3 sources but feeds it 2 in this branch (shape error at :173)
+            raise ValueError("num_views > 0 with enable_past_states and without enable_past_actions is shape-inconsistent")
         self.state_dim, self.act_dim, self.max_length = state_dim, act_dim, max_length
         self.hidden_size, self.max_ep_len = hidden_size, max_ep_len
         self.enable_past_actions, self.enable_past_states = bool(enable_past_actions), bool(enable_past_states)
@@ -656,6 +677,10 @@ class AutoRegressiveTransformer(nn.Module):
         self.predict_action_class_0_4 = nn.Linear(hidden_size, num_classes)
         self.predict_action_class_0_999 = nn.Linear(hidden_size, num_params * num_params_values)
         self.num_inputs = 1 + (1 if self.enable_past_states else 0)
+        if num_views > 0:
+            self.embed_multiview = nn.Linear(self.state_embedding_model_size * num_views if self.state_embedding_model_size
+                                             else A.VIT_DIM * num_views, hidden_size)
+            self.num_inputs += 1
         self.image_projection = nn.Linear(hidden_size * self.num_inputs, hidden_size)
         self.embed_action = nn.Linear(act_dim, hidden_size)
         if self.enable_timestep_embedding:
@@ -714,8 +739,7 @@ class AutoRegressiveTransformer(nn.Module):
     def forward(self, inputs, attention_mask=None):
         """AutoRegressiveTransformer.forward (autoregressive_transformer.py:121-220)."""
         ui_images, actions, cad_image = inputs["frames"], inputs["actions"], inputs["cad_image"]
-        if inputs.get("multiview_images", None) is not None and self.num_views > 0:
-            raise NotImplementedError("multiview conditioning is not implemented")
+        multiview_images = inputs.get("multiview_images", None)
         self._check_device(cad_image)
         st_r, cad_r, seq_r = self._get_runners()
         B, T = actions.shape[0], actions.shape[1]
@@ -728,7 +752,16 @@ class AutoRegressiveTransformer(nn.Module):
                 raise ValueError(f"frames carry {frames.shape[0]} images but actions are [{B},{T}]")
             state_cls = _VitFn.apply(st_r, training, p, seed, passes, frames, *st_r.params)
         cad_cls = _VitFn.apply(cad_r, training, p, seed, passes, cad_image, *cad_r.params)
-        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, actions, *seq_r.params)
+        mv_cls = None
+        if self.num_views > 0:
+            # process_multiview_images (trajectory_model.py:77-87): every view goes through the CAD encoder
+            if multiview_images is None:
+                raise ValueError("num_views > 0: inputs['multiview_images'] [B, num_views, 1, S, S] is required")
+            if multiview_images.shape[1] != self.num_views:
+                raise ValueError(f"expected {self.num_views} views, got {multiview_images.shape[1]}")
+            views = multiview_images.reshape(-1, *multiview_images.shape[2:])
+            mv_cls = _VitFn.apply(cad_r, training, p, seed + 1 if seed else 0, passes, views, *cad_r.params)
+        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, *seq_r.params)
         return cmds.view(B, T, self.num_classes), params.view(B, T, self.num_params, self.num_params_values)
 
     @torch.no_grad()

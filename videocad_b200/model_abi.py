@@ -44,6 +44,7 @@ class DecLayer(C.Structure):
 
 class SeqWeights(C.Structure):
     _fields_ = [("embed_state", Linear), ("embed_image", Linear), ("image_proj", Linear), ("head_params", Linear),
+                ("embed_multiview", Linear),
                 ("embed_action_w", vp), ("embed_action_b", vp), ("d_embed_action_w", vp), ("d_embed_action_b", vp),
                 ("head_cmd_w", vp), ("head_cmd_b", vp), ("d_head_cmd_w", vp), ("d_head_cmd_b", vp),
                 ("timestep_emb", vp), ("d_timestep_emb", vp),
@@ -53,7 +54,7 @@ class SeqWeights(C.Structure):
 class SeqCall(C.Structure):
     _fields_ = [("w", C.POINTER(SeqWeights)), ("B", i32), ("T", i32), ("H", i32), ("nhead", i32), ("Ff", i32), ("window", i32),
                 ("past_actions", i32), ("past_states", i32), ("act_dim", i32), ("num_cmd", i32), ("num_param_out", i32),
-                ("state_cls", vp), ("cad_cls", vp), ("actions", vp), ("dropout_p", f32), ("training", i32), ("seed", u64),
+                ("state_cls", vp), ("cad_cls", vp), ("actions", vp), ("num_views", i32), ("mv_cls", vp), ("dropout_p", f32), ("training", i32), ("seed", u64),
                 ("site_base", u32), ("seed_dev", vp), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cmds", vp), ("params", vp)]
 
 
@@ -62,8 +63,8 @@ L.EXTRA_PROTOS.update({
     "vc_vit_scratch_bytes": ([i32, i32], sz),
     "vc_vit_forward": ([C.POINTER(VitCall), vp], i32),
     "vc_vit_backward": ([C.POINTER(VitCall), vp, vp, sz, vp], i32),
-    "vc_seq_workspace_bytes": ([i32, i32, i32, i32, i32, i32, i32], sz),
-    "vc_seq_scratch_bytes": ([i32, i32, i32, i32, i32], sz),
+    "vc_seq_workspace_bytes": ([i32, i32, i32, i32, i32, i32, i32, i32], sz),
+    "vc_seq_scratch_bytes": ([i32, i32, i32, i32, i32, i32], sz),
     "vc_seq_forward": ([C.POINTER(SeqCall), vp], i32),
-    "vc_seq_backward": ([C.POINTER(SeqCall), vp, vp, vp, vp, vp, sz, vp], i32),
+    "vc_seq_backward": ([C.POINTER(SeqCall), vp, vp, vp, vp, vp, vp, sz, vp], i32),
 })
