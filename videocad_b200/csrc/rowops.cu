@@ -559,8 +559,9 @@ int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t l
   if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
   if (rows <= 0) return 0;
   RowLoader ld{x, ldx};
+  // one resident wave (3 CTAs/SM at ~165 registers): fewer blocks also means fewer gradient atomics per column
   int grid = cdiv(rows, LN_WARPS * 4);
-  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid > 148 * 3) grid = 148 * 3;
   LnFuse f;
   f.drop = gdrop; f.thresh = dropout_threshold(gdrop.p); f.scale = drop_scale(gdrop);
   f.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); f.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo); f.ldg = ldg;
