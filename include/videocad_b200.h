@@ -90,6 +90,7 @@ int vc_is_cuda_build(void);
  * tensor-core GEMM launch (events recorded on the launching stream around each launch while enabled) ---- */
 long long vc_launch_count(void);
 void vc_launch_count_reset(void);
+long long vc_gemm_pair_launch_count(void);           /* GEMM launches that used the 2-SM (cta_group::2) 256x256 kernel */
 void vc_gemm_profile(int enable);                  /* enable/disable + clear the event pool */
 int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches); /* synchronises the events */
 int vc_gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches); /* only launches >= min_flops */

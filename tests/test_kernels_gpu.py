@@ -37,7 +37,8 @@ def test_split_bit_exact(rows, cols):
     assert ((hi.float() + lo.float()) - x).abs().max() <= x.abs().max() * 2.0 ** -16
 
 
-GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (300, 136, 200), (50, 8, 512), (1000, 3072, 512), (14400, 512, 1024)]
+GEMM_SHAPES = [(128, 128, 64), (256, 256, 128), (300, 136, 200), (50, 8, 512), (1000, 3072, 512), (14400, 512, 1024),
+               (2560, 1024, 192), (12800, 512, 512)]  # the last two take the 2-SM (CTA-pair) 256x256 kernel
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
@@ -140,6 +141,95 @@ def test_gemm_splitk_wgrad_shape(splitk):
     L.gemm(L.split(dY), L.split(X), Nw, Kw, rows, a_mn=True, b_mn=True, splitk=splitk, bias=bias, out_f32=out)
     ref = dY.double().t() @ X.double() + bias.double()
     assert _relerr(out, ref) < 3e-5
+
+
+def _pair_count():
+    return L.load().vc_gemm_pair_launch_count()
+
+
+PAIR_SHAPE = (2560, 1024, 320)  # 10 x 4 tiles of 256 x 256: taken by the CTA-pair kernel
+
+
+def test_gemm_pair_kernel_is_used_for_encoder_shapes():
+    M, N, Kd = PAIR_SHAPE
+    A, B = _rand(M, Kd, seed=40), _rand(N, Kd, seed=41)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    before = _pair_count()
+    L.gemm(L.split(A), L.split(B), M, N, Kd, out_f32=out)
+    assert _pair_count() == before + 1
+    assert _relerr(out, A.double() @ B.double().t()) < 3e-5
+    # a decoder-sized problem stays on the single-CTA kernel
+    out2 = torch.empty(256, 512, device="cuda")
+    L.gemm(L.split(A[:256]), L.split(B[:512]), 256, 512, Kd, out_f32=out2)
+    assert _pair_count() == before + 1
+    assert _relerr(out2, A[:256].double() @ B[:512].double().t()) < 3e-5
+
+
+@pytest.mark.parametrize("variant", ["split_bias", "f32_drop_res", "split_act", "all"])
+def test_gemm_pair_epilogues(variant):
+    M, N, Kd = PAIR_SHAPE
+    T = 8
+    A, B = _rand(M, Kd, seed=42, scale=0.5), _rand(N, Kd, seed=43, scale=0.2)
+    bias, res, rowadd = _rand(N, seed=44), _rand(M, N, seed=45), _rand(T, N, seed=46)
+    drop = L.make_drop(0.1, 21, 777)
+    mask = K.dropout_mask(drop, M * N).reshape(M, N).double()
+    z = A.double() @ B.double().t() + bias.double()
+    before = _pair_count()
+    if variant == "split_bias":
+        outs = K.bf16_pair((M, N))
+        L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, out_split=outs)
+        assert _relerr(K.join(outs), z) < 3e-5
+    elif variant == "f32_drop_res":
+        out = torch.empty(M, N, device="cuda")
+        L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, drop=drop, residual=res, out_f32=out)
+        assert _relerr(out, z * mask + res.double()) < 3e-5
+    elif variant == "split_act":
+        outs = K.bf16_pair((M, N))
+        pre = torch.empty(M, N, device="cuda")
+        L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, preact=pre, act=L.ACT_GELU, drop=drop, out_split=outs)
+        assert _relerr(pre, z) < 3e-5
+        assert _relerr(K.join(outs), torch.nn.functional.gelu(z) * mask) < 3e-5
+    else:
+        out = torch.empty(M, N, device="cuda")
+        outs = K.bf16_pair((M, N))
+        pre = torch.empty(M, N, device="cuda")
+        L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, rowadd=rowadd, rowadd_div=1, rowadd_mod=T, preact=pre, act=L.ACT_TANH,
+               drop=drop, residual=res, out_f32=out, out_split=outs)
+        rows = torch.arange(M, device="cuda") % T
+        zz = z + rowadd.double()[rows]
+        assert _relerr(pre, zz) < 3e-5
+        assert _relerr(out, torch.tanh(zz) * mask + res.double()) < 3e-5
+        assert (K.join(outs) - out).abs().max() <= out.abs().max() * 2.0 ** -15
+    assert _pair_count() == before + 1
+
+
+def test_gemm_pair_backward_activation_and_colsum():
+    M, N, Kd = 2560, 1024, 512
+    G, W = _rand(M, Kd, seed=47, scale=0.5), _rand(Kd, N, seed=48, scale=0.2)
+    pre = _rand(M, N, seed=49)
+    drop = L.make_drop(0.1, 34, 99)
+    mask = K.dropout_mask(drop, M * N).reshape(M, N)
+    t = pre.double().requires_grad_(True)
+    torch.nn.functional.gelu(t).sum().backward()
+    outs = K.bf16_pair((M, N))
+    cs = torch.zeros(N, device="cuda")
+    before = _pair_count()
+    L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=L.ACT_GELU, act_backward=True, act_aux=pre, drop=drop, out_split=outs,
+           colsum=cs)
+    assert _pair_count() == before + 1
+    ref = (G.double() @ W.double()) * mask.double() * t.grad
+    assert _relerr(K.join(outs), ref) < 3e-5
+    assert _relerr(cs, ref.sum(0)) < 3e-5
+
+
+@pytest.mark.parametrize("rows,Nw,Kw", [(6400, 512, 512), (12800, 3072, 512), (3200, 512, 1024)])
+def test_gemm_pair_splitk_wgrad(rows, Nw, Kw):
+    dY, X = _rand(rows, Nw, seed=50), _rand(rows, Kw, seed=51)
+    out = torch.zeros(Nw, Kw, device="cuda")
+    before = _pair_count()
+    L.gemm(L.split(dY), L.split(X), Nw, Kw, rows, a_mn=True, b_mn=True, splitk=8, out_f32=out)
+    assert _pair_count() == before + 1
+    assert _relerr(out, dY.double().t() @ X.double()) < 3e-5
 
 
 def test_gemm_strided_outputs_and_views():

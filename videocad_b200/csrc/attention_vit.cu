@@ -91,6 +91,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void stage_copy(const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, long long ld, int n,
                                            __nv_bfloat16* hi, __nv_bfloat16* lo) {
@@ -313,8 +316,7 @@ __device__ __forceinline__ void store_pair(const VitBwdOut& out, int which, long
 }
 
 __global__ void __launch_bounds__(VA_THREADS)
-vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi, const __nv_bfloat16* __restrict__ o_lo,
-                        long long ldo, const float* __restrict__ lse, const float* __restrict__ dout,
+vit_attn_bwd_mma_kernel(const VitAttnP p, const float* __restrict__ lse, const float* __restrict__ dout,
                         const __nv_bfloat16* __restrict__ dout_hi, const __nv_bfloat16* __restrict__ dout_lo, long long lddo,
                         const VitBwdOut out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -323,19 +325,21 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
                 *Dh = Vl + NT * LDH, *Dl = Dh + NT * LDH;
   // P~ and dS (phase 2 operands) reuse the K / V tiles, which are dead once every warp has finished phase 1
   __nv_bfloat16 *Ph = Kh, *Pl = Kl, *Sh = Vh, *Sl = Vl;
-  float* delta = reinterpret_cast<float*>(Dl + NT * LDH);  // [64]
   const int h = blockIdx.x % p.nh, b = blockIdx.x / p.nh;
   const int n = p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const long long rowbase = (long long)b * n;
 
+  // two cp.async groups: {Q, K} first so that S = Q K^T can start while {V, dO} are still in flight
   if (p.qh != nullptr) {
     stage_copy(p.qh + rowbase * p.ldq + (long long)h * HD, p.ql + rowbase * p.ldq + (long long)h * HD, p.ldq, n, Qh, Ql);
     stage_copy(p.kh + rowbase * p.ldk + (long long)h * HD, p.kl + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    cp_async_commit();
     stage_copy(p.vh + rowbase * p.ldv + (long long)h * HD, p.vl + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
   } else {
     stage_split(p.q + rowbase * p.ldq + (long long)h * HD, p.ldq, n, Qh, Ql);
     stage_split(p.k + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
+    cp_async_commit();
     stage_split(p.v + rowbase * p.ldv + (long long)h * HD, p.ldv, n, Vh, Vl);
   }
   if (dout != nullptr) {
@@ -343,41 +347,8 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
   } else {
     stage_copy(dout_hi + rowbase * lddo + (long long)h * HD, dout_lo + rowbase * lddo + (long long)h * HD, lddo, n, Dh, Dl);
   }
-  // delta_i = dO_i . O_i  (warp w: rows 16w .. 16w+15, two columns per lane; the 16 rows' loads are all in flight together)
-  {
-    float part[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int row = warp * 16 + r;
-      part[r] = 0.f;
-      if (row < n) {
-        const long long oo = (rowbase + row) * ldo + (long long)h * HD + 2 * lane;
-        float2 d2;
-        if (dout != nullptr) {
-          d2 = *reinterpret_cast<const float2*>(dout + (rowbase + row) * lddo + (long long)h * HD + 2 * lane);
-        } else {
-          const long long doff = (rowbase + row) * lddo + (long long)h * HD + 2 * lane;
-          const __nv_bfloat162 dh2 = *reinterpret_cast<const __nv_bfloat162*>(dout_hi + doff);
-          const __nv_bfloat162 dl2 = *reinterpret_cast<const __nv_bfloat162*>(dout_lo + doff);
-          d2 = make_float2(__bfloat162float(dh2.x) + __bfloat162float(dl2.x), __bfloat162float(dh2.y) + __bfloat162float(dl2.y));
-        }
-        const __nv_bfloat162 oh = *reinterpret_cast<const __nv_bfloat162*>(o_hi + oo);
-        float ox = __bfloat162float(oh.x), oy = __bfloat162float(oh.y);
-        if (o_lo) {
-          const __nv_bfloat162 ol = *reinterpret_cast<const __nv_bfloat162*>(o_lo + oo);
-          ox += __bfloat162float(ol.x);
-          oy += __bfloat162float(ol.y);
-        }
-        part[r] = d2.x * ox + d2.y * oy;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const float sacc = warp_sum(part[r]);
-      if (lane == 0) delta[warp * 16 + r] = sacc;
-    }
-  }
-  cp_async_wait_all();
+  cp_async_commit();
+  cp_async_wait_group<1>();
   __syncthreads();
 
   // ---------------- phase 1: this warp's 16 query rows
@@ -396,6 +367,8 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
       ldsm_x4(al[kk], Ql + (warp * 16 + (lane & 15)) * LDH + kk * 16 + (lane >> 4) * 8);
     }
     mma_ABt(s, ah, al, Kh, Kl, lane);
+    cp_async_wait_group<0>();
+    __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       ldsm_x4(ah[kk], Dh + (warp * 16 + (lane & 15)) * LDH + kk * 16 + (lane >> 4) * 8);
@@ -403,14 +376,16 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
     }
     mma_ABt(dp, ah, al, Vh, Vl, lane);
 
-    // P~ (into s) and scale*dS (into dp)
+    // P (into s) and delta_i = dO_i . O_i = sum_j P~_ij dP_ij  (O = P~ V and dP = dO V^T, so the forward output is never
+    // re-read); then P~ (into s) and scale*dS (into dp).  The dropout decisions of pass 1 are kept as a bit mask.
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
       const int row = warp * 16 + g + rr * 8;
       const bool rv = row < n;
       const float l = rv ? lse[((long long)b * p.nh + h) * n + row] : 0.f;
-      const float dl = delta[row];
       const unsigned long long ibase = (((unsigned long long)b * p.nh + h) * n + (unsigned long long)(rv ? row : 0)) * (unsigned long long)n;
+      uint32_t keep = 0u;
+      float dl = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int col = 8 * j + 2 * t;
@@ -419,6 +394,20 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const __nv_bfloat16* __restrict__ o_hi
         else if (rv && col < n) { float dummy; drop_pair(p, ibase + col, f0, dummy); }
         const float p0 = (rv && col < n) ? __expf(s[j][rr * 2] * p.scale - l) : 0.f;
         const float p1 = (rv && col + 1 < n) ? __expf(s[j][rr * 2 + 1] * p.scale - l) : 0.f;
+        keep |= (f0 != 0.f ? 1u : 0u) << (2 * j);
+        keep |= (f1 != 0.f ? 1u : 0u) << (2 * j + 1);
+        s[j][rr * 2] = p0;
+        s[j][rr * 2 + 1] = p1;
+        dl = fmaf(p0 * f0, dp[j][rr * 2], dl);
+        dl = fmaf(p1 * f1, dp[j][rr * 2 + 1], dl);
+      }
+      dl += __shfl_xor_sync(0xffffffffu, dl, 1);
+      dl += __shfl_xor_sync(0xffffffffu, dl, 2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f0 = ((keep >> (2 * j)) & 1u) ? p.dscale : 0.f;
+        const float f1 = ((keep >> (2 * j + 1)) & 1u) ? p.dscale : 0.f;
+        const float p0 = s[j][rr * 2], p1 = s[j][rr * 2 + 1];
         s[j][rr * 2] = p0 * f0;
         s[j][rr * 2 + 1] = p1 * f1;
         dp[j][rr * 2] = p0 * (dp[j][rr * 2] * f0 - dl) * p.scale;
@@ -505,7 +494,7 @@ VitAttnP make_p(const AttnDesc& a) {
 }
 
 constexpr size_t FWD_SMEM = (size_t)4 * NT * LDH * 2;
-constexpr size_t BWD_SMEM = (size_t)8 * NT * LDH * 2 + NT * sizeof(float);
+constexpr size_t BWD_SMEM = (size_t)8 * NT * LDH * 2;
 
 }  // namespace
 
@@ -531,7 +520,8 @@ int vit_attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo
 static int launch_vit_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
                           const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, const VitBwdOut& out,
                           stream_t s) {
-  if (ldo % 2 != 0 || lddo % (dout ? 4 : 8) != 0) return set_error("vit_attention_bwd: unsupported strides");
+  (void)o_hi; (void)o_lo; (void)ldo;  // delta = rowsum(dO * O) is rebuilt from P~ and dP inside the kernel
+  if (lddo % (dout ? 4 : 8) != 0) return set_error("vit_attention_bwd: unsupported strides");
   if (!dout && !(dout_hi && dout_lo)) return set_error("vit_attention_bwd: no upstream gradient");
   static bool configured = false;
   if (!configured) {
@@ -540,7 +530,7 @@ static int launch_vit_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o
     configured = true;
   }
   vit_attn_bwd_mma_kernel<<<a.B * a.nh, VA_THREADS, BWD_SMEM, reinterpret_cast<cudaStream_t>(s)>>>(
-      make_p(a), reinterpret_cast<const __nv_bfloat16*>(o_hi), reinterpret_cast<const __nv_bfloat16*>(o_lo), ldo, lse, dout,
+      make_p(a), lse, dout,
       reinterpret_cast<const __nv_bfloat16*>(dout_hi), reinterpret_cast<const __nv_bfloat16*>(dout_lo), lddo, out);
   return check_launch("vit_attn_bwd_mma_kernel");
 }

@@ -161,8 +161,11 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
       float* o = p.out_f32 + row * p.ldo + col;
       if constexpr ((F & EF_ATOMIC) != 0) {
         if (p.splitk > 1) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) atomicAdd(o + i, v[i]);
+          // one 128-bit vector reduction instead of four scalar atomics (sm_90+): the split-K weight-gradient GEMMs issue
+          // 16 K reductions per 128x128 tile and split
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                       "f"(v[3])
+                       : "memory");
         } else {
           *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
         }
@@ -414,6 +417,267 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on the two SMs of a TPC computes one 256 x 256 tile.  Each CTA stages
+// 128 rows of A and 128 of the tile's 256 B rows per k-block and the leader's MMA reads both CTAs' shared memory, so the
+// operand bytes fetched from L2 per FLOP are half those of the 128 x 128 single-CTA kernel above - which ncu and the
+// VC_GEMM_DEBUG=4 experiment (profiles/r01b_gemm_epilogue_experiment.txt) showed to be bound by L2->SM operand traffic
+// (64 KiB per k-block per SM in split-bf16 mode), not by the tensor pipe.
+//   warp 0      TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
+//   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs
+//   warps 2..9  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; 16-column chunks
+// ---------------------------------------------------------------------------------------------------
+constexpr int P_BM = 256, P_BN = 256;
+constexpr int P_THREADS = 320;
+constexpr int P_STAGES = 3;
+constexpr int P_TILE_BYTES = 128 * BK * 2;           // 16 KiB: one 128-row operand tile (hi or lo)
+constexpr int P_STAGE_BYTES = 4 * P_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
+constexpr int P_CW = 16;                             // epilogue chunk width (columns)
+constexpr int P_STG_LD = 20;                         // floats per staged row (80 B)
+constexpr int P_STG_BYTES = 8 * 32 * P_STG_LD * 4;
+constexpr int P_BAR_BYTES = 256;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + P_BAR_BYTES + 1024;
+constexpr int P_TMEM_COLS = 512;                     // two 256-column accumulator stages
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <uint32_t F>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                    const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);  // used in the leader CTA only
+  uint64_t* empty_bar = full_bar + P_STAGES;
+  uint64_t* tfull_bar = empty_bar + P_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;                        // used in the leader CTA only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t tiles_off = ((raw_addr + P_BAR_BYTES + 1023u) & ~1023u) - raw_addr;
+  uint8_t* tiles = smem_raw + tiles_off;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (p.passes == 3) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < P_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, P_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + P_BM - 1) / P_BM;
+  const int num_n = (p.N + P_BN - 1) / P_BN;
+  const int total_tiles = num_m * num_n * p.splitk;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * 2 * P_TILE_BYTES) * 2u;  // both CTAs' loads of one stage
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int n_idx = tile % num_n;
+        const int t2 = tile / num_n;
+        const int m_idx = t2 % num_m;
+        const int split = t2 / num_m;
+        const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + (int)rank * 128;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          mbar_wait_cluster(&empty_bar[s], ph ^ 1u);
+          uint8_t* st = tiles + s * P_STAGE_BYTES;
+          uint8_t* sA_hi = st;
+          uint8_t* sA_lo = st + P_TILE_BYTES;
+          uint8_t* sB_hi = st + 2 * P_TILE_BYTES;
+          uint8_t* sB_lo = st + 3 * P_TILE_BYTES;
+          if (leader) mbar_expect_tx(&full_bar[s], tx_bytes);
+          const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+          const int k0 = kb * BK;
+          if (!p.a_mn) {
+            tma_load_2d_pair(sA_hi, &tmA_hi, fb, k0, m0);
+            if (p.passes == 3) tma_load_2d_pair(sA_lo, &tmA_lo, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d_pair(sA_hi + j * 8192, &tmA_hi, fb, m0 + 64 * j, k0);
+              if (p.passes == 3) tma_load_2d_pair(sA_lo + j * 8192, &tmA_lo, fb, m0 + 64 * j, k0);
+            }
+          }
+          if (!p.b_mn) {
+            tma_load_2d_pair(sB_hi, &tmB_hi, fb, k0, n0);
+            if (p.passes == 3) tma_load_2d_pair(sB_lo, &tmB_lo, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              tma_load_2d_pair(sB_hi + j * 8192, &tmB_hi, fb, n0 + 64 * j, k0);
+              if (p.passes == 3) tma_load_2d_pair(sB_lo + j * 8192, &tmB_lo, fb, n0 + 64 * j, k0);
+            }
+          }
+        }
+      }
+      // tail: wait until every stage-free arrival the leader's MMA commits multicast to this CTA has landed, so that no
+      // remote arrival can target this CTA's shared memory after it exits
+      for (uint32_t j = 0; j < (uint32_t)P_STAGES; ++j, ++it) {
+        const uint32_t s = it % P_STAGES;
+        const uint32_t ph = (it / P_STAGES) & 1u;
+        mbar_wait_cluster(&empty_bar[s], ph ^ 1u);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA)
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
+      const uint32_t adv_a = p.a_mn ? 2048u : 32u;  // bytes per k16 step
+      const uint32_t adv_b = p.b_mn ? 2048u : 32u;
+      uint32_t it = 0, acc_it = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
+        const int t2 = tile / num_n;
+        const int split = t2 / num_m;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const uint32_t a = acc_it & 1u;
+        const uint32_t aph = (acc_it >> 1) & 1u;
+        mbar_wait_cluster(&tempty_bar[a], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * P_BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1u;
+          mbar_wait_cluster(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sA_hi = smem_u32(tiles + s * P_STAGE_BYTES);
+          const uint32_t sA_lo = sA_hi + P_TILE_BYTES;
+          const uint32_t sB_hi = sA_hi + 2 * P_TILE_BYTES;
+          const uint32_t sB_lo = sA_hi + 3 * P_TILE_BYTES;
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) {
+            const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
+            const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
+            const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
+            umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, accumulate);
+            if (p.passes == 3) {
+              const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
+              const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
+              umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, 1u);
+              umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1u);
+            }
+          }
+          umma_commit_pair(&empty_bar[s]);  // frees this smem stage in both CTAs
+        }
+        umma_commit_pair(&tfull_bar[a]);  // accumulator complete -> both CTAs' epilogue warps
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue warps (this CTA's 128 rows x 256 columns)
+    const int g = warp & 3;          // TMEM lane quarter this warp may access
+    const int hc = (warp - 2) >> 2;  // column half
+    const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
+    const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+    float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
+    uint32_t acc_it = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
+      const int n_idx = tile % num_n;
+      const int t2 = tile / num_n;
+      const int m_idx = t2 % num_m;
+      const int split = t2 / num_m;
+      const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + hc * 128;
+      const uint32_t a = acc_it & 1u;
+      const uint32_t aph = (acc_it >> 1) & 1u;
+      mbar_wait_cluster(&tfull_bar[a], aph);
+      tc_fence_after();
+      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? 2 : 4;  // bound the code size
+#pragma unroll 1
+      for (int c = 0; c < 128 / P_CW; ++c) {
+        uint32_t r[P_CW];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * 128 + c * P_CW, r);
+        tmem_ld_wait();
+        if (c == 128 / P_CW - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(a ? tempty_remote1 : tempty_remote0);
+        }
+        const int col0 = n0 + c * P_CW;
+        float* myrow = stg + lane * P_STG_LD;
+#pragma unroll
+        for (int q = 0; q < P_CW / 4; ++q)
+          *reinterpret_cast<float4*>(myrow + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                  __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+        __syncwarp();
+        const int q = lane & 3;
+        const int col = col0 + 4 * q;
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll kUnrollIt
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2);
+          const long long row = (long long)m0 + g * 32 + rr;
+          if (row < p.M && col < p.N) {
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * q);
+            float v[4] = {t4.x, t4.y, t4.z, t4.w};
+            epilogue_quad<F>(p, v, row, col, split == 0);
+            if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
+          }
+        }
+        if constexpr ((F & EF_COLSUM) != 0) {
+          if (p.colsum != nullptr) {  // combine the 8 lanes that share a column quad
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+            }
+            if (lane < 4 && col < p.N) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, P_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -516,6 +780,9 @@ uint32_t required_features(const GemmDesc& d) {
 
 template <int BN, uint32_t F>
 int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream);
+struct GemmParams;
+void fill_params(GemmParams& p, const GemmDesc& d, int splitk_req);
+int make_operand_maps(const GemmDesc& d, CUtensorMap& tA_hi, CUtensorMap& tA_lo, CUtensorMap& tB_hi, CUtensorMap& tB_lo, int bn);
 
 // variants, most specific first; the first whose mask covers the required features is used
 constexpr uint32_t V_F32 = EF_F32;
@@ -547,13 +814,52 @@ template <int BN, uint32_t F>
 int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream) {
   using C = Cfg<BN>;
   GemmParams p;
+  fill_params(p, d, d.splitk);
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, BN)) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int num_m = (d.M + BM - 1) / BM, num_n = (d.N + BN - 1) / BN;
+  const long long tiles = (long long)num_m * num_n * p.splitk;
+  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  int slot = -1;
+  char tag[64];
+  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
+           d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
+  const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
+  gemm_tc_kernel<BN, F><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  if (prof) gemm_profile_end(stream, slot);
+  return check_launch("gemm_tc_kernel");
+}
+
+
+// split count for an accumulating (split-K) GEMM of `tiles` output tiles and `num_kb` k-blocks on `units` concurrent
+// CTAs / CTA pairs: minimise waves x (k-blocks per split + a per-tile epilogue allowance)
+int choose_splitk(long long tiles, int num_kb, int units) {
+  int best = 1;
+  long long best_cost = -1;
+  const int smax = num_kb / 4 > 0 ? num_kb / 4 : 1;
+  for (int s = 1; s <= smax; ++s) {
+    const long long waves = (tiles * s + units - 1) / units;
+    const long long cost = waves * ((num_kb + s - 1) / s + 4);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+void fill_params(GemmParams& p, const GemmDesc& d, int splitk_req) {
   memset(&p, 0, sizeof p);
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.passes = d.passes;
   p.a_mn = d.a_mn_major ? 1 : 0;
   p.b_mn = d.b_mn_major ? 1 : 0;
   p.num_kb = (d.K + BK - 1) / BK;
-  int splitk = d.splitk < 1 ? 1 : d.splitk;
+  int splitk = splitk_req < 1 ? 1 : splitk_req;
   if (splitk > p.num_kb) splitk = p.num_kb;
   p.kb_per_split = (p.num_kb + splitk - 1) / splitk;
   p.splitk = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
@@ -583,44 +889,87 @@ int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream) {
     if (dbg < 0) { const char* e = getenv("VC_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
+}
 
-  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+int make_operand_maps(const GemmDesc& d, CUtensorMap& tA_hi, CUtensorMap& tA_lo, CUtensorMap& tB_hi, CUtensorMap& tB_lo, int bn) {
   int rc = 0;
   const bf16_t* a_lo = d.passes == 3 ? d.a_lo : d.a_hi;
   const bf16_t* b_lo = d.passes == 3 ? d.b_lo : d.b_hi;
-  if (!p.a_mn) {
+  if (!d.a_mn_major) {
     rc |= make_tmap(&tA_hi, d.a_hi, d.M, d.K, d.lda, BK, BM);
     rc |= make_tmap(&tA_lo, a_lo, d.M, d.K, d.lda, BK, BM);
   } else {
     rc |= make_tmap(&tA_hi, d.a_hi, d.K, d.M, d.lda, 64, BK);
     rc |= make_tmap(&tA_lo, a_lo, d.K, d.M, d.lda, 64, BK);
   }
-  if (!p.b_mn) {
-    rc |= make_tmap(&tB_hi, d.b_hi, d.N, d.K, d.ldb, BK, BN);
-    rc |= make_tmap(&tB_lo, b_lo, d.N, d.K, d.ldb, BK, BN);
+  if (!d.b_mn_major) {
+    rc |= make_tmap(&tB_hi, d.b_hi, d.N, d.K, d.ldb, BK, bn);
+    rc |= make_tmap(&tB_lo, b_lo, d.N, d.K, d.ldb, BK, bn);
   } else {
     rc |= make_tmap(&tB_hi, d.b_hi, d.K, d.N, d.ldb, 64, BK);
     rc |= make_tmap(&tB_lo, b_lo, d.K, d.N, d.ldb, 64, BK);
   }
-  if (rc) return rc;
+  return rc;
+}
 
+template <uint32_t F>
+int launch_gemm_pair_variant(const GemmDesc& d, int splitk, cudaStream_t stream) {
+  GemmParams p;
+  fill_params(p, d, splitk);
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, 128)) return rc;  // each CTA stages 128 of the tile's 256 B rows
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     attr_set = true;
   }
-  const int num_m = (d.M + BM - 1) / BM, num_n = (d.N + BN - 1) / BN;
-  const long long tiles = (long long)num_m * num_n * p.splitk;
-  const int grid = (int)(tiles < num_sms() ? tiles : num_sms());
+  const long long tiles = (long long)((d.M + P_BM - 1) / P_BM) * ((d.N + P_BN - 1) / P_BN) * p.splitk;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   int slot = -1;
   char tag[64];
-  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
+  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  gemm_tc_kernel<BN, F><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  gemm_tc_pair_kernel<F><<<grid, P_THREADS, P_SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
-  return check_launch("gemm_tc_kernel");
+  return check_launch("gemm_tc_pair_kernel");
+}
+
+int launch_gemm_pair(const GemmDesc& d, int splitk, cudaStream_t stream) {
+  GemmDesc dd = d;
+  dd.splitk = splitk;
+  const uint32_t req = required_features(dd);
+#define VC_TRY_VARIANT(V) if ((req & ~(V)) == 0) return launch_gemm_pair_variant<(V)>(d, splitk, stream);
+  VC_TRY_VARIANT(V_F32)
+  VC_TRY_VARIANT(V_F32_BIAS)
+  VC_TRY_VARIANT(V_ATOMIC)
+  VC_TRY_VARIANT(V_F32_RES)
+  VC_TRY_VARIANT(V_F32_DROP_RES)
+  VC_TRY_VARIANT(V_SPLIT)
+  VC_TRY_VARIANT(V_SPLIT_ACT)
+  VC_TRY_VARIANT(V_SPLIT_BWD)
+#undef VC_TRY_VARIANT
+  return launch_gemm_pair_variant<EF_ALL>(d, splitk, stream);
+}
+
+// The CTA-pair kernel handles problems whose M and N are multiples of its 256 x 256 tile and that keep at least half of the
+// 74 SM pairs busy (the image-encoder GEMMs); everything else (decoder-sized, ragged N) uses the single-CTA kernel.
+bool pair_eligible(const GemmDesc& d, int* splitk_out) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("VC_GEMM_PAIR"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return false;
+  if (d.M % P_BM != 0 || d.N % P_BN != 0) return false;
+  const long long tiles = (long long)(d.M / P_BM) * (d.N / P_BN);
+  const int num_kb = (d.K + BK - 1) / BK;
+  const int pairs = num_sms() / 2;
+  int s = 1;
+  if (d.splitk > 1) s = choose_splitk(tiles, num_kb, pairs);
+  if (tiles * s < pairs / 2) return false;
+  *splitk_out = s;
+  return true;
 }
 
 }  // namespace
@@ -650,6 +999,8 @@ int gemm(const GemmDesc& d, stream_t stream) {
     return set_error("gemm: epilogue leading dimensions must be multiples of 4");
   // decoder-sized problems fill only a few SMs with 128x128 tiles: halve the tile width so that twice as many CTAs each
   // run half the MMA work
+  int pair_splitk = 1;
+  if (pair_eligible(d, &pair_splitk)) return launch_gemm_pair(d, pair_splitk, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles128 = (long long)((d.M + BM - 1) / BM) * ((d.N + 127) / 128) * (d.splitk > 1 ? d.splitk : 1);
   if (tiles128 <= 48 && d.N >= 64) return launch_gemm<64>(d, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<128>(d, reinterpret_cast<cudaStream_t>(stream));

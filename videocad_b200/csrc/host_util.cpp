@@ -21,6 +21,9 @@ static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
 void launch_count_reset() { g_launches.store(0); }
+static std::atomic<long long> g_pair_launches{0};
+void count_pair_launch() { g_pair_launches.fetch_add(1, std::memory_order_relaxed); }
+long long pair_launch_count() { return g_pair_launches.load(); }
 
 #if !VC_CUDA_BUILD
 void gemm_profile_enable(int) {}

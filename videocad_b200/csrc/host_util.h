@@ -10,6 +10,9 @@ const char* last_error();
 void count_launch();
 long long launch_count();
 void launch_count_reset();
+// launches that took the CTA-pair (cta_group::2) GEMM kernel
+void count_pair_launch();
+long long pair_launch_count();
 // GEMM profiling hooks (CUDA build: event pairs around each launch; emulation build: no-ops)
 void gemm_profile_enable(int enable);
 int gemm_profile_read(double* total_ms, double* total_flops, long long* launches);
