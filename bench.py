@@ -157,7 +157,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--config", default="c1", choices=sorted(CONFIGS))
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "bf16"])
+    ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
+                    help="trainer loss: the native fused kernels (default) or the torch restatement (videocad_b200/loss.py)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -167,7 +171,9 @@ def main():
     import torch.distributed as dist
     from videocad_b200 import AutoRegressiveTransformer
     from videocad_b200 import lib as L
-    from videocad_b200.loss import compute_loss
+    from videocad_b200 import loss as vloss
+
+    compute_loss = vloss.compute_loss_fused if args.loss == "fused" else vloss.compute_loss
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,15 +237,35 @@ def main():
         sampler.start()  # nvidia-smi needs a few hundred ms to deliver its first sample: start it before the warm-up
     for i in range(args.warmup):
         train_step(dev_batches[i % NUM_BATCHES])
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        train_step(dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if rank == 0:
+            sampler.stop()
+        return
     ms, launches = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps)
     clocks = sampler.stop() if rank == 0 else None
     frames_per_step = world * B * T
     value = frames_per_step * args.steps / (ms / 1000.0)
 
-    # ---------------- roofline pass: the same K steps with the native segments launched kernel by kernel (CUDA-graph
-    # replay off) so that a CUDA-event pair can be recorded around every GEMM launch on the launching stream
+    # ---------------- segment pass: CUDA events around each of the six graph replays of a step (frame ViT, CAD ViT and
+    # sequence transformer, forward and backward); what remains of the step is loss, clip, Adam and input staging
     import videocad_b200.model as vmodel
 
+    segments = None
+    if vmodel._GRAPHS:
+        vmodel.timing_begin()
+        ms_seg, _ = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps)
+        rep = vmodel.timing_report()
+        segments = {k: round(v[1] / args.steps, 4) for k, v in sorted(rep.items())}
+        segments["step_ms"] = round(ms_seg / args.steps, 4)
+        segments["outside_graphs_ms"] = round(ms_seg / args.steps - sum(v[1] for v in rep.values()) / args.steps, 4)
+
+    # ---------------- roofline pass: the same K steps with the native segments launched kernel by kernel (CUDA-graph
+    # replay off) so that a CUDA-event pair can be recorded around every GEMM launch on the launching stream
     graphs_were_on = vmodel._GRAPHS
     vmodel._GRAPHS = False
     train_step(dev_batches[0])
@@ -324,7 +350,7 @@ def main():
                 dtype="f32 (3-pass split-bf16 tensor-core GEMMs, fp32 accumulate)" if passes == 3 else "bf16",
                 data="synthetic", impl="native",
                 config=dict(workload=f"{args.config}: {world} x (batch {B}, T={T}, {S}x{S} frames), H={cfg['model']['hidden_size']}, "
-                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0",
+                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0, {args.loss} loss",
                             global_batch=world * B, parallelism=f"dp{world}" if world > 1 else "single",
                             l2="inputs rotate over 4 distinct batches (232 MB of frames at c1 > 126 MB L2); activations (>5 GB/step) stream through HBM",
                             fwd_gflop_per_sample=f_fwd / 1e9),
@@ -332,7 +358,8 @@ def main():
                                         ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches_inst, gpu_launches_note="native kernels per %d steps (%d per step); with CUDA-graph replay "
                 "the same kernels run from 6 graph launches per step" % (args.steps, launches_inst // max(args.steps, 1)),
-                cuda_graphs=bool(graphs_were_on), roofline=roofline, cpu_baseline=cpu_baseline)
+                cuda_graphs=bool(graphs_were_on), segments_ms_per_step=segments, roofline=roofline,
+                cpu_baseline=cpu_baseline)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -148,6 +148,29 @@ int vc_embed_action_fwd(const float* actions, int64_t R, int A, int H, const flo
                         int T, float* y, vc_bf16* y_hi, vc_bf16* y_lo, void* stream);
 int vc_embed_action_bwd(const float* dy, const float* y, const float* actions, int64_t R, int A, int H, int T, float* dW,
                         float* db, float* dE, void* stream);
+/* ---- training loss of the reference trainer, fused (MultiClassesTrainer.compute_loss with use_mse=True,
+ * /root/reference/trainer.py:935-966 and flexible_cross_entropy :853-916; restated in videocad_b200/loss.py):
+ *   loss = 2 * CE_w(cmds, tgt[:,0]; ignore -1, class weights cmd_w)
+ *        + sum_i cmd_w[param_to_label[i]] * mean_{selected rows}( -mean_{c in [t, min(t+tol_i-1, NV-1)]} log_softmax(params[:,i,:])[c] )
+ * where a row is selected when its target is not -1 and its argmax lies outside the window; an empty selection contributes 0
+ * and a NaN term is dropped.  Three launches forward (row pass, finalize), one backward; nothing leaves the device.
+ * cmds [R,NC] fp32, params [R,NP,NV] fp32, targets [R, 1+NP] fp32 (integers stored as floats, -1 = ignore).
+ * ws: vc_loss_workspace_floats(R, NP) floats kept from forward to backward. */
+#define VC_LOSS_MAX_PARAMS 8
+#define VC_LOSS_MAX_CLASSES 16
+typedef struct vc_loss_cfg {
+  int R, NC, NP, NV;
+  float cmd_w[VC_LOSS_MAX_CLASSES];     /* class weights of the command head */
+  int tolerance[VC_LOSS_MAX_PARAMS];     /* window length of parameter i (the reference's tolerance_i) */
+  int param_to_label[VC_LOSS_MAX_PARAMS];
+} vc_loss_cfg;
+size_t vc_loss_workspace_floats(int R, int NP);
+int vc_loss_forward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out,
+                    void* stream);
+/* dcmds [R,NC], dparams [R,NP,NV] = upstream[0] * d loss / d logits (upstream: device scalar) */
+int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, const float* ws,
+                     const float* upstream, float* dcmds, float* dparams, void* stream);
+
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream);
 int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
                       int accumulate_dx, float* dW, float* db, void* stream);

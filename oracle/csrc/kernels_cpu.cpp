@@ -528,6 +528,106 @@ int embed_action_bwd(const float* dy, const float* y, const float* actions, int6
   return 0;
 }
 
+// ---- fused training loss (CPU restatement of videocad_b200/csrc/loss.cu; same workspace layout)
+size_t loss_workspace_floats(int R, int NP) { return (size_t)4 * R * NP + (size_t)3 * R + 16; }
+
+namespace {
+struct LossWsC {
+  float *lse, *sel, *rowloss, *nwc, *cnum, *cden, *clse, *scal;
+};
+LossWsC loss_carve(float* ws, int R, int NP) {
+  LossWsC w;
+  const size_t rp = (size_t)R * NP;
+  w.lse = ws; w.sel = ws + rp; w.rowloss = ws + 2 * rp; w.nwc = ws + 3 * rp;
+  w.cnum = ws + 4 * rp; w.cden = w.cnum + R; w.clse = w.cden + R; w.scal = w.clse + R;
+  return w;
+}
+void loss_window(const LossCfg& c, int i, float target, bool& valid, long long& t, long long& hi, float& count) {
+  const long long tg = (long long)target;
+  valid = tg != -1;
+  t = tg < 0 ? 0 : tg;
+  hi = t + (c.tolerance[i] - 1);
+  if (hi > c.NV - 1) hi = c.NV - 1;
+  count = (float)(hi - t + 1);
+}
+}  // namespace
+
+int loss_forward(const LossCfg& c, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out, stream_t) {
+  if (c.NP > VC_LOSS_MAX_PARAMS || c.NC > VC_LOSS_MAX_CLASSES || c.R <= 0) return set_error("loss: unsupported configuration");
+  LossWsC w = loss_carve(ws, c.R, c.NP);
+  const int ldt = 1 + c.NP;
+  for (int r = 0; r < c.R; ++r) {
+    const float* z = cmds + (size_t)r * c.NC;
+    const long long tg = (long long)targets[(size_t)r * ldt];
+    const bool valid = tg >= 0 && tg < c.NC;
+    float m = -INFINITY, s = 0.f;
+    for (int k = 0; k < c.NC; ++k) m = fmaxf(m, z[k]);
+    for (int k = 0; k < c.NC; ++k) s += expf(z[k] - m);
+    const float lse = m + logf(s), wt = valid ? c.cmd_w[tg] : 0.f;
+    w.clse[r] = lse; w.cden[r] = wt; w.cnum[r] = valid ? wt * (lse - z[tg]) : 0.f;
+    for (int i = 0; i < c.NP; ++i) {
+      const float* zp = params + ((size_t)r * c.NP + i) * c.NV;
+      bool v; long long t, hi; float count;
+      loss_window(c, i, targets[(size_t)r * ldt + 1 + i], v, t, hi, count);
+      float best = -INFINITY; int bi = 0;
+      for (int k = 0; k < c.NV; ++k) if (zp[k] > best) { best = zp[k]; bi = k; }
+      double se = 0, sw = 0; float nw = 0.f;
+      for (int k = 0; k < c.NV; ++k) {
+        se += exp((double)zp[k] - best);
+        if (k >= t && k <= hi) { sw += zp[k]; nw += 1.f; }
+      }
+      const float l = best + (float)log(se);
+      const float sel = (v && !(bi >= t && bi <= hi)) ? 1.f : 0.f;
+      const size_t o = (size_t)r * c.NP + i;
+      w.lse[o] = l; w.sel[o] = sel;
+      w.rowloss[o] = (-((float)sw - nw * l) / count) * sel;
+      w.nwc[o] = nw / count;
+    }
+  }
+  float loss = 0.f;
+  for (int i = 0; i < c.NP; ++i) {
+    double S = 0, n = 0;
+    for (int r = 0; r < c.R; ++r) { S += w.rowloss[(size_t)r * c.NP + i]; n += w.sel[(size_t)r * c.NP + i]; }
+    const float denom = n > 1.0 ? (float)n : 1.f;
+    float term = (float)S / denom, coef = c.cmd_w[c.param_to_label[i]] / denom;
+    if (term != term) { term = 0.f; coef = 0.f; }
+    w.scal[i] = coef;
+    loss += term * c.cmd_w[c.param_to_label[i]];
+  }
+  double num = 0, den = 0;
+  for (int r = 0; r < c.R; ++r) { num += w.cnum[r]; den += w.cden[r]; }
+  loss += 2.f * (float)(num / den);
+  w.scal[c.NP] = 2.f / (float)den;
+  loss_out[0] = loss;
+  return 0;
+}
+
+int loss_backward(const LossCfg& c, const float* cmds, const float* params, const float* targets, const float* ws, const float* upstream,
+                  float* dcmds, float* dparams, stream_t) {
+  LossWsC w = loss_carve(const_cast<float*>(ws), c.R, c.NP);
+  const int ldt = 1 + c.NP;
+  const float up = upstream[0];
+  for (int r = 0; r < c.R; ++r) {
+    const float* z = cmds + (size_t)r * c.NC;
+    const long long tg = (long long)targets[(size_t)r * ldt];
+    const float wt = w.cden[r];
+    for (int k = 0; k < c.NC; ++k)
+      dcmds[(size_t)r * c.NC + k] = wt != 0.f ? wt * w.scal[c.NP] * up * (expf(z[k] - w.clse[r]) - (k == tg ? 1.f : 0.f)) : 0.f;
+    for (int i = 0; i < c.NP; ++i) {
+      const size_t o = (size_t)r * c.NP + i;
+      const float* zp = params + o * c.NV;
+      float* dz = dparams + o * c.NV;
+      const float coef = w.scal[i] * w.sel[o] * up;
+      if (coef == 0.f) { for (int k = 0; k < c.NV; ++k) dz[k] = 0.f; continue; }
+      bool v; long long t, hi; float count;
+      loss_window(c, i, targets[(size_t)r * ldt + 1 + i], v, t, hi, count);
+      for (int k = 0; k < c.NV; ++k)
+        dz[k] = coef * (w.nwc[o] * expf(zp[k] - w.lse[o]) - ((k >= t && k <= hi) ? 1.f / count : 0.f));
+    }
+  }
+  return 0;
+}
+
 int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t) {
   if (C > 8 || H % 4 != 0) return set_error("head_small_fwd: C <= 8 and H % 4 == 0 required");
   for (int64_t r = 0; r < R; ++r)

@@ -53,7 +53,7 @@ def _worker(rank, world, port, emu_path, out_path):
         shard = {k: v[rank * 2:(rank + 1) * 2] for k, v in inp.items()}
         _loss(ddp, shard).backward()
         if rank == 0:
-            torch.save({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}, out_path)
+            torch.save({k: p.grad.clone() for k, p in m.named_weights() if p.grad is not None}, out_path)
     finally:
         dist.destroy_process_group()
 
@@ -68,7 +68,7 @@ def test_ddp_world2_gloo_gradients_equal_full_batch(tmp_path):
     inp = to.model_inputs_from_batch(to.synthetic_batch(4, 4, 64, seed=77))
     _loss(m, inp).backward()
     assert len(got) > 100
-    for k, p in m.named_parameters():
+    for k, p in m.named_weights():
         assert k in got, k
         ref = p.grad
         assert (got[k] - ref).abs().max() <= 2e-5 * ref.abs().max() + 1e-7, k

@@ -73,7 +73,8 @@ def test_module_contract_and_errors():
     sd = {"module._orig_mod." + k: v for k, v in to.seeded_state_dict(cfg, 2).items()}
     sd["transformer.wte.weight"] = torch.zeros(1, 128)  # dead GPT-2 key of a reference checkpoint: ignored (strict=False)
     m2, _ = ModelFactory().create_model("x", dict(cfg, state_dim=1644, act_dim=7, encoder="vit"), "cpu", state_dict=sd)
-    assert torch.equal(m2.embed_action.weight, sd["module._orig_mod.embed_action.weight"])
+    assert torch.equal(dict(m2.named_weights())["embed_action.weight"].data, sd["module._orig_mod.embed_action.weight"])
+    assert [tuple(p.shape) for p in m2.parameters()] == [(m2._spec.total,), (m2.state_embedding_model._spec.total,), (m2.cad_embedding_model._spec.total,)]
     assert list(m.cad_embedding_model.parameters()) and list(m.state_embedding_model.parameters())
     with pytest.raises(ValueError):
         AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=128, encoder="resnet")
@@ -113,7 +114,7 @@ def test_orchestration_forward_backward_vs_fp64_oracle(emu, mode):
     wc, wp = torch.randn(cmds.shape, generator=g), torch.randn(params.shape, generator=g) * 0.05
     ((cmds * wc).sum() + (params * wp).sum()).backward()
     ((oc * wc.double()).sum() + (op * wp.double()).sum()).backward()
-    for name, p in m.named_parameters():
+    for name, p in m.named_weights():
         ref = sdd[name].grad
         if p.grad is None:
             assert ref is None or ref.abs().max() == 0, f"{name}: missing gradient"
@@ -136,11 +137,12 @@ def test_orchestration_multiview_vs_fp64_oracle(emu, mode):
     assert (cmds.double() - oc).abs().max() < 1e-4 and (params.double() - op).abs().max() < 1e-4
     (cmds.sum() + params.sum() * 0.01).backward()
     (oc.sum() + op.sum() * 0.01).backward()
-    for name, p in m.named_parameters():
+    for name, p in m.named_weights():
         ref = sdd[name].grad
         if p.grad is None:
             assert ref is None or ref.abs().max() == 0, name
             continue
+        ref = ref if ref is not None else torch.zeros_like(p.grad, dtype=torch.double)  # unused weight: zero slice of the flat gradient
         assert (p.grad.double() - ref).abs().max() < 2e-4 * ref.abs().max() + 1e-9, name
     with pytest.raises(ValueError):
         m({k: v for k, v in inp.items() if k != "multiview_images"})
@@ -179,11 +181,11 @@ def test_training_mode_dropout_bookkeeping(emu):
     g = torch.Generator().manual_seed(1)
     wc = torch.randn(c1.shape, generator=g)
     (c1 * wc).sum().backward()
-    for prm, idx in ((m.embed_action.bias, 5), (m.state_embedding_model.transformer.layers[3][1].net[1].bias, 17),
-                     (m.transformer_decoder.layers[0].norm2.weight, 3), (m.cad_embedding_model.cls_token.view(-1), 100)):
-        base = prm.view(-1) if prm.dim() else prm
-        analytic = (prm.grad if prm.grad is not None else m.cad_embedding_model.cls_token.grad.view(-1))[idx].item() \
-            if prm.is_leaf else m.cad_embedding_model.cls_token.grad.view(-1)[idx].item()
+    W = dict(m.named_weights())
+    for key, idx in (("embed_action.bias", 5), ("state_embedding_model.transformer.layers.3.1.net.1.bias", 17),
+                     ("transformer_decoder.layers.0.norm2.weight", 3), ("cad_embedding_model.cls_token", 100)):
+        base = W[key].data.view(-1)  # a view of the owning segment's flat parameter
+        analytic = W[key].grad.view(-1)[idx].item()
         eps = 1e-2
         with torch.no_grad():
             old = base[idx].item()

@@ -64,7 +64,7 @@ def test_forward_backward_vs_reference_golden(name):
     assert abs(loss.item() - float(z["loss"])) < 5e-3
     loss.backward()
     worst = 0.0
-    for k, p in m.named_parameters():
+    for k, p in m.named_weights():
         if k not in norms:
             assert p.grad is None or p.grad.abs().max().item() == 0.0, f"{k} should be unused"
             continue
@@ -113,7 +113,7 @@ def test_c3_width_small_batch_forward_backward_vs_oracle():
     oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
     ((oc * wc.cuda().double()).sum() + (op * wp.cuda().double()).sum()).backward()
     assert (cmds.double() - oc).abs().max() < LOGIT_TOL and (params.double() - op).abs().max() < LOGIT_TOL
-    for k, p in m.named_parameters():
+    for k, p in m.named_weights():
         ref = sdd[k].grad
         if ref is None:
             continue
@@ -209,7 +209,7 @@ def test_cuda_graph_replay_matches_eager():
             c, p = m(inp)
             ((c * wc.cuda()).sum() + (p * wp.cuda()).sum()).backward()
             outs.append((c.detach().clone(), p.detach().clone()))
-            grads.append({k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+            grads.append({k: v.grad.clone() for k, v in m.named_weights() if v.grad is not None})
         for it in range(1, 4):
             assert torch.equal(outs[it][0], outs[0][0]) and torch.equal(outs[it][1], outs[0][1]), (mode, it)
             for k in grads[0]:
@@ -219,8 +219,9 @@ def test_cuda_graph_replay_matches_eager():
     m.eval()
     with torch.no_grad():
         before, _ = m(inp)
-        m.embed_action.weight.add_(0.05)
-        m.cad_embedding_model.transformer.layers[0][1].net[1].weight.mul_(1.1)
+        W = dict(m.named_weights())
+        W["embed_action.weight"].data.add_(0.05)
+        W["cad_embedding_model.transformer.layers.0.1.net.1.weight"].data.mul_(1.1)
         after, _ = m(inp)
     assert (after - before).abs().max() > 1e-4
 

@@ -123,6 +123,18 @@ int vc_embed_action_bwd(const float* dy, const float* y, const float* actions, i
                         float* db, float* dE, void* stream) {
   return vck::embed_action_bwd(dy, y, actions, R, A, H, T, dW, db, dE, stream);
 }
+size_t vc_loss_workspace_floats(int R, int NP) { return vck::loss_workspace_floats(R, NP); }
+int vc_loss_forward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out,
+                    void* stream) {
+  if (!cfg) return vck::set_error("vc_loss_forward: null cfg");
+  return vck::loss_forward(*cfg, cmds, params, targets, ws, loss_out, stream);
+}
+int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, const float* ws,
+                     const float* upstream, float* dcmds, float* dparams, void* stream) {
+  if (!cfg) return vck::set_error("vc_loss_backward: null cfg");
+  return vck::loss_backward(*cfg, cmds, params, targets, ws, upstream, dcmds, dparams, stream);
+}
+
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream) {
   return vck::head_small_fwd(x, R, H, W, b, C, out, stream);
 }

@@ -119,6 +119,13 @@ int embed_action_bwd(const float* dy, const float* y, const float* actions, int6
                      float* db, float* dE, stream_t s);
 
 // narrow head: out[r, c] = x[r,:] . W[c,:] + b[c], C small (5)
+// fused training loss (see include/videocad_b200.h, vc_loss_*)
+typedef vc_loss_cfg LossCfg;
+size_t loss_workspace_floats(int R, int NP);
+int loss_forward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out, stream_t s);
+int loss_backward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, const float* ws,
+                  const float* upstream, float* dcmds, float* dparams, stream_t s);
+
 int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t s);
 // dx[r,:] (+)= dout[r,:] W ; dW += dout^T x ; db += colsum(dout)   (dW/db accumulated, pre-zeroed)
 int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,

@@ -25,6 +25,12 @@ class Drop(C.Structure):
     _fields_ = [("p", C.c_float), ("site", C.c_uint32), ("seed", C.c_uint64), ("seed_ptr", C.c_void_p)]
 
 
+class LossCfg(C.Structure):
+    """mirror of vc_loss_cfg"""
+    _fields_ = [("R", C.c_int), ("NC", C.c_int), ("NP", C.c_int), ("NV", C.c_int), ("cmd_w", C.c_float * 16),
+                ("tolerance", C.c_int * 8), ("param_to_label", C.c_int * 8)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", vp), ("a_lo", vp), ("lda", i64), ("a_mn_major", i32),
@@ -83,6 +89,9 @@ _PROTOS = {
     "vc_broadcast_rows": ([vp, i64, i64, i32, i32, vp, i64, vp, vp, i64, vp], i32),
     "vc_embed_action_fwd": ([vp, i64, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp], i32),
     "vc_embed_action_bwd": ([vp, vp, vp, i64, i32, i32, i32, vp, vp, vp, vp], i32),
+    "vc_loss_workspace_floats": ([i32, i32], C.c_size_t),
+    "vc_loss_forward": ([vp, vp, vp, vp, vp, vp, vp], i32),
+    "vc_loss_backward": ([vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
     "vc_head_small_fwd": ([vp, i64, i32, vp, vp, i32, vp, vp], i32),
     "vc_head_small_bwd": ([vp, vp, i64, i32, vp, i32, vp, i32, vp, vp, vp], i32),
     "vc_add_f32": ([vp, vp, vp, i64, vp], i32),

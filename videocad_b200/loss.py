@@ -10,16 +10,23 @@ Follows MultiClassesTrainer.compute_loss (/root/reference/trainer.py:935-966) wi
 in the window are dropped, the soft target is uniform over the (clamped) window, the mean runs over the remaining
 rows; an empty selection contributes 0 and NaN terms are skipped.
 
-The reference builds the soft targets with Python loops and ~30 `.item()` calls per step; here the window is a
-class-index mask, masks replace boolean indexing and nothing leaves the device.  This module is
-host-side glue around the native model (SURVEY.md 8(f) rank 1 lists a fused kernel for it as the next row).
+The reference builds the soft targets with Python loops and ~30 `.item()` calls per step.  Two implementations here:
+
+* `compute_loss`          -- the torch restatement (class-index masks instead of boolean indexing, nothing leaves the
+                             device); ~300 small kernels per step with its autograd backward.  Kept as the readable
+                             definition and as the checker of the fused kernel (tests/test_loss.py).
+* `compute_loss_fused`    -- SURVEY.md 8(f) rank 1: the same loss as three native kernels (row pass, finalize, gradient)
+                             behind `vc_loss_forward` / `vc_loss_backward` (videocad_b200/csrc/loss.cu).
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Optional, Sequence
 
 import torch
 import torch.nn.functional as F
+
+from . import lib as L
 
 TOLERANCE = 3
 TOLERANCES = (TOLERANCE - 1, TOLERANCE - 1, 50, 200, 500, TOLERANCE - 1)
@@ -42,17 +49,35 @@ def flexible_cross_entropy(logits: torch.Tensor, targets: torch.Tensor, toleranc
     cls = torch.arange(num_classes, device=logits.device).unsqueeze(0)
     window = ((cls >= t.unsqueeze(1)) & (cls <= hi.unsqueeze(1))).to(logp.dtype)
     count = (hi - t + 1).to(logp.dtype)
-    per_row = -(logp * window).sum(dim=1) / count
+    # an out-of-range target (t == num_classes) has an empty window and count == 0: the reference's 0/0 makes the whole term
+    # NaN, which compute_loss then skips (trainer.py:959-960).  Same outcome here, without NaNs entering the backward.
+    poisoned = (count == 0).any()
+    per_row = -(logp * window).sum(dim=1) / torch.where(count == 0, torch.ones_like(count), count)
     sel = select.to(logp.dtype)
     n = sel.sum()
-    return (per_row * sel).sum() / n.clamp(min=1.0)
+    val = (per_row * sel).sum() / n.clamp(min=1.0)
+    return torch.where(poisoned, torch.zeros_like(val), val)
+
+
+_W_CACHE = {}
+
+
+def _weights_on(device, values):
+    """class weights as a device tensor, built once per (device, values): torch.tensor(..., device=cuda) is a pageable
+    host-to-device copy, i.e. a stream synchronisation in the middle of every training step."""
+    key = (str(device), values)
+    w = _W_CACHE.get(key)
+    if w is None:
+        w = torch.tensor(values, dtype=torch.float32, device=device)
+        _W_CACHE[key] = w
+    return w
 
 
 def compute_loss(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequence[float]] = None) -> torch.Tensor:
     """action_preds = (cmds [B,T,5], params [B,T,6,1000]); actions [B,T,7] raw targets (-1 = ignore)."""
     pred_cmd, pred_params = action_preds
     actions = actions.long()
-    w = torch.tensor(cmd_weights if cmd_weights is not None else DEFAULT_CMD_WEIGHTS, dtype=torch.float32, device=pred_cmd.device)
+    w = _weights_on(pred_cmd.device, tuple(cmd_weights) if cmd_weights is not None else DEFAULT_CMD_WEIGHTS)
     loss_cmd = F.cross_entropy(pred_cmd.reshape(-1, pred_cmd.shape[-1]), actions[..., 0].reshape(-1), weight=w, ignore_index=-1)
     loss = 2.0 * loss_cmd
     for i in range(pred_params.shape[-2]):
@@ -60,3 +85,50 @@ def compute_loss(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequ
         lp = torch.where(torch.isnan(lp), torch.zeros_like(lp), lp)
         loss = loss + lp * w[PARAM_TO_LABEL[i]]
     return loss
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cmds, params, targets, cfg, lib):
+        cmds, params, targets = cmds.contiguous().float(), params.contiguous().float(), targets.contiguous().float()
+        dev = cmds.device
+        stream = torch.cuda.current_stream(dev).cuda_stream if cmds.is_cuda else None
+        ws = torch.empty(lib.vc_loss_workspace_floats(cfg.R, cfg.NP), dtype=torch.float32, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        L.check(lib.vc_loss_forward(C.byref(cfg), cmds.data_ptr(), params.data_ptr(), targets.data_ptr(), ws.data_ptr(), loss.data_ptr(),
+                                    stream), lib)
+        ctx.save_for_backward(cmds, params, targets, ws)
+        ctx.cfg, ctx.lib = cfg, lib
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        cmds, params, targets, ws = ctx.saved_tensors
+        cfg, lib = ctx.cfg, ctx.lib
+        g = g.contiguous().float().view(1)
+        dcmds, dparams = torch.empty_like(cmds), torch.empty_like(params)
+        stream = torch.cuda.current_stream(cmds.device).cuda_stream if cmds.is_cuda else None
+        L.check(lib.vc_loss_backward(C.byref(cfg), cmds.data_ptr(), params.data_ptr(), targets.data_ptr(), ws.data_ptr(), g.data_ptr(),
+                                     dcmds.data_ptr(), dparams.data_ptr(), stream), lib)
+        return dcmds, dparams, None, None, None
+
+
+def compute_loss_fused(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequence[float]] = None, _lib=None) -> torch.Tensor:
+    """Same value and gradients as `compute_loss`, computed by the native fused kernels (no CPU fallback: `_lib` is the
+    tests' hook for the CPU emulation library)."""
+    pred_cmd, pred_params = action_preds
+    if not pred_cmd.is_cuda and _lib is None:
+        raise RuntimeError("compute_loss_fused runs on CUDA tensors only")
+    lib = _lib if _lib is not None else L.load()
+    NC, NP, NV = pred_cmd.shape[-1], pred_params.shape[-2], pred_params.shape[-1]
+    w = tuple(cmd_weights) if cmd_weights is not None else DEFAULT_CMD_WEIGHTS
+    if NP > len(TOLERANCES) or NP > 8 or NC > 16 or len(w) < NC:
+        raise ValueError("compute_loss_fused: unsupported head sizes")
+    cfg = L.LossCfg()
+    cfg.R, cfg.NC, cfg.NP, cfg.NV = pred_cmd.numel() // NC, NC, NP, NV
+    for i in range(NC):
+        cfg.cmd_w[i] = float(w[i])
+    for i in range(NP):
+        cfg.tolerance[i] = TOLERANCES[i]
+        cfg.param_to_label[i] = PARAM_TO_LABEL[i]
+    return _FusedLoss.apply(pred_cmd.reshape(-1, NC), pred_params.reshape(-1, NP, NV), actions.reshape(-1, 1 + NP), cfg, lib)

@@ -5,9 +5,14 @@ Same constructor kwargs, same parameter names/shapes, sam
 ``forward(inputs: dict) -> (cmds [B,T,5], params [B,T,6,1000])`` and ``sequential_inference``; the arithmetic runs
 in libvideocad_b200.so (hand-written sm_100a kernels) through three autograd nodes (frame ViT, CAD ViT, sequence
 transformer) so that DDP can start all-reducing the decoder / CAD-encoder gradients while the frame encoder's
-backward is still running.  The torch modules constructed here are PARAMETER CONTAINERS only (they give the
-reference's state_dict keys and default initialisation); their forward() is never called and there is no
-eager/CPU fallback.
+backward is still running.  There is no eager/CPU fallback.
+
+Parameter storage: each of the three segments keeps ALL its weights in ONE flat fp32 nn.Parameter (`flat_params`,
+64-element aligned slices).  `state_dict()` / `load_state_dict()` speak the reference's key schema (views into the flat
+buffers), so checkpoints are interchangeable, while `parameters()` - what Adam, `clip_grad_norm_` and DDP iterate over -
+yields three large tensors instead of ~320 small ones: the optimizer runs three bandwidth-bound passes, DDP all-reduces
+three buckets (no per-parameter copy kernels), and a backward returns its whole gradient arena as one tensor.  The torch
+modules the reference would construct are built once, for their default initialisation and key names, and discarded.
 
 Not constructed (dead in the reference's forward): transformer.* (GPT2Model), embed_timestep,
 embed_ln, predict_action.  Checkpoints carrying those keys load with strict=False exactly as
@@ -28,6 +33,27 @@ from . import model_abi as A
 # CUDA-graph replay of the native call sequences (one graph per segment, direction and problem shape); "0" disables
 _GRAPHS = os.environ.get("VIDEOCAD_B200_GRAPHS", "1") != "0"
 _MAX_SLOTS = 3
+# run the CAD image encoder on a second stream, concurrently with the frame encoder ("0" disables)
+_OVERLAP = os.environ.get("VIDEOCAD_B200_OVERLAP", "1") != "0"
+_TIMING = None  # bench.py: list of (segment.direction, start event, end event) around every CUDA-graph replay
+
+
+def timing_begin():
+    global _TIMING
+    _TIMING = []
+
+
+def timing_report():
+    """-> {segment.direction: (replays, total ms)}; synchronises the device."""
+    global _TIMING
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in _TIMING or []:
+        n, ms = out.get(name, (0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1))
+    _TIMING = None
+    return out
+
 
 _SITE_STATE_VIT = 0x100
 _SITE_CAD_VIT = 0x200
@@ -72,9 +98,9 @@ class _TransformerParams(_NoForward):
             [nn.ModuleList([_AttnParams(dim, heads, dim_head, dropout), _FFParams(dim, mlp_dim, dropout)]) for _ in range(depth)])
 
 
-class ViTParams(_NoForward):
+class _ViTContainers(_NoForward):
     """vit_pytorch.ViT(image_size=224, patch_size=32, dim=512, depth=6, heads=16, mlp_dim=512, channels=1) with
-    mlp_head = Identity (trajectory_model.py:54-67)."""
+    mlp_head = Identity (trajectory_model.py:54-67): built for its key names and default initialisation only."""
 
     def __init__(self, dropout=0.1, emb_dropout=0.1):
         super().__init__()
@@ -85,7 +111,107 @@ class ViTParams(_NoForward):
         self.dropout = nn.Dropout(emb_dropout)
         self.transformer = _TransformerParams(A.VIT_DIM, A.VIT_DEPTH, A.VIT_HEADS, A.VIT_DHEAD, A.VIT_MLP, dropout)
         self.mlp_head = nn.Identity()
+
+
+class _FlatSpec:
+    """Key names, shapes and (64-element aligned) offsets of one segment's weights inside its flat buffer."""
+
+    def __init__(self, named):
+        self.names, self.shapes, self.offs, self.numels = [], [], [], []
+        total = 0
+        for name, t in named:
+            self.names.append(name)
+            self.shapes.append(tuple(t.shape))
+            self.offs.append(total)
+            self.numels.append(t.numel())
+            total += (t.numel() + 63) // 64 * 64
+        self.total = total
+        self.index = {n: i for i, n in enumerate(self.names)}
+
+    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+        i = self.index[name]
+        return flat[self.offs[i]: self.offs[i] + self.numels[i]].view(self.shapes[i])
+
+
+class WeightView:
+    """(value, grad) of one named weight: views into the owning segment's flat parameter / flat gradient."""
+
+    def __init__(self, value, grad):
+        self.data, self.grad, self.shape = value, grad, value.shape
+
+
+class _FlatOwner(_NoForward):
+    """Module whose only registered parameter is `flat_params`; (de)serialises under the reference's key names."""
+
+    def _init_flat(self, named):
+        self._spec = _FlatSpec(named)
+        flat = torch.zeros(self._spec.total)
+        for name, t in named:
+            self._spec.view(flat, name).copy_(t.detach())
+        self.flat_params = nn.Parameter(flat)
+
+    def _own_named_views(self, grads=False):
+        flat = self.flat_params
+        src = flat.grad if grads else flat.detach()  # detach(): same storage AND version counter (in-place loads invalidate caches)
+        for name in self._spec.names:
+            yield name, (self._spec.view(src, name) if src is not None else None)
+
+    def _flat_children(self):
+        return [(n, m) for n, m in self._modules.items() if isinstance(m, _FlatOwner)]
+
+    def named_weights(self, prefix=""):
+        """(reference key, WeightView) for every weight, children first (the reference's registration order)."""
+        for cname, child in self._flat_children():
+            yield from child.named_weights(prefix + cname + ".")
+        g = self.flat_params.grad
+        for name, v in self._own_named_views():
+            yield prefix + name, WeightView(v, self._spec.view(g, name) if g is not None else None)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        if len(args) > 0:  # legacy positional form (destination, prefix, keep_vars)
+            destination = args[0]
+            prefix = args[1] if len(args) > 1 else prefix
+            keep_vars = args[2] if len(args) > 2 else keep_vars
+        if destination is None:
+            import collections
+
+            destination = collections.OrderedDict()
+            destination._metadata = collections.OrderedDict()
+        for cname, child in self._flat_children():
+            child.state_dict(destination=destination, prefix=prefix + cname + ".", keep_vars=keep_vars)
+        for name, v in self._own_named_views():
+            destination[prefix + name] = v
+        return destination
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        own = set()
+        with torch.no_grad():
+            for name, v in self._own_named_views():
+                key = prefix + name
+                own.add(key)
+                if key not in state_dict:
+                    missing_keys.append(key)
+                    continue
+                src = state_dict[key]
+                if tuple(src.shape) != tuple(v.shape):
+                    error_msgs.append(f"size mismatch for {key}: copying a param with shape {tuple(src.shape)} from checkpoint, "
+                                      f"the shape in current model is {tuple(v.shape)}.")
+                else:
+                    v.copy_(src)
+        if strict:
+            child_prefixes = tuple(prefix + n + "." for n, m in self._modules.items() if m is not None)
+            for key in state_dict.keys():
+                if key.startswith(prefix) and key not in own and not (child_prefixes and key.startswith(child_prefixes)):
+                    unexpected_keys.append(key)
+
+
+class ViTParams(_FlatOwner):
+    """Weights of one vit_pytorch.ViT image encoder (trajectory_model.py:54-67) in one flat parameter."""
+
+    def __init__(self, dropout=0.1, emb_dropout=0.1):
+        super().__init__()
         self.dropout_p = dropout
+        self._init_flat(list(_ViTContainers(dropout, emb_dropout).named_parameters()))
 
 
 # =====================================================================================================
@@ -115,22 +241,27 @@ class _Lease:
 
 
 class _Segment:
-    def __init__(self):
-        self.params: List[nn.Parameter] = []
-        self._mats: List[nn.Parameter] = []
-        self._split = {}
+    def __init__(self, owner: _FlatOwner):
+        self.owner = owner
+        self.spec = owner._spec
+        self.total = self.spec.total
+        self._split = None  # (flat._version, flat.data_ptr(), hi, lo): split-bf16 mirror of the whole flat parameter
         self._slots = {}
         self._sig = None
         self._lib = None  # tests may inject the CPU emulation library; the product path loads the CUDA build
+
+    @property
+    def flat(self) -> nn.Parameter:
+        return self.owner.flat_params
 
     def graphs_enabled(self, t: torch.Tensor) -> bool:
         return _GRAPHS and t.is_cuda and self._lib is None
 
     def _check_storage(self):
-        """Persistent structs and graphs bake parameter addresses: drop them if a parameter's storage moved (.to(), ...)."""
-        sig = tuple(p.data_ptr() for p in self.params)
+        """Persistent structs and graphs bake parameter addresses: drop them if the flat parameter's storage moved (.to(), ...)."""
+        sig = self.flat.data_ptr()
         if sig != self._sig:
-            self._sig, self._slots, self._split, self._split_table = sig, {}, {}, None
+            self._sig, self._slots, self._split = sig, {}, None
 
     def _slot_for(self, key, make):
         slot = self._slots.get(key)
@@ -146,34 +277,38 @@ class _Segment:
             self._slots[key] = slot
         return slot
 
-    def resplit_all(self, stream):
-        """Unconditional refresh of every split-bf16 weight copy (body of the captured forward graph): one multi-tensor
-        launch driven by a device-resident pointer table (rebuilt whenever parameter storage moves, see _check_storage)."""
-        lib = self.lib()
-        tab = getattr(self, "_split_table", None)
-        if tab is None and self._mats and self._mats[0].is_cuda and all(p.numel() % 4 == 0 for p in self._mats):
-            rows, start = [], 0
-            for p in self._mats:
-                ent = self._split[id(p)]
-                n4 = p.numel() // 4
-                rows.append([p.data_ptr(), ent[2].data_ptr(), ent[3].data_ptr(), n4, start])
-                start += (n4 + 1023) // 1024
-            tab = (torch.tensor(rows, dtype=torch.int64).to(self._mats[0].device), len(rows), start)
-            self._split_table = tab
-        if tab is not None:
-            L.check(lib.vc_split_many(tab[0].data_ptr(), tab[1], tab[2], stream), lib)
-            return
-        for p in self._mats:
-            ent = self._split[id(p)]
-            rows, cols = p.shape[0], p.numel() // p.shape[0]
-            L.check(lib.vc_split_f32(p.data_ptr(), cols, rows, cols, ent[2].data_ptr(), ent[3].data_ptr(), cols, stream), lib)
-            self._split[id(p)] = (p._version, p.data_ptr(), ent[2], ent[3])
+    def ensure_split(self, stream, force=False):
+        """split-bf16 (hi, lo) mirror of the flat parameter, refreshed with ONE launch when the fp32 values changed
+        (optimizer step, load_state_dict, .to()); the GEMM weights are slices of it at the same element offsets."""
+        flat = self.flat
+        ent = self._split
+        if ent is None or ent[1] != flat.data_ptr() or ent[2].device != flat.device:
+            hi = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
+            lo = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
+            ent = None
+        else:
+            hi, lo = ent[2], ent[3]  # refreshed in place: captured graphs and cached structs keep these addresses
+        if force or ent is None or ent[0] != flat._version:
+            lib = self.lib()
+            L.check(lib.vc_split_f32(flat.data_ptr(), self.total, 1, self.total, hi.data_ptr(), lo.data_ptr(), self.total, stream), lib)
+            self._split = (flat._version, flat.data_ptr(), hi, lo)
+        return hi, lo
 
-    @staticmethod
-    def _launch(slot, name, body):
+    def resplit_all(self, stream):
+        """Unconditional refresh of the split-bf16 mirror (first node of the captured forward graph)."""
+        self.ensure_split(stream, force=True)
+
+    def _launch(self, slot, name, body):
         """Run `body` eagerly on first use, capture it into a CUDA graph on the second, replay afterwards."""
         g = slot.graphs.get(name)
         if g is not None:
+            if _TIMING is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                _TIMING.append((f"{getattr(self, 'tag', type(self).__name__)}.{name}", e0, e1))
+                return
             g.replay()
             return
         if slot.uses.get(name, 0) >= 1:
@@ -189,100 +324,55 @@ class _Segment:
     def lib(self):
         return self._lib if self._lib is not None else L.load()
 
-    def _register(self, p: nn.Parameter) -> int:
-        self.params.append(p)
-        return len(self.params) - 1
+    def _off(self, name: str) -> int:
+        return self.spec.offs[self.spec.index[name]]
 
-    def _layout(self):
-        offs, total = [], 0
-        for p in self.params:
-            offs.append(total)
-            total += (p.numel() + 63) // 64 * 64
-        return offs, total
+    def _ptr(self, name: str) -> int:
+        return self.flat.data_ptr() + 4 * self._off(name)
 
-    def split_of(self, p: nn.Parameter, stream):
-        """split-bf16 copies of a 2-D weight, refreshed when the fp32 tensor changed (optimizer step, load_state_dict, .to())."""
-        key = id(p)
-        ent = self._split.get(key)
-        if ent is None or ent[0] != p._version or ent[1] != p.data_ptr():
-            w = p.detach()
-            rows, cols = w.shape[0], w.numel() // w.shape[0]
-            if ent is not None and ent[2].shape == w.shape and ent[2].device == w.device:
-                hi, lo = ent[2], ent[3]  # refresh in place: captured graphs and cached structs keep these addresses
-            else:
-                hi = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-                lo = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
-            lib = self.lib()
-            L.check(lib.vc_split_f32(w.data_ptr(), cols, rows, cols, hi.data_ptr(), lo.data_ptr(), cols, stream), lib)
-            ent = (p._version, p.data_ptr(), hi, lo)
-            self._split[key] = ent
-        return ent[2], ent[3]
+    def _gptr(self, gflat, name: str):
+        return gflat.data_ptr() + 4 * self._off(name) if gflat is not None else None
 
-    def _fill_linear(self, s: A.Linear, w: nn.Parameter, b: Optional[nn.Parameter], stream, flat, offs, idx_w, idx_b):
-        if not any(w is m for m in self._mats):
-            self._mats.append(w)
-        hi, lo = self.split_of(w, stream)
-        s.w, s.w_hi, s.w_lo = w.data_ptr(), hi.data_ptr(), lo.data_ptr()
-        s.b = b.data_ptr() if b is not None else None
-        if flat is not None:
-            s.dw = flat.data_ptr() + 4 * offs[idx_w]
-            s.db = flat.data_ptr() + 4 * offs[idx_b] if b is not None else None
+    def _fill_linear(self, s: A.Linear, w: str, b: Optional[str], gflat):
+        hi, lo = self._split[2], self._split[3]
+        ow = self._off(w)
+        s.w, s.w_hi, s.w_lo = self._ptr(w), hi.data_ptr() + 2 * ow, lo.data_ptr() + 2 * ow
+        s.b = self._ptr(b) if b is not None else None
+        if gflat is not None:
+            s.dw = self._gptr(gflat, w)
+            s.db = self._gptr(gflat, b) if b is not None else None
 
-    @staticmethod
-    def _fill_norm(s: A.Norm, m: nn.LayerNorm, flat, offs, idx_w, idx_b):
-        s.w, s.b = m.weight.data_ptr(), m.bias.data_ptr()
-        if flat is not None:
-            s.dw = flat.data_ptr() + 4 * offs[idx_w]
-            s.db = flat.data_ptr() + 4 * offs[idx_b]
-
-    def grad_views(self, flat, offs, used=None):
-        out = []
-        for i, p in enumerate(self.params):
-            if not p.requires_grad or (used is not None and not used[i]):
-                out.append(None)
-            else:
-                out.append(flat[offs[i]: offs[i] + p.numel()].view(p.shape))
-        return out
+    def _fill_norm(self, s: A.Norm, prefix: str, gflat):
+        s.w, s.b = self._ptr(prefix + ".weight"), self._ptr(prefix + ".bias")
+        if gflat is not None:
+            s.dw, s.db = self._gptr(gflat, prefix + ".weight"), self._gptr(gflat, prefix + ".bias")
 
 
 class _VitRunner(_Segment):
     def __init__(self, vit: ViTParams, site_base: int):
-        super().__init__()
+        super().__init__(vit)
         self.site_base = site_base
-        v = vit
-        self.vit = vit
-        self.i_pos, self.i_cls = self._register(v.pos_embedding), self._register(v.cls_token)
-        pe = v.to_patch_embedding
-        self.i_pe = [self._register(t) for t in (pe[1].weight, pe[1].bias, pe[2].weight, pe[2].bias, pe[3].weight, pe[3].bias)]
-        self.i_layers = []
-        for attn, ff in v.transformer.layers:
-            ids = [self._register(t) for t in (attn.norm.weight, attn.norm.bias, attn.to_qkv.weight, attn.to_out[0].weight,
-                                                attn.to_out[0].bias, ff.net[0].weight, ff.net[0].bias, ff.net[1].weight,
-                                                ff.net[1].bias, ff.net[4].weight, ff.net[4].bias)]
-            self.i_layers.append(ids)
-        self.i_norm = [self._register(v.transformer.norm.weight), self._register(v.transformer.norm.bias)]
-        self.offs, self.total = self._layout()
+        self.tag = "vit_frames" if site_base == _SITE_STATE_VIT else "vit_cad"
 
-    def _weights(self, stream, flat=None) -> A.VitWeights:
-        v, o = self.vit, self.offs
+    def _weights(self, stream, gflat=None) -> A.VitWeights:
+        self.ensure_split(stream)
         W = A.VitWeights()
-        W.pos, W.cls = v.pos_embedding.data_ptr(), v.cls_token.data_ptr()
-        if flat is not None:
-            W.dpos = flat.data_ptr() + 4 * o[self.i_pos]
-            W.dcls = flat.data_ptr() + 4 * o[self.i_cls]
-        pe, ip = v.to_patch_embedding, self.i_pe
-        self._fill_norm(W.pe_ln1, pe[1], flat, o, ip[0], ip[1])
-        self._fill_linear(W.pe, pe[2].weight, pe[2].bias, stream, flat, o, ip[2], ip[3])
-        self._fill_norm(W.pe_ln2, pe[3], flat, o, ip[4], ip[5])
-        for l, (attn, ff) in enumerate(v.transformer.layers):
-            ids, Lw = self.i_layers[l], W.layer[l]
-            self._fill_norm(Lw.ln1, attn.norm, flat, o, ids[0], ids[1])
-            self._fill_linear(Lw.qkv, attn.to_qkv.weight, None, stream, flat, o, ids[2], None)
-            self._fill_linear(Lw.out, attn.to_out[0].weight, attn.to_out[0].bias, stream, flat, o, ids[3], ids[4])
-            self._fill_norm(Lw.ln2, ff.net[0], flat, o, ids[5], ids[6])
-            self._fill_linear(Lw.fc1, ff.net[1].weight, ff.net[1].bias, stream, flat, o, ids[7], ids[8])
-            self._fill_linear(Lw.fc2, ff.net[4].weight, ff.net[4].bias, stream, flat, o, ids[9], ids[10])
-        self._fill_norm(W.norm, v.transformer.norm, flat, o, self.i_norm[0], self.i_norm[1])
+        W.pos, W.cls = self._ptr("pos_embedding"), self._ptr("cls_token")
+        if gflat is not None:
+            W.dpos, W.dcls = self._gptr(gflat, "pos_embedding"), self._gptr(gflat, "cls_token")
+        pe = "to_patch_embedding."
+        self._fill_norm(W.pe_ln1, pe + "1", gflat)
+        self._fill_linear(W.pe, pe + "2.weight", pe + "2.bias", gflat)
+        self._fill_norm(W.pe_ln2, pe + "3", gflat)
+        for l in range(A.VIT_DEPTH):
+            at, ff, Lw = f"transformer.layers.{l}.0.", f"transformer.layers.{l}.1.net.", W.layer[l]
+            self._fill_norm(Lw.ln1, at + "norm", gflat)
+            self._fill_linear(Lw.qkv, at + "to_qkv.weight", None, gflat)
+            self._fill_linear(Lw.out, at + "to_out.0.weight", at + "to_out.0.bias", gflat)
+            self._fill_norm(Lw.ln2, ff + "0", gflat)
+            self._fill_linear(Lw.fc1, ff + "1.weight", ff + "1.bias", gflat)
+            self._fill_linear(Lw.fc2, ff + "4.weight", ff + "4.bias", gflat)
+        self._fill_norm(W.norm, "transformer.norm", gflat)
         return W
 
     def _make_slot(self, F_, S, dev, training, p, passes):
@@ -294,11 +384,11 @@ class _VitRunner(_Segment):
         sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
         sl.out = torch.empty(F_, A.VIT_DIM, dtype=torch.float32, device=dev)
         sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        sl.flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        sl.gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         sl.dcls = torch.empty(F_, A.VIT_DIM, dtype=torch.float32, device=dev)
         sl.sc_bytes = lib.vc_vit_scratch_bytes(F_, S)
         sl.scratch = None  # allocated at the first backward
-        sl.W, sl.Wg = self._weights(stream), self._weights(stream, sl.flat)
+        sl.W, sl.Wg = self._weights(stream), self._weights(stream, sl.gflat)
         for name, W in (("call", sl.W), ("call_b", sl.Wg)):
             c = A.VitCall()
             c.w = C.pointer(W)
@@ -311,10 +401,12 @@ class _VitRunner(_Segment):
 
     def forward(self, img: torch.Tensor, training: bool, p: float, seed: int, passes: int, need_grad: bool = True):
         lib = self.lib()
-        img = img.contiguous().float()
-        if img.dim() != 4 or img.shape[1] != 1 or img.shape[2] != img.shape[3]:
-            raise ValueError(f"ViT expects [F,1,S,S] images, got {tuple(img.shape)}")
-        F_, S = img.shape[0], img.shape[2]
+        if img.dtype != torch.float32:
+            img = img.float()
+        if img.dim() < 4 or img.shape[-3] != 1 or img.shape[-2] != img.shape[-1]:
+            raise ValueError(f"ViT expects [F,1,S,S] (or [B,T,1,S,S]) images, got {tuple(img.shape)}")
+        S = img.shape[-1]
+        F_ = img.numel() // (S * S)
         if S % A.PATCH != 0 or (S // A.PATCH) ** 2 > 49:
             raise ValueError(f"image size {S} unsupported: need a multiple of 32 and at most 224 (positional table has 50 rows)")
         if self.graphs_enabled(img):
@@ -322,7 +414,7 @@ class _VitRunner(_Segment):
             key = (F_, S, img.device, bool(training), float(p), passes)
             sl = self._slot_for(key, lambda: self._make_slot(F_, S, img.device, training, p, passes))
             if sl is not None and not sl.busy:
-                sl.img.copy_(img)
+                sl.img.view(img.shape).copy_(img)  # one (possibly strided) copy straight into the persistent input buffer
                 sl.seed_t.fill_(seed)
 
                 def body():
@@ -333,6 +425,7 @@ class _VitRunner(_Segment):
                 self._launch(sl, "fwd", body)
                 lease = _Lease(sl) if need_grad else None
                 return sl.out.clone(), ("slot", sl, lease)
+        img = img.reshape(F_, 1, S, S).contiguous()
         stream = _stream_of(img)
         ws_bytes = lib.vc_vit_workspace_bytes(F_, S)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=img.device)
@@ -348,6 +441,7 @@ class _VitRunner(_Segment):
         return out, (call, W, ws, img)
 
     def backward(self, saved, dcls: torch.Tensor):
+        """-> gradient of the flat parameter (one tensor, same layout)."""
         lib = self.lib()
         if saved[0] == "slot":
             _, sl, lease = saved
@@ -358,102 +452,66 @@ class _VitRunner(_Segment):
 
             def body():
                 st = torch.cuda.current_stream(dev).cuda_stream
-                sl.flat.zero_()
+                sl.gflat.zero_()
                 L.check(lib.vc_vit_backward(C.byref(sl.call_b), sl.dcls.data_ptr(), sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
 
             self._launch(sl, "bwd", body)
-            grads = self.grad_views(sl.flat.clone(), self.offs)
+            g = sl.gflat.clone()
             if lease is not None:
                 lease.release()
-            return grads
+            return g
         call, W, ws, img = saved
         stream = _stream_of(img)
-        flat = torch.zeros(self.total, dtype=torch.float32, device=img.device)
-        Wg = self._weights(stream, flat)
+        gflat = torch.zeros(self.total, dtype=torch.float32, device=img.device)
+        Wg = self._weights(stream, gflat)
         call.w = C.pointer(Wg)
         sc_bytes = lib.vc_vit_scratch_bytes(call.F, call.S)
         scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=img.device)
         dcls = dcls.contiguous().float()
         L.check(lib.vc_vit_backward(C.byref(call), dcls.data_ptr(), scratch.data_ptr(), sc_bytes, stream), lib)
-        return self.grad_views(flat, self.offs)
+        return gflat
 
 
 class _SeqRunner(_Segment):
     def __init__(self, model: "AutoRegressiveTransformer"):
-        super().__init__()
-        m = self.model = model
-        r = self._register
-        self.i_es = [r(m.embed_state.weight), r(m.embed_state.bias)]
-        self.i_ei = [r(m.embed_image.weight), r(m.embed_image.bias)]
-        self.i_ip = [r(m.image_projection.weight), r(m.image_projection.bias)]
-        self.i_ea = [r(m.embed_action.weight), r(m.embed_action.bias)]
-        self.i_ts = r(m.timestep_embedding.weight) if m.enable_timestep_embedding else None
-        self.i_mv = [r(m.embed_multiview.weight), r(m.embed_multiview.bias)] if m.num_views > 0 else None
-        self.i_layers = []
-        for layer in m.transformer_decoder.layers:
-            sa, ca = layer.self_attn, layer.multihead_attn
-            ids = [r(t) for t in (sa.in_proj_weight, sa.in_proj_bias, sa.out_proj.weight, sa.out_proj.bias,
-                                  ca.in_proj_weight, ca.in_proj_bias, ca.out_proj.weight, ca.out_proj.bias,
-                                  layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
-                                  layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias,
-                                  layer.norm3.weight, layer.norm3.bias)]
-            self.i_layers.append(ids)
-        self.i_hc = [r(m.predict_action_class_0_4.weight), r(m.predict_action_class_0_4.bias)]
-        self.i_hp = [r(m.predict_action_class_0_999.weight), r(m.predict_action_class_0_999.bias)]
-        self.offs, self.total = self._layout()
+        super().__init__(model)
+        self.model = model
+        self.tag = "seq"
 
-    def used_mask(self):
+    def _weights(self, stream, gflat=None):
+        self.ensure_split(stream)
         m = self.model
-        used = [True] * len(self.params)
-        mem_has_ui = m.enable_past_actions and m.enable_past_states
-        nsrc = (1 if mem_has_ui else 0) + 1 + (1 if m.num_views > 0 else 0)
-        if not m.enable_past_states:
-            for i in self.i_es:
-                used[i] = False
-        if nsrc == 1:
-            for i in self.i_ip:
-                used[i] = False
-        if not m.enable_past_actions:
-            for i in self.i_ea:
-                used[i] = False
-        if self.i_ts is not None and not (m.enable_past_actions or m.enable_past_states):
-            used[self.i_ts] = False
-        return used
-
-    def _weights(self, stream, flat=None):
-        m, o = self.model, self.offs
         W = A.SeqWeights()
         fl = self._fill_linear
-        fl(W.embed_state, m.embed_state.weight, m.embed_state.bias, stream, flat, o, *self.i_es)
-        fl(W.embed_image, m.embed_image.weight, m.embed_image.bias, stream, flat, o, *self.i_ei)
-        fl(W.image_proj, m.image_projection.weight, m.image_projection.bias, stream, flat, o, *self.i_ip)
-        fl(W.head_params, m.predict_action_class_0_999.weight, m.predict_action_class_0_999.bias, stream, flat, o, *self.i_hp)
-        if self.i_mv is not None:
-            fl(W.embed_multiview, m.embed_multiview.weight, m.embed_multiview.bias, stream, flat, o, *self.i_mv)
-        W.embed_action_w, W.embed_action_b = m.embed_action.weight.data_ptr(), m.embed_action.bias.data_ptr()
-        W.head_cmd_w, W.head_cmd_b = m.predict_action_class_0_4.weight.data_ptr(), m.predict_action_class_0_4.bias.data_ptr()
-        if self.i_ts is not None:
-            W.timestep_emb = m.timestep_embedding.weight.data_ptr()
-        if flat is not None:
-            base = flat.data_ptr()
-            W.d_embed_action_w, W.d_embed_action_b = base + 4 * o[self.i_ea[0]], base + 4 * o[self.i_ea[1]]
-            W.d_head_cmd_w, W.d_head_cmd_b = base + 4 * o[self.i_hc[0]], base + 4 * o[self.i_hc[1]]
-            if self.i_ts is not None:
-                W.d_timestep_emb = base + 4 * o[self.i_ts]
-        nl = len(m.transformer_decoder.layers)
+        fl(W.embed_state, "embed_state.weight", "embed_state.bias", gflat)
+        fl(W.embed_image, "embed_image.weight", "embed_image.bias", gflat)
+        fl(W.image_proj, "image_projection.weight", "image_projection.bias", gflat)
+        fl(W.head_params, "predict_action_class_0_999.weight", "predict_action_class_0_999.bias", gflat)
+        if m.num_views > 0:
+            fl(W.embed_multiview, "embed_multiview.weight", "embed_multiview.bias", gflat)
+        W.embed_action_w, W.embed_action_b = self._ptr("embed_action.weight"), self._ptr("embed_action.bias")
+        W.head_cmd_w, W.head_cmd_b = self._ptr("predict_action_class_0_4.weight"), self._ptr("predict_action_class_0_4.bias")
+        if m.enable_timestep_embedding:
+            W.timestep_emb = self._ptr("timestep_embedding.weight")
+        if gflat is not None:
+            W.d_embed_action_w, W.d_embed_action_b = self._gptr(gflat, "embed_action.weight"), self._gptr(gflat, "embed_action.bias")
+            W.d_head_cmd_w = self._gptr(gflat, "predict_action_class_0_4.weight")
+            W.d_head_cmd_b = self._gptr(gflat, "predict_action_class_0_4.bias")
+            if m.enable_timestep_embedding:
+                W.d_timestep_emb = self._gptr(gflat, "timestep_embedding.weight")
+        nl = m.num_decoder_layers
         arr = (A.DecLayer * nl)()
-        for l, layer in enumerate(m.transformer_decoder.layers):
-            ids, D = self.i_layers[l], arr[l]
-            sa, ca = layer.self_attn, layer.multihead_attn
-            fl(D.sa_in, sa.in_proj_weight, sa.in_proj_bias, stream, flat, o, ids[0], ids[1])
-            fl(D.sa_out, sa.out_proj.weight, sa.out_proj.bias, stream, flat, o, ids[2], ids[3])
-            fl(D.ca_in, ca.in_proj_weight, ca.in_proj_bias, stream, flat, o, ids[4], ids[5])
-            fl(D.ca_out, ca.out_proj.weight, ca.out_proj.bias, stream, flat, o, ids[6], ids[7])
-            fl(D.lin1, layer.linear1.weight, layer.linear1.bias, stream, flat, o, ids[8], ids[9])
-            fl(D.lin2, layer.linear2.weight, layer.linear2.bias, stream, flat, o, ids[10], ids[11])
-            self._fill_norm(D.n1, layer.norm1, flat, o, ids[12], ids[13])
-            self._fill_norm(D.n2, layer.norm2, flat, o, ids[14], ids[15])
-            self._fill_norm(D.n3, layer.norm3, flat, o, ids[16], ids[17])
+        for l in range(nl):
+            pre, D = f"transformer_decoder.layers.{l}.", arr[l]
+            fl(D.sa_in, pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias", gflat)
+            fl(D.sa_out, pre + "self_attn.out_proj.weight", pre + "self_attn.out_proj.bias", gflat)
+            fl(D.ca_in, pre + "multihead_attn.in_proj_weight", pre + "multihead_attn.in_proj_bias", gflat)
+            fl(D.ca_out, pre + "multihead_attn.out_proj.weight", pre + "multihead_attn.out_proj.bias", gflat)
+            fl(D.lin1, pre + "linear1.weight", pre + "linear1.bias", gflat)
+            fl(D.lin2, pre + "linear2.weight", pre + "linear2.bias", gflat)
+            self._fill_norm(D.n1, pre + "norm1", gflat)
+            self._fill_norm(D.n2, pre + "norm2", gflat)
+            self._fill_norm(D.n3, pre + "norm3", gflat)
         W.layers = C.cast(arr, C.POINTER(A.DecLayer))
         W.num_layers = nl
         return W, arr
@@ -462,7 +520,7 @@ class _SeqRunner(_Segment):
         lib, m = self.lib(), self.model
         nv = m.num_views
         stream = torch.cuda.current_stream(dev).cuda_stream
-        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, len(m.transformer_decoder.layers), m.nhead
+        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, m.num_decoder_layers, m.nhead
         NP, NC = m.num_params * m.num_params_values, m.num_classes
         R = B * T
         sl = _Slot()
@@ -476,13 +534,13 @@ class _SeqRunner(_Segment):
         sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
         sl.cmds, sl.params = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
         sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        sl.flat = torch.zeros(self.total, **f32)
+        sl.gflat = torch.zeros(self.total, **f32)
         sl.dcmds, sl.dparams = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
         sl.d_state = torch.empty(R, A.VIT_DIM, **f32) if (has_state and m.enable_past_states) else None
         sl.d_cad = torch.empty(B, A.VIT_DIM, **f32)
         sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP, nv)
         sl.scratch = None
-        (sl.W, sl.arr), (sl.Wg, sl.arrg) = self._weights(stream), self._weights(stream, sl.flat)
+        (sl.W, sl.arr), (sl.Wg, sl.arrg) = self._weights(stream), self._weights(stream, sl.gflat)
         for name, W in (("call", sl.W), ("call_b", sl.Wg)):
             c = A.SeqCall()
             c.w = C.pointer(W)
@@ -503,7 +561,7 @@ class _SeqRunner(_Segment):
         lib, m = self.lib(), self.model
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
-        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, len(m.transformer_decoder.layers), m.nhead
+        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, m.num_decoder_layers, m.nhead
         NP, NC = m.num_params * m.num_params_values, m.num_classes
         cad_cls = cad_cls.contiguous().float()
         actions = actions.contiguous().float().reshape(B * T, -1)
@@ -554,6 +612,7 @@ class _SeqRunner(_Segment):
         return cmds, params, (c, W, arr, ws, state_cls, cad_cls, actions, mv_cls)
 
     def backward(self, saved, dcmds, dparams):
+        """-> (d state_cls, d cad_cls, d mv_cls, gradient of the flat parameter)."""
         lib, m = self.lib(), self.model
         if saved[0] == "slot":
             _, sl, lease = saved
@@ -565,25 +624,25 @@ class _SeqRunner(_Segment):
 
             def body():
                 st = torch.cuda.current_stream(dev).cuda_stream
-                sl.flat.zero_()
+                sl.gflat.zero_()
                 L.check(lib.vc_seq_backward(C.byref(sl.call_b), sl.dcmds.data_ptr(), sl.dparams.data_ptr(),
                                            sl.d_state.data_ptr() if sl.d_state is not None else None, sl.d_cad.data_ptr(),
                                            sl.d_mv.data_ptr() if sl.d_mv is not None else None,
                                            sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
 
             self._launch(sl, "bwd", body)
-            grads = self.grad_views(sl.flat.clone(), self.offs, self.used_mask())
+            g = sl.gflat.clone()
             d_state = sl.d_state.clone() if sl.d_state is not None else None
             d_cad = sl.d_cad.clone()
             d_mv = sl.d_mv.clone() if sl.d_mv is not None else None
             if lease is not None:
                 lease.release()
-            return d_state, d_cad, d_mv, grads
+            return d_state, d_cad, d_mv, g
         c, W, arr, ws, state_cls, cad_cls, actions, mv_cls = saved
         dev = cad_cls.device
         stream = _stream_of(cad_cls)
-        flat = torch.zeros(self.total, dtype=torch.float32, device=dev)
-        Wg, arrg = self._weights(stream, flat)
+        gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        Wg, arrg = self._weights(stream, gflat)
         c.w = C.pointer(Wg)
         R = c.B * c.T
         d_state = torch.empty(R, A.VIT_DIM, dtype=torch.float32, device=dev) if state_cls is not None and m.enable_past_states else None
@@ -595,26 +654,26 @@ class _SeqRunner(_Segment):
         L.check(lib.vc_seq_backward(C.byref(c), dcmds.data_ptr(), dparams.data_ptr(),
                                    d_state.data_ptr() if d_state is not None else None, d_cad.data_ptr(),
                                    d_mv.data_ptr() if d_mv is not None else None, scratch.data_ptr(), sc_bytes, stream), lib)
-        return d_state, d_cad, d_mv, self.grad_views(flat, self.offs, self.used_mask())
+        return d_state, d_cad, d_mv, gflat
 
 
 class _VitFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, training, p, seed, passes, img, *params):
-        out, saved = runner.forward(img, training, p, seed, passes, need_grad=any(ctx.needs_input_grad))
+    def forward(ctx, runner, training, p, seed, passes, img, flat):
+        out, saved = runner.forward(img, training, p, seed, passes, need_grad=ctx.needs_input_grad[6])
         ctx.runner, ctx.saved = runner, saved
         return out
 
     @staticmethod
     def backward(ctx, dcls):
-        grads = ctx.runner.backward(ctx.saved, dcls)
+        g = ctx.runner.backward(ctx.saved, dcls)
         ctx.saved = None
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, g)
 
 
 class _SeqFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, runner, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, *params):
+    def forward(ctx, runner, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, flat):
         cmds, pars, saved = runner.forward(state_cls, cad_cls, actions, B, T, training, p, seed, passes,
                                            need_grad=any(ctx.needs_input_grad), mv_cls=mv_cls)
         ctx.runner, ctx.saved = runner, saved
@@ -622,15 +681,15 @@ class _SeqFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dcmds, dparams):
-        d_state, d_cad, d_mv, grads = ctx.runner.backward(ctx.saved, dcmds, dparams)
+        d_state, d_cad, d_mv, g = ctx.runner.backward(ctx.saved, dcmds, dparams)
         ctx.saved = None
-        return (None, None, None, None, None, None, None, d_state, d_cad, d_mv, None, *grads)
+        return (None, None, None, None, None, None, None, d_state, d_cad, d_mv, None, g)
 
 
 # =====================================================================================================
 # the drop-in module
 # =====================================================================================================
-class AutoRegressiveTransformer(nn.Module):
+class AutoRegressiveTransformer(_FlatOwner):
     def __init__(self, state_dim, act_dim, hidden_size, max_length=None, max_ep_len=1000, action_tanh=True,
                  enable_past_actions=False, enable_past_states=False, enable_timestep_embedding=False, num_classes=5,
                  num_params=6, num_params_values=1000, num_decoder_layers=8, dim_feedforward=512,
@@ -669,22 +728,25 @@ class AutoRegressiveTransformer(nn.Module):
             self.state_embedding_model_size = 0
         self.cad_embedding_model = ViTParams()
         self.cad_embedding_model_size = A.VIT_DIM
-        self.embed_state = nn.Linear(self.state_embedding_model_size, hidden_size)
-        self.embed_image = nn.Linear(self.cad_embedding_model_size, hidden_size)
-        self.transformer_decoder = nn.TransformerDecoder(
+        self.num_decoder_layers = num_decoder_layers
+        tmp = nn.Module()  # the reference's own sub-modules: built for default initialisation and key names, then discarded
+        tmp.embed_state = nn.Linear(self.state_embedding_model_size, hidden_size)
+        tmp.embed_image = nn.Linear(self.cad_embedding_model_size, hidden_size)
+        tmp.transformer_decoder = nn.TransformerDecoder(
             nn.TransformerDecoderLayer(d_model=hidden_size, nhead=nhead, dim_feedforward=dim_feedforward, dropout=dropout),
             num_layers=num_decoder_layers)
-        self.predict_action_class_0_4 = nn.Linear(hidden_size, num_classes)
-        self.predict_action_class_0_999 = nn.Linear(hidden_size, num_params * num_params_values)
+        tmp.predict_action_class_0_4 = nn.Linear(hidden_size, num_classes)
+        tmp.predict_action_class_0_999 = nn.Linear(hidden_size, num_params * num_params_values)
         self.num_inputs = 1 + (1 if self.enable_past_states else 0)
         if num_views > 0:
-            self.embed_multiview = nn.Linear(self.state_embedding_model_size * num_views if self.state_embedding_model_size
-                                             else A.VIT_DIM * num_views, hidden_size)
+            tmp.embed_multiview = nn.Linear(self.state_embedding_model_size * num_views if self.state_embedding_model_size
+                                            else A.VIT_DIM * num_views, hidden_size)
             self.num_inputs += 1
-        self.image_projection = nn.Linear(hidden_size * self.num_inputs, hidden_size)
-        self.embed_action = nn.Linear(act_dim, hidden_size)
+        tmp.image_projection = nn.Linear(hidden_size * self.num_inputs, hidden_size)
+        tmp.embed_action = nn.Linear(act_dim, hidden_size)
         if self.enable_timestep_embedding:
-            self.timestep_embedding = nn.Embedding(max_ep_len, hidden_size)
+            tmp.timestep_embedding = nn.Embedding(max_ep_len, hidden_size)
+        self._init_flat(list(tmp.named_parameters()))
         self.action_mask = torch.tensor([[1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 0, 1],
                                          [0, 0, 0, 0, 0, 0]]).float().to(device)
         if self.enable_past_states and self.state_embedding_model is None:
@@ -697,6 +759,13 @@ class AutoRegressiveTransformer(nn.Module):
             st = _VitRunner(self.state_embedding_model, _SITE_STATE_VIT) if self.state_embedding_model is not None else None
             object.__setattr__(self, "_runners", (st, _VitRunner(self.cad_embedding_model, _SITE_CAD_VIT), _SeqRunner(self)))
         return self._runners
+
+    def _side_stream(self, device):
+        streams = self.__dict__.setdefault("_side_streams", {})
+        key = (device.type, device.index)
+        if key not in streams:
+            streams[key] = torch.cuda.Stream(device=device)
+        return streams[key]
 
     def _use_library_for_tests(self, lib):
         """TESTS ONLY: run the host orchestration against oracle/_build/libvc_emu.so on CPU tensors."""
@@ -745,23 +814,48 @@ class AutoRegressiveTransformer(nn.Module):
         B, T = actions.shape[0], actions.shape[1]
         training, p, passes = self.training, self.dropout_p, self._passes
         seed = self._draw_seed() if (training and p > 0) else 0
-        state_cls = None
-        if self.enable_past_states:
-            frames = ui_images.reshape(-1, *ui_images.shape[2:])
-            if frames.shape[0] != B * T:
-                raise ValueError(f"frames carry {frames.shape[0]} images but actions are [{B},{T}]")
-            state_cls = _VitFn.apply(st_r, training, p, seed, passes, frames, *st_r.params)
-        cad_cls = _VitFn.apply(cad_r, training, p, seed, passes, cad_image, *cad_r.params)
-        mv_cls = None
         if self.num_views > 0:
             # process_multiview_images (trajectory_model.py:77-87): every view goes through the CAD encoder
             if multiview_images is None:
                 raise ValueError("num_views > 0: inputs['multiview_images'] [B, num_views, 1, S, S] is required")
             if multiview_images.shape[1] != self.num_views:
                 raise ValueError(f"expected {self.num_views} views, got {multiview_images.shape[1]}")
-            views = multiview_images.reshape(-1, *multiview_images.shape[2:])
-            mv_cls = _VitFn.apply(cad_r, training, p, seed + 1 if seed else 0, passes, views, *cad_r.params)
-        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, *seq_r.params)
+
+        def cad_branch():
+            cad_cls = _VitFn.apply(cad_r, training, p, seed, passes, cad_image, cad_r.flat)
+            mv_cls = None
+            if self.num_views > 0:
+                views = multiview_images.reshape(-1, *multiview_images.shape[2:])
+                mv_cls = _VitFn.apply(cad_r, training, p, seed + 1 if seed else 0, passes, views, cad_r.flat)
+            return cad_cls, mv_cls
+
+        # The CAD encoder sees B images against the frame encoder's B*T: its kernels fill a fraction of the SMs and are
+        # latency-bound, so it runs on a second stream, concurrently with the frame encoder (autograd replays the same
+        # stream assignment in the backward, where the two encoders' backward passes are independent as well).
+        overlap = _OVERLAP and cad_image.is_cuda and self.enable_past_states and cad_r._lib is None
+        if overlap:
+            cur = torch.cuda.current_stream(cad_image.device)
+            side = self._side_stream(cad_image.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                cad_cls, mv_cls = cad_branch()
+            cad_image.record_stream(side)
+            if multiview_images is not None:
+                multiview_images.record_stream(side)
+        state_cls = None
+        if self.enable_past_states:
+            n_img = ui_images.numel() // (ui_images.shape[-1] * ui_images.shape[-2])
+            if n_img != B * T:
+                raise ValueError(f"frames carry {n_img} images but actions are [{B},{T}]")
+            state_cls = _VitFn.apply(st_r, training, p, seed, passes, ui_images, st_r.flat)
+        if overlap:
+            cur.wait_stream(side)
+            cad_cls.record_stream(cur)
+            if mv_cls is not None:
+                mv_cls.record_stream(cur)
+        else:
+            cad_cls, mv_cls = cad_branch()
+        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, seq_r.flat)
         return cmds.view(B, T, self.num_classes), params.view(B, T, self.num_params, self.num_params_values)
 
     @torch.no_grad()
