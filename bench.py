@@ -146,10 +146,30 @@ def run_reference(args, cfg):
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=torch.get_num_threads(), kind="port",
                                   sample=f"{args.steps} steps at batch {B}, host_cpus={os.cpu_count()}"),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under NCCL_DEBUG): keep a
+    private duplicate of fd 1 for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -159,6 +179,9 @@ def main():
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "bf16"])
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="trainer loss: the native fused kernels (default) or the torch restatement (videocad_b200/loss.py)")
+    ap.add_argument("--optimizer", default="fused", choices=["fused", "torch"],
+                    help="clip_grad_norm_(1.0) + Adam: the native fused step (videocad_b200.optim.ClipAdam, default) or the two "
+                         "torch calls of the reference trainer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
@@ -195,7 +218,12 @@ def main():
         # the wrapper the reference builds (experiment.py:104-109)
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
                                                         find_unused_parameters=True)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5)
+    if args.optimizer == "fused":
+        from videocad_b200.optim import ClipAdam
+
+        opt = ClipAdam(model.parameters(), lr=1e-5, max_norm=1.0)  # clip_grad_norm_(1.0) + Adam.step() in one native step
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-5)
     B, T, S = cfg["B"], cfg["T"], cfg["S"]
 
     def train_step(batch):
@@ -205,7 +233,8 @@ def main():
                   "cad_image": batch["cad_image"]}
         loss = compute_loss(net(inputs), acts[:, 1:])
         loss.backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        if args.optimizer != "fused":
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         return loss
 
@@ -350,7 +379,7 @@ def main():
                 dtype="f32 (3-pass split-bf16 tensor-core GEMMs, fp32 accumulate)" if passes == 3 else "bf16",
                 data="synthetic", impl="native",
                 config=dict(workload=f"{args.config}: {world} x (batch {B}, T={T}, {S}x{S} frames), H={cfg['model']['hidden_size']}, "
-                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0, {args.loss} loss",
+                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0, {args.loss} loss, {args.optimizer} clip+Adam",
                             global_batch=world * B, parallelism=f"dp{world}" if world > 1 else "single",
                             l2="inputs rotate over 4 distinct batches (232 MB of frames at c1 > 126 MB L2); activations (>5 GB/step) stream through HBM",
                             fwd_gflop_per_sample=f_fwd / 1e9),
@@ -360,7 +389,7 @@ def main():
                 "the same kernels run from 6 graph launches per step" % (args.steps, launches_inst // max(args.steps, 1)),
                 cuda_graphs=bool(graphs_were_on), segments_ms_per_step=segments, roofline=roofline,
                 cpu_baseline=cpu_baseline)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

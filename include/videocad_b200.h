@@ -171,6 +171,21 @@ int vc_loss_forward(const vc_loss_cfg* cfg, const float* cmds, const float* para
 int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, const float* ws,
                      const float* upstream, float* dcmds, float* dparams, void* stream);
 
+/* ---- optimizer step of the reference trainer, fused: torch.nn.utils.clip_grad_norm_(params, max_norm) followed by
+ * torch.optim.Adam(...).step() (/root/reference/trainer.py:493-494, Adam defaults betas/eps, no weight decay, no amsgrad)
+ * over a few large (flat) tensors: a squared-norm pass, a single-CTA finalize producing the clip coefficient on the device,
+ * and one update pass that reads g, p, m, v once and writes g (clipped, as clip_grad_norm_ does), p, m, v once.
+ * step is the 1-based Adam step count of this call; lr is per tensor (parameter groups). */
+#define VC_ADAM_MAX_TENSORS 16
+typedef struct vc_adam_tensor {
+  float* p; float* g; float* m; float* v;
+  int64_t n;
+  float lr;
+} vc_adam_tensor;
+size_t vc_clip_adam_scratch_floats(void);
+int vc_clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double beta1, double beta2, double eps, double max_norm,
+                      int64_t step, float* scratch, float* total_norm_out, void* stream);
+
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream);
 int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
                       int accumulate_dx, float* dW, float* db, void* stream);

@@ -528,6 +528,34 @@ int embed_action_bwd(const float* dy, const float* y, const float* actions, int6
   return 0;
 }
 
+// ---- fused clip_grad_norm_ + Adam (CPU restatement of videocad_b200/csrc/optim.cu)
+size_t clip_adam_scratch_floats() { return (size_t)VC_ADAM_MAX_TENSORS * 1024 + 8; }
+int clip_adam_step(const vc_adam_tensor* t, int nt, double beta1, double beta2, double eps, double max_norm, int64_t step, float* scratch,
+                   float* total_norm_out, stream_t) {
+  if (!t || nt <= 0 || nt > VC_ADAM_MAX_TENSORS || step < 1 || !scratch) return set_error("clip_adam_step: bad arguments");
+  double ss = 0;
+  for (int i = 0; i < nt; ++i)
+    for (int64_t k = 0; k < t[i].n; ++k) ss += (double)t[i].g[k] * t[i].g[k];
+  const float total = (float)sqrt(ss);
+  float coef = 1.f;
+  if (max_norm > 0) coef = fminf((float)max_norm / (total + 1e-6f), 1.f);
+  if (total_norm_out) total_norm_out[0] = total;
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const float b2 = (float)beta2, omb1 = (float)(1.0 - beta1), omb2 = (float)(1.0 - beta2), e = (float)eps, bc2s = (float)sqrt(bc2);
+  for (int i = 0; i < nt; ++i) {
+    const float step_size = (float)((double)t[i].lr / bc1);
+    for (int64_t k = 0; k < t[i].n; ++k) {
+      float g = t[i].g[k] * coef, m = t[i].m[k], v = t[i].v[k];
+      m = m + omb1 * (g - m);
+      v = v * b2 + omb2 * g * g;
+      const float denom = sqrtf(v) / bc2s + e;
+      t[i].p[k] = t[i].p[k] - step_size * (m / denom);
+      t[i].g[k] = g; t[i].m[k] = m; t[i].v[k] = v;
+    }
+  }
+  return 0;
+}
+
 // ---- fused training loss (CPU restatement of videocad_b200/csrc/loss.cu; same workspace layout)
 size_t loss_workspace_floats(int R, int NP) { return (size_t)4 * R * NP + (size_t)3 * R + 16; }
 

@@ -135,6 +135,12 @@ int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* par
   return vck::loss_backward(*cfg, cmds, params, targets, ws, upstream, dcmds, dparams, stream);
 }
 
+size_t vc_clip_adam_scratch_floats(void) { return vck::clip_adam_scratch_floats(); }
+int vc_clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double beta1, double beta2, double eps, double max_norm,
+                      int64_t step, float* scratch, float* total_norm_out, void* stream) {
+  return vck::clip_adam_step(tensors, num_tensors, beta1, beta2, eps, max_norm, step, scratch, total_norm_out, stream);
+}
+
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream) {
   return vck::head_small_fwd(x, R, H, W, b, C, out, stream);
 }

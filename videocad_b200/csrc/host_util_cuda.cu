@@ -72,8 +72,8 @@ int gemm_profile_read(double* total_ms, double* total_flops, long long* launches
 }
 
 namespace {
-constexpr int kSide = 2, kEvents = 64;
-cudaStream_t g_side[kSide] = {nullptr, nullptr};
+constexpr int kSide = 4, kEvents = 128;  // 0,1: sequence transformer; 2,3: image encoders
+cudaStream_t g_side[kSide] = {nullptr, nullptr, nullptr, nullptr};
 cudaEvent_t g_ev[kEvents];
 bool g_side_init = false;
 int g_ev_next = 0;

@@ -126,6 +126,11 @@ int loss_forward(const LossCfg& cfg, const float* cmds, const float* params, con
 int loss_backward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, const float* ws,
                   const float* upstream, float* dcmds, float* dparams, stream_t s);
 
+// fused clip_grad_norm_ + Adam step (see include/videocad_b200.h, vc_clip_adam_step)
+size_t clip_adam_scratch_floats();
+int clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double beta1, double beta2, double eps, double max_norm, int64_t step,
+                   float* scratch, float* total_norm_out, stream_t s);
+
 int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t s);
 // dx[r,:] (+)= dout[r,:] W ; dW += dout^T x ; db += colsum(dout)   (dW/db accumulated, pre-zeroed)
 int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx, int accumulate_dx,
@@ -133,7 +138,7 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
 
 // fork/join onto auxiliary streams, so that small independent kernels (decoder-sized wgrad GEMMs, K/V projections)
 // can run next to the critical chain instead of serialising behind it.  Works under CUDA-graph capture (event edges).
-//   stream_fork: auxiliary stream `i` (0..1) first waits for everything enqueued so far on `main`; returned in *side
+//   stream_fork: auxiliary stream `i` (0..3) first waits for everything enqueued so far on `main`; returned in *side
 //   stream_join: `main` waits for everything enqueued so far on auxiliary stream `i`
 // The CPU emulation returns `main` itself (everything is serial there).
 int stream_fork(stream_t main, int i, stream_t* side);

@@ -31,6 +31,11 @@ class LossCfg(C.Structure):
                 ("tolerance", C.c_int * 8), ("param_to_label", C.c_int * 8)]
 
 
+class AdamTensor(C.Structure):
+    """mirror of vc_adam_tensor"""
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("lr", C.c_float)]
+
+
 class GemmDesc(C.Structure):
     _fields_ = [
         ("a_hi", vp), ("a_lo", vp), ("lda", i64), ("a_mn_major", i32),
@@ -92,6 +97,8 @@ _PROTOS = {
     "vc_loss_workspace_floats": ([i32, i32], C.c_size_t),
     "vc_loss_forward": ([vp, vp, vp, vp, vp, vp, vp], i32),
     "vc_loss_backward": ([vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
+    "vc_clip_adam_scratch_floats": ([], C.c_size_t),
+    "vc_clip_adam_step": ([vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp, vp, vp], i32),
     "vc_head_small_fwd": ([vp, i64, i32, vp, vp, i32, vp, vp], i32),
     "vc_head_small_bwd": ([vp, vp, i64, i32, vp, i32, vp, i32, vp, vp, vp], i32),
     "vc_add_f32": ([vp, vp, vp, i64, vp], i32),
