@@ -58,6 +58,13 @@ def fwd_flops_per_sample(cfg, T, S):
     return T * f_vit + f_vit + glue + dec + head
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_tc_pair_kernel launch (to_qkv forward, M=12800 N=3072 K=512), from the
+# `ncu --set full` capture summarised in profiles/ (see profiles/README.md); None until a capture exists
+PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH = 136857600
+PAIR_KERNEL_TRAFFIC_NOTE = ("profiles/r01h_ncu_gemm_pair_qkv_fwd_summary.txt: 32.5 MB read (= the split-bf16 operands, read once) + 104.3 MB written "
+                            "of the 157.3 MB fp32 output (the rest was still in L2 when the kernel ended); algorithmic bytes 189.8 MB")
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -297,6 +304,9 @@ def main():
     # replay off) so that a CUDA-event pair can be recorded around every GEMM launch on the launching stream
     graphs_were_on = vmodel._GRAPHS
     vmodel._GRAPHS = False
+    overlap_was_on = vmodel._OVERLAP
+    vmodel._OVERLAP = False          # per-launch durations need the kernels one after the other: no second encoder stream,
+    lib.vc_side_streams_enable(0)    # no auxiliary streams inside the library
     train_step(dev_batches[0])
     ms_inst, launches_inst = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps, profile_gemm=True)
     g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
@@ -306,6 +316,8 @@ def main():
     if os.environ.get("VC_GEMM_DUMP"):
         lib.vc_gemm_profile_dump(os.environ["VC_GEMM_DUMP"].encode())
     lib.vc_gemm_profile(0)
+    lib.vc_side_streams_enable(1)
+    vmodel._OVERLAP = overlap_was_on
     vmodel._GRAPHS = graphs_were_on
     if not graphs_were_on:
         launches = launches_inst
@@ -356,18 +368,25 @@ def main():
     gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
     step_tflops = value / world * 3.0 * f_fwd / T / 1e12  # per GPU, whole step (fwd + 2x bwd) algorithmic
     passes = 3 if args.precision == "fp32x3" else 1
-    roofline = dict(bound="tensor", kernel="gemm_tc_kernel<128> (tcgen05, split-bf16)", achieved=gemm_tflops, peak=peak["tflops"],
-                    unit="TFLOP/s", frac=gemm_tflops / peak["tflops"], traffic=None, peak_source=peak["source"],
-                    mma_passes_per_flop=passes, mma_issue_frac=passes * gemm_tflops / peak["tflops"],
-                    gemm_launches_per_step=g_n.value / args.steps, gemm_ms_per_step=g_ms.value / args.steps,
-                    gemm_share_of_step=(g_ms.value / args.steps) / (ms / args.steps),
-                    large_gemms=dict(note="launches of >= 5 GFLOP (the image-encoder GEMMs, %.0f%% of all GEMM FLOPs)" %
-                                     (100.0 * b_fl.value / max(g_fl.value, 1.0)),
-                                     launches_per_step=b_n.value / args.steps, ms_per_step=b_ms.value / args.steps,
-                                     achieved=(b_fl.value / 1e12) / (b_ms.value / 1e3) if b_ms.value > 0 else 0.0,
-                                     frac=((b_fl.value / 1e12) / (b_ms.value / 1e3) / peak["tflops"]) if b_ms.value > 0 else 0.0),
-                    measured_in=f"instrumented pass of the same {args.steps} steps without CUDA-graph replay "
-                                f"({ms_inst / args.steps:.2f} ms/step); the headline value uses graph replay",
+    big_tflops = (b_fl.value / 1e12) / (b_ms.value / 1e3) if b_ms.value > 0 else 0.0
+    pair_launches = lib.vc_gemm_pair_launch_count()
+    # dominant kernel: the 2-SM 256x256 GEMM (gemm_tc_pair_kernel) that runs every image-encoder GEMM of >= 5 GFLOP
+    roofline = dict(bound="tensor", kernel="gemm_tc_pair_kernel (tcgen05 cta_group::2, 256x256 tiles, split-bf16 x3)",
+                    achieved=big_tflops, peak=peak["tflops"], unit="TFLOP/s", frac=big_tflops / peak["tflops"],
+                    traffic=PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH, traffic_note=PAIR_KERNEL_TRAFFIC_NOTE,
+                    peak_source=peak["source"], mma_passes_per_flop=passes, mma_issue_frac=passes * big_tflops / peak["tflops"],
+                    launches_per_step=b_n.value / args.steps, ms_per_step=b_ms.value / args.steps,
+                    share_of_step=(b_ms.value / args.steps) / (ms_inst / args.steps),
+                    flops_share_of_all_gemms=b_fl.value / max(g_fl.value, 1.0),
+                    algorithmic_flops="2*M*N*K per launch (SURVEY.md 8(d)); each is issued as 3 bf16 MMA passes",
+                    all_gemms=dict(note="every tensor-core GEMM launch of the step, decoder-sized ones included",
+                                   launches_per_step=g_n.value / args.steps, ms_per_step=g_ms.value / args.steps,
+                                   achieved=gemm_tflops, frac=gemm_tflops / peak["tflops"],
+                                   share_of_step=(g_ms.value / args.steps) / (ms_inst / args.steps)),
+                    pair_kernel_launches_total=int(pair_launches),
+                    measured_in=f"instrumented pass of the same {args.steps} steps without CUDA-graph replay and without stream overlap "
+                                f"({ms_inst / args.steps:.2f} ms/step, one CUDA-event pair per GEMM launch on the launching stream); "
+                                "the headline value uses graph replay",
                     whole_step_algorithmic_tflops_per_gpu=step_tflops, whole_step_frac=step_tflops / peak["tflops"])
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -91,6 +91,7 @@ int vc_is_cuda_build(void);
 long long vc_launch_count(void);
 void vc_launch_count_reset(void);
 long long vc_gemm_pair_launch_count(void);           /* GEMM launches that used the 2-SM (cta_group::2) 256x256 kernel */
+void vc_side_streams_enable(int enable);           /* 0: run auxiliary-stream work on the caller's stream (per-kernel timing); default 1 */
 void vc_gemm_profile(int enable);                  /* enable/disable + clear the event pool */
 int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches); /* synchronises the events */
 int vc_gemm_profile_read_min(double min_flops, double* total_ms, double* total_flops, long long* launches); /* only launches >= min_flops */

@@ -16,6 +16,7 @@ int vc_is_cuda_build(void) { return VC_CUDA_BUILD; }
 long long vc_launch_count(void) { return vck::launch_count(); }
 void vc_launch_count_reset(void) { vck::launch_count_reset(); }
 long long vc_gemm_pair_launch_count(void) { return vck::pair_launch_count(); }
+void vc_side_streams_enable(int enable) { vck::side_streams_enable(enable); }
 void vc_gemm_profile(int enable) { vck::gemm_profile_enable(enable); }
 int vc_gemm_profile_read(double* total_ms, double* total_flops, long long* launches) {
   return vck::gemm_profile_read(total_ms, total_flops, launches);

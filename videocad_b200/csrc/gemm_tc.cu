@@ -99,8 +99,12 @@ enum : uint32_t {
 };
 
 // Epilogue math on 4 consecutive columns of one output row, in the COALESCED layout (8 lanes cover 128 B of a row).
+// `pre_res` / `pre_aux`: the residual / activation-backward operand of this quad when the caller has already loaded them
+// (the pair kernel issues those global loads before it waits for TMEM, see below); otherwise they are loaded here.
 template <uint32_t F>
-__device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias) {
+__device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias,
+                                              bool use_pre_res = false, float4 pre_res = float4{0.f, 0.f, 0.f, 0.f},
+                                              bool use_pre_aux = false, float4 pre_aux = float4{0.f, 0.f, 0.f, 0.f}) {
   if constexpr ((F & EF_BIAS) != 0) {
     if (p.bias != nullptr && add_bias) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
@@ -136,10 +140,10 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   if constexpr ((F & EF_ACTBWD) != 0) {
     if (p.act_backward) {
       if (p.act == ACT_GELU) {
-        const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+        const float4 a = use_pre_aux ? pre_aux : *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
         v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
       } else if (p.act == ACT_TANH) {
-        const float4 a = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+        const float4 a = use_pre_aux ? pre_aux : *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
         v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
       } else if (p.act == ACT_RELU) {
         const uint2 a = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
@@ -152,7 +156,7 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   }
   if constexpr ((F & EF_RES) != 0) {
     if (p.residual != nullptr) {
-      const float4 b = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
+      const float4 b = use_pre_res ? pre_res : *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
       v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
   }
@@ -424,16 +428,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // (64 KiB per k-block per SM in split-bf16 mode), not by the tensor pipe.
 //   warp 0      TMA producer (both CTAs; transaction bytes of both land on the LEADER's full barrier)
 //   warp 1      MMA issuer (leader CTA only); tcgen05.commit multicasts stage-free / accumulator-ready to both CTAs
-//   warps 2..9  epilogue: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4; 16-column chunks
+//   warps 2..   epilogue (EW = 8 or 16 warps): TMEM lane quarter = warp % 4, column group = (warp - 2) / 4; 16-column chunks
+//               staged through an XOR-swizzled (unpadded) 32 x 16 fp32 buffer per warp
 // ---------------------------------------------------------------------------------------------------
 constexpr int P_BM = 256, P_BN = 256;
-constexpr int P_THREADS = 320;
+constexpr int P_MAX_EW = 16;                         // epilogue warps per CTA (template parameter EW: 8 or 16)
 constexpr int P_STAGES = 3;
 constexpr int P_TILE_BYTES = 128 * BK * 2;           // 16 KiB: one 128-row operand tile (hi or lo)
 constexpr int P_STAGE_BYTES = 4 * P_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int P_CW = 16;                             // epilogue chunk width (columns)
-constexpr int P_STG_LD = 20;                         // floats per staged row (80 B)
-constexpr int P_STG_BYTES = 8 * 32 * P_STG_LD * 4;
+constexpr int P_STG_LD = 16;                         // floats per staged row: unpadded, float4 slots XOR-swizzled by (row >> 1) & 3
+constexpr int P_STG_BYTES = P_MAX_EW * 32 * P_STG_LD * 4;
 constexpr int P_BAR_BYTES = 256;
 constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + P_BAR_BYTES + 1024;
 constexpr int P_TMEM_COLS = 512;                     // two 256-column accumulator stages
@@ -448,8 +453,8 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
-template <uint32_t F>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+template <uint32_t F, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GemmParams p) {
@@ -483,7 +488,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps x 2 CTAs
+      mbar_init(&tempty_bar[i], 2 * EW);  // EW epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -603,7 +608,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   } else {
     // ------------------------------------------------ epilogue warps (this CTA's 128 rows x 256 columns)
     const int g = warp & 3;          // TMEM lane quarter this warp may access
-    const int hc = (warp - 2) >> 2;  // column half
+    const int hc = (warp - 2) >> 2;  // column group
+    constexpr int kCols = P_BN * 4 / EW;  // columns per epilogue warp: 128 (EW = 8) or 64 (EW = 16)
     const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
@@ -613,18 +619,41 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int t2 = tile / num_n;
       const int m_idx = t2 % num_m;
       const int split = t2 / num_m;
-      const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + hc * 128;
+      const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + hc * kCols;
       const uint32_t a = acc_it & 1u;
       const uint32_t aph = (acc_it >> 1) & 1u;
       mbar_wait_cluster(&tfull_bar[a], aph);
       tc_fence_after();
-      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? 2 : 4;  // bound the code size
+      constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
-      for (int c = 0; c < 128 / P_CW; ++c) {
+      for (int c = 0; c < kCols / P_CW; ++c) {
+        // The epilogue is latency-bound (4 warps per scheduler, each iteration behind a global load): issue this chunk's
+        // residual / activation-backward operand loads first, so that they fly during the TMEM read and the staging.
+        constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
+        float4 pres[kPreRes ? 4 : 1], paux[kPreAux ? 4 : 1];
+        bool has_res = false, has_aux = false;
+        {
+          const int pcol = n0 + c * P_CW + 4 * (lane & 3);
+          if constexpr (kPreRes) has_res = p.residual != nullptr;
+          if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
+            const bool ok = prow < p.M && pcol < p.N;
+            if constexpr (kPreRes) {
+              pres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_res && ok) pres[it] = *reinterpret_cast<const float4*>(p.residual + prow * p.ld_res + pcol);
+            }
+            if constexpr (kPreAux) {
+              paux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_aux && ok) paux[it] = *reinterpret_cast<const float4*>(p.act_aux + prow * p.ld_act_aux + pcol);
+            }
+          }
+        }
         uint32_t r[P_CW];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * 128 + c * P_CW, r);
+        tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW, r);
         tmem_ld_wait();
-        if (c == 128 / P_CW - 1) {
+        if (c == kCols / P_CW - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(a ? tempty_remote1 : tempty_remote0);
@@ -633,8 +662,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         float* myrow = stg + lane * P_STG_LD;
 #pragma unroll
         for (int q = 0; q < P_CW / 4; ++q)
-          *reinterpret_cast<float4*>(myrow + 4 * q) = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                                  __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+          *reinterpret_cast<float4*>(myrow + 4 * (q ^ ((lane >> 1) & 3))) =
+              make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         __syncwarp();
         const int q = lane & 3;
         const int col = col0 + 4 * q;
@@ -644,9 +673,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const int rr = it * 8 + (lane >> 2);
           const long long row = (long long)m0 + g * 32 + rr;
           if (row < p.M && col < p.N) {
-            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * q);
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ ((rr >> 1) & 3)));
             float v[4] = {t4.x, t4.y, t4.z, t4.w};
-            epilogue_quad<F>(p, v, row, col, split == 0);
+            epilogue_quad<F>(p, v, row, col, split == 0, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
+                             paux[kPreAux ? it : 0]);
             if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
           }
         }
@@ -912,15 +942,32 @@ int make_operand_maps(const GemmDesc& d, CUtensorMap& tA_hi, CUtensorMap& tA_lo,
   return rc;
 }
 
+int pair_epilogue_warps() {
+  static int ew = 0;
+  if (ew == 0) {
+    const char* e = getenv("VC_GEMM_PAIR_EW");
+    ew = (e && atoi(e) == 8) ? 8 : 16;
+  }
+  return ew;
+}
+
+template <uint32_t F, int EW>
+int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream);
+
 template <uint32_t F>
 int launch_gemm_pair_variant(const GemmDesc& d, int splitk, cudaStream_t stream) {
+  return pair_epilogue_warps() == 8 ? launch_gemm_pair_ew<F, 8>(d, splitk, stream) : launch_gemm_pair_ew<F, 16>(d, splitk, stream);
+}
+
+template <uint32_t F, int EW>
+int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   GemmParams p;
   fill_params(p, d, splitk);
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, 128)) return rc;  // each CTA stages 128 of the tile's 256 B rows
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     attr_set = true;
   }
@@ -932,7 +979,7 @@ int launch_gemm_pair_variant(const GemmDesc& d, int splitk, cudaStream_t stream)
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  gemm_tc_pair_kernel<F><<<grid, P_THREADS, P_SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  gemm_tc_pair_kernel<F, EW><<<grid, 64 + 32 * EW, P_SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
   count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_pair_kernel");

@@ -93,9 +93,16 @@ cudaEvent_t next_event() {
 }
 }  // namespace
 
+static bool g_side_enabled = true;
+void side_streams_enable(int enable) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_side_enabled = enable != 0;
+}
+
 int stream_fork(void* main_s, int i, void** side) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (i < 0 || i >= kSide) return set_error("stream_fork: bad index");
+  if (!g_side_enabled) { *side = main_s; return 0; }  // serialised mode (per-kernel timing): everything on the caller's stream
   if (int rc = side_init()) return rc;
   cudaEvent_t e = next_event();
   if (cudaEventRecord(e, reinterpret_cast<cudaStream_t>(main_s)) != cudaSuccess) return set_error("stream_fork: event record failed");
@@ -107,6 +114,7 @@ int stream_fork(void* main_s, int i, void** side) {
 int stream_join(void* main_s, int i) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (i < 0 || i >= kSide) return set_error("stream_join: bad index");
+  if (!g_side_enabled) return 0;
   if (int rc = side_init()) return rc;
   cudaEvent_t e = next_event();
   if (cudaEventRecord(e, g_side[i]) != cudaSuccess) return set_error("stream_join: event record failed");

@@ -143,6 +143,8 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
 // The CPU emulation returns `main` itself (everything is serial there).
 int stream_fork(stream_t main, int i, stream_t* side);
 int stream_join(stream_t main, int i);
+// 0: stream_fork hands back the caller's stream (serialised execution, used when timing kernels one by one); 1: default
+void side_streams_enable(int enable);
 
 // misc
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s);  // out = a + b (b may alias out)

@@ -70,6 +70,7 @@ _PROTOS = {
     "vc_launch_count": ([], C.c_longlong),
     "vc_launch_count_reset": ([], None),
     "vc_gemm_pair_launch_count": ([], C.c_longlong),
+    "vc_side_streams_enable": ([i32], None),
     "vc_gemm_profile": ([i32], None),
     "vc_gemm_profile_read": ([C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], i32),
     "vc_gemm_profile_read_min": ([C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)], i32),
