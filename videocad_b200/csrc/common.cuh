@@ -175,23 +175,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster (shared::cluster address).  Default semantics, as CUTLASS'
+// ClusterBarrier::arrive(cta_id): the TMEM hand-off it guards is ordered by tcgen05.fence::before/after_thread_sync, and an
+// explicit .release.cluster / .acquire.cluster pair costs a MEMBAR on this side and an L1 invalidation (CCTL.IVALL) after
+// every successful wait on the other (ncu: the largest stall of the pair kernel's first version).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair into its OWN shared memory; the transaction bytes are counted on the mbarrier at
 // `bar_cluster_addr` (a shared::cluster address: the leader CTA's barrier)

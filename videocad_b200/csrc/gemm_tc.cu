@@ -519,7 +519,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1u;
-          mbar_wait_cluster(&empty_bar[s], ph ^ 1u);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* st = tiles + s * P_STAGE_BYTES;
           uint8_t* sA_hi = st;
           uint8_t* sA_lo = st + P_TILE_BYTES;
@@ -555,7 +555,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       for (uint32_t j = 0; j < (uint32_t)P_STAGES; ++j, ++it) {
         const uint32_t s = it % P_STAGES;
         const uint32_t ph = (it / P_STAGES) & 1u;
-        mbar_wait_cluster(&empty_bar[s], ph ^ 1u);
+        mbar_wait(&empty_bar[s], ph ^ 1u);
       }
     }
     __syncwarp();
@@ -574,13 +574,13 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         const uint32_t a = acc_it & 1u;
         const uint32_t aph = (acc_it >> 1) & 1u;
-        mbar_wait_cluster(&tempty_bar[a], aph ^ 1u);
+        mbar_wait(&tempty_bar[a], aph ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * P_BN;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1u;
-          mbar_wait_cluster(&full_bar[s], ph);
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sA_hi = smem_u32(tiles + s * P_STAGE_BYTES);
           const uint32_t sA_lo = sA_hi + P_TILE_BYTES;
@@ -622,7 +622,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + hc * kCols;
       const uint32_t a = acc_it & 1u;
       const uint32_t aph = (acc_it >> 1) & 1u;
-      mbar_wait_cluster(&tfull_bar[a], aph);
+      mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
