@@ -13,6 +13,7 @@
 #include <math.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 #include "attention_vit.h"
 
@@ -68,6 +69,7 @@ template <int DMAX>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(const AttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, long long ldo,
                 float* __restrict__ lse_out) {
+  pdl_grid_sync();
   constexpr int QB = AttCfg<DMAX>::QB_F, KT = AttCfg<DMAX>::KT_F, LDS = DMAX + 1;
   constexpr int CPT = DMAX > ATT_THREADS ? DMAX / ATT_THREADS : 1;  // columns per thread
   constexpr int RG = DMAX < ATT_THREADS ? ATT_THREADS / DMAX : 1;   // row groups
@@ -180,6 +182,7 @@ attn_bwd_kernel(const AttnP p, const __nv_bfloat16* __restrict__ o_hi, const __n
                 long long ldo, const float* __restrict__ lse, const float* __restrict__ dout, long long lddo,
                 float* __restrict__ dq, long long lddq, float* __restrict__ dk, long long lddk, float* __restrict__ dv,
                 long long lddv) {
+  pdl_grid_sync();
   constexpr int QB = AttCfg<DMAX>::QB_B, KT = AttCfg<DMAX>::KT_B, LDS = DMAX + 1;
   constexpr int CPT = DMAX > ATT_THREADS ? DMAX / ATT_THREADS : 1;
   constexpr int CW = DMAX < ATT_THREADS ? DMAX : ATT_THREADS;  // threads along columns
@@ -323,7 +326,7 @@ int launch_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float
     configured = 200 * 1024;
   }
   const int qblocks = (a.Tq + QB - 1) / QB;
-  attn_fwd_kernel<DMAX><<<a.B * a.nh * qblocks, ATT_THREADS, smem, st>>>(make_params(a), reinterpret_cast<__nv_bfloat16*>(o_hi),
+  VC_LAUNCH((attn_fwd_kernel<DMAX>), a.B * a.nh * qblocks, ATT_THREADS, smem, st, make_params(a), reinterpret_cast<__nv_bfloat16*>(o_hi),
                                                                         reinterpret_cast<__nv_bfloat16*>(o_lo), ldo, lse);
   return check_launch("attn_fwd_kernel");
 }
@@ -340,7 +343,7 @@ int launch_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_
     configured = true;
   }
   if (smem > 200 * 1024) return set_error("attention_bwd: sequence too long");
-  attn_bwd_kernel<DMAX><<<a.B * a.nh, ATT_THREADS, smem, st>>>(
+  VC_LAUNCH((attn_bwd_kernel<DMAX>), a.B * a.nh, ATT_THREADS, smem, st, 
       make_params(a), reinterpret_cast<const __nv_bfloat16*>(o_hi), reinterpret_cast<const __nv_bfloat16*>(o_lo), ldo, lse,
       dout, lddo, dq, lddq, dk, lddk, dv, lddv);
   return check_launch("attn_bwd_kernel");

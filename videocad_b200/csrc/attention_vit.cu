@@ -11,6 +11,7 @@
 #include <math.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 
 namespace vck {
@@ -204,6 +205,7 @@ __device__ __forceinline__ void c_to_a(const float (&c)[8][4], uint32_t (&ah)[4]
 __global__ void __launch_bounds__(VA_THREADS)
 vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, long long ldo,
                         float* __restrict__ lse_out) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* Kh = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* Kl = Kh + NT * LDH;
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(VA_THREADS)
 vit_attn_bwd_mma_kernel(const VitAttnP p, const float* __restrict__ lse, const float* __restrict__ dout,
                         const __nv_bfloat16* __restrict__ dout_hi, const __nv_bfloat16* __restrict__ dout_lo, long long lddo,
                         const VitBwdOut out) {
+  pdl_grid_sync();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16 *Qh = base, *Ql = Qh + NT * LDH, *Kh = Ql + NT * LDH, *Kl = Kh + NT * LDH, *Vh = Kl + NT * LDH, *Vl = Vh + NT * LDH,
@@ -512,7 +515,7 @@ int vit_attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     configured = true;
   }
-  vit_attn_fwd_mma_kernel<<<a.B * a.nh, VA_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(s)>>>(
+  VC_LAUNCH((vit_attn_fwd_mma_kernel), a.B * a.nh, VA_THREADS, FWD_SMEM, reinterpret_cast<cudaStream_t>(s), 
       make_p(a), reinterpret_cast<__nv_bfloat16*>(o_hi), reinterpret_cast<__nv_bfloat16*>(o_lo), ldo, lse);
   return check_launch("vit_attn_fwd_mma_kernel");
 }
@@ -529,7 +532,7 @@ static int launch_vit_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     configured = true;
   }
-  vit_attn_bwd_mma_kernel<<<a.B * a.nh, VA_THREADS, BWD_SMEM, reinterpret_cast<cudaStream_t>(s)>>>(
+  VC_LAUNCH((vit_attn_bwd_mma_kernel), a.B * a.nh, VA_THREADS, BWD_SMEM, reinterpret_cast<cudaStream_t>(s), 
       make_p(a), lse, dout,
       reinterpret_cast<const __nv_bfloat16*>(dout_hi), reinterpret_cast<const __nv_bfloat16*>(dout_lo), lddo, out);
   return check_launch("vit_attn_bwd_mma_kernel");

@@ -23,6 +23,7 @@
 #include <functional>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 #include "gemm_profile.h"
 
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const GemmParams p) {
+  pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -231,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int num_m = (p.M + BM - 1) / BM;
   const int num_n = (p.N + BN - 1) / BN;
@@ -458,6 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GemmParams p) {
+  pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);  // used in the leader CTA only
   uint64_t* empty_bar = full_bar + P_STAGES;
@@ -497,6 +501,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   const int num_m = (p.M + P_BM - 1) / P_BM;
   const int num_n = (p.N + P_BN - 1) / P_BN;
@@ -862,7 +867,7 @@ int launch_gemm_variant(const GemmDesc& d, cudaStream_t stream) {
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  gemm_tc_kernel<BN, F><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  VC_LAUNCH((gemm_tc_kernel<BN, F>), grid, GEMM_THREADS, C::SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_kernel");
 }
@@ -979,7 +984,7 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  gemm_tc_pair_kernel<F, EW><<<grid, 64 + 32 * EW, P_SMEM_BYTES, stream>>>(tA_hi, tA_lo, tB_hi, tB_lo, p);
+  VC_LAUNCH((gemm_tc_pair_kernel<F, EW>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
   count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_pair_kernel");

@@ -12,6 +12,7 @@
 #include <math.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 
 namespace vck {
@@ -64,6 +65,7 @@ __device__ __forceinline__ void window_of(const LossCfg& c, int i, float target,
 
 __global__ void __launch_bounds__(LT) loss_rows_kernel(const LossCfg c, const float* __restrict__ cmds, const float* __restrict__ params,
                                                        const float* __restrict__ targets, LossWs w) {
+  pdl_grid_sync();
   __shared__ float red[LT / 32];
   __shared__ float redv[LT / 32];
   __shared__ int redi[LT / 32];
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(LT) loss_rows_kernel(const LossCfg c, const fl
 
 // one CTA: fixed-order reductions over the rows, the scalar loss, and the per-term gradient coefficients
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const LossCfg c, LossWs w, float* __restrict__ loss_out) {
+  pdl_grid_sync();
   __shared__ float red[256];
   __shared__ float terms[VC_LOSS_MAX_PARAMS + 2];
   auto reduce = [&](const float* src, int stride, int off) -> float {
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const LossCfg c, Los
 __global__ void __launch_bounds__(LT) loss_grad_kernel(const LossCfg c, const float* __restrict__ cmds, const float* __restrict__ params,
                                                        const float* __restrict__ targets, LossWs w, const float* __restrict__ upstream,
                                                        float* __restrict__ dcmds, float* __restrict__ dparams) {
+  pdl_grid_sync();
   const int r = blockIdx.x, i = blockIdx.y;
   const int ldt = 1 + c.NP;
   const float up = upstream[0];
@@ -211,9 +215,9 @@ int loss_forward(const LossCfg& cfg, const float* cmds, const float* params, con
   if (!cmds || !params || !targets || !ws || !loss_out) return set_error("loss_forward: null argument");
   const LossWs w = carve(ws, cfg.R, cfg.NP);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
-  loss_rows_kernel<<<dim3(cfg.R, cfg.NP + 1), LT, 0, st>>>(cfg, cmds, params, targets, w);
+  VC_LAUNCH((loss_rows_kernel), dim3(cfg.R, cfg.NP + 1), LT, 0, st, cfg, cmds, params, targets, w);
   if (int rc = check_launch("loss_rows_kernel")) return rc;
-  loss_finalize_kernel<<<1, 256, 0, st>>>(cfg, w, loss_out);
+  VC_LAUNCH((loss_finalize_kernel), 1, 256, 0, st, cfg, w, loss_out);
   return check_launch("loss_finalize_kernel");
 }
 
@@ -222,7 +226,7 @@ int loss_backward(const LossCfg& cfg, const float* cmds, const float* params, co
   if (int rc = check_cfg(cfg)) return rc;
   if (!cmds || !params || !targets || !ws || !upstream || !dcmds || !dparams) return set_error("loss_backward: null argument");
   const LossWs w = carve(const_cast<float*>(ws), cfg.R, cfg.NP);
-  loss_grad_kernel<<<dim3(cfg.R, cfg.NP + 1), LT, 0, reinterpret_cast<cudaStream_t>(s)>>>(cfg, cmds, params, targets, w, upstream, dcmds,
+  VC_LAUNCH((loss_grad_kernel), dim3(cfg.R, cfg.NP + 1), LT, 0, reinterpret_cast<cudaStream_t>(s), cfg, cmds, params, targets, w, upstream, dcmds,
                                                                                         dparams);
   return check_launch("loss_grad_kernel");
 }

@@ -6,6 +6,7 @@
 #include <math.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 
 namespace vck {
@@ -16,6 +17,7 @@ constexpr int kPartials = 1024;  // per-tensor partial sums of squares
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) sqnorm_partial_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
+  pdl_grid_sync();
   __shared__ float red[kThreads / 32];
   float acc = 0.f;
   const long long n4 = n >> 2;
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(kThreads) sqnorm_partial_kernel(const float* _
 // scal[0] = total norm, scal[1] = clip coefficient (clamped to 1)
 __global__ void __launch_bounds__(kThreads) clip_finalize_kernel(const float* __restrict__ partials, int count, float max_norm,
                                                                   float* __restrict__ scal, float* __restrict__ total_norm_out) {
+  pdl_grid_sync();
   __shared__ float red[kThreads];
   float a = 0.f;
   for (int i = threadIdx.x; i < count; i += kThreads) a += partials[i];
@@ -75,6 +78,7 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
 __global__ void __launch_bounds__(kThreads) adam_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                                 float* __restrict__ v, long long n, const float* __restrict__ scal,
                                                                 AdamScalars a) {
+  pdl_grid_sync();
   const float coef = scal[1];
   const long long n4 = n >> 2;
   float4 *p4 = reinterpret_cast<float4*>(p), *g4 = reinterpret_cast<float4*>(g), *m4 = reinterpret_cast<float4*>(m),
@@ -111,11 +115,11 @@ int clip_adam_step(const vc_adam_tensor* t, int nt, double beta1, double beta2, 
     long long blocks = (t[i].n / 4 + kThreads * 4 - 1) / (kThreads * 4);
     if (blocks < 1) blocks = 1;
     if (blocks > kPartials) blocks = kPartials;
-    sqnorm_partial_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(t[i].g, t[i].n, scratch + count);
+    VC_LAUNCH((sqnorm_partial_kernel), (unsigned)blocks, kThreads, 0, st, t[i].g, t[i].n, scratch + count);
     if (int rc = check_launch("sqnorm_partial_kernel")) return rc;
     count += (int)blocks;
   }
-  clip_finalize_kernel<<<1, kThreads, 0, st>>>(scratch, count, (float)max_norm, scal, total_norm_out);
+  VC_LAUNCH((clip_finalize_kernel), 1, kThreads, 0, st, scratch, count, (float)max_norm, scal, total_norm_out);
   if (int rc = check_launch("clip_finalize_kernel")) return rc;
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   for (int i = 0; i < nt; ++i) {
@@ -127,7 +131,7 @@ int clip_adam_step(const vc_adam_tensor* t, int nt, double beta1, double beta2, 
     long long blocks = (t[i].n / 4 + kThreads * 2 - 1) / (kThreads * 2);
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    adam_update_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(t[i].p, t[i].g, t[i].m, t[i].v, t[i].n, scal, a);
+    VC_LAUNCH((adam_update_kernel), (unsigned)blocks, kThreads, 0, st, t[i].p, t[i].g, t[i].m, t[i].v, t[i].n, scal, a);
     if (int rc = check_launch("adam_update_kernel")) return rc;
   }
   return 0;

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.cuh"
 #include "host_util.h"
 
 namespace vck {
@@ -24,6 +25,7 @@ __device__ __forceinline__ void drop4(float (&v)[4], const Drop& d, uint32_t thr
 // ------------------------------------------------------------------------------------------- split
 __global__ void split_kernel(const float* __restrict__ x, long long ldx, long long rows, long long cols4,
                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldo) {
+  pdl_grid_sync();
   const long long total = rows * cols4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols4, c = (i % cols4) * 4;
@@ -38,6 +40,7 @@ __global__ void split_kernel(const float* __restrict__ x, long long ldx, long lo
 
 // one launch for all weight matrices: block -> item by binary search over block_start (n_items is small)
 __global__ void __launch_bounds__(256) split_many_kernel(const vc_split_item* __restrict__ items, int n_items) {
+  pdl_grid_sync();
   int lo = 0, hi = n_items - 1;
   const long long b = blockIdx.x;
   while (lo < hi) {
@@ -111,6 +114,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(Loader ld, long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
               float* __restrict__ y, long long ldy, __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo,
               long long ldys, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -156,6 +160,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
               const float* __restrict__ rstd, const float* __restrict__ gamma, long long rows, int C,
               const float* __restrict__ dres, long long lddres, float* __restrict__ dx, long long lddx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, const LnFuse fuse) {
+  pdl_grid_sync();
   __shared__ float4 red[LN_WARPS][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 dg[NV], db[NV], cs[kFuse ? NV : 1];
@@ -242,6 +247,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
 __global__ void vit_assemble_fwd_kernel(const float* __restrict__ e, int F, int N, int C, const float* __restrict__ cls,
                                         const float* __restrict__ pos, Drop drop, uint32_t thresh, float scale,
                                         float* __restrict__ x) {
+  pdl_grid_sync();
   const int n = N + 1, C4 = C / 4;
   const long long total = (long long)F * n * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -262,6 +268,7 @@ __global__ void vit_assemble_fwd_kernel(const float* __restrict__ e, int F, int 
 __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, int F, int N, int C, Drop drop, uint32_t thresh,
                                         float scale, float* __restrict__ de, float* __restrict__ dcls,
                                         float* __restrict__ dpos, int f_per_block) {
+  pdl_grid_sync();
   const int n = N + 1, C4 = C / 4;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n * C4) return;
@@ -296,6 +303,7 @@ act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M
                        long long ldaux_hi, Drop drop, uint32_t thresh, float scale, float* __restrict__ g, long long ldg,
                        __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo, long long ldgs,
                        float* __restrict__ colsum, int rows_per_block) {
+  pdl_grid_sync();
   __shared__ float4 red[ADB_RG][128];
   const int q = blockIdx.x * 128 + threadIdx.x;
   const bool active = q * 4 < N;
@@ -349,6 +357,7 @@ act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M
 
 __global__ void row_reduce_mod_kernel(const float* __restrict__ x, long long ldx, long long M, int N, int div, int mod,
                                       float* __restrict__ out) {
+  pdl_grid_sync();
   const long long total = M * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / N;
@@ -360,6 +369,7 @@ __global__ void row_reduce_mod_kernel(const float* __restrict__ x, long long ldx
 __global__ void broadcast_rows_kernel(const float* __restrict__ src, long long lds, long long M, int N, int div,
                                       float* __restrict__ dst, long long ldd, __nv_bfloat16* __restrict__ d_hi,
                                       __nv_bfloat16* __restrict__ d_lo, long long ldds) {
+  pdl_grid_sync();
   const int N4 = N / 4;
   const long long total = M * N4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -382,6 +392,7 @@ __global__ void embed_action_fwd_kernel(const float* __restrict__ actions, long 
                                         const float* __restrict__ W, const float* __restrict__ b,
                                         const float* __restrict__ E, int T, float* __restrict__ y,
                                         __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo) {
+  pdl_grid_sync();
   const long long total = R * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / H;
@@ -405,6 +416,7 @@ __global__ void embed_action_bwd_kernel(const float* __restrict__ dy, const floa
                                         const float* __restrict__ actions, long long R, int A, int H, int T,
                                         float* __restrict__ dW, float* __restrict__ db, float* __restrict__ dE,
                                         int rows_per_block) {
+  pdl_grid_sync();
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -426,6 +438,7 @@ __global__ void embed_action_bwd_kernel(const float* __restrict__ dy, const floa
 constexpr int HEAD_MAXC = 8;
 __global__ void head_small_fwd_kernel(const float* __restrict__ x, long long R, int H, const float* __restrict__ W,
                                       const float* __restrict__ b, int C, float* __restrict__ out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -455,6 +468,7 @@ __global__ void head_small_fwd_kernel(const float* __restrict__ x, long long R, 
 __global__ void head_small_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x, long long R, int H,
                                       const float* __restrict__ W, int C, float* __restrict__ dx, int accumulate_dx,
                                       float* __restrict__ dW, float* __restrict__ db, int rows_per_block) {
+  pdl_grid_sync();
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q * 4 >= H) return;
   const int h = q * 4;
@@ -498,11 +512,13 @@ __global__ void head_small_bwd_kernel(const float* __restrict__ dout, const floa
 }
 
 __global__ void add_kernel(const float* __restrict__ a, const float* b, float* out, long long n) {
+  pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + b[i];
 }
 
 __global__ void dropout_mask_kernel(Drop drop, uint32_t thresh, float scale, long long n, float* out) {
+  pdl_grid_sync();
   const long long n4 = (n + 3) / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const Philox4 w = dropout_words(drop_seed(drop), drop.site, (unsigned long long)i);
@@ -526,14 +542,14 @@ inline float drop_scale(const Drop& d) { return d.p > 0.f ? 1.0f / (1.0f - d.p) 
 int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t s) {
   if (cols % 4 != 0 || ldx % 4 != 0 || ldo % 4 != 0) return set_error("split_f32: cols/ld must be multiples of 4");
   if (rows <= 0 || cols <= 0) return 0;
-  split_kernel<<<ew_grid(rows * cols / 4, 256), 256, 0, cs(s)>>>(x, ldx, rows, cols / 4, reinterpret_cast<__nv_bfloat16*>(hi),
+  VC_LAUNCH((split_kernel), ew_grid(rows * cols / 4, 256), 256, 0, cs(s), x, ldx, rows, cols / 4, reinterpret_cast<__nv_bfloat16*>(hi),
                                                                 reinterpret_cast<__nv_bfloat16*>(lo), ldo);
   return check_launch("split_kernel");
 }
 
 int split_many(const vc_split_item* items, int n_items, int64_t total_blocks, stream_t s) {
   if (n_items <= 0 || total_blocks <= 0) return 0;
-  split_many_kernel<<<(unsigned)total_blocks, 256, 0, cs(s)>>>(items, n_items);
+  VC_LAUNCH((split_many_kernel), (unsigned)total_blocks, 256, 0, cs(s), items, n_items);
   return check_launch("split_many_kernel");
 }
 
@@ -546,9 +562,9 @@ int layernorm_fwd(const float* x, int64_t ldx, int64_t rows, int C, const float*
   __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(y_hi);
   __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(y_lo);
   const int grid = cdiv(rows, LN_WARPS);
-  if (C <= 256) ln_fwd_kernel<RowLoader, 2><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
-  else if (C <= 512) ln_fwd_kernel<RowLoader, 4><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
-  else ln_fwd_kernel<RowLoader, 8><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
+  if (C <= 256) VC_LAUNCH((ln_fwd_kernel<RowLoader, 2>), grid, LN_WARPS * 32, 0, cs(s), ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
+  else if (C <= 512) VC_LAUNCH((ln_fwd_kernel<RowLoader, 4>), grid, LN_WARPS * 32, 0, cs(s), ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
+  else VC_LAUNCH((ln_fwd_kernel<RowLoader, 8>), grid, LN_WARPS * 32, 0, cs(s), ld, rows, C, gamma, beta, eps, y, ldy, yh, yl, ldy_split, mean, rstd);
   return check_launch("ln_fwd_kernel");
 }
 
@@ -567,7 +583,7 @@ int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t l
   f.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); f.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo); f.ldg = ldg;
   f.colsum = g_colsum;
 #define VC_LN_BWD(FUSE, NVV)                                                                                              \
-  ln_bwd_kernel<RowLoader, true, FUSE, NVV><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, lddy, mean, rstd, gamma, rows, C, dres, \
+  VC_LAUNCH((ln_bwd_kernel<RowLoader, true, FUSE, NVV>), grid, LN_WARPS * 32, 0, cs(s), ld, dy, lddy, mean, rstd, gamma, rows, C, dres, \
                                                                                lddres, dx, lddx, dgamma, dbeta, f)
   if (g_hi != nullptr) {
     if (g_lo == nullptr) return set_error("layernorm_bwd_fused: g_lo required with g_hi");
@@ -593,7 +609,7 @@ int patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, cons
   const long long rows = (long long)F * N;
   if (rows <= 0) return 0;
   PatchLoader ld{img, S, wp, N};
-  ln_fwd_kernel<PatchLoader, 8><<<cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s)>>>(
+  VC_LAUNCH((ln_fwd_kernel<PatchLoader, 8>), cdiv(rows, LN_WARPS), LN_WARPS * 32, 0, cs(s), 
       ld, rows, 1024, gamma, beta, eps, nullptr, 0, reinterpret_cast<__nv_bfloat16*>(y_hi),
       reinterpret_cast<__nv_bfloat16*>(y_lo), 1024, mean, rstd);
   return check_launch("ln_fwd_kernel<patch>");
@@ -610,7 +626,7 @@ int patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean
   if (grid > 148 * 4) grid = 148 * 4;
   LnFuse f;
   f.drop = no_drop(); f.thresh = 0; f.scale = 1.f; f.g_hi = f.g_lo = nullptr; f.ldg = 0; f.colsum = nullptr;
-  ln_bwd_kernel<PatchLoader, false, false, 8><<<grid, LN_WARPS * 32, 0, cs(s)>>>(ld, dy, 1024, mean, rstd, nullptr, rows, 1024,
+  VC_LAUNCH((ln_bwd_kernel<PatchLoader, false, false, 8>), grid, LN_WARPS * 32, 0, cs(s), ld, dy, 1024, mean, rstd, nullptr, rows, 1024,
                                                                               nullptr, 0, nullptr, 0, dgamma, dbeta, f);
   return check_launch("ln_bwd_kernel<patch>");
 }
@@ -620,7 +636,7 @@ int vit_assemble_fwd(const float* e, int F, int N, int C, const float* cls, cons
   if (C % 4 != 0) return set_error("vit_assemble_fwd: C % 4 != 0");
   const long long total = (long long)F * (N + 1) * (C / 4);
   if (total <= 0) return 0;
-  vit_assemble_fwd_kernel<<<ew_grid(total, 256), 256, 0, cs(s)>>>(e, F, N, C, cls, pos, drop, dropout_threshold(drop.p),
+  VC_LAUNCH((vit_assemble_fwd_kernel), ew_grid(total, 256), 256, 0, cs(s), e, F, N, C, cls, pos, drop, dropout_threshold(drop.p),
                                                                   drop_scale(drop), x);
   return check_launch("vit_assemble_fwd_kernel");
 }
@@ -630,7 +646,7 @@ int vit_assemble_bwd(const float* dx, int F, int N, int C, Drop drop, float* de,
   if (F <= 0) return 0;
   const int f_per_block = 8;
   dim3 grid(cdiv((long long)(N + 1) * (C / 4), 128), cdiv(F, f_per_block));
-  vit_assemble_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dx, F, N, C, drop, dropout_threshold(drop.p), drop_scale(drop), de, dcls,
+  VC_LAUNCH((vit_assemble_bwd_kernel), grid, 128, 0, cs(s), dx, F, N, C, drop, dropout_threshold(drop.p), drop_scale(drop), de, dcls,
                                                    dpos, f_per_block);
   return check_launch("vit_assemble_bwd_kernel");
 }
@@ -644,7 +660,7 @@ int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, co
   if (M <= 0) return 0;
   const int rows_per_block = 32;
   dim3 grid(cdiv(N / 4, 128), cdiv(M, rows_per_block));
-  act_dropout_bwd_kernel<<<grid, dim3(128, ADB_RG), 0, cs(s)>>>(dy, lddy, M, N, act, aux, ldaux,
+  VC_LAUNCH((act_dropout_bwd_kernel), grid, dim3(128, ADB_RG), 0, cs(s), dy, lddy, M, N, act, aux, ldaux,
                                                   reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldaux_hi, drop,
                                                   dropout_threshold(drop.p), drop_scale(drop), g, ldg,
                                                   reinterpret_cast<__nv_bfloat16*>(g_hi),
@@ -655,7 +671,7 @@ int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, co
 int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t s) {
   if (M <= 0 || N <= 0) return 0;
   if (div < 1 || mod < 1) return set_error("row_reduce_mod: div/mod must be >= 1");
-  row_reduce_mod_kernel<<<ew_grid(M * N, 256), 256, 0, cs(s)>>>(x, ldx, M, N, div, mod, out);
+  VC_LAUNCH((row_reduce_mod_kernel), ew_grid(M * N, 256), 256, 0, cs(s), x, ldx, M, N, div, mod, out);
   return check_launch("row_reduce_mod_kernel");
 }
 
@@ -663,7 +679,7 @@ int broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, flo
                    bf16_t* d_lo, int64_t ldd_split, stream_t s) {
   if (N % 4 != 0) return set_error("broadcast_rows: N % 4 != 0");
   if (M <= 0) return 0;
-  broadcast_rows_kernel<<<ew_grid(M * N / 4, 256), 256, 0, cs(s)>>>(src, lds, M, N, div, dst, ldd,
+  VC_LAUNCH((broadcast_rows_kernel), ew_grid(M * N / 4, 256), 256, 0, cs(s), src, lds, M, N, div, dst, ldd,
                                                                    reinterpret_cast<__nv_bfloat16*>(d_hi),
                                                                    reinterpret_cast<__nv_bfloat16*>(d_lo), ldd_split);
   return check_launch("broadcast_rows_kernel");
@@ -672,7 +688,7 @@ int broadcast_rows(const float* src, int64_t lds, int64_t M, int N, int div, flo
 int embed_action_fwd(const float* actions, int64_t R, int A, int H, const float* W, const float* b, const float* E, int T,
                      float* y, bf16_t* y_hi, bf16_t* y_lo, stream_t s) {
   if (R <= 0) return 0;
-  embed_action_fwd_kernel<<<ew_grid(R * H, 256), 256, 0, cs(s)>>>(actions, R, A, H, W, b, E, T, y,
+  VC_LAUNCH((embed_action_fwd_kernel), ew_grid(R * H, 256), 256, 0, cs(s), actions, R, A, H, W, b, E, T, y,
                                                                  reinterpret_cast<__nv_bfloat16*>(y_hi),
                                                                  reinterpret_cast<__nv_bfloat16*>(y_lo));
   return check_launch("embed_action_fwd_kernel");
@@ -684,14 +700,14 @@ int embed_action_bwd(const float* dy, const float* y, const float* actions, int6
   if (R <= 0) return 0;
   const int rows_per_block = 16;
   dim3 grid(cdiv(H, 128), cdiv(R, rows_per_block));
-  embed_action_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dy, y, actions, R, A, H, T, dW, db, dE, rows_per_block);
+  VC_LAUNCH((embed_action_bwd_kernel), grid, 128, 0, cs(s), dy, y, actions, R, A, H, T, dW, db, dE, rows_per_block);
   return check_launch("embed_action_bwd_kernel");
 }
 
 int head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, stream_t s) {
   if (C > HEAD_MAXC || H % 4 != 0) return set_error("head_small_fwd: C <= 8 and H % 4 == 0 required");
   if (R <= 0) return 0;
-  head_small_fwd_kernel<<<cdiv(R, 4), 128, 0, cs(s)>>>(x, R, H, W, b, C, out);
+  VC_LAUNCH((head_small_fwd_kernel), cdiv(R, 4), 128, 0, cs(s), x, R, H, W, b, C, out);
   return check_launch("head_small_fwd_kernel");
 }
 
@@ -701,13 +717,13 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
   if (R <= 0) return 0;
   const int rows_per_block = 16;
   dim3 grid(cdiv(H / 4, 128), cdiv(R, rows_per_block));
-  head_small_bwd_kernel<<<grid, 128, 0, cs(s)>>>(dout, x, R, H, W, C, dx, accumulate_dx, dW, db, rows_per_block);
+  VC_LAUNCH((head_small_bwd_kernel), grid, 128, 0, cs(s), dout, x, R, H, W, C, dx, accumulate_dx, dW, db, rows_per_block);
   return check_launch("head_small_bwd_kernel");
 }
 
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s) {
   if (n <= 0) return 0;
-  add_kernel<<<ew_grid(n, 256), 256, 0, cs(s)>>>(a, b, out, n);
+  VC_LAUNCH((add_kernel), ew_grid(n, 256), 256, 0, cs(s), a, b, out, n);
   return check_launch("add_kernel");
 }
 
@@ -719,7 +735,7 @@ int zero_f32(float* x, int64_t n, stream_t s) {
 
 int dropout_mask_debug(Drop drop, int64_t n, float* out, stream_t s) {
   if (n <= 0) return 0;
-  dropout_mask_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, cs(s)>>>(drop, dropout_threshold(drop.p), drop_scale(drop), n, out);
+  VC_LAUNCH((dropout_mask_kernel), ew_grid((n + 3) / 4, 256), 256, 0, cs(s), drop, dropout_threshold(drop.p), drop_scale(drop), n, out);
   return check_launch("dropout_mask_kernel");
 }
 
