@@ -274,7 +274,7 @@ def test_layernorm_bwd_fused_second_output(rows, C):
     drop = L.make_drop(0.1, 21, 31337)
     dx_ref, dg_ref, db_ref = K.layernorm_bwd(dy, x, mean, rstd, gamma, dres)
     dx, dg, db, gs, cs = K.layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres, drop)
-    assert torch.equal(dx, dx_ref)
+    assert (dx - dx_ref).abs().max() <= 2e-6 * dx_ref.abs().max()  # two instantiations of one template: FMA contraction may differ
     assert _relerr(dg, dg_ref) < 1e-5 and _relerr(db, db_ref) < 1e-5
     mask = K.dropout_mask(drop, rows * C).reshape(rows, C)
     g = dx * mask

@@ -154,6 +154,90 @@ struct LnFuse {  // optional second output: g = dx * dropout_mask -> split-bf16 
   float* colsum;
 };
 
+// one row's operands in registers (loaded one row ahead of their use, see ln_bwd_kernel)
+template <int NV>
+struct LnBwdRow {
+  float4 x[NV], d[NV], r[NV];
+  float mu, rs;
+};
+
+template <class Loader, bool kNeedDx, int NV>
+__device__ __forceinline__ void ln_bwd_load(const Loader& ld, const float* __restrict__ dy, long long lddy, const float* __restrict__ mean,
+                                            const float* __restrict__ rstd, const float* __restrict__ dres, long long lddres,
+                                            long long row, int C, int lane, LnBwdRow<NV>& R) {
+  R.mu = mean[row];
+  R.rs = rstd[row];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      R.x[i] = ld.load(row, c);
+      R.d[i] = *reinterpret_cast<const float4*>(dy + row * lddy + c);
+      if (kNeedDx && dres) R.r[i] = *reinterpret_cast<const float4*>(dres + row * lddres + c);
+    }
+  }
+}
+
+template <bool kNeedDx, bool kFuse, int NV>
+__device__ __forceinline__ void ln_bwd_row(LnBwdRow<NV>& R, long long row, int C, int lane, float invC, const float* __restrict__ gamma,
+                                           bool has_res, float* __restrict__ dx, long long lddx, const LnFuse& fuse, float4 (&dg)[NV],
+                                           float4 (&db)[NV], float4 (&cs)[kFuse ? NV : 1]) {
+  const float mu = R.mu, rs = R.rs;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < C) {
+      const float4 xv = R.x[i];
+      const float4 d = R.d[i];
+      const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+      R.x[i] = xh;
+      dg[i].x += d.x * xh.x; dg[i].y += d.y * xh.y; dg[i].z += d.z * xh.z; dg[i].w += d.w * xh.w;
+      db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+      if (kNeedDx) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        R.d[i] = g;
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+      }
+    }
+  }
+  if (kNeedDx) {
+    s1 = warp_sum(s1) * invC;
+    s2 = warp_sum(s2) * invC;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < C) {
+        const float4 xh = R.x[i], g = R.d[i];
+        float4 o;
+        o.x = rs * (g.x - s1 - xh.x * s2);
+        o.y = rs * (g.y - s1 - xh.y * s2);
+        o.z = rs * (g.z - s1 - xh.z * s2);
+        o.w = rs * (g.w - s1 - xh.w * s2);
+        if (has_res) {
+          const float4 r = R.r[i];
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(dx + row * lddx + c) = o;
+        if (kFuse) {
+          float v[4] = {o.x, o.y, o.z, o.w};
+          if (fuse.drop.p > 0.f) drop4(v, fuse.drop, fuse.thresh, fuse.scale, (unsigned long long)row * C + c);
+          uint2 h, l;
+          split4(v, h, l);
+          *reinterpret_cast<uint2*>(fuse.g_hi + row * fuse.ldg + c) = h;
+          *reinterpret_cast<uint2*>(fuse.g_lo + row * fuse.ldg + c) = l;
+          cs[i].x += v[0]; cs[i].y += v[1]; cs[i].z += v[2]; cs[i].w += v[3];
+        }
+      }
+    }
+  }
+}
+
+// Each warp walks its rows with a stride; the NEXT row's operands (x, dy, residual gradient: 12 x 128-bit loads per lane at
+// C = 512) are requested before the current row's reductions and stores, so loads stay in flight continuously (the first
+// version alternated load and compute phases and reached only ~3 TB/s).
 template <class Loader, bool kNeedDx, bool kFuse, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const float* __restrict__ mean,
@@ -169,55 +253,27 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
 #pragma unroll
   for (int i = 0; i < (kFuse ? NV : 1); ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / (float)C;
-  for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float4 xh[NV], g[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = lane * 4 + i * 128;
-      if (c < C) {
-        const float4 xv = ld.load(row, c);
-        const float4 d = *reinterpret_cast<const float4*>(dy + row * lddy + c);
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
-        db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
-        if (kNeedDx) {
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
-          g[i] = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
-          s1 += g[i].x + g[i].y + g[i].z + g[i].w;
-          s2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-        }
-      }
+  const bool has_res = kNeedDx && dres != nullptr;
+  const long long stride = (long long)gridDim.x * LN_WARPS;
+  long long row = (long long)blockIdx.x * LN_WARPS + warp;
+  constexpr bool kPrefetch = NV <= 4;  // two rows of operands in registers; at C = 1024 that would spill
+  if constexpr (kPrefetch) {
+    LnBwdRow<NV> A, B;
+    if (row < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row, C, lane, A);
+    while (row < rows) {
+      if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, B);
+      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
+      row += stride;
+      if (row >= rows) break;
+      if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, A);
+      ln_bwd_row<kNeedDx, kFuse, NV>(B, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
+      row += stride;
     }
-    if (kNeedDx) {
-      s1 = warp_sum(s1) * invC;
-      s2 = warp_sum(s2) * invC;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = lane * 4 + i * 128;
-        if (c < C) {
-          float4 o;
-          o.x = rs * (g[i].x - s1 - xh[i].x * s2);
-          o.y = rs * (g[i].y - s1 - xh[i].y * s2);
-          o.z = rs * (g[i].z - s1 - xh[i].z * s2);
-          o.w = rs * (g[i].w - s1 - xh[i].w * s2);
-          if (dres) {
-            const float4 r = *reinterpret_cast<const float4*>(dres + row * lddres + c);
-            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-          }
-          *reinterpret_cast<float4*>(dx + row * lddx + c) = o;
-          if (kFuse) {
-            float v[4] = {o.x, o.y, o.z, o.w};
-            if (fuse.drop.p > 0.f) drop4(v, fuse.drop, fuse.thresh, fuse.scale, (unsigned long long)row * C + c);
-            uint2 h, l;
-            split4(v, h, l);
-            *reinterpret_cast<uint2*>(fuse.g_hi + row * fuse.ldg + c) = h;
-            *reinterpret_cast<uint2*>(fuse.g_lo + row * fuse.ldg + c) = l;
-            cs[i].x += v[0]; cs[i].y += v[1]; cs[i].z += v[2]; cs[i].w += v[3];
-          }
-        }
-      }
+  } else {
+    LnBwdRow<NV> A;
+    for (; row < rows; row += stride) {
+      ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row, C, lane, A);
+      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
     }
   }
   // cross-warp reduction of the parameter grads, then one atomicAdd per column per block
@@ -575,9 +631,9 @@ int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t l
   if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
   if (rows <= 0) return 0;
   RowLoader ld{x, ldx};
-  // one resident wave (3 CTAs/SM at ~165 registers): fewer blocks also means fewer gradient atomics per column
+  // one resident wave (2-3 CTAs/SM at ~200 registers with the row prefetch): fewer blocks also means fewer gradient atomics per column
   int grid = cdiv(rows, LN_WARPS * 4);
-  if (grid > 148 * 3) grid = 148 * 3;
+  if (grid > 148 * 2) grid = 148 * 2;
   LnFuse f;
   f.drop = gdrop; f.thresh = dropout_threshold(gdrop.p); f.scale = drop_scale(gdrop);
   f.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); f.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo); f.ldg = ldg;
