@@ -132,12 +132,14 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.train_port import CpuTrainStep
+    from oracle.train_port import CpuTrainStep, pick_threads
     from oracle import torch_oracle as to
 
     B, T, S = cfg["cpu_B"], cfg["T"], cfg["S"]
     runner = CpuTrainStep(cfg["model"])
     batches = [to.synthetic_batch(B, T + 1, S, seed=100 + i) for i in range(2)]
+    runner.step(batches[0])
+    pick_threads(runner, batches[1])  # all the host threads that help (torchrun would pin OMP_NUM_THREADS=1)
     for i in range(args.warmup):
         runner.step(batches[i % 2])
     t0 = time.perf_counter()

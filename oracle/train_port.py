@@ -31,10 +31,29 @@ class CpuTrainStep:
         return float(loss.item())
 
 
+def pick_threads(runner: "CpuTrainStep", batch: dict) -> int:
+    """Thread count that runs a step fastest on this host: a small batch does not scale to every hardware thread (64 threads
+    were 2.4x slower than 8 on the GPU box's 128-CPU host), and torchrun pins OMP_NUM_THREADS=1.  One probe step per candidate."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({n for n in (4, 8, 16, 32, 64, ncpu // 2, ncpu) if 1 <= n <= ncpu})
+    best, best_dt = torch.get_num_threads(), None
+    for n in cands:
+        torch.set_num_threads(n)
+        t0 = time.perf_counter()
+        runner.step(batch)
+        dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best, best_dt = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def time_cpu_train(cfg: dict, B: int, T: int, S: int, steps: int = 2, warmup: int = 1):
-    """frames/s of the CPU port on the host cores (all threads torch will use)."""
+    """frames/s of the CPU port on the host cores (thread count chosen by pick_threads)."""
     runner = CpuTrainStep(cfg)
     batches = [to.synthetic_batch(B, T + 1, S, seed=100 + i) for i in range(2)]
+    runner.step(batches[0])  # first step pays allocator / thread-pool start-up
+    pick_threads(runner, batches[1])
     for i in range(warmup):
         runner.step(batches[i % 2])
     t0 = time.perf_counter()
