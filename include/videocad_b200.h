@@ -127,6 +127,17 @@ int vc_layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_
 int vc_attention_bwd_split(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
                            const float* dout, const vc_bf16* dout_hi, const vc_bf16* dout_lo, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
                            vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, void* stream);
+/* the same for attention behind a packed in_proj WITH bias (torch nn.MultiheadAttention, F.multi_head_attention_forward's
+ * in_proj_bias; reference: TransformerDecoderLayer built at model/autoregressive_transformer.py:54-62): fp32 upstream gradient,
+ * and the bias gradient (column sums of dq / dk / dv) accumulated into dbq / dbk / dbv ([nh*d] each, caller-zeroed, may be NULL).
+ * Sequences with Tq == Tk <= 32 take one fused launch (csrc/attention_small.cu). */
+int vc_attention_bwd_split_bias(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
+                                const float* dout, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
+                                vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
+                                void* stream);
+/* 0: short-sequence attention (Tq == Tk <= 32) runs on the generic kernels instead of csrc/attention_small.cu (parity tests, A/B
+ * timing); default 1 */
+void vc_attention_small_enable(int enable);
 int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
                            vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream);
 int vc_patch_layernorm_bwd_params(const float* img, int F, int S, const float* mean, const float* rstd, const float* dy,

@@ -473,6 +473,24 @@ int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, co
   return 0;
 }
 
+int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                             const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                             bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
+                             stream_t st) {
+  if (!scratch) return set_error("attention_bwd_split_bias: scratch required");
+  if (!dout) return set_error("attention_bwd_split_bias: an fp32 upstream gradient is required");
+  const int64_t W = (int64_t)a.nh * a.d, Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  float* dq = scratch;
+  float* dk = dq + Rq * W;
+  float* dv = dk + Rk * W;
+  if (int rc = attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, W, dk, W, dv, W, st)) return rc;
+  if (int rc = act_dropout_bwd(dq, W, Rq, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dq_hi, dq_lo, ld_split, dbq, st)) return rc;
+  if (int rc = act_dropout_bwd(dk, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dk_hi, dk_lo, ld_split, dbk, st)) return rc;
+  return act_dropout_bwd(dv, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dv_hi, dv_lo, ld_split, dbv, st);
+}
+
+void attention_small_enable(int) {}
+
 int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t) {
   if (div < 1 || mod < 1) return set_error("row_reduce_mod: div/mod must be >= 1");
   for (int64_t m = 0; m < M; ++m)

@@ -145,6 +145,19 @@ def attention_bwd_split(a, o, lse, dout_split, B, T, nh, d):
     return dq, dk, dv
 
 
+def attention_bwd_split_bias(a, o, lse, dout, B, T, nh, d):
+    """dq | dk | dv as ONE split-bf16 [B*T, 3W] operand (the decoder's in_proj layout) + the packed bias gradient [3W]"""
+    W = nh * d
+    g = bf16_pair((B * T, 3 * W))
+    db = torch.zeros(3 * W, device="cuda")
+    scratch = torch.empty(3 * B * T * W, device="cuda")
+    L.check(L.load().vc_attention_bwd_split_bias(C.byref(a), L.ptr(o[0]), L.ptr(o[1]), W, L.ptr(lse), L.ptr(dout), dout.stride(0),
+                                                L.ptr(scratch), L.ptr(g[0]), L.ptr(g[1]), L.ptr(g[0][:, W:]), L.ptr(g[1][:, W:]),
+                                                L.ptr(g[0][:, 2 * W:]), L.ptr(g[1][:, 2 * W:]), 3 * W, L.ptr(db), L.ptr(db[W:]),
+                                                L.ptr(db[2 * W:]), L.cur_stream()))
+    return g, db
+
+
 def act_dropout_bwd(dy, act, aux=None, aux_hi=None, drop=None, want_colsum=True):
     M, N = dy.shape
     g = torch.empty_like(dy)

@@ -348,6 +348,15 @@ ATTN_CASES = [
     (2, 186, 4, 256, L.MASK_WINDOW, 10, 0.1),
     (2, 100, 4, 64, L.MASK_WINDOW, 1, 0.0),
     (2, 33, 4, 64, L.MASK_CAUSAL, 1, 0.1),
+    # short sequences: csrc/attention_small.cu (Tq == Tk <= 32)
+    (32, 8, 4, 128, L.MASK_CAUSAL, 1, 0.1),
+    (32, 8, 4, 128, L.MASK_WINDOW, 10, 0.1),
+    (3, 32, 4, 256, L.MASK_CAUSAL, 1, 0.1),
+    (3, 32, 4, 256, L.MASK_WINDOW, 10, 0.1),
+    (2, 2, 4, 64, L.MASK_CAUSAL, 1, 0.0),
+    (2, 1, 4, 64, L.MASK_WINDOW, 1, 0.0),
+    (2, 17, 4, 64, L.MASK_WINDOW, 3, 0.1),
+    (2, 31, 2, 192, L.MASK_NONE, 1, 0.1),
 ]
 
 
@@ -373,6 +382,43 @@ def test_attention_fwd_bwd(B, T, nh, d, mask, window, p):
         assert torch.isfinite(got).all(), name
         err = (got.double() - want).abs().max().item() / max(1.0, want.abs().max().item())
         assert err < 1e-4, f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("B,T,nh,d,mask,window,p", [(32, 8, 4, 128, L.MASK_CAUSAL, 1, 0.1), (4, 8, 4, 128, L.MASK_WINDOW, 10, 0.1),
+                                                    (3, 32, 4, 256, L.MASK_WINDOW, 10, 0.1), (2, 17, 4, 64, L.MASK_CAUSAL, 1, 0.0),
+                                                    (2, 40, 4, 64, L.MASK_WINDOW, 3, 0.1)])
+def test_attention_bwd_split_bias(B, T, nh, d, mask, window, p):
+    """Decoder attention backward delivering dq|dk|dv as one split-bf16 [R, 3W] operand plus the in_proj bias gradient: the fused
+    short-sequence kernel (T <= 32) and the generic fallback (T = 40) against fp64, and the short kernel against the generic one."""
+    H = nh * d
+    qkv = _rand(B * T, 3 * H, seed=54, scale=1.0)
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    drop = L.make_drop(p, 5, 79)
+    a = K.attn_desc(q, k, v, B, T, T, nh, d, mask=mask, window=window, drop=drop)
+    o, lse = K.attention_fwd(a, B, T, nh, d)
+    pmask = K.dropout_mask(drop, B * nh * T * T).reshape(B, nh, T, T).double() if p > 0 else None
+    qd, kd, vd = (t.double().contiguous().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _attn_ref(qd, kd, vd, B, T, T, nh, d, mask, window, pmask)
+    dout = _rand(B * T, H, seed=55)
+    ref.backward(dout.double())
+    g, db = K.attention_bwd_split_bias(a, o, lse, dout, B, T, nh, d)
+    want = torch.cat([qd.grad, kd.grad, vd.grad], 1)
+    got = K.join(g).double()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() / max(1.0, want.abs().max().item()) < 1e-4
+    assert _relerr(db, want.sum(0)) < 1e-4
+    if T <= 32:
+        lib = L.load()
+        lib.vc_attention_small_enable(0)
+        try:
+            o2, lse2 = K.attention_fwd(a, B, T, nh, d)
+            g2, db2 = K.attention_bwd_split_bias(a, o2, lse2, dout, B, T, nh, d)
+        finally:
+            lib.vc_attention_small_enable(1)
+        assert (K.join(o2) - K.join(o)).abs().max() < 2e-5
+        assert (lse2 - lse).abs().max() < 2e-5
+        assert (K.join(g2) - K.join(g)).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+        assert _relerr(db2, db.double()) < 1e-4
 
 
 @pytest.mark.parametrize("B,T,p", [(5, 50, 0.0), (5, 50, 0.1), (3, 5, 0.1), (2, 64, 0.0)])

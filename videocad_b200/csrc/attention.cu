@@ -16,6 +16,7 @@
 #include "launch.cuh"
 #include "host_util.h"
 #include "attention_vit.h"
+#include "attention_small.h"
 
 namespace vck {
 
@@ -359,6 +360,7 @@ int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, fl
   if (int rc = validate(a, "attention_fwd")) return rc;
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
+  if (attention_small_eligible(a) && ldo % 4 == 0) return attention_small_fwd(a, o_hi, o_lo, ldo, lse, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_fwd<64>(a, o_hi, o_lo, ldo, lse, st);
   if (a.d <= 128) return launch_fwd<128>(a, o_hi, o_lo, ldo, lse, st);
@@ -373,6 +375,9 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr))
     return vit_attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, s);
+  if (attention_small_eligible(a) && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0)
+    return attention_small_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, nullptr, nullptr, nullptr, nullptr,
+                               nullptr, nullptr, 0, nullptr, nullptr, nullptr, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_bwd<64>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
   if (a.d <= 128) return launch_bwd<128>(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, st);
@@ -398,6 +403,30 @@ int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_l
   if (int rc = split_f32(dq, W, Rq, W, dq_hi, dq_lo, ld_split, s)) return rc;
   if (int rc = split_f32(dk, W, Rk, W, dk_hi, dk_lo, ld_split, s)) return rc;
   return split_f32(dv, W, Rk, W, dv_hi, dv_lo, ld_split, s);
+}
+
+// attention_bwd_split for attention behind a packed in_proj WITH bias (nn.MultiheadAttention): also accumulates the bias
+// gradient, i.e. the column sums of dq / dk / dv, into dbq / dbk / dbv ([nh*d] each, caller-zeroed, any may be null).
+int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                             const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                             bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
+                             stream_t s) {
+  if (int rc = validate(a, "attention_bwd_split_bias")) return rc;
+  if (a.B <= 0 || a.Tq <= 0) return 0;
+  if (!dout) return set_error("attention_bwd_split_bias: an fp32 upstream gradient is required");
+  if (attention_small_eligible(a) && ldo % 4 == 0 && lddo % 4 == 0 && ld_split % 4 == 0)
+    return attention_small_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, nullptr, 0, nullptr, 0, nullptr, 0, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi,
+                               dv_lo, ld_split, dbq, dbk, dbv, s);
+  if (!scratch) return set_error("attention_bwd_split_bias: scratch required");
+  const int64_t W = (int64_t)a.nh * a.d;
+  const int64_t Rq = (int64_t)a.B * a.Tq, Rk = (int64_t)a.B * a.Tk;
+  float* dq = scratch;
+  float* dk = dq + Rq * W;
+  float* dv = dk + Rk * W;
+  if (int rc = attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, W, dk, W, dv, W, s)) return rc;
+  if (int rc = act_dropout_bwd(dq, W, Rq, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dq_hi, dq_lo, ld_split, dbq, s)) return rc;
+  if (int rc = act_dropout_bwd(dk, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dk_hi, dk_lo, ld_split, dbk, s)) return rc;
+  return act_dropout_bwd(dv, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dv_hi, dv_lo, ld_split, dbv, s);
 }
 
 }  // namespace vck

@@ -77,6 +77,15 @@ int vc_attention_bwd_split(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_
   return vck::attention_bwd_split(*a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, scratch, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi,
                                   dv_lo, ld_split, stream);
 }
+int vc_attention_bwd_split_bias(const vc_attn_desc* a, const vc_bf16* o_hi, const vc_bf16* o_lo, int64_t ldo, const float* lse,
+                                const float* dout, int64_t lddo, float* scratch, vc_bf16* dq_hi, vc_bf16* dq_lo, vc_bf16* dk_hi,
+                                vc_bf16* dk_lo, vc_bf16* dv_hi, vc_bf16* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
+                                void* stream) {
+  if (!a) return vck::set_error("vc_attention_bwd_split_bias: null descriptor");
+  return vck::attention_bwd_split_bias(*a, o_hi, o_lo, ldo, lse, dout, lddo, scratch, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo, ld_split,
+                                       dbq, dbk, dbv, stream);
+}
+void vc_attention_small_enable(int enable) { vck::attention_small_enable(enable); }
 int vc_patch_layernorm_fwd(const float* img, int F, int S, const float* gamma, const float* beta, float eps,
                            vc_bf16* y_hi, vc_bf16* y_lo, float* mean, float* rstd, void* stream) {
   return vck::patch_layernorm_fwd(img, F, S, gamma, beta, eps, y_hi, y_lo, mean, rstd, stream);

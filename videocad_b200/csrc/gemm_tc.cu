@@ -102,13 +102,18 @@ enum : uint32_t {
 // Epilogue math on 4 consecutive columns of one output row, in the COALESCED layout (8 lanes cover 128 B of a row).
 // `pre_res` / `pre_aux`: the residual / activation-backward operand of this quad when the caller has already loaded them
 // (the pair kernel issues those global loads before it waits for TMEM, see below); otherwise they are loaded here.
+// `seed`: the dropout seed of this launch, read ONCE per thread by the caller (epilogue_seed) - a per-quad read of the
+// device-resident seed word sat behind the preceding global stores (possible aliasing) and cost a load latency per quad.
 template <uint32_t F>
 __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias,
+                                              uint64_t seed,
                                               bool use_pre_res = false, float4 pre_res = float4{0.f, 0.f, 0.f, 0.f},
-                                              bool use_pre_aux = false, float4 pre_aux = float4{0.f, 0.f, 0.f, 0.f}) {
+                                              bool use_pre_aux = false, float4 pre_aux = float4{0.f, 0.f, 0.f, 0.f},
+                                              bool use_pre_relu = false, uint2 pre_relu = uint2{0u, 0u},
+                                              bool use_pre_bias = false, float4 pre_bias = float4{0.f, 0.f, 0.f, 0.f}) {
   if constexpr ((F & EF_BIAS) != 0) {
     if (p.bias != nullptr && add_bias) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      const float4 b = use_pre_bias ? pre_bias : __ldg(reinterpret_cast<const float4*>(p.bias + col));
       v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
   }
@@ -132,7 +137,6 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   if constexpr ((F & EF_DROP) != 0) {
     if (p.drop_on) {
       const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
-      const uint64_t seed = p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
       const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
@@ -147,7 +151,7 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
         const float4 a = use_pre_aux ? pre_aux : *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
         v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
       } else if (p.act == ACT_RELU) {
-        const uint2 a = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
+        const uint2 a = use_pre_relu ? pre_relu : *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
         if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
         if ((a.x & 0x7fff0000u) == 0u) v[1] = 0.f;
         if ((a.y & 0x7fffu) == 0u) v[2] = 0.f;
@@ -187,6 +191,33 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
       if (p.out_lo != nullptr) *reinterpret_cast<uint2*>(p.out_lo + row * p.ldo_split + col) = lo;
     }
   }
+}
+
+// element o*U + j of an 8-entry register array with a compile-time j (U = unroll factor of the store loop): static indices
+// plus selects, so that the array never becomes addressable (local memory)
+template <int U, class T, int N>
+__device__ __forceinline__ T epi_pick(const T (&arr)[N], int o, int j) {
+  if constexpr (N < 8) {
+    return arr[0];
+  } else if constexpr (U >= 8) {
+    return arr[j];
+  } else if constexpr (U == 4) {
+    return o == 0 ? arr[j] : arr[4 + j];
+  } else {
+    T r = arr[j];
+    if (o == 1) r = arr[2 + j];
+    if (o == 2) r = arr[4 + j];
+    if (o == 3) r = arr[6 + j];
+    return r;
+  }
+}
+
+template <uint32_t F>
+__device__ __forceinline__ uint64_t epilogue_seed(const GemmParams& p) {
+  if constexpr ((F & EF_DROP) != 0) {
+    if (p.drop_on) return p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
+  }
+  return 0ull;
 }
 
 template <int BN, uint32_t F>
@@ -337,7 +368,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ------------------------------------------------ epilogue warps (TMEM -> registers -> global)
     const int g = warp & 3;  // TMEM lane quarter this warp may access
+    const uint64_t seed = epilogue_seed<F>(p);
+    // Operands of the epilogue that do not depend on the accumulator (residual, activation-backward operand, bias) are
+    // requested one 32-column chunk AHEAD: the first chunk's loads are issued before the wait for the accumulator, so for
+    // the decoder-sized problems (one tile per CTA) they fly during the whole main loop; later chunks' loads fly during the
+    // previous chunk's TMEM read / staging / stores.  Loading them inside the store loop put every load behind the
+    // preceding global stores (the compiler must assume out_f32 aliases residual): ~8 dependent L2 round trips per chunk,
+    // which doubled the duration of the 16-CTA decoder GEMMs (profiles/r01j launch list: 19.5 us vs 10.7 us).
+    constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0, kPreBias = (F & EF_BIAS) != 0;
+    struct Pre {
+      float4 res[kPreRes ? 8 : 1];
+      float4 aux[kPreAux ? 8 : 1];
+      uint2 relu[kPreAux ? 8 : 1];
+      float4 bias;
+    };
+    const bool has_res = kPreRes && p.residual != nullptr;
+    const bool has_aux = kPreAux && p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+    const bool has_relu = kPreAux && p.act_backward && p.act == ACT_RELU;
+    const bool has_bias = kPreBias && p.bias != nullptr;
+    auto preload = [&](Pre& P, int m0, int col0) {
+      const int col = col0 + 4 * (lane & 7);
+      const bool col_ok = col < p.N;
+      if constexpr (kPreBias) {
+        P.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && col_ok) P.bias = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long row = (long long)m0 + g * 32 + it * 4 + (lane >> 3);
+        const bool ok = col_ok && row < p.M;
+        if constexpr (kPreRes) {
+          P.res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && ok) P.res[it] = *reinterpret_cast<const float4*>(p.residual + row * p.ld_res + col);
+        }
+        if constexpr (kPreAux) {
+          P.aux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          P.relu[it] = make_uint2(0u, 0u);
+          if (has_aux && ok) P.aux[it] = *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+          if (has_relu && ok) P.relu[it] = *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
+        }
+      }
+    };
     uint32_t acc_it = 0;
+    Pre nxt;
+    bool nxt_valid = false;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++acc_it) {
       const int n_idx = tile % num_n;
       const int t2 = tile / num_n;
@@ -346,6 +420,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int m0 = m_idx * BM, n0 = n_idx * BN;
       const uint32_t a = acc_it & 1u;
       const uint32_t aph = (acc_it >> 1) & 1u;
+      if (!nxt_valid && !(p.debug & 6)) preload(nxt, m0, n0);
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       // Each thread owns one accumulator ROW in TMEM (tcgen05.ld 32x32b).  Storing rows directly would scatter every
@@ -353,7 +428,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // contiguous bytes of a row.  The TMEM stage is handed back to the MMA issuer as soon as the last chunk has been
       // read, before that chunk's store phase.
       float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
-      constexpr int kUnrollIt = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? ((F & EF_ROWADD) ? 2 : 4) : 8;  // bound the code size
+      // store-loop unroll factor: the heavy bodies (erf, Philox) are not fully unrolled, to bound the code size (instruction
+      // cache); the preloaded operands are then picked with static indices + selects (epi_pick)
+      constexpr int kU = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? ((F & EF_ROWADD) ? 2 : 4) : 8;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -370,6 +447,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if ((p.debug & 2) && r[0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the loads alive
           continue;
         }
+        const Pre cur = nxt;
+        nxt_valid = false;
+        if (c + 1 < BN / 32) {
+          if (n0 + (c + 1) * 32 < p.N) preload(nxt, m0, n0 + (c + 1) * 32);  // warp-uniform
+        } else {
+          const int ntile = tile + gridDim.x;
+          if (ntile < total_tiles) {  // first chunk of this CTA's next tile
+            preload(nxt, ((ntile / num_n) % num_m) * BM, (ntile % num_n) * BN);
+            nxt_valid = true;
+          }
+        }
         const int col0 = n0 + c * 32;
         if (col0 < p.N) {  // warp-uniform
           float* myrow = stg + lane * STG_LD;
@@ -381,8 +469,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int q = lane & 7;
           const int col = col0 + 4 * q;
           float cs[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll kUnrollIt
-          for (int it = 0; it < 8; ++it) {
+#pragma unroll 1
+          for (int o = 0; o < 8 / kU; ++o) {
+#pragma unroll
+          for (int j = 0; j < kU; ++j) {
+            const int it = o * kU + j;
             const int rr = it * 4 + (lane >> 3);
             const long long row = (long long)m0 + g * 32 + rr;
             if (row < p.M && col < p.N) {
@@ -391,10 +482,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (p.debug & 1) {
                 if (v[0] == 123.456f) p.out_f32[0] = v[1];
               } else {
-                epilogue_quad<F>(p, v, row, col, split == 0);
+                epilogue_quad<F>(p, v, row, col, split == 0, seed, has_res, epi_pick<kU>(cur.res, o, j), has_aux,
+                                 epi_pick<kU>(cur.aux, o, j), has_relu, epi_pick<kU>(cur.relu, o, j), has_bias, cur.bias);
               }
               if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
             }
+          }
           }
           if constexpr ((F & EF_COLSUM) != 0) {
             if (p.colsum != nullptr) {  // column sums of the final values: combine the 4 lanes that share a column quad
@@ -618,6 +711,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
+    const uint64_t seed = epilogue_seed<F>(p);
     uint32_t acc_it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
       const int n_idx = tile % num_n;
@@ -680,7 +774,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (row < p.M && col < p.N) {
             const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ ((rr >> 1) & 3)));
             float v[4] = {t4.x, t4.y, t4.z, t4.w};
-            epilogue_quad<F>(p, v, row, col, split == 0, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
+            epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
                              paux[kPreAux ? it : 0]);
             if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
           }

@@ -98,6 +98,16 @@ int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_l
                         const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
                         bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s);
 
+// the same for attention behind a packed in_proj with bias (nn.MultiheadAttention): fp32 upstream gradient only; additionally
+// accumulates the bias gradient = column sums of dq / dk / dv into dbq / dbk / dbv ([nh*d] each, caller-zeroed, may be null)
+int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_t ldo, const float* lse,
+                             const float* dout, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
+                             bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
+                             stream_t s);
+// 0 routes short-sequence decoder attention (Tq == Tk <= 32) through the generic kernels (tests / A-B timing); default 1.
+// No effect in the CPU emulation.
+void attention_small_enable(int enable);
+
 // backward of "v = dropout(act(pre))":  g = dy * mask*scale * act'(.)
 //   act GELU: aux = pre-activation fp32; TANH: aux = forward output fp32; RELU: aux_hi = forward output hi (bf16) != 0
 //   outputs (all optional): g fp32, g split, colsum[n] += sum_m g[m,n] (atomic, pre-zeroed)

@@ -367,9 +367,10 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
     const Split x_inS = (l > 0) ? w.l[l - 1].x3S
                                 : (d.past_actions ? w.actS : (d.past_states ? (d.mem_has_ui ? mk_split(w.catS.hi, w.catS.lo, ldc) : w.uiS) : w.memS));
     // ---- feed-forward block
-    VC_TRY(layernorm_bwd(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev), nullptr, 0,
-                           s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
+    // LayerNorm backward with the fused second output: dropout-masked gradient of the sublayer output as split-bf16 operand
+    // of its dgrad/wgrad GEMMs + the bias gradient (column sums); s.Y keeps the unmasked d y for the residual path
+    VC_TRY(layernorm_bwd_fused(s.A, H, Y.y3, H, Y.m3, Y.r3, LW.n3.w, R, H, nullptr, 0, s.Y, H, LW.n3.dw, LW.n3.db,
+                               site_drop(p, c->training, c->seed, s0 + 5, c->seed_dev), s.gH.hi, s.gH.lo, H, LW.lin2.db, st));
     VC_TRY(stream_fork(st, 0, &side));
     VC_TRY(linear_wgrad(s.gH, Y.f, R, H, Ff, LW.lin2.dw, P, side));
     {
@@ -390,9 +391,10 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       VC_TRY(gemm(g, st));
     }
     // ---- cross-attention block
-    VC_TRY(layernorm_bwd(s.Bf, H, Y.y2, H, Y.m2, Y.r2, LW.n2.w, R, H, nullptr, 0, s.Y, H, LW.n2.dw, LW.n2.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev), nullptr, 0,
-                           s.gH_ca.hi, s.gH_ca.lo, H, LW.ca_out.db, st));
+    // LayerNorm backward with the fused second output: dropout-masked gradient of the sublayer output as split-bf16 operand
+    // of its dgrad/wgrad GEMMs + the bias gradient (column sums); s.Y keeps the unmasked d y for the residual path
+    VC_TRY(layernorm_bwd_fused(s.Bf, H, Y.y2, H, Y.m2, Y.r2, LW.n2.w, R, H, nullptr, 0, s.Y, H, LW.n2.dw, LW.n2.db,
+                               site_drop(p, c->training, c->seed, s0 + 3, c->seed_dev), s.gH_ca.hi, s.gH_ca.lo, H, LW.ca_out.db, st));
     VC_TRY(stream_fork(st, 0, &side));
     VC_TRY(linear_wgrad(s.gH_ca, Y.c, R, H, H, LW.ca_out.dw, P, side));
     {
@@ -401,10 +403,11 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_bwd(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev)), Y.c.hi, Y.c.lo, H, Y.ca_lse, s.dAtt, H,
-                         s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
-    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS.hi, s.dqkvS.lo,
-                           3 * H, LW.ca_in.db, st));
+    // dq | dk | dv delivered as the split-bf16 operand [R, 3H] of the in_proj dgrad/wgrad GEMMs, in_proj bias gradient included
+    VC_TRY(attention_bwd_split_bias(cross_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev)), Y.c.hi, Y.c.lo, H,
+                                    Y.ca_lse, s.dAtt, H, s.dqkv, s.dqkvS.hi, s.dqkvS.lo, s.dqkvS.hi + H, s.dqkvS.lo + H,
+                                    s.dqkvS.hi + 2 * H, s.dqkvS.lo + 2 * H, 3 * H, LW.ca_in.db, LW.ca_in.db ? LW.ca_in.db + H : nullptr,
+                                    LW.ca_in.db ? LW.ca_in.db + 2 * H : nullptr, st));
     VC_TRY(stream_fork(st, 0, &side));
     VC_TRY(linear_wgrad(cols(s.dqkvS, 0), Y.x1S, R, H, H, LW.ca_in.dw, P, side));
     VC_TRY(linear_wgrad(cols(s.dqkvS, H), w.memS, R, 2 * H, H, LW.ca_in.dw + (size_t)H * H, P, side));
@@ -423,9 +426,10 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       VC_TRY(gemm(g, st));
     }
     // ---- self-attention block
-    VC_TRY(layernorm_bwd(s.A, H, Y.y1, H, Y.m1, Y.r1, LW.n1.w, R, H, nullptr, 0, s.Y, H, LW.n1.dw, LW.n1.db, st));
-    VC_TRY(act_dropout_bwd(s.Y, H, R, H, VC_ACT_NONE, nullptr, 0, nullptr, 0, site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), nullptr, 0,
-                           s.gH_sa.hi, s.gH_sa.lo, H, LW.sa_out.db, st));
+    // LayerNorm backward with the fused second output: dropout-masked gradient of the sublayer output as split-bf16 operand
+    // of its dgrad/wgrad GEMMs + the bias gradient (column sums); s.Y keeps the unmasked d y for the residual path
+    VC_TRY(layernorm_bwd_fused(s.A, H, Y.y1, H, Y.m1, Y.r1, LW.n1.w, R, H, nullptr, 0, s.Y, H, LW.n1.dw, LW.n1.db,
+                               site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), s.gH_sa.hi, s.gH_sa.lo, H, LW.sa_out.db, st));
     VC_TRY(stream_fork(st, 0, &side));
     VC_TRY(linear_wgrad(s.gH_sa, Y.a, R, H, H, LW.sa_out.dw, P, side));
     {
@@ -434,10 +438,10 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
       g.out_f32 = s.dAtt; g.ldo = H;
       VC_TRY(gemm(g, st));
     }
-    VC_TRY(attention_bwd(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev)), Y.a.hi, Y.a.lo, H, Y.sa_lse, s.dAtt, H,
-                         s.dqkv, 3 * H, s.dqkv + H, 3 * H, s.dqkv + 2 * H, 3 * H, st));
-    VC_TRY(act_dropout_bwd(s.dqkv, 3 * H, R, 3 * H, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, s.dqkvS_sa.hi, s.dqkvS_sa.lo,
-                           3 * H, LW.sa_in.db, st));
+    VC_TRY(attention_bwd_split_bias(self_attn_desc(c, d, Y, site_drop(p, c->training, c->seed, s0 + 0, c->seed_dev)), Y.a.hi, Y.a.lo, H,
+                                    Y.sa_lse, s.dAtt, H, s.dqkv, s.dqkvS_sa.hi, s.dqkvS_sa.lo, s.dqkvS_sa.hi + H, s.dqkvS_sa.lo + H,
+                                    s.dqkvS_sa.hi + 2 * H, s.dqkvS_sa.lo + 2 * H, 3 * H, LW.sa_in.db, LW.sa_in.db ? LW.sa_in.db + H : nullptr,
+                                    LW.sa_in.db ? LW.sa_in.db + 2 * H : nullptr, st));
     VC_TRY(stream_fork(st, 0, &side));
     VC_TRY(linear_wgrad(s.dqkvS_sa, x_inS, R, 3 * H, H, LW.sa_in.dw, P, side));
     {

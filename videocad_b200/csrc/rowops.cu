@@ -631,8 +631,10 @@ int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t l
   if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
   if (rows <= 0) return 0;
   RowLoader ld{x, ldx};
-  // one resident wave (2-3 CTAs/SM at ~200 registers with the row prefetch): fewer blocks also means fewer gradient atomics per column
+  // one resident wave (2-3 CTAs/SM at ~200 registers with the row prefetch): fewer blocks also means fewer gradient atomics per
+  // column; decoder-sized problems (a few hundred rows) get one row per warp instead of four
   int grid = cdiv(rows, LN_WARPS * 4);
+  if (grid < 148) grid = cdiv(rows, LN_WARPS) < 148 ? cdiv(rows, LN_WARPS) : 148;
   if (grid > 148 * 2) grid = 148 * 2;
   LnFuse f;
   f.drop = gdrop; f.thresh = dropout_threshold(gdrop.p); f.scale = drop_scale(gdrop);
@@ -714,7 +716,10 @@ int act_dropout_bwd(const float* dy, int64_t lddy, int64_t M, int N, int act, co
   if ((act == VC_ACT_GELU || act == VC_ACT_TANH) && aux == nullptr) return set_error("act_dropout_bwd: aux required");
   if (act == VC_ACT_RELU && aux_hi == nullptr) return set_error("act_dropout_bwd: aux_hi required for relu");
   if (M <= 0) return 0;
-  const int rows_per_block = 32;
+  // 8 rows per thread for the image-encoder sizes; decoder-sized problems (a few hundred rows) get one row per thread,
+  // otherwise a handful of CTAs would each walk their rows one dependent load at a time
+  int rows_per_block = 32;
+  while (rows_per_block > ADB_RG && (long long)cdiv(N / 4, 128) * cdiv(M, rows_per_block) < 148) rows_per_block >>= 1;
   dim3 grid(cdiv(N / 4, 128), cdiv(M, rows_per_block));
   VC_LAUNCH((act_dropout_bwd_kernel), grid, dim3(128, ADB_RG), 0, cs(s), dy, lddy, M, N, act, aux, ldaux,
                                                   reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldaux_hi, drop,

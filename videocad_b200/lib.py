@@ -84,6 +84,8 @@ _PROTOS = {
     "vc_layernorm_bwd": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, vp], i32),
     "vc_layernorm_bwd_fused": ([vp, i64, vp, i64, vp, vp, vp, i64, i32, vp, i64, vp, i64, vp, vp, Drop, vp, vp, i64, vp, vp], i32),
     "vc_attention_bwd_split": ([C.POINTER(AttnDesc), vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp], i32),
+    "vc_attention_bwd_split_bias": ([C.POINTER(AttnDesc), vp, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp], i32),
+    "vc_attention_small_enable": ([i32], None),
     "vc_patch_layernorm_fwd": ([vp, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp], i32),
     "vc_patch_layernorm_bwd_params": ([vp, i32, i32, vp, vp, vp, vp, vp, vp], i32),
     "vc_vit_assemble_fwd": ([vp, i32, i32, i32, vp, vp, Drop, vp, vp], i32),
