@@ -5,13 +5,13 @@
 // Never linked into, loaded by, or shipped with the product library.
 //
 // Each function follows the contract documented in kernels.h; arithmetic mirrors the CUDA kernels (same split-bf16
-// operand model, same Philox dropout masks) but accumulates in double.
+// operand model, same dropout masks) but accumulates in double.
 #include <math.h>
 #include <string.h>
 #include <vector>
 #include "kernels.h"
 #include "host_util.h"
-#include "philox.h"
+#include "dropout_rng.h"
 
 namespace vck {
 
@@ -36,7 +36,7 @@ inline void split1(float x, bf16_t& hi, bf16_t& lo) {
 }
 inline float keep_scale(const Drop& d, uint64_t idx) {
   if (d.p <= 0.f) return 1.0f;
-  const Philox4 w = dropout_words(drop_seed(d), d.site, idx >> 2);
+  const Rand4 w = dropout_words(drop_seed(d), d.site, idx >> 2);
   return (w.v[idx & 3u] >= dropout_threshold(d.p)) ? 1.0f / (1.0f - d.p) : 0.0f;
 }
 inline double gelu_d(double x) { return 0.5 * x * (1.0 + erf(x * 0.70710678118654752440)); }

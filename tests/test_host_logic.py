@@ -163,7 +163,7 @@ def test_orchestration_matches_reference_golden(emu):
 
 
 def test_training_mode_dropout_bookkeeping(emu):
-    """Forward and backward regenerate identical Philox masks: with dropout on, the analytic gradient must match a
+    """Forward and backward regenerate identical dropout masks: with dropout on, the analytic gradient must match a
     finite difference of the (fixed-seed) stochastic forward."""
     cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
@@ -196,6 +196,37 @@ def test_training_mode_dropout_bookkeeping(emu):
             base[idx] = old
         fd = (lp - lm) / (2 * eps)
         assert abs(fd - analytic) < 2e-2 * max(1.0, abs(analytic)), (fd, analytic)
+
+
+def _mask(emu, p, site, seed, n):
+    out = np.empty(n, dtype=np.float32)
+    L.check(emu.vc_dropout_mask_debug(L.make_drop(p, site, seed), n, out.ctypes.data, None), emu)
+    return out
+
+
+def test_dropout_mask_statistics(emu):
+    """The dropout generator (csrc/dropout_rng.h, shared by the CUDA kernels and the emulation): keep-rate, uniformity of the
+    underlying 16-bit draws (through the keep-rate at several p), independence across neighbouring elements, tensor rows /
+    columns, sites and seeds.  Thresholds are ~5 sigma for the sample sizes used."""
+    n = 1 << 21
+    for p in (0.1, 0.2, 0.5):
+        for site, seed in ((0, 0), (3, 1234), (40, 2 ** 40 + 7)):
+            m = _mask(emu, p, site, seed, n)
+            assert set(np.unique(m)) <= {0.0, np.float32(1.0 / (1.0 - p))}
+            keep = (m != 0).astype(np.float64)
+            assert abs(keep.mean() - (1.0 - p)) < 5 * np.sqrt(p * (1 - p) / n) + 1e-5, (p, site, seed, keep.mean())
+            for lag in (1, 2, 3, 4, 50, 64, 512, 3072):
+                c = np.corrcoef(keep[:-lag], keep[lag:])[0, 1]
+                assert abs(c) < 5 / np.sqrt(n), (p, site, seed, lag, c)
+    a = (_mask(emu, 0.1, 5, 77, n) != 0).astype(np.float64)
+    b = (_mask(emu, 0.1, 6, 77, n) != 0).astype(np.float64)   # another site
+    c = (_mask(emu, 0.1, 5, 78, n) != 0).astype(np.float64)   # the next seed
+    assert abs(np.corrcoef(a, b)[0, 1]) < 5 / np.sqrt(n)
+    assert abs(np.corrcoef(a, c)[0, 1]) < 5 / np.sqrt(n)
+    assert (a != b).mean() > 0.15 and (a != c).mean() > 0.15
+    k = a.reshape(-1, 512)  # [4096, 512]: column and row keep-rates scatter as a binomial would
+    assert 0.85 < k.mean(0).std() / np.sqrt(0.09 / k.shape[0]) < 1.15
+    assert 0.93 < k.mean(1).std() / np.sqrt(0.09 / 512) < 1.07
 
 
 def test_sequential_inference_matches_oracle(emu):

@@ -415,9 +415,10 @@ def test_attention_bwd_split_bias(B, T, nh, d, mask, window, p):
             g2, db2 = K.attention_bwd_split_bias(a, o2, lse2, dout, B, T, nh, d)
         finally:
             lib.vc_attention_small_enable(1)
-        assert (K.join(o2) - K.join(o)).abs().max() < 2e-5
+        # both round their fp32 results to split-bf16 (2^-16 relative): agreement to a few units of that rounding
+        assert (K.join(o2) - K.join(o)).abs().max() < 1e-4
         assert (lse2 - lse).abs().max() < 2e-5
-        assert (K.join(g2) - K.join(g)).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+        assert (K.join(g2) - K.join(g)).abs().max().item() <= 1e-4 * max(1.0, want.abs().max().item())
         assert _relerr(db2, db.double()) < 1e-4
 
 

@@ -48,10 +48,9 @@ __device__ __forceinline__ bool tile_masked(int mask, int window, int q0, int nq
   if (mask == VC_MASK_WINDOW && (k0 + nk - 1) <= q0 - window) return true;
   return false;
 }
-__device__ __forceinline__ float drop_factor(const AttnP& p, unsigned long long idx) {
+__device__ __forceinline__ float drop_factor(const AttnP& p, const DropKey& key, unsigned long long idx) {
   if (p.drop.p <= 0.f) return 1.0f;
-  const Philox4 w = dropout_words(drop_seed(p.drop), p.drop.site, idx >> 2);
-  return (w.v[idx & 3ull] >= p.thresh) ? p.dscale : 0.0f;
+  return (dropout_element(key, idx) >= p.thresh) ? p.dscale : 0.0f;
 }
 
 // cooperative load of `rows` rows x d floats (global row stride ld) into smem with row stride LDS
@@ -87,6 +86,7 @@ attn_fwd_kernel(const AttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* 
   const int q0 = qb * QB, nq = min(QB, p.Tq - q0);
   const int d = p.d, Tk = p.Tk;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const DropKey dkey = drop_key_of(p.drop);
 
   load_rows<LDS>(Qs, p.q + ((long long)b * p.Tq + q0) * p.ldq + (long long)h * d, p.ldq, nq, d);
 
@@ -127,7 +127,7 @@ attn_fwd_kernel(const AttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* 
     const unsigned long long base = (((unsigned long long)b * p.nh + h) * p.Tq + (q0 + i)) * (unsigned long long)Tk;
     for (int j = lane; j < Tk; j += 32) {
       const float pj = __expf(row[j] - lse);
-      row[j] = pj * drop_factor(p, base + j);
+      row[j] = pj * drop_factor(p, dkey, base + j);
     }
     if (lane == 0) lse_out[((long long)b * p.nh + h) * p.Tq + q0 + i] = lse;
   }
@@ -203,6 +203,7 @@ attn_bwd_kernel(const AttnP p, const __nv_bfloat16* __restrict__ o_hi, const __n
   const int d = p.d, Tk = p.Tk, Tq = p.Tq;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = threadIdx.x % CW, rg = threadIdx.x / CW;
+  const DropKey dkey = drop_key_of(p.drop);
 
   // ---- prologue: delta_i = dO_i . O_i ; dq slice := 0
   for (int i = warp; i < Tq; i += ATT_THREADS / 32) {
@@ -252,7 +253,7 @@ attn_bwd_kernel(const AttnP p, const __nv_bfloat16* __restrict__ o_hi, const __n
           }
           const long long gi = ((long long)b * p.nh + h) * Tq + q0 + i;
           const float pr = __expf(s * p.scale - lse[gi]);
-          const float m = drop_factor(p, (unsigned long long)gi * (unsigned long long)Tk + (k0 + j));
+          const float m = drop_factor(p, dkey, (unsigned long long)gi * (unsigned long long)Tk + (k0 + j));
           pt = pr * m;
           ds = pr * (dp * m - delta[q0 + i]) * p.scale;
         }

@@ -51,10 +51,9 @@ __device__ __forceinline__ void query_range(const SmallP& p, int j, int& ilo, in
   if (p.mask != VC_MASK_NONE) ilo = j;
   if (p.mask == VC_MASK_WINDOW) ihi = min(p.T - 1, j + p.window - 1);
 }
-__device__ __forceinline__ float keep_factor(const SmallP& p, uint64_t seed, unsigned long long idx) {
+__device__ __forceinline__ float keep_factor(const SmallP& p, const DropKey& key, unsigned long long idx) {
   if (p.drop.p <= 0.f) return 1.0f;
-  const Philox4 w = dropout_words(seed, p.drop.site, idx >> 2);
-  return (w.v[idx & 3ull] >= p.thresh) ? p.dscale : 0.0f;
+  return (dropout_element(key, idx) >= p.thresh) ? p.dscale : 0.0f;
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
@@ -102,7 +101,7 @@ attn_small_fwd_kernel(const SmallP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfl
     *reinterpret_cast<float4*>(Ks + r * d + c) = k4;
     *reinterpret_cast<float4*>(Vs + r * d + c) = v4;
   }
-  const uint64_t seed = p.drop.p > 0.f ? drop_seed(p.drop) : 0ull;
+  const DropKey seed = drop_key_of(p.drop);
   __syncthreads();
 
   for (int i = warp; i < T; i += AS_WARPS) {
@@ -193,7 +192,7 @@ attn_small_bwd_kernel(const SmallP p, const __nv_bfloat16* __restrict__ o_hi, co
     *reinterpret_cast<float4*>(Vs + r * d + c) = v4;
     *reinterpret_cast<float4*>(dOs + r * d + c) = g4;
   }
-  const uint64_t seed = p.drop.p > 0.f ? drop_seed(p.drop) : 0ull;
+  const DropKey seed = drop_key_of(p.drop);
   __syncthreads();
 
   // ---- phase A (warp <-> query row i): P~, scale*dS and dQ_i = sum_j dS_ij K_j

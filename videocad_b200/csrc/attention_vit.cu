@@ -6,7 +6,7 @@
 // warp-level tensor path: one CTA per (image, head), 4 warps, each warp owns 16 query rows (forward, backward
 // phase 1) or 16 key rows (backward phase 2).  K, V (and Q, dO in the backward) are converted to split-bf16 on the way
 // into shared memory; scores/probabilities live in registers (forward) or make one trip through shared memory
-// (backward, to transpose P~ and dS).  Dropout masks are regenerated from the Philox counter.
+// (backward, to transpose P~ and dS).  Dropout masks are regenerated from the counter-based generator (dropout_rng.h).
 #include <cuda_runtime.h>
 #include <math.h>
 #include "common.cuh"
@@ -54,22 +54,21 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const __nv_bfloat16*
 }
 
 // split two floats into packed (hi, lo) bf16x2 words
-__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 xh, xl, yh, yl;
-  split_bf16(x, xh, xl);
-  split_bf16(y, yh, yl);
-  hi = pack_bf16x2(xh, yh);
-  lo = pack_bf16x2(xl, yl);
-}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) { split_pair(x, y, hi, lo); }
 
-// dropout factors for two consecutive elements idx, idx+1
-__device__ __forceinline__ void drop_pair(const VitAttnP& p, unsigned long long idx, float& f0, float& f1) {
+// dropout factors for two consecutive elements idx, idx+1: ONE hash when idx is even (both elements live in the same 32-bit
+// word of the generator, see dropout_rng.h) -- always the case for an even token count such as the ViT's n = 50
+__device__ __forceinline__ void drop_pair(const VitAttnP& p, const DropKey& key, unsigned long long idx, float& f0, float& f1) {
   if (p.drop.p <= 0.f) { f0 = f1 = 1.0f; return; }
-  const uint64_t seed = drop_seed(p.drop);
-  Philox4 w = dropout_words(seed, p.drop.site, idx >> 2);
-  f0 = (w.v[idx & 3ull] >= p.thresh) ? p.dscale : 0.0f;
-  if ((idx & 3ull) == 3ull) w = dropout_words(seed, p.drop.site, (idx + 1) >> 2);
-  f1 = (w.v[(idx + 1) & 3ull] >= p.thresh) ? p.dscale : 0.0f;
+  const uint32_t w = dropout_word(key, idx >> 1);
+  if ((idx & 1ull) == 0ull) {
+    f0 = ((w << 16) >= p.thresh) ? p.dscale : 0.0f;
+    f1 = ((w & 0xffff0000u) >= p.thresh) ? p.dscale : 0.0f;
+  } else {
+    const uint32_t w1 = dropout_word(key, (idx >> 1) + 1ull);
+    f0 = ((w & 0xffff0000u) >= p.thresh) ? p.dscale : 0.0f;
+    f1 = ((w1 << 16) >= p.thresh) ? p.dscale : 0.0f;
+  }
 }
 
 // cooperative: rows [0,64) x 64 fp32 columns from global (row stride ld) -> split-bf16 smem tiles; rows >= n are zero
@@ -215,6 +214,7 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
   const int n = p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const long long rowbase = (long long)b * n;
+  const DropKey dkey = drop_key_of(p.drop);
   uint32_t qh[4][4], ql[4][4];
   if (p.qh != nullptr) {
     stage_copy(p.kh + rowbase * p.ldk + (long long)h * HD, p.kl + rowbase * p.ldk + (long long)h * HD, p.ldk, n, Kh, Kl);
@@ -270,8 +270,7 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
     for (int j = 0; j < 8; ++j) {
       const int col = 8 * j + 2 * t;
       float f0 = 1.f, f1 = 1.f;
-      if (col + 1 < n) drop_pair(p, base + col, f0, f1);
-      else if (col < n) { float dummy; drop_pair(p, base + col, f0, dummy); }
+      if (col < n) drop_pair(p, dkey, base + col, f0, f1);  // f1 is unused when col + 1 == n (its probability is 0)
       s[j][rr * 2 + 0] *= inv * f0;
       s[j][rr * 2 + 1] *= inv * f1;
     }
@@ -332,6 +331,7 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const float* __restrict__ lse, const f
   const int n = p.n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const long long rowbase = (long long)b * n;
+  const DropKey dkey = drop_key_of(p.drop);
 
   // two cp.async groups: {Q, K} first so that S = Q K^T can start while {V, dO} are still in flight
   if (p.qh != nullptr) {
@@ -393,8 +393,7 @@ vit_attn_bwd_mma_kernel(const VitAttnP p, const float* __restrict__ lse, const f
       for (int j = 0; j < 8; ++j) {
         const int col = 8 * j + 2 * t;
         float f0 = 1.f, f1 = 1.f;
-        if (rv && col + 1 < n) drop_pair(p, ibase + col, f0, f1);
-        else if (rv && col < n) { float dummy; drop_pair(p, ibase + col, f0, dummy); }
+        if (rv && col < n) drop_pair(p, dkey, ibase + col, f0, f1);  // f1 is unused when col + 1 == n (p1 = 0)
         const float p0 = (rv && col < n) ? __expf(s[j][rr * 2] * p.scale - l) : 0.f;
         const float p1 = (rv && col + 1 < n) ? __expf(s[j][rr * 2 + 1] * p.scale - l) : 0.f;
         keep |= (f0 != 0.f ? 1u : 0u) << (2 * j);

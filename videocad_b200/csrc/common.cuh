@@ -3,7 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
-#include "philox.h"
+#include "dropout_rng.h"
 
 namespace vck {
 
@@ -21,13 +21,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two floats -> packed (hi, lo) bf16x2 words (x in the low half): two packed round-to-nearest conversions (F2FP.BF16.PACK_AB)
+// instead of four scalar ones + packing; bit-identical to split_bf16 on each element
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float xh = __uint_as_float(hi << 16), yh = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - xh, y - yh);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // split 4 floats -> packed hi (2 x u32) and lo (2 x u32)
 __device__ __forceinline__ void split4(const float v[4], uint2& hi, uint2& lo) {
-  __nv_bfloat16 h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) split_bf16(v[i], h[i], l[i]);
-  hi = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-  lo = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  split_pair(v[0], v[1], hi.x, lo.x);
+  split_pair(v[2], v[3], hi.y, lo.y);
 }
 
 // ---------------------------------------------------------------------------------------------

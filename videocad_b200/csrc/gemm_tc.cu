@@ -102,11 +102,11 @@ enum : uint32_t {
 // Epilogue math on 4 consecutive columns of one output row, in the COALESCED layout (8 lanes cover 128 B of a row).
 // `pre_res` / `pre_aux`: the residual / activation-backward operand of this quad when the caller has already loaded them
 // (the pair kernel issues those global loads before it waits for TMEM, see below); otherwise they are loaded here.
-// `seed`: the dropout seed of this launch, read ONCE per thread by the caller (epilogue_seed) - a per-quad read of the
+// `dkey`: the dropout key of this launch, derived ONCE per thread by the caller (epilogue_seed) - a per-quad read of the
 // device-resident seed word sat behind the preceding global stores (possible aliasing) and cost a load latency per quad.
 template <uint32_t F>
 __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4], long long row, int col, bool add_bias,
-                                              uint64_t seed,
+                                              const DropKey& dkey,
                                               bool use_pre_res = false, float4 pre_res = float4{0.f, 0.f, 0.f, 0.f},
                                               bool use_pre_aux = false, float4 pre_aux = float4{0.f, 0.f, 0.f, 0.f},
                                               bool use_pre_relu = false, uint2 pre_relu = uint2{0u, 0u},
@@ -137,7 +137,7 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
   if constexpr ((F & EF_DROP) != 0) {
     if (p.drop_on) {
       const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
-      const Philox4 w = dropout_words(seed, p.drop_site, idx >> 2);
+      const Rand4 w = dropout_words(dkey, idx >> 2);
 #pragma unroll
       for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
     }
@@ -213,11 +213,11 @@ __device__ __forceinline__ T epi_pick(const T (&arr)[N], int o, int j) {
 }
 
 template <uint32_t F>
-__device__ __forceinline__ uint64_t epilogue_seed(const GemmParams& p) {
+__device__ __forceinline__ DropKey epilogue_seed(const GemmParams& p) {
   if constexpr ((F & EF_DROP) != 0) {
-    if (p.drop_on) return p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed;
+    if (p.drop_on) return drop_key(p.drop_seed_ptr != nullptr ? *p.drop_seed_ptr : p.drop_seed, p.drop_site);
   }
-  return 0ull;
+  return DropKey{0u, 0u};
 }
 
 template <int BN, uint32_t F>
@@ -368,7 +368,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else {
     // ------------------------------------------------ epilogue warps (TMEM -> registers -> global)
     const int g = warp & 3;  // TMEM lane quarter this warp may access
-    const uint64_t seed = epilogue_seed<F>(p);
+    const DropKey seed = epilogue_seed<F>(p);
     // Operands of the epilogue that do not depend on the accumulator (residual, activation-backward operand, bias) are
     // requested one 32-column chunk AHEAD: the first chunk's loads are issued before the wait for the accumulator, so for
     // the decoder-sized problems (one tile per CTA) they fly during the whole main loop; later chunks' loads fly during the
@@ -428,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // contiguous bytes of a row.  The TMEM stage is handed back to the MMA issuer as soon as the last chunk has been
       // read, before that chunk's store phase.
       float* stg = reinterpret_cast<float*>(tiles + C::STAGES * C::STAGE_BYTES) + (warp - 2) * 32 * STG_LD;
-      // store-loop unroll factor: the heavy bodies (erf, Philox) are not fully unrolled, to bound the code size (instruction
+      // store-loop unroll factor: the heavy bodies (erf, dropout RNG) are not fully unrolled, to bound the code size (instruction
       // cache); the preloaded operands are then picked with static indices + selects (epi_pick)
       constexpr int kU = ((F & (EF_ACT | EF_ACTBWD | EF_DROP | EF_PREACT | EF_ATOMIC)) != 0) ? ((F & EF_ROWADD) ? 2 : 4) : 8;
 #pragma unroll 1
@@ -711,7 +711,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
-    const uint64_t seed = epilogue_seed<F>(p);
+    const DropKey seed = epilogue_seed<F>(p);
     uint32_t acc_it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
       const int n_idx = tile % num_n;

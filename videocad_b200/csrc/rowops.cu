@@ -16,8 +16,8 @@ namespace {
 inline cudaStream_t cs(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-__device__ __forceinline__ void drop4(float (&v)[4], const Drop& d, uint32_t thresh, float scale, unsigned long long idx) {
-  const Philox4 w = dropout_words(drop_seed(d), d.site, idx >> 2);
+__device__ __forceinline__ void drop4(float (&v)[4], const DropKey& key, uint32_t thresh, float scale, unsigned long long idx) {
+  const Rand4 w = dropout_words(key, idx >> 2);
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= thresh) ? v[i] * scale : 0.0f;
 }
@@ -180,7 +180,7 @@ __device__ __forceinline__ void ln_bwd_load(const Loader& ld, const float* __res
 
 template <bool kNeedDx, bool kFuse, int NV>
 __device__ __forceinline__ void ln_bwd_row(LnBwdRow<NV>& R, long long row, int C, int lane, float invC, const float* __restrict__ gamma,
-                                           bool has_res, float* __restrict__ dx, long long lddx, const LnFuse& fuse, float4 (&dg)[NV],
+                                           bool has_res, float* __restrict__ dx, long long lddx, const LnFuse& fuse, const DropKey& fkey, float4 (&dg)[NV],
                                            float4 (&db)[NV], float4 (&cs)[kFuse ? NV : 1]) {
   const float mu = R.mu, rs = R.rs;
   float s1 = 0.f, s2 = 0.f;
@@ -223,7 +223,7 @@ __device__ __forceinline__ void ln_bwd_row(LnBwdRow<NV>& R, long long row, int C
         *reinterpret_cast<float4*>(dx + row * lddx + c) = o;
         if (kFuse) {
           float v[4] = {o.x, o.y, o.z, o.w};
-          if (fuse.drop.p > 0.f) drop4(v, fuse.drop, fuse.thresh, fuse.scale, (unsigned long long)row * C + c);
+          if (fuse.drop.p > 0.f) drop4(v, fkey, fuse.thresh, fuse.scale, (unsigned long long)row * C + c);
           uint2 h, l;
           split4(v, h, l);
           *reinterpret_cast<uint2*>(fuse.g_hi + row * fuse.ldg + c) = h;
@@ -253,6 +253,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
 #pragma unroll
   for (int i = 0; i < (kFuse ? NV : 1); ++i) cs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   const float invC = 1.0f / (float)C;
+  const DropKey fkey = kFuse ? drop_key_of(fuse.drop) : DropKey{0u, 0u};
   const bool has_res = kNeedDx && dres != nullptr;
   const long long stride = (long long)gridDim.x * LN_WARPS;
   long long row = (long long)blockIdx.x * LN_WARPS + warp;
@@ -262,18 +263,18 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
     if (row < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row, C, lane, A);
     while (row < rows) {
       if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, B);
-      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
+      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, fkey, dg, db, cs);
       row += stride;
       if (row >= rows) break;
       if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, A);
-      ln_bwd_row<kNeedDx, kFuse, NV>(B, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
+      ln_bwd_row<kNeedDx, kFuse, NV>(B, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, fkey, dg, db, cs);
       row += stride;
     }
   } else {
     LnBwdRow<NV> A;
     for (; row < rows; row += stride) {
       ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row, C, lane, A);
-      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, dg, db, cs);
+      ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, fkey, dg, db, cs);
     }
   }
   // cross-warp reduction of the parameter grads, then one atomicAdd per column per block
@@ -305,6 +306,7 @@ __global__ void vit_assemble_fwd_kernel(const float* __restrict__ e, int F, int 
                                         float* __restrict__ x) {
   pdl_grid_sync();
   const int n = N + 1, C4 = C / 4;
+  const DropKey dkey = drop_key_of(drop);
   const long long total = (long long)F * n * C4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C4) * 4;
@@ -315,7 +317,7 @@ __global__ void vit_assemble_fwd_kernel(const float* __restrict__ e, int F, int 
                               : *reinterpret_cast<const float4*>(e + (f * N + (t - 1)) * (long long)C + c);
     const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (long long)t * C + c));
     float v[4] = {a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w};
-    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)ft * C + c);
+    if (drop.p > 0.f) drop4(v, dkey, thresh, scale, (unsigned long long)ft * C + c);
     *reinterpret_cast<float4*>(x + ft * C + c) = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
@@ -328,6 +330,7 @@ __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, int F, int
   const int n = N + 1, C4 = C / 4;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n * C4) return;
+  const DropKey dkey = drop_key_of(drop);
   const int t = j / C4, c = (j % C4) * 4;
   const int f0 = blockIdx.y * f_per_block;
   const int f1 = min(F, f0 + f_per_block);
@@ -336,7 +339,7 @@ __global__ void vit_assemble_bwd_kernel(const float* __restrict__ dx, int F, int
     const long long ft = (long long)f * n + t;
     const float4 d = *reinterpret_cast<const float4*>(dx + ft * C + c);
     float v[4] = {d.x, d.y, d.z, d.w};
-    if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)ft * C + c);
+    if (drop.p > 0.f) drop4(v, dkey, thresh, scale, (unsigned long long)ft * C + c);
     if (t > 0) *reinterpret_cast<float4*>(de + ((long long)f * N + (t - 1)) * C + c) = make_float4(v[0], v[1], v[2], v[3]);
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i] += v[i];
@@ -367,11 +370,12 @@ act_dropout_bwd_kernel(const float* __restrict__ dy, long long lddy, long long M
   const long long r0 = (long long)blockIdx.y * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const DropKey dkey = drop_key_of(drop);
   if (active) {
     for (long long r = r0 + threadIdx.y; r < r1; r += ADB_RG) {
       const float4 d = *reinterpret_cast<const float4*>(dy + r * lddy + c);
       float v[4] = {d.x, d.y, d.z, d.w};
-      if (drop.p > 0.f) drop4(v, drop, thresh, scale, (unsigned long long)r * N + c);
+      if (drop.p > 0.f) drop4(v, dkey, thresh, scale, (unsigned long long)r * N + c);
       if (act == ACT_GELU) {
         const float4 a = *reinterpret_cast<const float4*>(aux + r * ldaux + c);
         v[0] *= gelu_grad_f(a.x); v[1] *= gelu_grad_f(a.y); v[2] *= gelu_grad_f(a.z); v[3] *= gelu_grad_f(a.w);
@@ -577,7 +581,7 @@ __global__ void dropout_mask_kernel(Drop drop, uint32_t thresh, float scale, lon
   pdl_grid_sync();
   const long long n4 = (n + 3) / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const Philox4 w = dropout_words(drop_seed(drop), drop.site, (unsigned long long)i);
+    const Rand4 w = dropout_words(drop_seed(drop), drop.site, (unsigned long long)i);
     for (int k = 0; k < 4; ++k)
       if (i * 4 + k < n) out[i * 4 + k] = (w.v[k] >= thresh) ? scale : 0.f;
   }
