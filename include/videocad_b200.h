@@ -103,6 +103,9 @@ size_t vc_abi_sizeof(int which);
 /* ---- per-kernel entry points (unit parity tests call these; the model-level calls below chain them) ---- */
 void vc_gemm_desc_init(vc_gemm_desc* d);
 int vc_gemm(const vc_gemm_desc* d, void* stream);
+/* tile width of the 2-SM (cta_group::2) GEMM kernel: 0 = chosen per problem (default), 128 / 256 = forced where N allows (parity
+ * tests of both widths, experiments) */
+void vc_gemm_pair_force_tile(int bn);
 int vc_split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, vc_bf16* hi, vc_bf16* lo, int64_t ldo, void* stream);
 /* many fp32 -> split conversions in ONE launch (all weight matrices of a segment after an optimizer step).
  * `items` is a DEVICE array; item i converts n4 float4 groups and owns blocks [block_start, block_start + ceil(n4/1024)). */

@@ -490,6 +490,7 @@ int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t
 }
 
 void attention_small_enable(int) {}
+void gemm_pair_force_tile(int) {}
 
 int row_reduce_mod(const float* x, int64_t ldx, int64_t M, int N, int div, int mod, float* out, stream_t) {
   if (div < 1 || mod < 1) return set_error("row_reduce_mod: div/mod must be >= 1");

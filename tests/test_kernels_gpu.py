@@ -165,8 +165,31 @@ def test_gemm_pair_kernel_is_used_for_encoder_shapes():
     assert _relerr(out2, A[:256].double() @ B[:512].double().t()) < 3e-5
 
 
+@pytest.fixture(params=[0, 128, 256, -2], ids=["default", "bn128", "bn256", "wave-model"])
+def pair_tile(request):
+    """both tile widths of the 2-SM kernel (256 x 256 and 256 x 128), and the automatic choice"""
+    lib = L.load()
+    lib.vc_gemm_pair_force_tile(request.param)
+    yield request.param
+    lib.vc_gemm_pair_force_tile(0)
+
+
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,Kd", [(12800, 512, 512), (5120, 384, 192), (5120, 1024, 64)])
+def test_gemm_pair_tile_widths(pair_tile, M, N, Kd, b_mn):
+    if pair_tile == 256 and N % 256 != 0:
+        pytest.skip("N is not a multiple of 256")
+    A = _rand(M, Kd, seed=38)
+    B = _rand(Kd, N, seed=39) if b_mn else _rand(N, Kd, seed=39)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    before = _pair_count()
+    L.gemm(L.split(A), L.split(B), M, N, Kd, b_mn=b_mn, out_f32=out)
+    assert _pair_count() == before + 1
+    assert _relerr(out, A.double() @ (B.double() if b_mn else B.double().t())) < 3e-5
+
+
 @pytest.mark.parametrize("variant", ["split_bias", "f32_drop_res", "split_act", "all"])
-def test_gemm_pair_epilogues(variant):
+def test_gemm_pair_epilogues(variant, pair_tile):
     M, N, Kd = PAIR_SHAPE
     T = 8
     A, B = _rand(M, Kd, seed=42, scale=0.5), _rand(N, Kd, seed=43, scale=0.2)
@@ -203,7 +226,7 @@ def test_gemm_pair_epilogues(variant):
     assert _pair_count() == before + 1
 
 
-def test_gemm_pair_backward_activation_and_colsum():
+def test_gemm_pair_backward_activation_and_colsum(pair_tile):
     M, N, Kd = 2560, 1024, 512
     G, W = _rand(M, Kd, seed=47, scale=0.5), _rand(Kd, N, seed=48, scale=0.2)
     pre = _rand(M, N, seed=49)
@@ -223,7 +246,7 @@ def test_gemm_pair_backward_activation_and_colsum():
 
 
 @pytest.mark.parametrize("rows,Nw,Kw", [(6400, 512, 512), (12800, 3072, 512), (3200, 512, 1024)])
-def test_gemm_pair_splitk_wgrad(rows, Nw, Kw):
+def test_gemm_pair_splitk_wgrad(rows, Nw, Kw, pair_tile):
     dY, X = _rand(rows, Nw, seed=50), _rand(rows, Kw, seed=51)
     out = torch.zeros(Nw, Kw, device="cuda")
     before = _pair_count()

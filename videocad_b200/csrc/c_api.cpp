@@ -42,6 +42,7 @@ size_t vc_abi_sizeof(int which) {
 }
 
 void vc_gemm_desc_init(vc_gemm_desc* d) { vck::gemm_desc_init(d); }
+void vc_gemm_pair_force_tile(int bn) { vck::gemm_pair_force_tile(bn); }
 int vc_gemm(const vc_gemm_desc* d, void* stream) {
   if (!d) return vck::set_error("vc_gemm: null descriptor");
   return vck::gemm(*d, stream);

@@ -527,17 +527,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 //   warps 2..   epilogue (EW = 8 or 16 warps): TMEM lane quarter = warp % 4, column group = (warp - 2) / 4; 16-column chunks
 //               staged through an XOR-swizzled (unpadded) 32 x 16 fp32 buffer per warp
 // ---------------------------------------------------------------------------------------------------
-constexpr int P_BM = 256, P_BN = 256;
+constexpr int P_BM = 256;
 constexpr int P_MAX_EW = 16;                         // epilogue warps per CTA (template parameter EW: 8 or 16)
-constexpr int P_STAGES = 3;
 constexpr int P_TILE_BYTES = 128 * BK * 2;           // 16 KiB: one 128-row operand tile (hi or lo)
-constexpr int P_STAGE_BYTES = 4 * P_TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int P_CW = 16;                             // epilogue chunk width (columns)
 constexpr int P_STG_LD = 16;                         // floats per staged row: unpadded, float4 slots XOR-swizzled by (row >> 1) & 3
 constexpr int P_STG_BYTES = P_MAX_EW * 32 * P_STG_LD * 4;
 constexpr int P_BAR_BYTES = 256;
-constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + P_STG_BYTES + P_BAR_BYTES + 1024;
-constexpr int P_TMEM_COLS = 512;                     // two 256-column accumulator stages
+// Tile width PBN (template parameter): 256, or 128 for problems whose 256-wide tiling leaves the last wave mostly empty.
+// The N = 512 image-encoder GEMMs at C1 are 100 tiles of 256 x 256 on 74 SM pairs: two waves for 1.35 waves of work, and
+// the second wave's (heavy) epilogue runs on a third of the chip -- 26.6 us with the epilogue removed altogether against
+// 14.6 us of MMA work (profiles/r01l_gemm_debug.txt).  As 200 tiles of 256 x 128 the same problem is 2.7 waves of half-size
+// tiles; each CTA then stages 128 rows of A and 64 of the tile's 128 B rows per k-block (48 KiB, four stages).
+template <int PBN>
+struct PCfg {
+  static constexpr int B_ROWS = PBN / 2;                             // B rows staged by each CTA of the pair
+  static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;               // 16 or 8 KiB
+  static constexpr int STAGE_BYTES = 2 * P_TILE_BYTES + 2 * B_TILE_BYTES;  // A_hi, A_lo, B_hi, B_lo
+  static constexpr int STAGES = PBN == 256 ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + P_STG_BYTES + P_BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = 2 * PBN;                          // two accumulator stages
+};
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -549,12 +559,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
-template <uint32_t F, int EW>
+template <uint32_t F, int EW, int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                     const GemmParams p) {
   pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
+  using C = PCfg<PBN>;
+  constexpr int P_STAGES = C::STAGES, P_STAGE_BYTES = C::STAGE_BYTES, P_BN = PBN;
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);  // used in the leader CTA only
   uint64_t* empty_bar = full_bar + P_STAGES;
@@ -589,7 +601,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc_pair(tmem_slot, P_TMEM_COLS);
+  if (warp == 2) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   cluster_sync_all();
   tc_fence_after();
@@ -600,7 +612,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const int num_n = (p.N + P_BN - 1) / P_BN;
   const int total_tiles = num_m * num_n * p.splitk;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * 2 * P_TILE_BYTES) * 2u;  // both CTAs' loads of one stage
+  const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * (P_TILE_BYTES + C::B_TILE_BYTES)) * 2u;  // both CTAs' loads of one stage
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs)
@@ -611,7 +623,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int t2 = tile / num_n;
         const int m_idx = t2 % num_m;
         const int split = t2 / num_m;
-        const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + (int)rank * 128;
+        const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + (int)rank * C::B_ROWS;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -622,7 +634,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           uint8_t* sA_hi = st;
           uint8_t* sA_lo = st + P_TILE_BYTES;
           uint8_t* sB_hi = st + 2 * P_TILE_BYTES;
-          uint8_t* sB_lo = st + 3 * P_TILE_BYTES;
+          uint8_t* sB_lo = sB_hi + C::B_TILE_BYTES;
           if (leader) mbar_expect_tx(&full_bar[s], tx_bytes);
           const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
           const int k0 = kb * BK;
@@ -641,7 +653,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             if (p.passes == 3) tma_load_2d_pair(sB_lo, &tmB_lo, fb, k0, n0);
           } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < C::B_ROWS / 64; ++j) {
               tma_load_2d_pair(sB_hi + j * 8192, &tmB_hi, fb, n0 + 64 * j, k0);
               if (p.passes == 3) tma_load_2d_pair(sB_lo + j * 8192, &tmB_lo, fb, n0 + 64 * j, k0);
             }
@@ -683,7 +695,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sA_hi = smem_u32(tiles + s * P_STAGE_BYTES);
           const uint32_t sA_lo = sA_hi + P_TILE_BYTES;
           const uint32_t sB_hi = sA_hi + 2 * P_TILE_BYTES;
-          const uint32_t sB_lo = sA_hi + 3 * P_TILE_BYTES;
+          const uint32_t sB_lo = sB_hi + C::B_TILE_BYTES;
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
@@ -750,12 +762,18 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
         }
         uint32_t r[P_CW];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW, r);
-        tmem_ld_wait();
+        if (!(p.debug & 4)) {
+          tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW, r);
+          tmem_ld_wait();
+        }
         if (c == kCols / P_CW - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(a ? tempty_remote1 : tempty_remote0);
+        }
+        if (p.debug & 6) {  // VC_GEMM_DEBUG experiments: 2 = TMEM loads only, 4 = not even those
+          if ((p.debug & 2) && r[0] == 0x7fc12345u) p.out_f32[0] = 1.f;  // keep the loads alive
+          continue;
         }
         const int col0 = n0 + c * P_CW;
         float* myrow = stg + lane * P_STG_LD;
@@ -774,8 +792,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           if (row < p.M && col < p.N) {
             const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ ((rr >> 1) & 3)));
             float v[4] = {t4.x, t4.y, t4.z, t4.w};
-            epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
-                             paux[kPreAux ? it : 0]);
+            if (p.debug & 1) {  // VC_GEMM_DEBUG = 1: no epilogue math, no global stores
+              if (v[0] == 123.456f) p.out_f32[0] = v[1];
+            } else {
+              epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
+                               paux[kPreAux ? it : 0]);
+            }
             if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
           }
         }
@@ -802,7 +824,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_pair(tmem_base, P_TMEM_COLS);
+    tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -1050,23 +1072,27 @@ int pair_epilogue_warps() {
   return ew;
 }
 
-template <uint32_t F, int EW>
+template <uint32_t F, int EW, int PBN>
 int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream);
 
 template <uint32_t F>
-int launch_gemm_pair_variant(const GemmDesc& d, int splitk, cudaStream_t stream) {
-  return pair_epilogue_warps() == 8 ? launch_gemm_pair_ew<F, 8>(d, splitk, stream) : launch_gemm_pair_ew<F, 16>(d, splitk, stream);
+int launch_gemm_pair_variant(const GemmDesc& d, int splitk, int pbn, cudaStream_t stream) {
+  if (pbn == 128)
+    return pair_epilogue_warps() == 8 ? launch_gemm_pair_ew<F, 8, 128>(d, splitk, stream) : launch_gemm_pair_ew<F, 16, 128>(d, splitk, stream);
+  return pair_epilogue_warps() == 8 ? launch_gemm_pair_ew<F, 8, 256>(d, splitk, stream) : launch_gemm_pair_ew<F, 16, 256>(d, splitk, stream);
 }
 
-template <uint32_t F, int EW>
+template <uint32_t F, int EW, int PBN>
 int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
+  using C = PCfg<PBN>;
+  constexpr int P_SMEM_BYTES = C::SMEM_BYTES, P_BN = PBN;
   GemmParams p;
   fill_params(p, d, splitk);
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
-  if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, 128)) return rc;  // each CTA stages 128 of the tile's 256 B rows
+  if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, C::B_ROWS)) return rc;  // each CTA stages half of the tile's B rows
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F, EW, PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1075,20 +1101,20 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   const int grid = 2 * (int)(tiles < pairs ? tiles : pairs);
   int slot = -1;
   char tag[64];
-  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
-           d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act);
+  snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
+           d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act, PBN);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  VC_LAUNCH((gemm_tc_pair_kernel<F, EW>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
+  VC_LAUNCH((gemm_tc_pair_kernel<F, EW, PBN>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
   count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_pair_kernel");
 }
 
-int launch_gemm_pair(const GemmDesc& d, int splitk, cudaStream_t stream) {
+int launch_gemm_pair(const GemmDesc& d, int splitk, int pbn, cudaStream_t stream) {
   GemmDesc dd = d;
   dd.splitk = splitk;
   const uint32_t req = required_features(dd);
-#define VC_TRY_VARIANT(V) if ((req & ~(V)) == 0) return launch_gemm_pair_variant<(V)>(d, splitk, stream);
+#define VC_TRY_VARIANT(V) if ((req & ~(V)) == 0) return launch_gemm_pair_variant<(V)>(d, splitk, pbn, stream);
   VC_TRY_VARIANT(V_F32)
   VC_TRY_VARIANT(V_F32_BIAS)
   VC_TRY_VARIANT(V_ATOMIC)
@@ -1098,27 +1124,47 @@ int launch_gemm_pair(const GemmDesc& d, int splitk, cudaStream_t stream) {
   VC_TRY_VARIANT(V_SPLIT_ACT)
   VC_TRY_VARIANT(V_SPLIT_BWD)
 #undef VC_TRY_VARIANT
-  return launch_gemm_pair_variant<EF_ALL>(d, splitk, stream);
+  return launch_gemm_pair_variant<EF_ALL>(d, splitk, pbn, stream);
 }
 
-// The CTA-pair kernel handles problems whose M and N are multiples of its 256 x 256 tile and that keep at least half of the
-// 74 SM pairs busy (the image-encoder GEMMs); everything else (decoder-sized, ragged N) uses the single-CTA kernel.
-bool pair_eligible(const GemmDesc& d, int* splitk_out) {
+// The CTA-pair kernel handles problems whose M is a multiple of 256 and whose N is a multiple of its tile width (256 or 128) and
+// that keep at least half of the 74 SM pairs busy (the image-encoder GEMMs); everything else (decoder-sized, ragged N) uses the
+// single-CTA kernel.  Tile width: 256 whenever N allows it.  A wave model (waves x (k-blocks per tile x MMA time per k-block +
+// epilogue allowance); VC_GEMM_PAIR_BN=-2 selects it) picks 128 for the N = 512 GEMMs, whose 100 wide tiles leave the second
+// wave two-thirds empty, and each such GEMM alone does run 4-9 us faster -- but the training step got 1.7 % SLOWER
+// (profiles/r01l_tile_width_ab.txt): inside the step those idle SMs are not idle, they run the CAD encoder and the
+// weight-gradient GEMMs of the auxiliary streams, and the narrow tile moves 1.5x the operand bytes per FLOP through L2.
+int g_pair_force_bn = -1;  // -1: undecided (VC_GEMM_PAIR_BN in the environment), 0: default policy, 128 / 256: forced, -2: wave model
+
+bool pair_eligible(const GemmDesc& d, int* splitk_out, int* pbn_out) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("VC_GEMM_PAIR"); enabled = e ? atoi(e) : 1; }
+  if (g_pair_force_bn == -1) { const char* e = getenv("VC_GEMM_PAIR_BN"); g_pair_force_bn = e ? atoi(e) : 0; }
+  const int force_bn = g_pair_force_bn;
   if (!enabled) return false;
-  if (d.M % P_BM != 0 || d.N % P_BN != 0) return false;
-  const long long tiles = (long long)(d.M / P_BM) * (d.N / P_BN);
+  if (d.M % P_BM != 0 || d.N % 128 != 0) return false;
   const int num_kb = (d.K + BK - 1) / BK;
   const int pairs = num_sms() / 2;
-  int s = 1;
-  if (d.splitk > 1) s = choose_splitk(tiles, num_kb, pairs);
-  if (tiles * s < pairs / 2) return false;
-  *splitk_out = s;
-  return true;
+  double best_cost = -1.0;
+  for (int pbn = 256; pbn >= 128; pbn -= 128) {
+    if (d.N % pbn != 0) continue;
+    if (force_bn == 128 || force_bn == 256) { if (pbn != force_bn && d.N % force_bn == 0) continue; }
+    const long long tiles = (long long)(d.M / P_BM) * (d.N / pbn);
+    int s = 1;
+    if (d.splitk > 1) s = choose_splitk(tiles, num_kb, pairs);
+    if (tiles * s < pairs / 2) continue;
+    const long long waves = (tiles * s + pairs - 1) / pairs;
+    const double kb = (double)((num_kb + s - 1) / s);
+    double cost = pbn == 256 ? (double)waves * (kb + 4.0) : (double)waves * (kb * 0.55 + 2.0);
+    if (force_bn != -2 && pbn == 128) cost += 1e9;  // default policy: the narrow tile only where the wide one does not apply
+    if (best_cost < 0.0 || cost < best_cost) { best_cost = cost; *splitk_out = s; *pbn_out = pbn; }
+  }
+  return best_cost >= 0.0;
 }
 
 }  // namespace
+
+void gemm_pair_force_tile(int bn) { g_pair_force_bn = (bn == 128 || bn == 256 || bn == -2) ? bn : 0; }
 
 void gemm_desc_init(GemmDesc* d) {
   memset(d, 0, sizeof *d);
@@ -1145,8 +1191,8 @@ int gemm(const GemmDesc& d, stream_t stream) {
     return set_error("gemm: epilogue leading dimensions must be multiples of 4");
   // decoder-sized problems fill only a few SMs with 128x128 tiles: halve the tile width so that twice as many CTAs each
   // run half the MMA work
-  int pair_splitk = 1;
-  if (pair_eligible(d, &pair_splitk)) return launch_gemm_pair(d, pair_splitk, reinterpret_cast<cudaStream_t>(stream));
+  int pair_splitk = 1, pair_bn = 256;
+  if (pair_eligible(d, &pair_splitk, &pair_bn)) return launch_gemm_pair(d, pair_splitk, pair_bn, reinterpret_cast<cudaStream_t>(stream));
   const long long tiles128 = (long long)((d.M + BM - 1) / BM) * ((d.N + 127) / 128) * (d.splitk > 1 ? d.splitk : 1);
   if (tiles128 <= 48 && d.N >= 64) return launch_gemm<64>(d, reinterpret_cast<cudaStream_t>(stream));
   return launch_gemm<128>(d, reinterpret_cast<cudaStream_t>(stream));

@@ -41,6 +41,9 @@ static inline Drop make_drop(float p, uint32_t site, uint64_t seed, const uint64
 typedef vc_gemm_desc GemmDesc;
 void gemm_desc_init(GemmDesc* d);
 int gemm(const GemmDesc& d, stream_t stream);
+// tile width of the 2-SM GEMM kernel: 0 = chosen per problem by the wave model (default), 128 / 256 = forced where N allows
+// (tests, experiments).  No effect in the CPU emulation.
+void gemm_pair_force_tile(int bn);
 
 // x[rows, cols] fp32 -> (hi, lo)
 int split_f32(const float* x, int64_t ldx, int64_t rows, int64_t cols, bf16_t* hi, bf16_t* lo, int64_t ldo, stream_t s);

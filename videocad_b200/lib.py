@@ -77,6 +77,7 @@ _PROTOS = {
     "vc_gemm_profile_dump": ([C.c_char_p], i32),
     "vc_abi_sizeof": ([i32], C.c_size_t),
     "vc_gemm_desc_init": ([C.POINTER(GemmDesc)], None),
+    "vc_gemm_pair_force_tile": ([i32], None),
     "vc_gemm": ([C.POINTER(GemmDesc), vp], i32),
     "vc_split_f32": ([vp, i64, i64, i64, vp, vp, i64, vp], i32),
     "vc_split_many": ([vp, i32, i64, vp], i32),
