@@ -204,6 +204,12 @@ int vc_clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double bet
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream);
 int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
                       int accumulate_dx, float* dW, float* db, void* stream);
+/* ---- frame ingestion: uint8 grey-level frames -> the normalised fp32 tensor the model consumes.
+ * Replaces transforms.ToTensor() + transforms.Normalize([0.5], [0.5]) of the reference's loader (main.py:103-110, applied per
+ * frame on the CPU in DatasetBase.__getitem__, data_loader/data_loader.py:434-508) and lets the batch cross PCIe as bytes:
+ * dst[i] = (float(src[i]) / 255 - mean) / std with the same fp32 operations in the same order (bit-exact).
+ * src and dst 16-byte aligned, n = number of pixels. */
+int vc_frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, void* stream);
 int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 int vc_zero_f32(float* x, int64_t n, void* stream);
 int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream);

@@ -489,6 +489,17 @@ int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t
   return act_dropout_bwd(dv, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dv_hi, dv_lo, ld_split, dbv, st);
 }
 
+int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t) {
+  if (n > 0 && (!src || !dst)) return set_error("frames_u8_normalize: null pointer");
+  if (!(std != 0.f)) return set_error("frames_u8_normalize: std must be non-zero");
+  for (int64_t i = 0; i < n; ++i) {
+    volatile float v = (float)src[i] / 255.0f;  // one correctly-rounded fp32 operation per step, as torchvision does
+    volatile float w = v - mean;
+    dst[i] = w / std;
+  }
+  return 0;
+}
+
 void attention_small_enable(int) {}
 void gemm_pair_force_tile(int) {}
 

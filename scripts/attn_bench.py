@@ -66,6 +66,20 @@ def main():
         K.attention_bwd_split(a, o, lse, dsplit, F, n, nh, d)
         torch.cuda.synchronize()
 
+    # ---- image-encoder LayerNorm forward / backward (with the fused dropout-mask + split second output), [12800, 512]
+    rows, Cc = F * n, 512
+    x = torch.randn(rows, Cc, device="cuda", generator=g)
+    gamma, beta = torch.randn(Cc, device="cuda", generator=g), torch.randn(Cc, device="cuda", generator=g)
+    dy, dres = torch.randn(rows, Cc, device="cuda", generator=g), torch.randn(rows, Cc, device="cuda", generator=g)
+    y, ys, mean, rstd = K.layernorm_fwd(x, gamma, beta, want_f32=False)
+    us = timeit(lambda: K.layernorm_fwd(x, gamma, beta, want_f32=False), iters, flush) if not args.once else 0.0
+    by = rows * Cc * (4 + 4)
+    print(f"ln fwd  [{rows},{Cc}] -> split: {us:8.1f} us  {by / 1e6:7.1f} MB algorithmic  {by / max(us, 1e-9) / 1e6:8.2f} TB/s", flush=True)
+    K.layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres, drop)
+    us = timeit(lambda: K.layernorm_bwd_fused(dy, x, mean, rstd, gamma, dres, drop), iters, flush) if not args.once else 0.0
+    by = rows * Cc * (4 * 3 + 4 + 4)
+    print(f"ln bwd fused [{rows},{Cc}]:       {us:8.1f} us  {by / 1e6:7.1f} MB algorithmic  {by / max(us, 1e-9) / 1e6:8.2f} TB/s", flush=True)
+
     # ---- decoder attention (fp32 q/k/v from the in_proj GEMM), short-sequence kernels vs the generic ones
     for (B, T, nh2, d2, mask, window) in [(32, 8, 4, 128, L.MASK_CAUSAL, 1), (32, 8, 4, 128, L.MASK_WINDOW, 10),
                                          (32, 32, 4, 256, L.MASK_WINDOW, 10)]:

@@ -229,6 +229,33 @@ def test_dropout_mask_statistics(emu):
     assert 0.93 < k.mean(1).std() / np.sqrt(0.09 / 512) < 1.07
 
 
+def _torch_ingest(u8):
+    """transforms.ToTensor() + transforms.Normalize([0.5], [0.5]) on an already grey, already sized uint8 image (main.py:103-110)"""
+    return u8.to(torch.float32).div(255).sub_(0.5).div_(0.5)
+
+
+def test_frame_ingestion_u8_bit_exact_and_model_equivalence(emu):
+    """uint8 frames normalised by vc_frames_u8_normalize == the reference loader's ToTensor + Normalize, bit for bit (all 256 grey
+    levels, ragged length), and the model fed uint8 frames returns exactly what it returns for the normalised fp32 frames."""
+    levels = torch.arange(256, dtype=torch.uint8).repeat(3)[:733]  # ragged: exercises the tail path of the CUDA kernel's twin
+    dst = torch.empty(levels.numel(), dtype=torch.float32)
+    L.check(emu.vc_frames_u8_normalize(levels.data_ptr(), levels.numel(), 0.5, 0.5, dst.data_ptr(), None), emu)
+    assert torch.equal(dst, _torch_ingest(levels))
+    assert dst.min() == -1.0 and dst.max() == 1.0
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, _ = build_emu_model(emu, cfg)
+    m.eval()
+    g = torch.Generator().manual_seed(3)
+    acts = to.model_inputs_from_batch(to.synthetic_batch(2, 4, 64))["actions"]
+    frames = torch.randint(0, 256, (2, acts.shape[1], 1, 64, 64), dtype=torch.uint8, generator=g)
+    cad = torch.randint(0, 256, (2, 1, 64, 64), dtype=torch.uint8, generator=g)
+    with torch.no_grad():
+        c8, p8 = m({"frames": frames, "actions": acts, "cad_image": cad})
+        cf, pf = m({"frames": _torch_ingest(frames), "actions": acts, "cad_image": _torch_ingest(cad)})
+    assert torch.equal(c8, cf) and torch.equal(p8, pf)
+
+
 def test_sequential_inference_matches_oracle(emu):
     cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)

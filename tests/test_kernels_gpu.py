@@ -473,6 +473,19 @@ def test_vit_attention_split_inputs(B, T, p):
         assert err < 1e-4, f"{name}: {err:.3e}"
 
 
+@pytest.mark.parametrize("n", [16, 733, 8 * 224 * 224 + 5])
+def test_frames_u8_normalize_bit_exact(n):
+    """uint8 frame ingestion == ToTensor() + Normalize([0.5], [0.5]) of the reference's loader (main.py:103-110), bit for bit"""
+    g = torch.Generator(device="cuda").manual_seed(n)
+    u8 = torch.randint(0, 256, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    u8[:min(n, 256)] = torch.arange(min(n, 256), dtype=torch.uint8, device="cuda")
+    dst = torch.full((n,), float("nan"), device="cuda")
+    L.check(L.load().vc_frames_u8_normalize(u8.data_ptr(), n, 0.5, 0.5, dst.data_ptr(), L.cur_stream()))
+    ref = u8.to(torch.float32).div(255).sub_(0.5).div_(0.5)
+    assert torch.equal(dst, ref)
+    assert torch.equal(dst.cpu(), u8.cpu().to(torch.float32).div(255).sub_(0.5).div_(0.5))  # and the CPU loader's values
+
+
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])
 def test_act_dropout_bwd(act):
     M, N = 777, 512

@@ -226,6 +226,33 @@ def test_cuda_graph_replay_matches_eager():
     assert (after - before).abs().max() > 1e-4
 
 
+def test_uint8_frame_ingestion_equals_normalised_float_frames():
+    """uint8 grey-level frames / CAD image handed to the module are normalised on the device exactly as
+    the reference's loader does on the CPU (ToTensor + Normalize([0.5], [0.5]), main.py:103-110): identical logits and gradients,
+    on the eager, captured and replayed paths."""
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=3,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, _ = build(cfg, dropout=0.0)
+    m.eval()
+    inp, _ = cuda_inputs(3, 4, 64)
+    g = torch.Generator().manual_seed(11)
+    f8 = torch.randint(0, 256, tuple(inp["frames"].shape), dtype=torch.uint8, generator=g).cuda()
+    c8 = torch.randint(0, 256, tuple(inp["cad_image"].shape), dtype=torch.uint8, generator=g).cuda()
+    norm = lambda u: u.to(torch.float32).div(255).sub_(0.5).div_(0.5)
+    wc, wp = loss_weights((3, 4, 5), (3, 4, 6, 1000))
+    res = []
+    for frames, cad in ((f8, c8), (norm(f8), norm(c8))):
+        for it in range(3):
+            m.zero_grad(set_to_none=True)
+            c, p = m({"frames": frames, "actions": inp["actions"], "cad_image": cad})
+            ((c * wc.cuda()).sum() + (p * wp.cuda()).sum()).backward()
+            res.append((c.detach().clone(), p.detach().clone(),
+                        dict(m.named_weights())["state_embedding_model.to_patch_embedding.2.weight"].grad.clone()))
+    for r in res[1:]:
+        assert torch.equal(r[0], res[0][0]) and torch.equal(r[1], res[0][1])
+        assert (r[2] - res[0][2]).abs().max() <= 1e-4 * res[0][2].abs().max() + 1e-9  # split-K atomics reorder sums
+
+
 def test_full_size_c1_batch_properties():
     """BASELINE C1 at full size (B=32, T=8, 224x224, H=512): size-independent properties."""
     cfg = dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,

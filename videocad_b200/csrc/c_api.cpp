@@ -159,6 +159,9 @@ int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const
                       int accumulate_dx, float* dW, float* db, void* stream) {
   return vck::head_small_bwd(dout, x, R, H, W, C, dx, accumulate_dx, dW, db, stream);
 }
+int vc_frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, void* stream) {
+  return vck::frames_u8_normalize(src, n, mean, std, dst, stream);
+}
 int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) { return vck::add_f32(a, b, out, n, stream); }
 int vc_zero_f32(float* x, int64_t n, void* stream) { return vck::zero_f32(x, n, stream); }
 int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream) {

@@ -159,6 +159,11 @@ int stream_join(stream_t main, int i);
 // 0: stream_fork hands back the caller's stream (serialised execution, used when timing kernels one by one); 1: default
 void side_streams_enable(int enable);
 
+// frame ingestion: uint8 grey-level frames -> the fp32 tensor the reference's loader hands the model,
+// i.e. torchvision ToTensor (u / 255) followed by Normalize(mean, std) (/root/reference/main.py:103-110: mean = std = 0.5):
+// dst[i] = (float(src[i]) / 255 - mean) / std, evaluated with the same fp32 operations in the same order (bit-exact)
+int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t s);
+
 // misc
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s);  // out = a + b (b may alias out)
 int zero_f32(float* x, int64_t n, stream_t s);

@@ -69,12 +69,16 @@ constexpr int LN_WARPS = 4;
 
 struct RowLoader {  // plain strided rows
   const float* x; long long ldx;
+  static constexpr bool kContiguous = true;
   __device__ __forceinline__ float4 load(long long row, int c) const {
     return *reinterpret_cast<const float4*>(x + row * ldx + c);
   }
+  __device__ __forceinline__ const float* ptr(long long row, int c) const { return x + row * ldx + c; }
 };
 struct PatchLoader {  // 'f 1 (h 32) (w 32) -> (f h w) (32 32)' gather; C = 1024
   const float* img; int S, wp, N;
+  static constexpr bool kContiguous = false;
+  __device__ __forceinline__ const float* ptr(long long, int) const { return nullptr; }
   __device__ __forceinline__ float4 load(long long row, int c) const {
     const long long f = row / N;
     const int pidx = (int)(row % N);
@@ -235,9 +239,21 @@ __device__ __forceinline__ void ln_bwd_row(LnBwdRow<NV>& R, long long row, int C
   }
 }
 
-// Each warp walks its rows with a stride; the NEXT row's operands (x, dy, residual gradient: 12 x 128-bit loads per lane at
-// C = 512) are requested before the current row's reductions and stores, so loads stay in flight continuously (the first
-// version alternated load and compute phases and reached only ~3 TB/s).
+// Each warp walks its rows with a stride.  The operands of the next LNB_DEPTH - 1 rows (x, dy, residual gradient: 12 x 128-bit
+// loads per lane and row at C = 512) are kept in flight with cp.async into a per-warp shared-memory ring: every lane copies and
+// later reads only ITS OWN 16-byte slots, so the only synchronisation is cp.async.wait_group.  History: alternating load and
+// compute phases reached ~3 TB/s; a one-row register prefetch 2.6-2.9 TB/s at 183 registers (two resident CTAs per SM, ncu:
+// 2.3 long-scoreboard stall cycles per issued instruction, profiles/r01l_ncu_attn_ln_summary.txt); the ring needs registers for
+// one row only.
+constexpr int LNB_DEPTH = 3;
+
+__device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void ln_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ln_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <class Loader, bool kNeedDx, bool kFuse, int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const float* __restrict__ mean,
@@ -246,6 +262,7 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
               float* __restrict__ dgamma, float* __restrict__ dbeta, const LnFuse fuse) {
   pdl_grid_sync();
   __shared__ float4 red[LN_WARPS][32];
+  extern __shared__ float4 ln_ring[];  // [LN_WARPS][LNB_DEPTH][3 (x, dy, dres)][NV][32 lanes] (ring variant only)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 dg[NV], db[NV], cs[kFuse ? NV : 1];
 #pragma unroll
@@ -257,19 +274,50 @@ ln_bwd_kernel(Loader ld, const float* __restrict__ dy, long long lddy, const flo
   const bool has_res = kNeedDx && dres != nullptr;
   const long long stride = (long long)gridDim.x * LN_WARPS;
   long long row = (long long)blockIdx.x * LN_WARPS + warp;
-  constexpr bool kPrefetch = NV <= 4;  // two rows of operands in registers; at C = 1024 that would spill
-  if constexpr (kPrefetch) {
-    LnBwdRow<NV> A, B;
-    if (row < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row, C, lane, A);
+  constexpr bool kRing = Loader::kContiguous && NV <= 4;  // contiguous rows of <= 512 columns: the image encoders and the decoder
+  if constexpr (kRing) {
+    float4* wring = ln_ring + (size_t)warp * (LNB_DEPTH * 3 * NV * 32);
+    auto issue = [&](long long r, int slot) {
+      if (r < rows) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane * 4 + i * 128;
+          if (c < C) {
+            ln_cp_async16(&wring[((slot * 3 + 0) * NV + i) * 32 + lane], ld.ptr(r, c));
+            ln_cp_async16(&wring[((slot * 3 + 1) * NV + i) * 32 + lane], dy + r * lddy + c);
+            if (has_res) ln_cp_async16(&wring[((slot * 3 + 2) * NV + i) * 32 + lane], dres + r * lddres + c);
+          }
+        }
+      }
+      ln_cp_async_commit();  // one group per ring step, empty past the last row: the wait below counts groups
+    };
+#pragma unroll
+    for (int dpt = 0; dpt < LNB_DEPTH - 1; ++dpt) issue(row + dpt * stride, dpt);
+    float mu_n = 0.f, rs_n = 0.f;
+    if (row < rows) { mu_n = mean[row]; rs_n = rstd[row]; }
+    int slot = 0;
     while (row < rows) {
-      if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, B);
+      int nslot = slot + LNB_DEPTH - 1;
+      if (nslot >= LNB_DEPTH) nslot -= LNB_DEPTH;
+      issue(row + (LNB_DEPTH - 1) * stride, nslot);  // overwrites the slot consumed in the previous iteration
+      LnBwdRow<NV> A;
+      A.mu = mu_n; A.rs = rs_n;
+      if (row + stride < rows) { mu_n = mean[row + stride]; rs_n = rstd[row + stride]; }
+      ln_cp_async_wait<LNB_DEPTH - 1>();  // this row's group has landed
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < C) {
+          A.x[i] = wring[((slot * 3 + 0) * NV + i) * 32 + lane];
+          A.d[i] = wring[((slot * 3 + 1) * NV + i) * 32 + lane];
+          if (has_res) A.r[i] = wring[((slot * 3 + 2) * NV + i) * 32 + lane];
+        }
+      }
       ln_bwd_row<kNeedDx, kFuse, NV>(A, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, fkey, dg, db, cs);
       row += stride;
-      if (row >= rows) break;
-      if (row + stride < rows) ln_bwd_load<Loader, kNeedDx, NV>(ld, dy, lddy, mean, rstd, dres, lddres, row + stride, C, lane, A);
-      ln_bwd_row<kNeedDx, kFuse, NV>(B, row, C, lane, invC, gamma, has_res, dx, lddx, fuse, fkey, dg, db, cs);
-      row += stride;
+      slot = slot + 1 == LNB_DEPTH ? 0 : slot + 1;
     }
+    ln_cp_async_wait<0>();
   } else {
     LnBwdRow<NV> A;
     for (; row < rows; row += stride) {
@@ -571,6 +619,28 @@ __global__ void head_small_bwd_kernel(const float* __restrict__ dout, const floa
   }
 }
 
+// uint8 frames -> normalised fp32 (16 pixels per thread: one 128-bit load, four 128-bit stores)
+__global__ void frames_u8_normalize_kernel(const uint8_t* __restrict__ src, long long n, float mean, float std, float* __restrict__ dst) {
+  pdl_grid_sync();
+  const long long n16 = n >> 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 w = *reinterpret_cast<const uint4*>(src + 16 * i);
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 o;
+      o.x = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(ws[k] & 0xffu), 255.0f), mean), std);
+      o.y = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((ws[k] >> 8) & 0xffu), 255.0f), mean), std);
+      o.z = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((ws[k] >> 16) & 0xffu), 255.0f), mean), std);
+      o.w = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(ws[k] >> 24), 255.0f), mean), std);
+      *reinterpret_cast<float4*>(dst + 16 * i + 4 * k) = o;
+    }
+  }
+  // tail (n not a multiple of 16)
+  for (long long i = (n16 << 4) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)src[i], 255.0f), mean), std);
+}
+
 __global__ void add_kernel(const float* __restrict__ a, const float* b, float* out, long long n) {
   pdl_grid_sync();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -635,18 +705,27 @@ int layernorm_bwd_fused(const float* dy, int64_t lddy, const float* x, int64_t l
   if (C % 128 != 0 || C > 128 * LN_MAXV) return set_error("layernorm_bwd: C must be a multiple of 128 and <= 1024");
   if (rows <= 0) return 0;
   RowLoader ld{x, ldx};
-  // one resident wave (2-3 CTAs/SM at ~200 registers with the row prefetch): fewer blocks also means fewer gradient atomics per
-  // column; decoder-sized problems (a few hundred rows) get one row per warp instead of four
+  // one resident wave (3 CTAs/SM: 145 registers, 72 KiB of operand ring at C = 512): fewer blocks also means fewer gradient
+  // atomics per column; decoder-sized problems (a few hundred rows) get one row per warp instead of four
   int grid = cdiv(rows, LN_WARPS * 4);
   if (grid < 148) grid = cdiv(rows, LN_WARPS) < 148 ? cdiv(rows, LN_WARPS) : 148;
-  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid > 148 * 3) grid = 148 * 3;
   LnFuse f;
   f.drop = gdrop; f.thresh = dropout_threshold(gdrop.p); f.scale = drop_scale(gdrop);
   f.g_hi = reinterpret_cast<__nv_bfloat16*>(g_hi); f.g_lo = reinterpret_cast<__nv_bfloat16*>(g_lo); f.ldg = ldg;
   f.colsum = g_colsum;
 #define VC_LN_BWD(FUSE, NVV)                                                                                              \
-  VC_LAUNCH((ln_bwd_kernel<RowLoader, true, FUSE, NVV>), grid, LN_WARPS * 32, 0, cs(s), ld, dy, lddy, mean, rstd, gamma, rows, C, dres, \
-                                                                               lddres, dx, lddx, dgamma, dbeta, f)
+  do {                                                                                                                    \
+    const size_t ring = (NVV) <= 4 ? sizeof(float4) * LN_WARPS * LNB_DEPTH * 3 * (NVV) * 32 : 0;                         \
+    static bool configured = false;                                                                                       \
+    if (ring > 48 * 1024 && !configured) {                                                                                \
+      cudaError_t e = cudaFuncSetAttribute(ln_bwd_kernel<RowLoader, true, FUSE, NVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring); \
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));                                                      \
+      configured = true;                                                                                                  \
+    }                                                                                                                     \
+    VC_LAUNCH((ln_bwd_kernel<RowLoader, true, FUSE, NVV>), grid, LN_WARPS * 32, ring, cs(s), ld, dy, lddy, mean, rstd, gamma, rows, C, dres, \
+                                                                                 lddres, dx, lddx, dgamma, dbeta, f);     \
+  } while (0)
   if (g_hi != nullptr) {
     if (g_lo == nullptr) return set_error("layernorm_bwd_fused: g_lo required with g_hi");
     if (C <= 256) VC_LN_BWD(true, 2); else if (C <= 512) VC_LN_BWD(true, 4); else VC_LN_BWD(true, 8);
@@ -784,6 +863,16 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
   dim3 grid(cdiv(H / 4, 128), cdiv(R, rows_per_block));
   VC_LAUNCH((head_small_bwd_kernel), grid, 128, 0, cs(s), dout, x, R, H, W, C, dx, accumulate_dx, dW, db, rows_per_block);
   return check_launch("head_small_bwd_kernel");
+}
+
+int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t s) {
+  if (n <= 0) return 0;
+  if (!src || !dst) return set_error("frames_u8_normalize: null pointer");
+  if (!(std != 0.f)) return set_error("frames_u8_normalize: std must be non-zero");
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) != 0 || (reinterpret_cast<uintptr_t>(dst) & 15u) != 0)
+    return set_error("frames_u8_normalize: src and dst must be 16-byte aligned");
+  VC_LAUNCH((frames_u8_normalize_kernel), ew_grid((n + 15) / 16, 256), 256, 0, cs(s), src, (long long)n, mean, std, dst);
+  return check_launch("frames_u8_normalize_kernel");
 }
 
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s) {

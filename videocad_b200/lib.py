@@ -105,6 +105,7 @@ _PROTOS = {
     "vc_clip_adam_step": ([vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp, vp, vp], i32),
     "vc_head_small_fwd": ([vp, i64, i32, vp, vp, i32, vp, vp], i32),
     "vc_head_small_bwd": ([vp, vp, i64, i32, vp, i32, vp, i32, vp, vp, vp], i32),
+    "vc_frames_u8_normalize": ([vp, i64, f32, f32, vp, vp], i32),
     "vc_add_f32": ([vp, vp, vp, i64, vp], i32),
     "vc_zero_f32": ([vp, i64, vp], i32),
     "vc_dropout_mask_debug": ([Drop, i64, vp, vp], i32),

@@ -401,7 +401,10 @@ class _VitRunner(_Segment):
 
     def forward(self, img: torch.Tensor, training: bool, p: float, seed: int, passes: int, need_grad: bool = True):
         lib = self.lib()
-        if img.dtype != torch.float32:
+        # uint8 grey-level frames are normalised on the device, straight into the encoder's input buffer (frame ingestion,
+        # SURVEY.md 8(f) rank 3): ToTensor + Normalize([0.5], [0.5]) of the reference's loader (main.py:103-110), bit-exact
+        raw_u8 = img.dtype == torch.uint8
+        if not raw_u8 and img.dtype != torch.float32:
             img = img.float()
         if img.dim() < 4 or img.shape[-3] != 1 or img.shape[-2] != img.shape[-1]:
             raise ValueError(f"ViT expects [F,1,S,S] (or [B,T,1,S,S]) images, got {tuple(img.shape)}")
@@ -414,7 +417,10 @@ class _VitRunner(_Segment):
             key = (F_, S, img.device, bool(training), float(p), passes)
             sl = self._slot_for(key, lambda: self._make_slot(F_, S, img.device, training, p, passes))
             if sl is not None and not sl.busy:
-                sl.img.view(img.shape).copy_(img)  # one (possibly strided) copy straight into the persistent input buffer
+                if raw_u8:
+                    self._normalize_u8(img, sl.img)
+                else:
+                    sl.img.view(img.shape).copy_(img)  # one (possibly strided) copy straight into the persistent input buffer
                 sl.seed_t.fill_(seed)
 
                 def body():
@@ -425,6 +431,8 @@ class _VitRunner(_Segment):
                 self._launch(sl, "fwd", body)
                 lease = _Lease(sl) if need_grad else None
                 return sl.out.clone(), ("slot", sl, lease)
+        if raw_u8:
+            img = self._normalize_u8(img, torch.empty(F_, 1, S, S, dtype=torch.float32, device=img.device))
         img = img.reshape(F_, 1, S, S).contiguous()
         stream = _stream_of(img)
         ws_bytes = lib.vc_vit_workspace_bytes(F_, S)
@@ -439,6 +447,12 @@ class _VitRunner(_Segment):
         call.ws, call.ws_bytes, call.cls_out = ws.data_ptr(), ws_bytes, out.data_ptr()
         L.check(lib.vc_vit_forward(C.byref(call), stream), lib)
         return out, (call, W, ws, img)
+
+    def _normalize_u8(self, img_u8: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+        lib = self.lib()
+        src = img_u8.contiguous()
+        L.check(lib.vc_frames_u8_normalize(src.data_ptr(), src.numel(), 0.5, 0.5, dst.data_ptr(), _stream_of(dst)), lib)
+        return dst
 
     def backward(self, saved, dcls: torch.Tensor):
         """-> gradient of the flat parameter (one tensor, same layout)."""
