@@ -481,9 +481,9 @@ def test_frames_u8_normalize_bit_exact(n):
     u8[:min(n, 256)] = torch.arange(min(n, 256), dtype=torch.uint8, device="cuda")
     dst = torch.full((n,), float("nan"), device="cuda")
     L.check(L.load().vc_frames_u8_normalize(u8.data_ptr(), n, 0.5, 0.5, dst.data_ptr(), L.cur_stream()))
-    ref = u8.to(torch.float32).div(255).sub_(0.5).div_(0.5)
-    assert torch.equal(dst, ref)
-    assert torch.equal(dst.cpu(), u8.cpu().to(torch.float32).div(255).sub_(0.5).div_(0.5))  # and the CPU loader's values
+    # the reference's loader runs these ops on the CPU, where div is a true fp32 division (torch's CUDA kernel multiplies by the
+    # rounded reciprocal of a scalar divisor instead, which differs in the last bit for some grey levels)
+    assert torch.equal(dst.cpu(), u8.cpu().to(torch.float32).div(255).sub_(0.5).div_(0.5))
 
 
 @pytest.mark.parametrize("act", [L.ACT_NONE, L.ACT_GELU, L.ACT_RELU, L.ACT_TANH])

@@ -238,7 +238,7 @@ def test_uint8_frame_ingestion_equals_normalised_float_frames():
     g = torch.Generator().manual_seed(11)
     f8 = torch.randint(0, 256, tuple(inp["frames"].shape), dtype=torch.uint8, generator=g).cuda()
     c8 = torch.randint(0, 256, tuple(inp["cad_image"].shape), dtype=torch.uint8, generator=g).cuda()
-    norm = lambda u: u.to(torch.float32).div(255).sub_(0.5).div_(0.5)
+    norm = lambda u: u.cpu().to(torch.float32).div(255).sub_(0.5).div_(0.5).cuda()  # the loader's CPU arithmetic (true division)
     wc, wp = loss_weights((3, 4, 5), (3, 4, 6, 1000))
     res = []
     for frames, cad in ((f8, c8), (norm(f8), norm(c8))):
