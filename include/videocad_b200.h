@@ -185,6 +185,31 @@ int vc_loss_forward(const vc_loss_cfg* cfg, const float* cmds, const float* para
 /* dcmds [R,NC], dparams [R,NP,NV] = upstream[0] * d loss / d logits (upstream: device scalar) */
 int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* params, const float* targets, const float* ws,
                      const float* upstream, float* dcmds, float* dparams, void* stream);
+/* The metrics half of compute_loss (trainer.py:968-1061): integer counts from the argmax predictions that vc_loss_forward left
+ * in ws (call it after vc_loss_forward on the same ws).  The reference gathers them with ~30 .item() synchronisations per step;
+ * here one single-CTA kernel writes VC_METRIC_COUNT int64 counters to device memory, to be read back with ONE copy:
+ *   CORRECT / TOTAL                  correct_predictions / total_predictions
+ *   CMD_CORRECTS+k / CMD_COUNTS+k    cmd_corrects[k] / cmd_counts[k], k < NC
+ *   PARAM_CORRECTS+i / PARAM_COUNTS+i  param_corrects[i] / param_counts[i], i < NP (parameter i counts only where the command is
+ *                                    right; correct = 0 <= pred - target < tolerance[i] if above[i], else |pred - target| < abs_tolerance)
+ *   *_TOPK                           the same sums over the first `topk` time steps of every sequence (rows are b * T + t)
+ * perfect_sequences / perfect_commands / total_sequences are constant 0 in the reference (trainer.py:1017-1034 is commented out). */
+enum {
+  VC_METRIC_CORRECT = 0, VC_METRIC_TOTAL = 1,
+  VC_METRIC_CMD_CORRECTS = 2, VC_METRIC_CMD_COUNTS = 2 + VC_LOSS_MAX_CLASSES,
+  VC_METRIC_PARAM_CORRECTS = 2 + 2 * VC_LOSS_MAX_CLASSES, VC_METRIC_PARAM_COUNTS = 2 + 2 * VC_LOSS_MAX_CLASSES + VC_LOSS_MAX_PARAMS,
+  VC_METRIC_CMD_CORRECT_TOPK = 2 + 2 * VC_LOSS_MAX_CLASSES + 2 * VC_LOSS_MAX_PARAMS,
+  VC_METRIC_CMD_COUNTS_TOPK, VC_METRIC_PARAM_CORRECT_TOPK, VC_METRIC_PARAM_COUNTS_TOPK,
+  VC_METRIC_COUNT
+};
+typedef struct vc_metrics_cfg {
+  int above[VC_LOSS_MAX_PARAMS];        /* trainer.py:829 self.above */
+  int tolerance[VC_LOSS_MAX_PARAMS];    /* trainer.py:827 self.tolerances */
+  int abs_tolerance;                    /* trainer.py TOLERANCE (3) */
+  int topk;                             /* trainer.py:1003 k = 30 */
+} vc_metrics_cfg;
+int vc_loss_metrics(const vc_loss_cfg* cfg, const vc_metrics_cfg* mcfg, const float* targets, const float* ws, int T, int64_t* counts,
+                    void* stream);
 
 /* ---- optimizer step of the reference trainer, fused: torch.nn.utils.clip_grad_norm_(params, max_norm) followed by
  * torch.optim.Adam(...).step() (/root/reference/trainer.py:493-494, Adam defaults betas/eps, no weight decay, no amsgrad)

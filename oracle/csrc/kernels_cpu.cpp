@@ -587,17 +587,18 @@ int clip_adam_step(const vc_adam_tensor* t, int nt, double beta1, double beta2, 
 }
 
 // ---- fused training loss (CPU restatement of videocad_b200/csrc/loss.cu; same workspace layout)
-size_t loss_workspace_floats(int R, int NP) { return (size_t)4 * R * NP + (size_t)3 * R + 16; }
+size_t loss_workspace_floats(int R, int NP) { return (size_t)5 * R * NP + (size_t)4 * R + 16; }
 
 namespace {
 struct LossWsC {
-  float *lse, *sel, *rowloss, *nwc, *cnum, *cden, *clse, *scal;
+  float *lse, *sel, *rowloss, *nwc, *cnum, *cden, *clse, *scal, *pred, *cpred;
 };
 LossWsC loss_carve(float* ws, int R, int NP) {
   LossWsC w;
   const size_t rp = (size_t)R * NP;
   w.lse = ws; w.sel = ws + rp; w.rowloss = ws + 2 * rp; w.nwc = ws + 3 * rp;
   w.cnum = ws + 4 * rp; w.cden = w.cnum + R; w.clse = w.cden + R; w.scal = w.clse + R;
+  w.pred = w.scal + 16; w.cpred = w.pred + rp;
   return w;
 }
 void loss_window(const LossCfg& c, int i, float target, bool& valid, long long& t, long long& hi, float& count) {
@@ -619,7 +620,9 @@ int loss_forward(const LossCfg& c, const float* cmds, const float* params, const
     const long long tg = (long long)targets[(size_t)r * ldt];
     const bool valid = tg >= 0 && tg < c.NC;
     float m = -INFINITY, s = 0.f;
-    for (int k = 0; k < c.NC; ++k) m = fmaxf(m, z[k]);
+    int am = 0;
+    for (int k = 0; k < c.NC; ++k) if (z[k] > m) { m = z[k]; am = k; }
+    w.cpred[r] = (float)am;
     for (int k = 0; k < c.NC; ++k) s += expf(z[k] - m);
     const float lse = m + logf(s), wt = valid ? c.cmd_w[tg] : 0.f;
     w.clse[r] = lse; w.cden[r] = wt; w.cnum[r] = valid ? wt * (lse - z[tg]) : 0.f;
@@ -640,6 +643,7 @@ int loss_forward(const LossCfg& c, const float* cmds, const float* params, const
       w.lse[o] = l; w.sel[o] = sel;
       w.rowloss[o] = (-((float)sw - nw * l) / count) * sel;
       w.nwc[o] = nw / count;
+      w.pred[o] = (float)bi;
     }
   }
   float loss = 0.f;
@@ -657,6 +661,35 @@ int loss_forward(const LossCfg& c, const float* cmds, const float* params, const
   loss += 2.f * (float)(num / den);
   w.scal[c.NP] = 2.f / (float)den;
   loss_out[0] = loss;
+  return 0;
+}
+
+int loss_metrics(const LossCfg& c, const vc_metrics_cfg& mc, const float* targets, const float* ws, int T, int64_t* counts, stream_t) {
+  if (!targets || !ws || !counts) return set_error("loss_metrics: null argument");
+  if (T <= 0 || c.R % T != 0) return set_error("loss_metrics: R must be a multiple of T");
+  LossWsC w = loss_carve(const_cast<float*>(ws), c.R, c.NP);
+  for (int k = 0; k < VC_METRIC_COUNT; ++k) counts[k] = 0;
+  const int ldt = 1 + c.NP;
+  for (int r = 0; r < c.R; ++r) {
+    const long long tc = (long long)targets[(size_t)r * ldt], pc = (long long)w.cpred[r];
+    const bool cmd_mask = tc != -1, cmd_ok = cmd_mask && pc == tc, in_topk = (r % T) < mc.topk;
+    counts[VC_METRIC_TOTAL] += cmd_mask;
+    counts[VC_METRIC_CORRECT] += cmd_ok;
+    if (tc >= 0 && tc < c.NC) { counts[VC_METRIC_CMD_COUNTS + tc] += 1; counts[VC_METRIC_CMD_CORRECTS + tc] += (pc == tc); }
+    counts[VC_METRIC_CMD_COUNTS_TOPK] += (in_topk && cmd_mask);
+    counts[VC_METRIC_CMD_CORRECT_TOPK] += (in_topk && cmd_ok);
+    for (int i = 0; i < c.NP; ++i) {
+      const long long tp = (long long)targets[(size_t)r * ldt + 1 + i];
+      if (!cmd_mask || tp == -1) continue;
+      counts[VC_METRIC_PARAM_COUNTS + i] += 1;
+      counts[VC_METRIC_TOTAL] += 1;
+      counts[VC_METRIC_PARAM_COUNTS_TOPK] += in_topk;
+      if (!cmd_ok) continue;
+      const long long diff = (long long)w.pred[(size_t)r * c.NP + i] - tp;
+      const bool ok = mc.above[i] ? (diff >= 0 && diff < mc.tolerance[i]) : ((diff < 0 ? -diff : diff) < mc.abs_tolerance);
+      if (ok) { counts[VC_METRIC_PARAM_CORRECTS + i] += 1; counts[VC_METRIC_CORRECT] += 1; counts[VC_METRIC_PARAM_CORRECT_TOPK] += in_topk; }
+    }
+  }
   return 0;
 }
 

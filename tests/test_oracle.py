@@ -144,9 +144,45 @@ def test_loss_port_matches_reference_trainer(tmp_path, monkeypatch):
                     v = int(tgt[b, tt, 1 + i].item())
                     if v >= 0:
                         params[b, tt, i, min(v + 1, 999)] += 20
-    lr, _ = t.compute_loss((cmds, params), tgt)
+    with torch.no_grad():  # and make some commands right, so that the parameter counters (which need a right command) move
+        for b in range(B):
+            for tt in range(1, T, 2):
+                c = int(tgt[b, tt, 0].item())
+                if c >= 0:
+                    cmds[b, tt, c] += 10
+    lr, metrics_ref = t.compute_loss((cmds, params), tgt)
     lm = compute_loss((cmds, params), tgt)
     assert abs(lr.item() - lm.item()) < 1e-5 * abs(lr.item())
+    # the metrics half (trainer.py:968-1061) through the native counters (CPU twin of vc_loss_metrics), T > top-k window too
+    from oracle import build_emu
+    from videocad_b200 import lib as L
+    from videocad_b200.loss import compute_loss_and_metrics_fused, metrics_from_counts
+
+    emu = L.load(build_emu.build(), require_cuda_build=False)
+    _, counts = compute_loss_and_metrics_fused((cmds.detach(), params.detach()), tgt, _lib=emu)
+    got = metrics_from_counts(counts)
+    assert got["total_predictions"] > 0 and got["correct_predictions"] > 0 and sum(got["param_corrects"]) > 0
+    for k, v in metrics_ref.items():
+        assert got[k] == v, (k, got[k], v)
+    B2, T2 = 2, 34  # longer than k = 30: the *_topk counters differ from the totals
+    tgt2 = to.synthetic_batch(B2, T2 + 1, 32, seed=9)["actions"][:, 1:]
+    g2 = torch.Generator().manual_seed(4)
+    cm2, pa2 = torch.randn(B2, T2, 5, generator=g2), torch.randn(B2, T2, 6, 1000, generator=g2)
+    for b in range(B2):
+        for tt in range(T2):
+            c = int(tgt2[b, tt, 0].item())
+            if c >= 0 and tt % 3:
+                cm2[b, tt, c] += 10
+            for i in range(6):
+                v = int(tgt2[b, tt, 1 + i].item())
+                if v >= 0 and (tt + i) % 2:
+                    pa2[b, tt, i, min(v + 1, 999)] += 20
+    _, m2_ref = t.compute_loss((cm2, pa2), tgt2)
+    _, c2 = compute_loss_and_metrics_fused((cm2, pa2), tgt2, _lib=emu)
+    got2 = metrics_from_counts(c2)
+    assert got2["cmd_counts_topk"] < got2["total_predictions"] and got2["param_correct_topk"] > 0
+    for k, v in m2_ref.items():
+        assert got2[k] == v, (k, got2[k], v)
     gr = torch.autograd.grad(lr, [cmds, params])
     gm = torch.autograd.grad(lm, [cmds, params])
     assert (gr[0] - gm[0]).abs().max() < 1e-6 and (gr[1] - gm[1]).abs().max() < 1e-6

@@ -145,6 +145,11 @@ int vc_loss_backward(const vc_loss_cfg* cfg, const float* cmds, const float* par
   if (!cfg) return vck::set_error("vc_loss_backward: null cfg");
   return vck::loss_backward(*cfg, cmds, params, targets, ws, upstream, dcmds, dparams, stream);
 }
+int vc_loss_metrics(const vc_loss_cfg* cfg, const vc_metrics_cfg* mcfg, const float* targets, const float* ws, int T, int64_t* counts,
+                    void* stream) {
+  if (!cfg || !mcfg) return vck::set_error("vc_loss_metrics: null cfg");
+  return vck::loss_metrics(*cfg, *mcfg, targets, ws, T, counts, stream);
+}
 
 size_t vc_clip_adam_scratch_floats(void) { return vck::clip_adam_scratch_floats(); }
 int vc_clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double beta1, double beta2, double eps, double max_norm,

@@ -138,6 +138,8 @@ size_t loss_workspace_floats(int R, int NP);
 int loss_forward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out, stream_t s);
 int loss_backward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, const float* ws,
                   const float* upstream, float* dcmds, float* dparams, stream_t s);
+// metrics of compute_loss from the argmax predictions loss_forward left in ws (see vc_loss_metrics in include/videocad_b200.h)
+int loss_metrics(const LossCfg& cfg, const vc_metrics_cfg& mc, const float* targets, const float* ws, int T, int64_t* counts, stream_t s);
 
 // fused clip_grad_norm_ + Adam step (see include/videocad_b200.h, vc_clip_adam_step)
 size_t clip_adam_scratch_floats();

@@ -24,7 +24,8 @@ constexpr int LT = 128;  // threads per CTA
 struct LossWs {
   float *lse, *sel, *rowloss, *nwin_over_count;  // [R*NP]
   float *cnum, *cden, *clse;                      // [R]
-  float* scal;                                    // coef[NP], coef_cmd, (pad)
+  float* scal;                                    // coef[NP], coef_cmd, (pad to 16)
+  float *pred, *cpred;                            // argmax of every parameter head [R*NP] and of the command head [R] (metrics)
 };
 
 __host__ __device__ inline LossWs carve(float* ws, int R, int NP) {
@@ -33,6 +34,7 @@ __host__ __device__ inline LossWs carve(float* ws, int R, int NP) {
   w.lse = ws; w.sel = ws + rp; w.rowloss = ws + 2 * rp; w.nwin_over_count = ws + 3 * rp;
   w.cnum = ws + 4 * rp; w.cden = w.cnum + R; w.clse = w.cden + R;
   w.scal = w.clse + R;
+  w.pred = w.scal + 16; w.cpred = w.pred + rp;
   return w;
 }
 
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(LT) loss_rows_kernel(const LossCfg c, const fl
       const long long tg = (long long)targets[(size_t)r * ldt];
       const bool valid = tg >= 0 && tg < c.NC;
       float m = -INFINITY;
-      for (int k = 0; k < c.NC; ++k) m = fmaxf(m, z[k]);
+      int am = 0;
+      for (int k = 0; k < c.NC; ++k) if (z[k] > m) { m = z[k]; am = k; }  // first maximum, as torch.argmax
+      w.cpred[r] = (float)am;
       float s = 0.f;
       for (int k = 0; k < c.NC; ++k) s += expf(z[k] - m);
       const float lse = m + logf(s);
@@ -122,7 +126,52 @@ __global__ void __launch_bounds__(LT) loss_rows_kernel(const LossCfg c, const fl
     w.sel[o] = sel;
     w.rowloss[o] = per_row * sel;
     w.nwin_over_count[o] = nw / count;
+    w.pred[o] = (float)best.i;
   }
+}
+
+// Metrics of MultiClassesTrainer.compute_loss (/root/reference/trainer.py:968-1061): integer counts from the argmax predictions
+// of the row pass.  One CTA, shared-memory integer atomics (exact, order-independent).  Counter layout: see VC_METRIC_* in
+// include/videocad_b200.h.
+__global__ void __launch_bounds__(256) loss_metrics_kernel(const LossCfg c, const float* __restrict__ targets, LossWs w, int T, int topk,
+                                                           const vc_metrics_cfg mc, unsigned long long* __restrict__ out) {
+  pdl_grid_sync();
+  __shared__ unsigned long long cnt[VC_METRIC_COUNT];
+  for (int k = threadIdx.x; k < VC_METRIC_COUNT; k += 256) cnt[k] = 0ull;
+  __syncthreads();
+  const int ldt = 1 + c.NP;
+  for (int r = threadIdx.x; r < c.R; r += 256) {
+    const long long tc = (long long)targets[(size_t)r * ldt];
+    const long long pc = (long long)w.cpred[r];
+    const bool cmd_mask = tc != -1;
+    const bool cmd_ok = cmd_mask && pc == tc;
+    const bool in_topk = (r % T) < topk;
+    if (cmd_mask) atomicAdd(&cnt[VC_METRIC_TOTAL], 1ull);
+    if (cmd_ok) atomicAdd(&cnt[VC_METRIC_CORRECT], 1ull);
+    if (tc >= 0 && tc < c.NC) {
+      atomicAdd(&cnt[VC_METRIC_CMD_COUNTS + tc], 1ull);
+      if (pc == tc) atomicAdd(&cnt[VC_METRIC_CMD_CORRECTS + tc], 1ull);
+    }
+    if (in_topk && cmd_mask) atomicAdd(&cnt[VC_METRIC_CMD_COUNTS_TOPK], 1ull);
+    if (in_topk && cmd_ok) atomicAdd(&cnt[VC_METRIC_CMD_CORRECT_TOPK], 1ull);
+    for (int i = 0; i < c.NP; ++i) {
+      const long long tp = (long long)targets[(size_t)r * ldt + 1 + i];
+      if (!cmd_mask || tp == -1) continue;  // param_mask
+      atomicAdd(&cnt[VC_METRIC_PARAM_COUNTS + i], 1ull);
+      atomicAdd(&cnt[VC_METRIC_TOTAL], 1ull);
+      if (in_topk) atomicAdd(&cnt[VC_METRIC_PARAM_COUNTS_TOPK], 1ull);
+      if (!cmd_ok) continue;                // params_mask additionally needs the command to be right
+      const long long diff = (long long)w.pred[(size_t)r * c.NP + i] - tp;
+      const bool ok = mc.above[i] ? (diff >= 0 && diff < mc.tolerance[i]) : ((diff < 0 ? -diff : diff) < mc.abs_tolerance);
+      if (ok) {
+        atomicAdd(&cnt[VC_METRIC_PARAM_CORRECTS + i], 1ull);
+        atomicAdd(&cnt[VC_METRIC_CORRECT], 1ull);
+        if (in_topk) atomicAdd(&cnt[VC_METRIC_PARAM_CORRECT_TOPK], 1ull);
+      }
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < VC_METRIC_COUNT; k += 256) out[k] = cnt[k];
 }
 
 // one CTA: fixed-order reductions over the rows, the scalar loss, and the per-term gradient coefficients
@@ -208,7 +257,17 @@ int check_cfg(const LossCfg& c) {
 
 }  // namespace
 
-size_t loss_workspace_floats(int R, int NP) { return (size_t)4 * R * NP + (size_t)3 * R + 16; }
+size_t loss_workspace_floats(int R, int NP) { return (size_t)5 * R * NP + (size_t)4 * R + 16; }
+
+int loss_metrics(const LossCfg& cfg, const vc_metrics_cfg& mc, const float* targets, const float* ws, int T, int64_t* counts, stream_t s) {
+  if (int rc = check_cfg(cfg)) return rc;
+  if (!targets || !ws || !counts) return set_error("loss_metrics: null argument");
+  if (T <= 0 || cfg.R % T != 0) return set_error("loss_metrics: R must be a multiple of T");
+  const LossWs w = carve(const_cast<float*>(ws), cfg.R, cfg.NP);
+  VC_LAUNCH((loss_metrics_kernel), 1, 256, 0, reinterpret_cast<cudaStream_t>(s), cfg, targets, w, T, mc.topk, mc,
+            reinterpret_cast<unsigned long long*>(counts));
+  return check_launch("loss_metrics_kernel");
+}
 
 int loss_forward(const LossCfg& cfg, const float* cmds, const float* params, const float* targets, float* ws, float* loss_out, stream_t s) {
   if (int rc = check_cfg(cfg)) return rc;

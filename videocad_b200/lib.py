@@ -31,6 +31,17 @@ class LossCfg(C.Structure):
                 ("tolerance", C.c_int * 8), ("param_to_label", C.c_int * 8)]
 
 
+class MetricsCfg(C.Structure):
+    """mirror of vc_metrics_cfg"""
+    _fields_ = [("above", C.c_int * 8), ("tolerance", C.c_int * 8), ("abs_tolerance", C.c_int), ("topk", C.c_int)]
+
+
+# counter layout of vc_loss_metrics (VC_METRIC_* in include/videocad_b200.h)
+METRIC_CORRECT, METRIC_TOTAL, METRIC_CMD_CORRECTS, METRIC_CMD_COUNTS = 0, 1, 2, 18
+METRIC_PARAM_CORRECTS, METRIC_PARAM_COUNTS = 34, 42
+METRIC_CMD_CORRECT_TOPK, METRIC_CMD_COUNTS_TOPK, METRIC_PARAM_CORRECT_TOPK, METRIC_PARAM_COUNTS_TOPK, METRIC_COUNT = 50, 51, 52, 53, 54
+
+
 class AdamTensor(C.Structure):
     """mirror of vc_adam_tensor"""
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("lr", C.c_float)]
@@ -101,6 +112,7 @@ _PROTOS = {
     "vc_loss_workspace_floats": ([i32, i32], C.c_size_t),
     "vc_loss_forward": ([vp, vp, vp, vp, vp, vp, vp], i32),
     "vc_loss_backward": ([vp, vp, vp, vp, vp, vp, vp, vp, vp], i32),
+    "vc_loss_metrics": ([vp, vp, vp, vp, i32, vp, vp], i32),
     "vc_clip_adam_scratch_floats": ([], C.c_size_t),
     "vc_clip_adam_step": ([vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp, vp, vp], i32),
     "vc_head_small_fwd": ([vp, i64, i32, vp, vp, i32, vp, vp], i32),

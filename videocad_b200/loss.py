@@ -89,7 +89,7 @@ def compute_loss(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequ
 
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, cmds, params, targets, cfg, lib):
+    def forward(ctx, cmds, params, targets, cfg, lib, metrics):
         cmds, params, targets = cmds.contiguous().float(), params.contiguous().float(), targets.contiguous().float()
         dev = cmds.device
         stream = torch.cuda.current_stream(dev).cuda_stream if cmds.is_cuda else None
@@ -97,12 +97,17 @@ class _FusedLoss(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         L.check(lib.vc_loss_forward(C.byref(cfg), cmds.data_ptr(), params.data_ptr(), targets.data_ptr(), ws.data_ptr(), loss.data_ptr(),
                                     stream), lib)
+        counts = torch.empty(L.METRIC_COUNT if metrics is not None else 0, dtype=torch.int64, device=dev)
+        if metrics is not None:
+            mcfg, T = metrics
+            L.check(lib.vc_loss_metrics(C.byref(cfg), C.byref(mcfg), targets.data_ptr(), ws.data_ptr(), T, counts.data_ptr(), stream), lib)
         ctx.save_for_backward(cmds, params, targets, ws)
         ctx.cfg, ctx.lib = cfg, lib
-        return loss.view(())
+        ctx.mark_non_differentiable(counts)
+        return loss.view(()), counts
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, _gcounts=None):
         cmds, params, targets, ws = ctx.saved_tensors
         cfg, lib = ctx.cfg, ctx.lib
         g = g.contiguous().float().view(1)
@@ -110,10 +115,42 @@ class _FusedLoss(torch.autograd.Function):
         stream = torch.cuda.current_stream(cmds.device).cuda_stream if cmds.is_cuda else None
         L.check(lib.vc_loss_backward(C.byref(cfg), cmds.data_ptr(), params.data_ptr(), targets.data_ptr(), ws.data_ptr(), g.data_ptr(),
                                      dcmds.data_ptr(), dparams.data_ptr(), stream), lib)
-        return dcmds, dparams, None, None, None
+        return dcmds, dparams, None, None, None, None
 
 
-def compute_loss_fused(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequence[float]] = None, _lib=None) -> torch.Tensor:
+ABOVE = (False, False, True, True, True, False)   # trainer.py:829
+TOPK = 30                                          # trainer.py:1003
+
+
+def metrics_from_counts(counts, NC: int = 5, NP: int = 6) -> dict:
+    """The `metrics` dict of MultiClassesTrainer.compute_loss (trainer.py:1036-1058) from the counters of vc_loss_metrics:
+    ONE device-to-host copy (`counts` may already be a host tensor / list) instead of ~30 `.item()` calls."""
+    c = counts.tolist() if torch.is_tensor(counts) else list(counts)
+    m = {
+        "correct_predictions": c[L.METRIC_CORRECT], "total_predictions": c[L.METRIC_TOTAL],
+        "cmd_corrects": c[L.METRIC_CMD_CORRECTS:L.METRIC_CMD_CORRECTS + NC], "cmd_counts": c[L.METRIC_CMD_COUNTS:L.METRIC_CMD_COUNTS + NC],
+        "param_corrects": c[L.METRIC_PARAM_CORRECTS:L.METRIC_PARAM_CORRECTS + NP],
+        "param_counts": c[L.METRIC_PARAM_COUNTS:L.METRIC_PARAM_COUNTS + NP],
+        "cmd_correct_topk": c[L.METRIC_CMD_CORRECT_TOPK], "cmd_counts_topk": c[L.METRIC_CMD_COUNTS_TOPK],
+        "param_correct_topk": c[L.METRIC_PARAM_CORRECT_TOPK], "param_counts_topk": c[L.METRIC_PARAM_COUNTS_TOPK],
+        "perfect_sequences": 0, "perfect_commands": 0, "total_sequences": 0, "perfect_sequence_accuracy": 0,
+    }
+    for i in range(NP):
+        m[f"param_corrects_{i}"], m[f"param_counts_{i}"] = m["param_corrects"][i], m["param_counts"][i]
+    for i in range(NC):
+        m[f"cmd_corrects_{i}"], m[f"cmd_counts_{i}"] = m["cmd_corrects"][i], m["cmd_counts"][i]
+    return m
+
+
+def compute_loss_and_metrics_fused(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequence[float]] = None, _lib=None):
+    """(loss, counts): `compute_loss_fused` plus the metrics half of compute_loss (trainer.py:968-1061) as a device tensor of
+    integer counters (one extra single-CTA kernel, no host synchronisation); `metrics_from_counts(counts)` builds the
+    reference's dict with a single copy whenever the caller wants the numbers on the host."""
+    return compute_loss_fused(action_preds, actions, cmd_weights, _lib=_lib, _with_metrics=True)
+
+
+def compute_loss_fused(action_preds, actions: torch.Tensor, cmd_weights: Optional[Sequence[float]] = None, _lib=None,
+                       _with_metrics: bool = False):
     """Same value and gradients as `compute_loss`, computed by the native fused kernels (no CPU fallback: `_lib` is the
     tests' hook for the CPU emulation library)."""
     pred_cmd, pred_params = action_preds
@@ -131,4 +168,15 @@ def compute_loss_fused(action_preds, actions: torch.Tensor, cmd_weights: Optiona
     for i in range(NP):
         cfg.tolerance[i] = TOLERANCES[i]
         cfg.param_to_label[i] = PARAM_TO_LABEL[i]
-    return _FusedLoss.apply(pred_cmd.reshape(-1, NC), pred_params.reshape(-1, NP, NV), actions.reshape(-1, 1 + NP), cfg, lib)
+    metrics = None
+    if _with_metrics:
+        if actions.dim() != 3:
+            raise ValueError("metrics need actions as [B, T, 1 + NP] (the top-k counters are per time step)")
+        mcfg = L.MetricsCfg()
+        for i in range(NP):
+            mcfg.above[i] = int(ABOVE[i])
+            mcfg.tolerance[i] = TOLERANCES[i]
+        mcfg.abs_tolerance, mcfg.topk = TOLERANCE, TOPK
+        metrics = (mcfg, int(actions.shape[1]))
+    loss, counts = _FusedLoss.apply(pred_cmd.reshape(-1, NC), pred_params.reshape(-1, NP, NV), actions.reshape(-1, 1 + NP), cfg, lib, metrics)
+    return (loss, counts) if _with_metrics else loss
