@@ -65,6 +65,8 @@ def _metrics_torch(cmds, params, tgt):
 
 
 def _check_metrics(cmds, params, tgt, lib=None):
+    dev = cmds.device
+    cmds, params, tgt = cmds.cpu(), params.cpu(), tgt.cpu()  # the loops below index element by element
     with torch.no_grad():  # some right commands and right parameters, so that every counter moves
         a = tgt.long()
         for b in range(cmds.shape[0]):
@@ -74,6 +76,7 @@ def _check_metrics(cmds, params, tgt, lib=None):
                 for i in range(6):
                     if a[b, t, 1 + i] >= 0 and (b + t + i) % 3 == 0:
                         params[b, t, i, min(int(a[b, t, 1 + i]) + (1 if ABOVE[i] else -1), 999)] += 40
+    cmds, params, tgt = cmds.to(dev), params.to(dev), tgt.to(dev)
     loss, counts = compute_loss_and_metrics_fused((cmds, params), tgt, _lib=lib)
     ref_loss = compute_loss_fused((cmds, params), tgt, _lib=lib)
     assert torch.equal(loss, ref_loss)

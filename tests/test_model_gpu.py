@@ -134,12 +134,13 @@ def test_bf16_single_pass_mode_is_looser_but_close():
     assert 1e-4 < d < 0.1, d
 
 
-def test_prefix_invariance_and_rollout():
+@pytest.mark.parametrize("T", [6, 19])  # 19 steps cross the rollout's prefix-length buckets (8, 16, 19), each a CUDA graph
+def test_prefix_invariance_and_rollout(T):
     cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=2,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build(cfg)
     m.eval()
-    B, T, S = 2, 6, 64
+    B, S = 2, 64
     inp, _ = cuda_inputs(B, T, S)
     with torch.no_grad():
         full_c, full_p = m(inp)
@@ -152,10 +153,11 @@ def test_prefix_invariance_and_rollout():
         zc, zp = m({"frames": inp["frames"], "actions": torch.zeros_like(inp["actions"]), "cad_image": inp["cad_image"]})
         assert (rc - zc).abs().max() < 1e-6 and (rp - zp).abs().max() < 1e-6
         # rollout with action feedback against the oracle's O(T^2) recompute
-        ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
         oc, op = to.rollout(sd, cfg, inp["frames"].cpu(), inp["cad_image"].cpu(), action=True)
-        assert (ac.cpu().argmax(-1) == oc.argmax(-1)).all()
-        assert (ac.cpu() - oc).abs().max() < LOGIT_TOL and (ap.cpu() - op).abs().max() < LOGIT_TOL
+        for rep in range(3):  # eager, graph capture, graph replay
+            ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
+            assert (ac.cpu().argmax(-1) == oc.argmax(-1)).all()
+            assert (ac.cpu() - oc).abs().max() < LOGIT_TOL and (ap.cpu() - op).abs().max() < LOGIT_TOL, rep
 
 
 def test_training_mode_dropout_is_reproducible_and_trains():

@@ -33,6 +33,7 @@ from . import model_abi as A
 # CUDA-graph replay of the native call sequences (one graph per segment, direction and problem shape); "0" disables
 _GRAPHS = os.environ.get("VIDEOCAD_B200_GRAPHS", "1") != "0"
 _MAX_SLOTS = 3
+_MAX_INFER_SLOTS = 12  # forward-only slots (no gradient arena): the rollout's prefix-length buckets
 # run the CAD image encoder on a second stream, concurrently with the frame encoder ("0" disables)
 _OVERLAP = os.environ.get("VIDEOCAD_B200_OVERLAP", "1") != "0"
 _TIMING = None  # bench.py: list of (segment.direction, start event, end event) around every CUDA-graph replay
@@ -247,6 +248,7 @@ class _Segment:
         self.total = self.spec.total
         self._split = None  # (flat._version, flat.data_ptr(), hi, lo): split-bf16 mirror of the whole flat parameter
         self._slots = {}
+        self._islots = {}  # forward-only slots (need_grad=False callers: the rollout), no gradient arena
         self._sig = None
         self._lib = None  # tests may inject the CPU emulation library; the product path loads the CUDA build
 
@@ -261,20 +263,21 @@ class _Segment:
         """Persistent structs and graphs bake parameter addresses: drop them if the flat parameter's storage moved (.to(), ...)."""
         sig = self.flat.data_ptr()
         if sig != self._sig:
-            self._sig, self._slots, self._split = sig, {}, None
+            self._sig, self._slots, self._islots, self._split = sig, {}, {}, None
 
-    def _slot_for(self, key, make):
-        slot = self._slots.get(key)
+    def _slot_for(self, key, make, infer=False):
+        slots, cap = (self._islots, _MAX_INFER_SLOTS) if infer else (self._slots, _MAX_SLOTS)
+        slot = slots.get(key)
         if slot is None:
-            if len(self._slots) >= _MAX_SLOTS:
-                for k in list(self._slots):
-                    if not self._slots[k].busy:
-                        del self._slots[k]
+            if len(slots) >= cap:
+                for k in list(slots):
+                    if not slots[k].busy:
+                        del slots[k]
                         break
-            if len(self._slots) >= _MAX_SLOTS:
+            if len(slots) >= cap:
                 return None
             slot = make()
-            self._slots[key] = slot
+            slots[key] = slot
         return slot
 
     def ensure_split(self, stream, force=False):
@@ -530,7 +533,7 @@ class _SeqRunner(_Segment):
         W.num_layers = nl
         return W, arr
 
-    def _make_slot(self, B, T, dev, training, p, passes, has_state):
+    def _make_slot(self, B, T, dev, training, p, passes, has_state, need_grad=True):
         lib, m = self.lib(), self.model
         nv = m.num_views
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -548,14 +551,18 @@ class _SeqRunner(_Segment):
         sl.ws = torch.empty(sl.ws_bytes, dtype=torch.uint8, device=dev)
         sl.cmds, sl.params = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
         sl.seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
-        sl.gflat = torch.zeros(self.total, **f32)
-        sl.dcmds, sl.dparams = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
-        sl.d_state = torch.empty(R, A.VIT_DIM, **f32) if (has_state and m.enable_past_states) else None
-        sl.d_cad = torch.empty(B, A.VIT_DIM, **f32)
-        sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP, nv)
-        sl.scratch = None
-        (sl.W, sl.arr), (sl.Wg, sl.arrg) = self._weights(stream), self._weights(stream, sl.gflat)
-        for name, W in (("call", sl.W), ("call_b", sl.Wg)):
+        sl.W, sl.arr = self._weights(stream)
+        calls = [("call", sl.W)]
+        if need_grad:
+            sl.gflat = torch.zeros(self.total, **f32)
+            sl.dcmds, sl.dparams = torch.empty(R, NC, **f32), torch.empty(R, NP, **f32)
+            sl.d_state = torch.empty(R, A.VIT_DIM, **f32) if (has_state and m.enable_past_states) else None
+            sl.d_cad = torch.empty(B, A.VIT_DIM, **f32)
+            sl.sc_bytes = lib.vc_seq_scratch_bytes(B, T, H, Ff, NP, nv)
+            sl.scratch = None
+            sl.Wg, sl.arrg = self._weights(stream, sl.gflat)
+            calls.append(("call_b", sl.Wg))
+        for name, W in calls:
             c = A.SeqCall()
             c.w = C.pointer(W)
             c.B, c.T, c.H, c.nhead, c.Ff, c.window = B, T, H, nh, Ff, m.window_size
@@ -589,7 +596,8 @@ class _SeqRunner(_Segment):
         if allow_graph and self.graphs_enabled(cad_cls):
             self._check_storage()
             key = (B, T, dev, bool(training), float(p), passes, state_cls is not None)
-            sl = self._slot_for(key, lambda: self._make_slot(B, T, dev, training, p, passes, state_cls is not None))
+            sl = self._slot_for(key, lambda: self._make_slot(B, T, dev, training, p, passes, state_cls is not None, need_grad),
+                                infer=not need_grad)
             if sl is not None and not sl.busy:
                 if sl.state is not None:
                     sl.state.copy_(state_cls)
@@ -892,18 +900,23 @@ class AutoRegressiveTransformer(_FlatOwner):
             cmds, params, _ = seq_r.forward(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, zeros, B, T,
                                             False, 0.0, 0, passes, need_grad=False)
             return cmds.view(B, T, -1), params.view(B, T, self.num_params, self.num_params_values)
-        actions = torch.zeros(B, 1, self.act_dim, device=dev)
+        # Step t needs the outputs at position t of the prefix [0, t].  The forward is causal (prefix-invariant), so the prefix may
+        # be padded up to a bucket length Tp >= t + 1 -- real frame features (all frames are already encoded), zero actions
+        # beyond t -- without changing position t: eight shapes instead of T, each captured into a CUDA graph and replayed.
+        actions = torch.zeros(B, T, self.act_dim, device=dev)
+        buckets = sorted({min(b, T) for b in (8, 16, 32, 64, 96, 128, 160, T)})
         out_c, out_p = [], []
         for t in range(T):
-            sc = state_cls[:, : t + 1].reshape(B * (t + 1), -1) if state_cls is not None else None
-            cmds, params, _ = seq_r.forward(sc, cad_cls, actions, B, t + 1, False, 0.0, 0, passes, need_grad=False,
-                                            allow_graph=False)  # T grows every step: no point capturing
-            cmd = cmds.view(B, t + 1, -1)[:, -1]
-            par = params.view(B, t + 1, self.num_params, self.num_params_values)[:, -1]
+            Tp = next(b for b in buckets if b >= t + 1)
+            sc = state_cls[:, :Tp].reshape(B * Tp, -1) if state_cls is not None else None
+            cmds, params, _ = seq_r.forward(sc, cad_cls, actions[:, :Tp], B, Tp, False, 0.0, 0, passes, need_grad=False)
+            cmd = cmds.view(B, Tp, -1)[:, t]
+            par = params.view(B, Tp, self.num_params, self.num_params_values)[:, t]
             out_c.append(cmd)
             out_p.append(par)
             cmd_pred, par_pred = cmd.argmax(-1), par.argmax(-1)
             nxt = self.apply_action_mask(cmd_pred.unsqueeze(1), par_pred.unsqueeze(1)).float()
             nxt = torch.cat([cmd_pred.reshape(B, 1, 1).float(), nxt], dim=2)
-            actions = torch.cat([actions, self.normalize_actions(nxt)], dim=1)
+            if t + 1 < T:
+                actions[:, t + 1] = self.normalize_actions(nxt)[:, 0]
         return torch.stack(out_c, 1), torch.stack(out_p, 1)
