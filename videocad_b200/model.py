@@ -786,7 +786,10 @@ class AutoRegressiveTransformer(_FlatOwner):
         streams = self.__dict__.setdefault("_side_streams", {})
         key = (device.type, device.index)
         if key not in streams:
-            streams[key] = torch.cuda.Stream(device=device)
+            # VIDEOCAD_B200_SIDE_PRIORITY=-1: high-priority stream for the CAD encoder (experiment: it then finishes early
+            # instead of interleaving with the frame encoder to the end, and under DDP its gradient all-reduce overlaps the
+            # rest of the frame encoder's backward)
+            streams[key] = torch.cuda.Stream(device=device, priority=int(os.environ.get("VIDEOCAD_B200_SIDE_PRIORITY", "0")))
         return streams[key]
 
     def _use_library_for_tests(self, lib):
