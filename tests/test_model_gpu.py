@@ -96,6 +96,37 @@ def test_c1_shape_vs_oracle_fp64():
     assert dc < LOGIT_TOL and dp < LOGIT_TOL
 
 
+def test_c2_full_shape_forward_backward_vs_oracle():
+    """BASELINE config C2 at its full shape: model_configs/vid_pretrained.json "base_model" (H = 256, window 3, defaults nhead = 4,
+    8 layers, Ff = 512) with the frame encoder enabled, batch 8, 16-frame context, 224 x 224 (128 frames: the 2-SM GEMM path with
+    25 row blocks; decoder head dim 64, T = 16 short-sequence attention): logits and every gradient against the fp64 oracle."""
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=3,
+               enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
+    m, sd = build(cfg, dropout=0.0)
+    m.train()
+    inp, _ = cuda_inputs(8, 16, 224)
+    wc, wp = loss_weights((8, 16, 5), (8, 16, 6, 1000))
+    for it in range(3):  # eager, graph capture, graph replay
+        m.zero_grad(set_to_none=True)
+        cmds, params = m(inp)
+        ((cmds * wc.cuda()).sum() + (params * wp.cuda()).sum()).backward()
+    sdd = {k: v.double().cuda().requires_grad_(True) for k, v in sd.items()}
+    oc, op = to.forward(sdd, cfg, {k: v.double() for k, v in inp.items()})
+    ((oc * wc.cuda().double()).sum() + (op * wp.cuda().double()).sum()).backward()
+    dc, dp = (cmds.double() - oc).abs().max().item(), (params.double() - op).abs().max().item()
+    print(f"C2 logits max|d|: cmds {dc:.3e} params {dp:.3e}")
+    assert dc < LOGIT_TOL and dp < LOGIT_TOL
+    worst = 0.0
+    for k, p in m.named_weights():
+        ref = sdd[k].grad
+        if ref is None:
+            continue
+        err = (p.grad.double() - ref).abs().max().item() / (ref.abs().max().item() + 1e-6)
+        worst = max(worst, err)
+        assert err < GRAD_REL_TOL, f"{k}: {err:.3e}"
+    print(f"C2 worst relative gradient error {worst:.3e}")
+
+
 def test_c3_width_small_batch_forward_backward_vs_oracle():
     """BASELINE config C3 model width (H = Ff = 1024, head dim 256) at a small batch: logits and a few gradients against
     the fp64 oracle (covers the d = 256 attention kernels, the 64-wide GEMM tiles and the auxiliary-stream fork/join)."""
