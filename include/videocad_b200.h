@@ -79,6 +79,10 @@ typedef struct vc_attn_desc {
   int mask, window;
   float scale;
   vc_drop drop;
+  /* optional batch strides (elements) of q / k / v: sample b starts at row offset b * bs instead of b * T * ld.  0 = dense
+   * (b * Tq * ldq, b * Tk * ldk, b * Tk * ldv).  Non-zero strides are accepted by the forward only (fp32 inputs): they let a
+   * decoding step attend from ONE query row per sequence to the first Tk rows of a [B, Tmax, .] key/value cache. */
+  int64_t bsq, bsk, bsv;
 } vc_attn_desc;
 
 const char* vc_last_error(void);
@@ -229,6 +233,12 @@ int vc_clip_adam_step(const vc_adam_tensor* tensors, int num_tensors, double bet
 int vc_head_small_fwd(const float* x, int64_t R, int H, const float* W, const float* b, int C, float* out, void* stream);
 int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const float* W, int C, float* dx,
                       int accumulate_dx, float* dW, float* db, void* stream);
+/* nn.Linear on M <= 16 rows (one token per sequence of a decoding step), exact fp32: out = act(x W^T + bias) + residual with W the
+ * fp32 [N, K] weight; x fp32 or split-bf16 (exactly one of x / x_hi non-NULL); fp32 and/or split outputs.  Used by
+ * vc_seq_decode_step, where a 128-row tensor-core tile would be almost entirely padding. */
+int vc_linear_rows_fwd(const float* x, const vc_bf16* x_hi, const vc_bf16* x_lo, int64_t ldx, int M, const float* W, const float* bias, int N,
+                       int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, vc_bf16* out_hi, vc_bf16* out_lo,
+                       int64_t ldo_split, void* stream);
 /* ---- frame ingestion: uint8 grey-level frames -> the normalised fp32 tensor the model consumes.
  * Replaces transforms.ToTensor() + transforms.Normalize([0.5], [0.5]) of the reference's loader (main.py:103-110, applied per
  * frame on the CPU in DatasetBase.__getitem__, data_loader/data_loader.py:434-508) and lets the batch cross PCIe as bytes:
@@ -336,6 +346,15 @@ typedef struct vc_seq_call {
 size_t vc_seq_workspace_bytes(int B, int T, int H, int Ff, int num_layers, int nhead, int num_param_out, int num_views);
 size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out, int num_views);
 int vc_seq_forward(const vc_seq_call* c, void* stream);
+/* Incremental decoding for the rollout with action feedback (sequential_inference, autoregressive_transformer.py:222-275): after ONE
+ * vc_seq_forward over the full length T (any actions; eval mode) on call `c`, vc_seq_decode_step(c, t, ...) for t = 0, 1, ... pushes
+ * one token per sequence through the decoder, using c->ws as the key/value cache (self-attention rows [0, t], cross-attention
+ * window of the memory tokens) instead of re-running the prefix.  actions_t [B, act_dim] normalised actions of step t (zeros at
+ * t = 0); cmds_t [B, num_cmd], params_t [B, num_param_out] receive the logits of position t; scratch >=
+ * vc_seq_decode_scratch_bytes.  Requires past_actions; results equal vc_seq_forward on the prefix [0, t] at position t. */
+size_t vc_seq_decode_scratch_bytes(int B, int H, int Ff, int nhead);
+int vc_seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* scratch, size_t scratch_bytes, float* cmds_t,
+                       float* params_t, void* stream);
 /* dcmds [B*T,num_cmd], dparams [B*T,num_param_out]; d_state_cls [B*T,512] (may be null unless past_states),
  * d_cad_cls [B,512] and d_mv_cls [B*num_views,512] (may be null when num_views == 0) are OVERWRITTEN */
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,

@@ -335,16 +335,19 @@ int attention_fwd(const AttnDesc& a_in, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo,
   const AttnDesc& a = joined.d;
   if (int rc = attn_validate(a)) return rc;
   const int d = a.d;
+  if ((a_in.bsq || a_in.bsk || a_in.bsv) && a_in.q_hi != nullptr) return set_error("attention_fwd: batch strides need fp32 inputs");
+  const int64_t bsq = a_in.bsq ? a_in.bsq : (int64_t)a.Tq * a.ldq, bsk = a_in.bsk ? a_in.bsk : (int64_t)a.Tk * a.ldk,
+                bsv = a_in.bsv ? a_in.bsv : (int64_t)a.Tk * a.ldv;
 #pragma omp parallel for collapse(2) schedule(static)
   for (int b = 0; b < a.B; ++b)
     for (int h = 0; h < a.nh; ++h) {
       std::vector<double> s(a.Tk), acc(d);
       for (int i = 0; i < a.Tq; ++i) {
-        const float* q = a.q + ((int64_t)b * a.Tq + i) * a.ldq + (int64_t)h * d;
+        const float* q = a.q + (int64_t)b * bsq + (int64_t)i * a.ldq + (int64_t)h * d;
         double m = -INFINITY;
         for (int j = 0; j < a.Tk; ++j) {
           if (is_masked(a.mask, a.window, i, j)) { s[j] = -INFINITY; continue; }
-          const float* k = a.k + ((int64_t)b * a.Tk + j) * a.ldk + (int64_t)h * d;
+          const float* k = a.k + (int64_t)b * bsk + (int64_t)j * a.ldk + (int64_t)h * d;
           double t = 0;
           for (int c = 0; c < d; ++c) t += (double)q[c] * k[c];
           s[j] = t * a.scale;
@@ -359,7 +362,7 @@ int attention_fwd(const AttnDesc& a_in, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo,
           if (s[j] == -INFINITY) continue;
           const uint64_t idx = (((uint64_t)b * a.nh + h) * a.Tq + i) * (uint64_t)a.Tk + j;
           const double pj = exp(s[j] - l) * keep_scale(a.drop, idx);
-          const float* v = a.v + ((int64_t)b * a.Tk + j) * a.ldv + (int64_t)h * d;
+          const float* v = a.v + (int64_t)b * bsv + (int64_t)j * a.ldv + (int64_t)h * d;
           for (int c = 0; c < d; ++c) acc[c] += pj * v[c];
         }
         for (int c = 0; c < d; ++c) {
@@ -487,6 +490,35 @@ int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t
   if (int rc = act_dropout_bwd(dq, W, Rq, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dq_hi, dq_lo, ld_split, dbq, st)) return rc;
   if (int rc = act_dropout_bwd(dk, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dk_hi, dk_lo, ld_split, dbk, st)) return rc;
   return act_dropout_bwd(dv, W, Rk, (int)W, VC_ACT_NONE, nullptr, 0, nullptr, 0, no_drop(), nullptr, 0, dv_hi, dv_lo, ld_split, dbv, st);
+}
+
+int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int64_t ldx, int M, const float* W, const float* bias, int N,
+                    int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, bf16_t* out_hi, bf16_t* out_lo,
+                    int64_t ldo_split, stream_t) {
+  if (M > 16) return set_error("linear_rows_fwd: at most 16 rows");
+  if ((x == nullptr) == (x_hi == nullptr)) return set_error("linear_rows_fwd: give x either as fp32 or as split-bf16");
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0;
+      for (int k = 0; k < K; ++k) {
+        const float xv = x ? x[m * ldx + k] : bf2f(x_hi[m * ldx + k]) + (x_lo ? bf2f(x_lo[m * ldx + k]) : 0.f);
+        acc += (double)xv * W[(int64_t)n * K + k];
+      }
+      double v = acc + (bias ? bias[n] : 0.f);
+      if (act == VC_ACT_RELU) v = v > 0 ? v : 0;
+      else if (act == VC_ACT_TANH) v = tanh(v);
+      else if (act == VC_ACT_GELU) v = gelu_d(v);
+      if (residual) v += residual[m * ld_res + n];
+      const float vf = (float)v;
+      if (out_f32) out_f32[m * ldo + n] = vf;
+      if (out_hi) {
+        bf16_t hi, lo;
+        split1(vf, hi, lo);
+        out_hi[m * ldo_split + n] = hi;
+        if (out_lo) out_lo[m * ldo_split + n] = lo;
+      }
+    }
+  return 0;
 }
 
 int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t) {

@@ -45,7 +45,7 @@ def main():
             torch.cuda.synchronize()
             if it > 1:
                 ts.append(e0.elapsed_time(e1))
-        ms = sorted(ts)[len(ts) // 2]
+        ms = sorted(ts)[len(ts) // 2] if ts else float('nan')
         assert cmds.shape == (B, T, 5) and params.shape == (B, T, 6, 1000) and torch.isfinite(params).all()
         out["action_feedback" if action else "single_pass"] = dict(ms_per_rollout=ms, frames_per_s=B * T / (ms / 1e3))
     print(json.dumps(dict(metric="rollout frames/sec", n_gpus=1, config=dict(workload=f"c4: {B} sequences x {T} steps, H=1024, 224x224, eval"),

@@ -256,15 +256,20 @@ def test_frame_ingestion_u8_bit_exact_and_model_equivalence(emu):
     assert torch.equal(c8, cf) and torch.equal(p8, pf)
 
 
-def test_sequential_inference_matches_oracle(emu):
-    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2,
+@pytest.mark.parametrize("layers,window,L_", [(1, 2, 5), (3, 3, 8)])
+def test_sequential_inference_matches_oracle(emu, layers, window, L_):
+    """Rollout with action feedback through the incremental decoder (vc_seq_decode_step: one token per step against the key/value
+    cache) against the oracle's O(T^2) recompute of the reference loop; three layers exercise the layer-output ping-pong, T >
+    window the clipping of the cross-attention window."""
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=layers, dim_feedforward=128, window_size=window,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build_emu_model(emu, cfg)
     m.eval()
-    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 5, 64))
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, L_, 64))
     ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
     oc, op = to.rollout(sd, cfg, inp["frames"], inp["cad_image"], action=True)
     assert (ac - oc).abs().max() < 2e-4 and (ap - op).abs().max() < 2e-4
+    assert (ac.argmax(-1) == oc.argmax(-1)).all()
     zc, zp = m.sequential_inference(inp["frames"], inp["cad_image"], action=False)
     fc, fp = m(dict(inp, actions=torch.zeros_like(inp["actions"])))
     assert torch.equal(zc, fc.detach()) and torch.equal(zp, fp.detach())

@@ -473,6 +473,31 @@ def test_vit_attention_split_inputs(B, T, p):
         assert err < 1e-4, f"{name}: {err:.3e}"
 
 
+@pytest.mark.parametrize("M,N,Kd,act,split_in", [(8, 3072, 1024, L.ACT_NONE, False), (8, 512, 512, L.ACT_RELU, True), (3, 6000, 256, L.ACT_NONE, False),
+                                                   (16, 1024, 1024, L.ACT_TANH, True), (1, 40, 128, L.ACT_NONE, False)])
+def test_linear_rows_fwd(M, N, Kd, act, split_in):
+    """nn.Linear on a handful of rows (decoding step): exact fp32 against fp64, fp32 or split-bf16 input, bias / activation /
+    residual, fp32 and split outputs, strided output rows (the key/value cache slot)."""
+    x, Wt, bias, res = _rand(M, Kd, seed=70), _rand(N, Kd, seed=71, scale=0.1), _rand(N, seed=72), _rand(M, N, seed=73)
+    xs = L.split(x) if split_in else None
+    xin = (xs[0].float() + xs[1].float()) if split_in else x
+    ldo = 3 * N  # rows of the output live 3N apart
+    out = torch.full((M, ldo), float("nan"), device="cuda")
+    outs = K.bf16_pair((M, N))
+    L.check(L.load().vc_linear_rows_fwd(None if split_in else x.data_ptr(), xs[0].data_ptr() if split_in else None,
+                                       xs[1].data_ptr() if split_in else None, Kd, M, Wt.data_ptr(), bias.data_ptr(), N, Kd, act, res.data_ptr(), N,
+                                       out.data_ptr(), ldo, outs[0].data_ptr(), outs[1].data_ptr(), N, L.cur_stream()))
+    z = xin.double() @ Wt.double().t() + bias.double()
+    if act == L.ACT_RELU:
+        z = torch.relu(z)
+    elif act == L.ACT_TANH:
+        z = torch.tanh(z)
+    z = z + res.double()
+    assert _relerr(out[:, :N], z) < 2e-6
+    assert torch.isnan(out[:, N:]).all()
+    assert (K.join(outs) - out[:, :N]).abs().max() <= out[:, :N].abs().max() * 2.0 ** -15
+
+
 @pytest.mark.parametrize("n", [16, 733, 8 * 224 * 224 + 5])
 def test_frames_u8_normalize_bit_exact(n):
     """uint8 frame ingestion == ToTensor() + Normalize([0.5], [0.5]) of the reference's loader (main.py:103-110), bit for bit"""

@@ -165,13 +165,13 @@ def test_bf16_single_pass_mode_is_looser_but_close():
     assert 1e-4 < d < 0.1, d
 
 
-@pytest.mark.parametrize("T", [6, 19])  # 19 steps cross the rollout's prefix-length buckets (8, 16, 19), each a CUDA graph
-def test_prefix_invariance_and_rollout(T):
-    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=256, window_size=2,
+@pytest.mark.parametrize("B,T", [(2, 6), (2, 19), (18, 5)])  # 18 sequences: the decoding step's tensor-core path (> 16 rows)
+def test_prefix_invariance_and_rollout(B, T):
+    cfg = dict(hidden_size=256, nhead=4, num_decoder_layers=3, dim_feedforward=256, window_size=2,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build(cfg)
     m.eval()
-    B, S = 2, 64
+    S = 64
     inp, _ = cuda_inputs(B, T, S)
     with torch.no_grad():
         full_c, full_p = m(inp)

@@ -31,6 +31,7 @@ template <> struct AttCfg<256> { static constexpr int QB_F = 16, KT_F = 16, QB_B
 
 struct AttnP {
   const float *q, *k, *v; long long ldq, ldk, ldv;
+  long long bsq, bsk, bsv;  // batch strides (elements)
   int B, Tq, Tk, nh, d, mask, window;
   float scale;
   Drop drop; uint32_t thresh; float dscale;
@@ -88,14 +89,14 @@ attn_fwd_kernel(const AttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const DropKey dkey = drop_key_of(p.drop);
 
-  load_rows<LDS>(Qs, p.q + ((long long)b * p.Tq + q0) * p.ldq + (long long)h * d, p.ldq, nq, d);
+  load_rows<LDS>(Qs, p.q + (long long)b * p.bsq + (long long)q0 * p.ldq + (long long)h * d, p.ldq, nq, d);
 
   // ---- scores
   for (int k0 = 0; k0 < Tk; k0 += KT) {
     const int nk = min(KT, Tk - k0);
     const bool skip = tile_masked(p.mask, p.window, q0, nq, k0, nk);
     __syncthreads();
-    if (!skip) load_rows<LDS>(KVs, p.k + ((long long)b * Tk + k0) * p.ldk + (long long)h * d, p.ldk, nk, d);
+    if (!skip) load_rows<LDS>(KVs, p.k + (long long)b * p.bsk + (long long)k0 * p.ldk + (long long)h * d, p.ldk, nk, d);
     __syncthreads();
     for (int idx = threadIdx.x; idx < nq * KT; idx += ATT_THREADS) {
       const int i = idx / KT, j = idx % KT;
@@ -144,7 +145,7 @@ attn_fwd_kernel(const AttnP p, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* 
     const int nk = min(KT, Tk - k0);
     if (tile_masked(p.mask, p.window, q0, nq, k0, nk)) continue;  // uniform across the CTA
     __syncthreads();
-    load_rows<LDS>(KVs, p.v + ((long long)b * Tk + k0) * p.ldv + (long long)h * d, p.ldv, nk, d);
+    load_rows<LDS>(KVs, p.v + (long long)b * p.bsv + (long long)k0 * p.ldv + (long long)h * d, p.ldv, nk, d);
     __syncthreads();
 #pragma unroll
     for (int cc = 0; cc < CPT; ++cc) {
@@ -297,6 +298,9 @@ attn_bwd_kernel(const AttnP p, const __nv_bfloat16* __restrict__ o_hi, const __n
 inline AttnP make_params(const AttnDesc& a) {
   AttnP p;
   p.q = a.q; p.k = a.k; p.v = a.v; p.ldq = a.ldq; p.ldk = a.ldk; p.ldv = a.ldv;
+  p.bsq = a.bsq ? a.bsq : (long long)a.Tq * a.ldq;
+  p.bsk = a.bsk ? a.bsk : (long long)a.Tk * a.ldk;
+  p.bsv = a.bsv ? a.bsv : (long long)a.Tk * a.ldv;
   p.B = a.B; p.Tq = a.Tq; p.Tk = a.Tk; p.nh = a.nh; p.d = a.d; p.mask = a.mask; p.window = a.window;
   p.scale = a.scale;
   p.drop = a.drop;
@@ -357,11 +361,15 @@ int launch_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_
 static bool g_force_simt = false;
 void attention_force_simt(int on) { g_force_simt = on != 0; }
 
+static inline bool dense_batches(const AttnDesc& a) { return a.bsq == 0 && a.bsk == 0 && a.bsv == 0; }
+
 int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s) {
   if (int rc = validate(a, "attention_fwd")) return rc;
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
-  if (attention_small_eligible(a) && ldo % 4 == 0) return attention_small_fwd(a, o_hi, o_lo, ldo, lse, s);
+  if (!dense_batches(a) && (a.q_hi != nullptr || a.bsq % 4 != 0 || a.bsk % 4 != 0 || a.bsv % 4 != 0))
+    return set_error("attention_fwd: batch strides need fp32 inputs and multiples of 4");
+  if (dense_batches(a) && vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
+  if (dense_batches(a) && attention_small_eligible(a) && ldo % 4 == 0) return attention_small_fwd(a, o_hi, o_lo, ldo, lse, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_fwd<64>(a, o_hi, o_lo, ldo, lse, st);
   if (a.d <= 128) return launch_fwd<128>(a, o_hi, o_lo, ldo, lse, st);
@@ -372,6 +380,7 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
                   const float* dout, int64_t lddo, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                   int64_t lddv, stream_t s) {
   if (int rc = validate(a, "attention_bwd")) return rc;
+  if (!dense_batches(a)) return set_error("attention_bwd: batch strides are supported by the forward only");
   if (lddo % 4 != 0) return set_error("attention_bwd: dout stride must be a multiple of 4");
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr))
@@ -389,6 +398,7 @@ int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_l
                         const float* dout, const bf16_t* dout_hi, const bf16_t* dout_lo, int64_t lddo, float* scratch, bf16_t* dq_hi, bf16_t* dq_lo, bf16_t* dk_hi,
                         bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, stream_t s) {
   if (int rc = validate(a, "attention_bwd_split")) return rc;
+  if (!dense_batches(a)) return set_error("attention_bwd_split: batch strides are supported by the forward only");
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr || dout == nullptr))
     return vit_attention_bwd_split(a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo,
@@ -413,6 +423,7 @@ int attention_bwd_split_bias(const AttnDesc& a, const bf16_t* o_hi, const bf16_t
                              bf16_t* dk_lo, bf16_t* dv_hi, bf16_t* dv_lo, int64_t ld_split, float* dbq, float* dbk, float* dbv,
                              stream_t s) {
   if (int rc = validate(a, "attention_bwd_split_bias")) return rc;
+  if (!dense_batches(a)) return set_error("attention_bwd_split_bias: batch strides are supported by the forward only");
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (!dout) return set_error("attention_bwd_split_bias: an fp32 upstream gradient is required");
   if (attention_small_eligible(a) && ldo % 4 == 0 && lddo % 4 == 0 && ld_split % 4 == 0)

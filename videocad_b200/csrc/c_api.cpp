@@ -164,6 +164,11 @@ int vc_head_small_bwd(const float* dout, const float* x, int64_t R, int H, const
                       int accumulate_dx, float* dW, float* db, void* stream) {
   return vck::head_small_bwd(dout, x, R, H, W, C, dx, accumulate_dx, dW, db, stream);
 }
+int vc_linear_rows_fwd(const float* x, const vc_bf16* x_hi, const vc_bf16* x_lo, int64_t ldx, int M, const float* W, const float* bias, int N,
+                       int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, vc_bf16* out_hi, vc_bf16* out_lo,
+                       int64_t ldo_split, void* stream) {
+  return vck::linear_rows_fwd(x, x_hi, x_lo, ldx, M, W, bias, N, K, act, residual, ld_res, out_f32, ldo, out_hi, out_lo, ldo_split, stream);
+}
 int vc_frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, void* stream) {
   return vck::frames_u8_normalize(src, n, mean, std, dst, stream);
 }

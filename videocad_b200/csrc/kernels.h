@@ -161,6 +161,15 @@ int stream_join(stream_t main, int i);
 // 0: stream_fork hands back the caller's stream (serialised execution, used when timing kernels one by one); 1: default
 void side_streams_enable(int enable);
 
+// Linear layer on a HANDFUL of rows (M <= 16: one token per sequence of an incremental decoding step), exact fp32 SIMT:
+//   out[m, n] = act(sum_k x[m, k] * W[n, k] + bias[n]) + residual[m, n]      W fp32 [N, K] row-major (nn.Linear.weight)
+// x is fp32 (x != null) or split-bf16 (x_hi / x_lo, joined on the fly); outputs fp32 and/or split.  A 128-row tensor-core tile
+// would be 94 % padding here and each of its CTAs would stream its weight slab alone; this kernel spreads the N x K weight
+// matrix over all SMs (one warp per output column) so a step is bound by reading the weights once.
+int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int64_t ldx, int M, const float* W, const float* bias, int N,
+                    int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, bf16_t* out_hi, bf16_t* out_lo,
+                    int64_t ldo_split, stream_t s);
+
 // frame ingestion: uint8 grey-level frames -> the fp32 tensor the reference's loader hands the model,
 // i.e. torchvision ToTensor (u / 255) followed by Normalize(mean, std) (/root/reference/main.py:103-110: mean = std = 0.5):
 // dst[i] = (float(src[i]) / 255 - mean) / std, evaluated with the same fp32 operations in the same order (bit-exact)

@@ -320,6 +320,126 @@ int seq_forward(const vc_seq_call* c, stream_t st) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Incremental decoding (autoregressive rollout with action feedback, autoregressive_transformer.py:222-275).
+//
+// The reference re-runs the whole forward on the growing prefix at every step.  The forward is causal, so position t depends on
+// positions <= t only, and everything position t needs from the past is (i) the self-attention keys/values of every layer at
+// positions < t and (ii) the cross-attention keys/values of the memory tokens, which do not depend on the actions at all.
+// seq_forward() over the full length (any actions) leaves exactly these in its workspace: Y.kv2 = cross-attention K|V of all
+// positions, Y.qkv = self-attention q|k|v rows.  seq_decode_step(t) then pushes ONE token per sequence through the decoder:
+// its q|k|v row is written straight into row (b, t) of Y.qkv -- the key/value cache -- and the two attention calls read the
+// first t + 1 rows of the cache / the window of Y.kv2 through the batch strides of vc_attn_desc.  Steps must be issued in
+// order t = 0, 1, ... after one seq_forward() on the same workspace.  Eval mode only (no dropout), past_actions required.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct StepWs {
+  float* act; Split actS;
+  Split a, c, f;
+  float *y, *x1, *x2, *x3, *q2, *ff;
+  Split x1S, x2S, x3S;
+  float *lse, *mean, *rstd;
+};
+void step_carve(Arena& a, int B, int H, int Ff, int nh, StepWs& s) {
+  s.act = a.alloc<float>((size_t)B * H); s.actS = a.alloc_split(B, H);
+  s.a = a.alloc_split(B, H); s.c = a.alloc_split(B, H); s.f = a.alloc_split(B, Ff);
+  s.y = a.alloc<float>((size_t)B * H);
+  s.x1 = a.alloc<float>((size_t)B * H); s.x2 = a.alloc<float>((size_t)B * H); s.x3 = a.alloc<float>((size_t)B * H);
+  s.q2 = a.alloc<float>((size_t)B * H); s.ff = a.alloc<float>((size_t)B * Ff);
+  s.x1S = a.alloc_split(B, H); s.x2S = a.alloc_split(B, H); s.x3S = a.alloc_split(B, H);
+  s.lse = a.alloc<float>((size_t)B * nh); s.mean = a.alloc<float>(B); s.rstd = a.alloc<float>(B);
+}
+}  // namespace
+
+size_t seq_decode_scratch_bytes(int B, int H, int Ff, int nh) {
+  Arena a(nullptr, 0);
+  StepWs s;
+  step_carve(a, B, H, Ff, nh, s);
+  return a.used();
+}
+
+int seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* scratch, size_t scratch_bytes, float* cmds_t,
+                    float* params_t, stream_t st) {
+  VC_TRY(check_call(c));
+  if (!actions_t || !scratch || !cmds_t || !params_t) return set_error("seq_decode_step: null argument");
+  if (!c->past_actions) return set_error("seq_decode_step: enable_past_actions is required (the target tokens are the fed-back actions)");
+  if (c->training) return set_error("seq_decode_step: eval mode only");
+  if (t < 0 || t >= c->T) return set_error("seq_decode_step: step out of range");
+  const vc_seq_weights& W = *c->w;
+  const Dims d = dims_of(c);
+  const int B = d.B, T = d.T, H = d.H, Ff = d.Ff, P = c->passes;
+  Arena arena(c->ws, c->ws_bytes);
+  SeqWs w;
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, d.nv, w);
+  if (!arena.ok()) return set_error("seq_decode_step: workspace too small");
+  Arena sa(scratch, scratch_bytes);
+  StepWs s;
+  step_carve(sa, B, H, Ff, d.nh, s);
+  if (!sa.ok()) return set_error("seq_decode_step: scratch too small");
+
+  // One Linear of the step: x (fp32 and/or split) -> out.  Up to 16 sequences: the exact-fp32 row kernel (the N x K weights are
+  // spread over all SMs); larger batches: the tensor-core GEMM on the split operands, as in the full forward.
+  const bool rows_path = B <= 16 && H % 128 == 0 && Ff % 128 == 0;
+  auto linear = [&](const float* xf, const Split& xs, const vc_linear& Lw, int64_t row0, int N, int K, int act, const float* res,
+                    float* out, int64_t ldo, const Split* outS) -> int {
+    const float* bias = Lw.b ? Lw.b + row0 : nullptr;
+    if (rows_path) {
+      return linear_rows_fwd(xf, xf ? nullptr : xs.hi, xf ? nullptr : xs.lo, xf ? (int64_t)K : xs.ld, B, Lw.w + row0 * K, bias, N, K, act, res, H,
+                             out, ldo, outS ? outS->hi : nullptr, outS ? outS->lo : nullptr, outS ? outS->ld : 0, st);
+    }
+    GemmDesc g;
+    gemm_linear_fwd(g, xs, wsplit(Lw, K, row0), B, N, K, P);
+    g.bias = bias; g.act = act; g.residual = res; g.ld_res = H; g.out_f32 = out; g.ldo = ldo;
+    if (outS) { g.out_hi = outS->hi; g.out_lo = outS->lo; g.ldo_split = outS->ld; }
+    return gemm(g, st);
+  };
+
+  // token of step t: tanh(W_a a_t + b + E[t])   (embed_action_fwd indexes E by row % T: one row per sequence -> T = 1, E + t*H)
+  const float* E = W.timestep_emb ? W.timestep_emb + (int64_t)t * H : nullptr;
+  VC_TRY(embed_action_fwd(actions_t, B, c->act_dim, H, W.embed_action_w, W.embed_action_b, E, 1, s.act, s.actS.hi, s.actS.lo, st));
+  const float* x_in = s.act; Split x_inS = s.actS;
+  const float scale = 1.0f / sqrtf((float)d.dh);
+  for (int l = 0; l < d.L; ++l) {
+    const vc_dec_layer& LW = W.layers[l];
+    SeqWs::Layer& Y = w.l[l];
+    // q | k | v of the new token -> row (b, t) of the cache
+    VC_TRY(linear(x_in, x_inS, LW.sa_in, 0, 3 * H, H, VC_ACT_NONE, nullptr, Y.qkv + (int64_t)t * 3 * H, (int64_t)T * 3 * H, nullptr));
+    {  // self-attention of the new token over cache rows [0, t]: every cached key is in its causal past
+      AttnDesc a = {};
+      a.q = Y.qkv + (int64_t)t * 3 * H; a.ldq = 3 * H; a.bsq = (int64_t)T * 3 * H;
+      a.k = Y.qkv + H; a.v = Y.qkv + 2 * H; a.ldk = a.ldv = 3 * H; a.bsk = a.bsv = (int64_t)T * 3 * H;
+      a.B = B; a.Tq = 1; a.Tk = t + 1; a.nh = d.nh; a.d = d.dh;
+      a.mask = VC_MASK_NONE; a.window = 1; a.scale = scale; a.drop = no_drop();
+      VC_TRY(attention_fwd(a, s.a.hi, s.a.lo, H, s.lse, st));
+    }
+    VC_TRY(linear(nullptr, s.a, LW.sa_out, 0, H, H, VC_ACT_NONE, x_in, s.y, H, nullptr));
+    VC_TRY(layernorm_fwd(s.y, H, B, H, LW.n1.w, LW.n1.b, LN_EPS, s.x1, H, s.x1S.hi, s.x1S.lo, H, s.mean, s.rstd, st));
+    VC_TRY(linear(s.x1, s.x1S, LW.ca_in, 0, H, H, VC_ACT_NONE, nullptr, s.q2, H, nullptr));
+    {  // cross-attention over the memory window (t - W, t]
+      const int jlo = t - c->window + 1 > 0 ? t - c->window + 1 : 0;
+      AttnDesc a = {};
+      a.q = s.q2; a.ldq = H; a.bsq = H;
+      a.k = Y.kv2 + (int64_t)jlo * 2 * H; a.v = a.k + H; a.ldk = a.ldv = 2 * H; a.bsk = a.bsv = (int64_t)T * 2 * H;
+      a.B = B; a.Tq = 1; a.Tk = t - jlo + 1; a.nh = d.nh; a.d = d.dh;
+      a.mask = VC_MASK_NONE; a.window = 1; a.scale = scale; a.drop = no_drop();
+      VC_TRY(attention_fwd(a, s.c.hi, s.c.lo, H, s.lse, st));
+    }
+    VC_TRY(linear(nullptr, s.c, LW.ca_out, 0, H, H, VC_ACT_NONE, s.x1, s.y, H, nullptr));
+    VC_TRY(layernorm_fwd(s.y, H, B, H, LW.n2.w, LW.n2.b, LN_EPS, s.x2, H, s.x2S.hi, s.x2S.lo, H, s.mean, s.rstd, st));
+    VC_TRY(linear(s.x2, s.x2S, LW.lin1, 0, Ff, H, VC_ACT_RELU, nullptr, rows_path ? s.ff : nullptr, Ff, rows_path ? nullptr : &s.f));
+    VC_TRY(linear(rows_path ? s.ff : nullptr, s.f, LW.lin2, 0, H, Ff, VC_ACT_NONE, s.x2, s.y, H, nullptr));
+    // the layer output ping-pongs between the (x3, x3S) and (act, actS) buffers: it must not overwrite this layer's own input,
+    // which the residual connections above read
+    float* xo = (x_in == s.act) ? s.x3 : s.act;
+    const Split xoS = (x_in == s.act) ? s.x3S : s.actS;
+    VC_TRY(layernorm_fwd(s.y, H, B, H, LW.n3.w, LW.n3.b, LN_EPS, xo, H, xoS.hi, xoS.lo, H, s.mean, s.rstd, st));
+    x_in = xo; x_inS = xoS;
+  }
+  VC_TRY(head_small_fwd(x_in, B, H, W.head_cmd_w, W.head_cmd_b, d.NC, cmds_t, st));
+  VC_TRY(linear(x_in, x_inS, W.head_params, 0, d.NP, H, VC_ACT_NONE, nullptr, params_t, d.NP, nullptr));
+  return 0;
+}
+
 int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                  float* d_mv_cls, void* scratch, size_t scratch_bytes, stream_t st) {
   VC_TRY(check_call(c));
@@ -530,6 +650,11 @@ size_t vc_seq_scratch_bytes(int B, int T, int H, int Ff, int num_param_out, int 
   return vck::seq_scratch_bytes(B, T, H, Ff, num_param_out, num_views);
 }
 int vc_seq_forward(const vc_seq_call* c, void* stream) { return vck::seq_forward(c, stream); }
+size_t vc_seq_decode_scratch_bytes(int B, int H, int Ff, int nhead) { return vck::seq_decode_scratch_bytes(B, H, Ff, nhead); }
+int vc_seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* scratch, size_t scratch_bytes, float* cmds_t,
+                       float* params_t, void* stream) {
+  return vck::seq_decode_step(c, t, actions_t, scratch, scratch_bytes, cmds_t, params_t, stream);
+}
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                     float* d_mv_cls, void* scratch, size_t scratch_bytes, void* stream) {
   return vck::seq_backward(c, dcmds, dparams, d_state_cls, d_cad_cls, d_mv_cls, scratch, scratch_bytes, stream);

@@ -619,6 +619,76 @@ __global__ void head_small_bwd_kernel(const float* __restrict__ dout, const floa
   }
 }
 
+// Linear layer on M <= 16 rows: the rows live in shared memory, one warp per output column streams that column's K weights once
+constexpr int LR_MAXM = 16, LR_WARPS = 8;
+template <int MM>
+__global__ void __launch_bounds__(LR_WARPS * 32)
+linear_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ x_hi, const __nv_bfloat16* __restrict__ x_lo, long long ldx,
+                   int M, const float* __restrict__ W, const float* __restrict__ bias, int N, int K, int act,
+                   const float* __restrict__ residual, long long ld_res, float* __restrict__ out_f32, long long ldo,
+                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ldo_split) {
+  pdl_grid_sync();
+  extern __shared__ float4 lr_smem4[];
+  float* xs = reinterpret_cast<float*>(lr_smem4);  // [MM][K], rows >= M zero
+  const int K4 = K >> 2;
+  for (int idx = threadIdx.x; idx < MM * K4; idx += LR_WARPS * 32) {
+    const int m = idx / K4, k = (idx - m * K4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < M) {
+      if (x != nullptr) {
+        v = *reinterpret_cast<const float4*>(x + (long long)m * ldx + k);
+      } else {
+        const uint2 h = *reinterpret_cast<const uint2*>(x_hi + (long long)m * ldx + k);
+        v = make_float4(__uint_as_float(h.x << 16), __uint_as_float(h.x & 0xffff0000u), __uint_as_float(h.y << 16),
+                        __uint_as_float(h.y & 0xffff0000u));
+        if (x_lo != nullptr) {
+          const uint2 l = *reinterpret_cast<const uint2*>(x_lo + (long long)m * ldx + k);
+          v.x += __uint_as_float(l.x << 16); v.y += __uint_as_float(l.x & 0xffff0000u);
+          v.z += __uint_as_float(l.y << 16); v.w += __uint_as_float(l.y & 0xffff0000u);
+        }
+      }
+    }
+    *reinterpret_cast<float4*>(xs + m * K + k) = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int n = blockIdx.x * LR_WARPS + warp; n < N; n += gridDim.x * LR_WARPS) {
+    float acc[MM];
+#pragma unroll
+    for (int m = 0; m < MM; ++m) acc[m] = 0.f;
+    const float* wrow = W + (long long)n * K;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow + k));
+#pragma unroll
+      for (int m = 0; m < MM; ++m) {
+        const float4 x4 = *reinterpret_cast<const float4*>(xs + m * K + k);
+        acc[m] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[m]))));
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int m = 0; m < MM; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], off);
+    }
+    // lane m finishes row m
+    float v = 0.f;
+#pragma unroll
+    for (int m = 0; m < MM; ++m) if (lane == m) v = acc[m];
+    if (lane < M) {
+      if (bias != nullptr) v += __ldg(bias + n);
+      v = apply_act(v, act);
+      if (residual != nullptr) v += residual[(long long)lane * ld_res + n];
+      if (out_f32 != nullptr) out_f32[(long long)lane * ldo + n] = v;
+      if (out_hi != nullptr) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        out_hi[(long long)lane * ldo_split + n] = h;
+        if (out_lo != nullptr) out_lo[(long long)lane * ldo_split + n] = l;
+      }
+    }
+  }
+}
+
 // uint8 frames -> normalised fp32 (16 pixels per thread: one 128-bit load, four 128-bit stores)
 __global__ void frames_u8_normalize_kernel(const uint8_t* __restrict__ src, long long n, float mean, float std, float* __restrict__ dst) {
   pdl_grid_sync();
@@ -863,6 +933,36 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
   dim3 grid(cdiv(H / 4, 128), cdiv(R, rows_per_block));
   VC_LAUNCH((head_small_bwd_kernel), grid, 128, 0, cs(s), dout, x, R, H, W, C, dx, accumulate_dx, dW, db, rows_per_block);
   return check_launch("head_small_bwd_kernel");
+}
+
+int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int64_t ldx, int M, const float* W, const float* bias, int N,
+                    int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, bf16_t* out_hi, bf16_t* out_lo,
+                    int64_t ldo_split, stream_t s) {
+  if (M <= 0 || N <= 0) return 0;
+  if (M > LR_MAXM) return set_error("linear_rows_fwd: at most 16 rows");
+  if (K <= 0 || K % 128 != 0 || ldx % 4 != 0) return set_error("linear_rows_fwd: K must be a multiple of 128 and ldx of 4");
+  if ((x == nullptr) == (x_hi == nullptr)) return set_error("linear_rows_fwd: give x either as fp32 or as split-bf16");
+  if (!W || (out_f32 == nullptr && out_hi == nullptr)) return set_error("linear_rows_fwd: null weight or no output");
+  const int MM = M <= 8 ? 8 : 16;
+  const size_t smem = sizeof(float) * (size_t)MM * K;
+  if (smem > 200 * 1024) return set_error("linear_rows_fwd: K too large for the shared-memory row buffer");
+  int grid = cdiv(N, LR_WARPS);
+  if (grid > 148 * 4) grid = 148 * 4;
+#define VC_LR(MMV)                                                                                                          \
+  do {                                                                                                                      \
+    static size_t configured = 0;                                                                                           \
+    if (smem > 48 * 1024 && smem > configured) {                                                                            \
+      cudaError_t e = cudaFuncSetAttribute(linear_rows_kernel<MMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));                                                        \
+      configured = 200 * 1024;                                                                                              \
+    }                                                                                                                       \
+    VC_LAUNCH((linear_rows_kernel<MMV>), grid, LR_WARPS * 32, smem, cs(s), x, reinterpret_cast<const __nv_bfloat16*>(x_hi),  \
+              reinterpret_cast<const __nv_bfloat16*>(x_lo), (long long)ldx, M, W, bias, N, K, act, residual, (long long)ld_res, out_f32,        \
+              (long long)ldo, reinterpret_cast<__nv_bfloat16*>(out_hi), reinterpret_cast<__nv_bfloat16*>(out_lo), (long long)ldo_split);         \
+  } while (0)
+  if (MM == 8) VC_LR(8); else VC_LR(16);
+#undef VC_LR
+  return check_launch("linear_rows_kernel");
 }
 
 int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t s) {

@@ -72,6 +72,7 @@ class AttnDesc(C.Structure):
         ("mask", i32), ("window", i32),
         ("scale", C.c_float),
         ("drop", Drop),
+        ("bsq", i64), ("bsk", i64), ("bsv", i64),
     ]
 
 
@@ -117,6 +118,7 @@ _PROTOS = {
     "vc_clip_adam_step": ([vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, i64, vp, vp, vp], i32),
     "vc_head_small_fwd": ([vp, i64, i32, vp, vp, i32, vp, vp], i32),
     "vc_head_small_bwd": ([vp, vp, i64, i32, vp, i32, vp, i32, vp, vp, vp], i32),
+    "vc_linear_rows_fwd": ([vp, vp, vp, i64, i32, vp, vp, i32, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp], i32),
     "vc_frames_u8_normalize": ([vp, i64, f32, f32, vp, vp], i32),
     "vc_add_f32": ([vp, vp, vp, i64, vp], i32),
     "vc_zero_f32": ([vp, i64, vp], i32),

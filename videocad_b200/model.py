@@ -249,6 +249,7 @@ class _Segment:
         self._split = None  # (flat._version, flat.data_ptr(), hi, lo): split-bf16 mirror of the whole flat parameter
         self._slots = {}
         self._islots = {}  # forward-only slots (need_grad=False callers: the rollout), no gradient arena
+        self._dstates = {}  # persistent buffers + per-step CUDA graphs of incremental decoding, per (B, T)
         self._sig = None
         self._lib = None  # tests may inject the CPU emulation library; the product path loads the CUDA build
 
@@ -263,7 +264,7 @@ class _Segment:
         """Persistent structs and graphs bake parameter addresses: drop them if the flat parameter's storage moved (.to(), ...)."""
         sig = self.flat.data_ptr()
         if sig != self._sig:
-            self._sig, self._slots, self._islots, self._split = sig, {}, {}, None
+            self._sig, self._slots, self._islots, self._dstates, self._split = sig, {}, {}, {}, None
 
     def _slot_for(self, key, make, infer=False):
         slots, cap = (self._islots, _MAX_INFER_SLOTS) if infer else (self._slots, _MAX_SLOTS)
@@ -633,6 +634,80 @@ class _SeqRunner(_Segment):
         L.check(lib.vc_seq_forward(C.byref(c), stream), lib)
         return cmds, params, (c, W, arr, ws, state_cls, cad_cls, actions, mv_cls)
 
+    def decode_begin(self, state_cls, cad_cls, B, T, passes, mv_cls=None):
+        """One full-length eval pass (zero actions) whose workspace then serves as the key/value cache of decode_step.
+        With CUDA graphs enabled the buffers of a (B, T) rollout are persistent and every step's launch sequence is captured
+        on its second use (one graph per step index: the cache offsets and lengths are baked into the kernel arguments)."""
+        lib, m = self.lib(), self.model
+        dev = cad_cls.device
+        H, Ff, nl, nh = m.hidden_size, m.dim_feedforward, m.num_decoder_layers, m.nhead
+        NP, NC, nv = m.num_params * m.num_params_values, m.num_classes, m.num_views
+        persistent = self.graphs_enabled(cad_cls) and nv == 0
+        key = (B, T, dev, passes, state_cls is not None)
+        if persistent:
+            self._check_storage()
+        dec = self._dstates.get(key) if persistent else None
+        if dec is None:
+            f32 = dict(dtype=torch.float32, device=dev)
+            dec = dict(B=B, dev=dev, graphs={}, uses={}, persistent=persistent)
+            dec["state"] = torch.empty(B * T, A.VIT_DIM, **f32) if state_cls is not None else None
+            dec["cad"] = torch.empty(B, A.VIT_DIM, **f32)
+            dec["actions0"] = torch.zeros(B * T, m.act_dim, **f32)
+            dec["mv"] = mv_cls.contiguous().float() if nv > 0 else None
+            dec["ws_bytes"] = lib.vc_seq_workspace_bytes(B, T, H, Ff, nl, nh, NP, nv)
+            dec["ws"] = torch.empty(dec["ws_bytes"], dtype=torch.uint8, device=dev)
+            dec["cmds_full"], dec["params_full"] = torch.empty(B * T, NC, **f32), torch.empty(B * T, NP, **f32)
+            dec["sc_bytes"] = lib.vc_seq_decode_scratch_bytes(B, H, Ff, nh)
+            dec["scratch"] = torch.empty(dec["sc_bytes"], dtype=torch.uint8, device=dev)
+            dec["action_t"] = torch.zeros(B, m.act_dim, **f32)
+            dec["cmds"], dec["params"] = torch.empty(B, NC, **f32), torch.empty(B, NP, **f32)
+            W, arr = self._weights(_stream_of(cad_cls))
+            c = A.SeqCall()
+            c.w = C.pointer(W)
+            c.B, c.T, c.H, c.nhead, c.Ff, c.window = B, T, H, nh, Ff, m.window_size
+            c.past_actions, c.past_states = int(m.enable_past_actions), int(m.enable_past_states)
+            c.act_dim, c.num_cmd, c.num_param_out = m.act_dim, NC, NP
+            c.state_cls = dec["state"].data_ptr() if dec["state"] is not None else None
+            c.cad_cls, c.actions = dec["cad"].data_ptr(), dec["actions0"].data_ptr()
+            c.num_views, c.mv_cls = nv, (dec["mv"].data_ptr() if nv > 0 else None)
+            c.dropout_p, c.training, c.seed, c.site_base, c.passes = 0.0, 0, 0, _SITE_SEQ, passes
+            c.ws, c.ws_bytes, c.cmds, c.params = dec["ws"].data_ptr(), dec["ws_bytes"], dec["cmds_full"].data_ptr(), dec["params_full"].data_ptr()
+            dec["call"], dec["W"], dec["arr"] = c, W, arr
+            if persistent:
+                if len(self._dstates) >= 2:
+                    self._dstates.pop(next(iter(self._dstates)))
+                self._dstates[key] = dec
+        if dec["state"] is not None:
+            dec["state"].copy_(state_cls.reshape(dec["state"].shape))
+        dec["cad"].copy_(cad_cls.reshape(dec["cad"].shape))
+        stream = _stream_of(cad_cls)
+        self.ensure_split(stream)  # the split-bf16 mirror follows the fp32 weights (refreshed in place when they changed)
+        L.check(lib.vc_seq_forward(C.byref(dec["call"]), stream), lib)
+        return dec
+
+    def decode_step(self, dec, t, action_t):
+        lib = self.lib()
+        dec["action_t"].copy_(action_t.reshape(dec["action_t"].shape))
+
+        def body():
+            st = _stream_of(dec["cmds"])
+            L.check(lib.vc_seq_decode_step(C.byref(dec["call"]), t, dec["action_t"].data_ptr(), dec["scratch"].data_ptr(), dec["sc_bytes"],
+                                           dec["cmds"].data_ptr(), dec["params"].data_ptr(), st), lib)
+
+        g = dec["graphs"].get(t) if dec["persistent"] else None
+        if g is not None:
+            g.replay()
+        elif dec["persistent"] and dec["uses"].get(t, 0) >= 1:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                body()
+            dec["graphs"][t] = g
+            g.replay()
+        else:
+            body()
+            dec["uses"][t] = dec["uses"].get(t, 0) + 1
+        return dec["cmds"].clone(), dec["params"].clone()
+
     def backward(self, saved, dcmds, dparams):
         """-> (d state_cls, d cad_cls, d mv_cls, gradient of the flat parameter)."""
         lib, m = self.lib(), self.model
@@ -817,9 +892,12 @@ class AutoRegressiveTransformer(_FlatOwner):
 
     def apply_action_mask(self, cmd_pred, param_pred):
         """autoregressive_transformer.py:91-108."""
-        mask = self.action_mask.to(param_pred.device)[cmd_pred]
-        masked = param_pred.clone()
-        masked[mask == 0] = -1
+        cache = self.__dict__.setdefault("_action_mask_on", {})
+        am = cache.get(param_pred.device)
+        if am is None:  # self.action_mask lives on the constructor's device (as in the reference): copy it over once, not per call
+            am = cache[param_pred.device] = self.action_mask.to(param_pred.device)
+        mask = am[cmd_pred]
+        masked = torch.where(mask == 0, torch.full_like(param_pred, -1), param_pred)  # no boolean indexing: no host sync
         masked[:, :, 3] = torch.where((masked[:, :, 2] >= 200) & (masked[:, :, 2] < 250), masked[:, :, 3], -1)
         return masked
 
@@ -903,23 +981,25 @@ class AutoRegressiveTransformer(_FlatOwner):
             cmds, params, _ = seq_r.forward(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, zeros, B, T,
                                             False, 0.0, 0, passes, need_grad=False)
             return cmds.view(B, T, -1), params.view(B, T, self.num_params, self.num_params_values)
-        # Step t needs the outputs at position t of the prefix [0, t].  The forward is causal (prefix-invariant), so the prefix may
-        # be padded up to a bucket length Tp >= t + 1 -- real frame features (all frames are already encoded), zero actions
-        # beyond t -- without changing position t: eight shapes instead of T, each captured into a CUDA graph and replayed.
-        actions = torch.zeros(B, T, self.act_dim, device=dev)
-        buckets = sorted({min(b, T) for b in (8, 16, 32, 64, 96, 128, 160, T)})
+        if not self.enable_past_actions:
+            # without action tokens the "feedback" has no effect on the logits: one pass gives every position
+            zeros = torch.zeros(B, T, self.act_dim, device=dev)
+            cmds, params, _ = seq_r.forward(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, zeros, B, T,
+                                            False, 0.0, 0, passes, need_grad=False)
+            return cmds.view(B, T, -1), params.view(B, T, self.num_params, self.num_params_values)
+        # Incremental decoding: ONE full-length pass builds the memory tokens and the cross-attention keys/values of every layer
+        # (they do not depend on the actions); each step then pushes one token per sequence through the decoder against the
+        # key/value cache (vc_seq_decode_step) -- 186 single-token steps instead of 186 passes over the growing prefix.
+        dec = seq_r.decode_begin(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, B, T, passes)
+        action_t = torch.zeros(B, self.act_dim, device=dev)
         out_c, out_p = [], []
         for t in range(T):
-            Tp = next(b for b in buckets if b >= t + 1)
-            sc = state_cls[:, :Tp].reshape(B * Tp, -1) if state_cls is not None else None
-            cmds, params, _ = seq_r.forward(sc, cad_cls, actions[:, :Tp], B, Tp, False, 0.0, 0, passes, need_grad=False)
-            cmd = cmds.view(B, Tp, -1)[:, t]
-            par = params.view(B, Tp, self.num_params, self.num_params_values)[:, t]
+            cmd, par = seq_r.decode_step(dec, t, action_t)
+            par = par.view(B, self.num_params, self.num_params_values)
             out_c.append(cmd)
             out_p.append(par)
             cmd_pred, par_pred = cmd.argmax(-1), par.argmax(-1)
             nxt = self.apply_action_mask(cmd_pred.unsqueeze(1), par_pred.unsqueeze(1)).float()
             nxt = torch.cat([cmd_pred.reshape(B, 1, 1).float(), nxt], dim=2)
-            if t + 1 < T:
-                actions[:, t + 1] = self.normalize_actions(nxt)[:, 0]
+            action_t = self.normalize_actions(nxt)[:, 0].contiguous()
         return torch.stack(out_c, 1), torch.stack(out_p, 1)
