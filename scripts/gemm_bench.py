@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--only", default="", help="comma-separated substrings selecting shapes")
+    ap.add_argument("--no-flush", action="store_true", help="leave the operands in L2 between iterations (warm-cache timing)")
     args = ap.parse_args()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     only = [t for t in args.only.split(",") if t]
@@ -64,7 +65,9 @@ def main():
                       colsum=torch.zeros(N, device="cuda"))
         ts = []
         for it in range(args.iters + 2):
-            flush.zero_()
+            if not args.no_flush:
+                flush.zero_()
+            torch.cuda._sleep(200_000)  # the host enqueues the launch while the GPU is busy: events bracket device time only
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             L.gemm(a, b, M, N, K, a_mn=bool(a_mn), b_mn=bool(b_mn), passes=args.passes, splitk=sk, out_f32=o32, out_split=osp, **kw)

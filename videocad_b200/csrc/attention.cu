@@ -357,9 +357,6 @@ int launch_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int64_
 
 }  // namespace
 
-// tests can force the generic SIMT kernels for shapes the tensor-core specialisation would take
-static bool g_force_simt = false;
-void attention_force_simt(int on) { g_force_simt = on != 0; }
 
 static inline bool dense_batches(const AttnDesc& a) { return a.bsq == 0 && a.bsk == 0 && a.bsv == 0; }
 
@@ -368,7 +365,7 @@ int attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, fl
   if (a.B <= 0 || a.Tq <= 0) return 0;
   if (!dense_batches(a) && (a.q_hi != nullptr || a.bsq % 4 != 0 || a.bsk % 4 != 0 || a.bsv % 4 != 0))
     return set_error("attention_fwd: batch strides need fp32 inputs and multiples of 4");
-  if (dense_batches(a) && vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
+  if (dense_batches(a) && vit_attention_eligible(a)) return vit_attention_fwd(a, o_hi, o_lo, ldo, lse, s);
   if (dense_batches(a) && attention_small_eligible(a) && ldo % 4 == 0) return attention_small_fwd(a, o_hi, o_lo, ldo, lse, s);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
   if (a.d <= 64) return launch_fwd<64>(a, o_hi, o_lo, ldo, lse, st);
@@ -383,7 +380,7 @@ int attention_bwd(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_lo, int
   if (!dense_batches(a)) return set_error("attention_bwd: batch strides are supported by the forward only");
   if (lddo % 4 != 0) return set_error("attention_bwd: dout stride must be a multiple of 4");
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr))
+  if (vit_attention_eligible(a))
     return vit_attention_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, s);
   if (attention_small_eligible(a) && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0)
     return attention_small_bwd(a, o_hi, o_lo, ldo, lse, dout, lddo, dq, lddq, dk, lddk, dv, lddv, nullptr, nullptr, nullptr, nullptr,
@@ -400,7 +397,7 @@ int attention_bwd_split(const AttnDesc& a, const bf16_t* o_hi, const bf16_t* o_l
   if (int rc = validate(a, "attention_bwd_split")) return rc;
   if (!dense_batches(a)) return set_error("attention_bwd_split: batch strides are supported by the forward only");
   if (a.B <= 0 || a.Tq <= 0) return 0;
-  if (vit_attention_eligible(a) && (!g_force_simt || a.q_hi != nullptr || dout == nullptr))
+  if (vit_attention_eligible(a))
     return vit_attention_bwd_split(a, o_hi, o_lo, ldo, lse, dout, dout_hi, dout_lo, lddo, dq_hi, dq_lo, dk_hi, dk_lo, dv_hi, dv_lo,
                                    ld_split, s);
   if (!dout) return set_error("attention_bwd_split: the generic kernel needs an fp32 upstream gradient");
