@@ -227,6 +227,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const GemmParams p) {
   pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   using C = Cfg<BN>;
+  __shared__ long long tl[12];  // VC_GEMM_DEBUG & 8: clock64 timeline of CTA 0 (experiment)
+  const bool tlon = (p.debug & 8) && blockIdx.x == 0;
+  if (tlon && threadIdx.x == 0) tl[0] = clock64();
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + C::STAGES;
@@ -264,16 +267,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tlon && threadIdx.x == 0) tl[1] = clock64();
   pdl_wait();
+  if (tlon && threadIdx.x == 0) tl[2] = clock64();
 
   const int num_m = (p.M + BM - 1) / BM;
   const int num_n = (p.N + BN - 1) / BN;
   const int total_tiles = num_m * num_n * p.splitk;
   const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * (A_TILE_BYTES + C::B_TILE_BYTES));
 
+  // Producer and MMA warps: ALL 32 lanes walk the (warp-uniform) loops and wait on the barriers; one elected lane issues the TMA /
+  // tcgen05 instructions.  Running the loops under `if (lane == 0)` made the compiler treat every operand as per-thread data:
+  // it wrapped each tcgen05.mma in an ELECT / 5x R2UR / BRA.U.ANY loop, ~84 cycles of issue per MMA -- more than the 33 (64-wide
+  // tile) or 65 cycles (128-wide) the tensor pipe needs for one, so the single-CTA kernel's main loop was issue-bound
+  // (clock64 timeline: 1000 cycles per k-block of 12 MMAs, profiles/r01n_gemm_timeline.txt).
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_idx = tile % num_n;
@@ -287,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (!elect_one()) continue;
           uint8_t* st = tiles + s * C::STAGE_BYTES;
           uint8_t* sA_hi = st;
           uint8_t* sA_lo = st + A_TILE_BYTES;
@@ -314,13 +325,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (p.passes == 3) tma_load_2d(sB_lo + j * 8192, &tmB_lo, &full_bar[s], n0 + 64 * j, k0);
             }
           }
+          if (tlon && it == 0) tl[3] = clock64();
         }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       // instruction descriptor: D=f32, A=B=bf16, majors, N, M
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -342,26 +354,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t ph = (it / C::STAGES) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (tlon && it == 0 && lane == 0) tl[4] = clock64();
           const uint32_t sA_hi = smem_u32(tiles + s * C::STAGE_BYTES);
           const uint32_t sA_lo = sA_hi + A_TILE_BYTES;
           const uint32_t sB_hi = sA_hi + 2 * A_TILE_BYTES;
           const uint32_t sB_lo = sB_hi + C::B_TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
-            const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
-            const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
-            umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
-            if (p.passes == 3) {
-              const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
-              const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
-              umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
-              umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+            for (int k16 = 0; k16 < BK / 16; ++k16) {
+              const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
+              const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
+              const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
+              umma_bf16(d_tmem, da_hi, db_hi, idesc, accumulate);
+              if (p.passes == 3) {
+                const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
+                const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
+                umma_bf16(d_tmem, da_lo, db_hi, idesc, 1u);
+                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1u);
+              }
             }
+            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          __syncwarp();
         }
-        umma_commit(&tfull_bar[a]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[a]);  // accumulator complete -> epilogue (same elected lane as the MMAs)
+        __syncwarp();
+        if (tlon && lane == 0) tl[5] = clock64();
       }
     }
     __syncwarp();
@@ -423,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (!nxt_valid && !(p.debug & 6)) preload(nxt, m0, n0);
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
+      if (tlon && warp == 2 && lane == 0) tl[6] = clock64();
       // Each thread owns one accumulator ROW in TMEM (tcgen05.ld 32x32b).  Storing rows directly would scatter every
       // 128-bit store over 32 different lines: stage 32x32 chunks through shared memory so that 8 lanes write 128
       // contiguous bytes of a row.  The TMEM stage is handed back to the MMA issuer as soon as the last chunk has been
@@ -508,8 +527,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   }
 
+  if (tlon && warp == 2 && lane == 0) tl[7] = clock64();
   tc_fence_before();
   __syncthreads();
+  if (tlon && threadIdx.x == 0) {
+    tl[8] = clock64();
+    printf("gemm timeline M%d N%d K%d (cycles since entry): setup %lld | pdl_wait %lld | first TMA issued %lld | first stage landed %lld | "
+           "last MMA committed %lld | accumulator ready %lld | epilogue done %lld | all warps done %lld\n",
+           p.M, p.N, p.K, tl[1] - tl[0], tl[2] - tl[0], tl[3] - tl[0], tl[4] - tl[0], tl[5] - tl[0], tl[6] - tl[0], tl[7] - tl[0], tl[8] - tl[0]);
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -615,8 +641,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   const uint32_t tx_bytes = (uint32_t)((p.passes == 3 ? 2 : 1) * (P_TILE_BYTES + C::B_TILE_BYTES)) * 2u;  // both CTAs' loads of one stage
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs); warp-uniform loop, one elected lane issues
+    {
       uint32_t it = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int n_idx = tile % num_n;
@@ -630,6 +656,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (!elect_one()) continue;
           uint8_t* st = tiles + s * P_STAGE_BYTES;
           uint8_t* sA_hi = st;
           uint8_t* sA_lo = st + P_TILE_BYTES;
@@ -670,8 +697,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (leader CTA)
-    if (leader && lane == 0) {
+    // ------------------------------------------------ MMA issuer (leader CTA); warp-uniform loop, one elected lane issues
+    if (leader) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                              ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(P_BM >> 4) << 24);
       const uint32_t adv_a = p.a_mn ? 2048u : 32u;  // bytes per k16 step
@@ -696,22 +723,26 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t sA_lo = sA_hi + P_TILE_BYTES;
           const uint32_t sB_hi = sA_hi + 2 * P_TILE_BYTES;
           const uint32_t sB_lo = sB_hi + C::B_TILE_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k16 = 0; k16 < BK / 16; ++k16) {
-            const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
-            const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
-            const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
-            umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, accumulate);
-            if (p.passes == 3) {
-              const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
-              const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
-              umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, 1u);
-              umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1u);
+            for (int k16 = 0; k16 < BK / 16; ++k16) {
+              const uint64_t da_hi = make_smem_desc(sA_hi + k16 * adv_a, p.a_mn);
+              const uint64_t db_hi = make_smem_desc(sB_hi + k16 * adv_b, p.b_mn);
+              const uint32_t accumulate = (kb > kb0 || k16 > 0) ? 1u : 0u;
+              umma_bf16_pair(d_tmem, da_hi, db_hi, idesc, accumulate);
+              if (p.passes == 3) {
+                const uint64_t da_lo = make_smem_desc(sA_lo + k16 * adv_a, p.a_mn);
+                const uint64_t db_lo = make_smem_desc(sB_lo + k16 * adv_b, p.b_mn);
+                umma_bf16_pair(d_tmem, da_lo, db_hi, idesc, 1u);
+                umma_bf16_pair(d_tmem, da_hi, db_lo, idesc, 1u);
+              }
             }
+            umma_commit_pair(&empty_bar[s]);  // frees this smem stage in both CTAs
           }
-          umma_commit_pair(&empty_bar[s]);  // frees this smem stage in both CTAs
+          __syncwarp();
         }
-        umma_commit_pair(&tfull_bar[a]);  // accumulator complete -> both CTAs' epilogue warps
+        if (elect_one()) umma_commit_pair(&tfull_bar[a]);  // accumulator complete -> both CTAs' epilogue warps
+        __syncwarp();
       }
     }
     __syncwarp();
