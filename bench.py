@@ -60,8 +60,8 @@ def fwd_flops_per_sample(cfg, T, S):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_tc_pair_kernel launch (to_qkv forward, M=12800 N=3072 K=512), from the
 # `ncu --set full` capture summarised in profiles/ (see profiles/README.md); None until a capture exists
-PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH = 136857600
-PAIR_KERNEL_TRAFFIC_NOTE = ("profiles/r01h_ncu_gemm_pair_qkv_fwd_summary.txt: 32.5 MB read (= the split-bf16 operands, read once) + 104.3 MB written "
+PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH = 137445888
+PAIR_KERNEL_TRAFFIC_NOTE = ("profiles/r01m_ncu_gemm_pair_qkv_fwd_summary.txt: 32.9 MB read (= the split-bf16 operands, read once) + 104.5 MB written "
                             "of the 157.3 MB fp32 output (the rest was still in L2 when the kernel ended); algorithmic bytes 189.8 MB")
 
 
