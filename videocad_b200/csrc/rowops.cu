@@ -242,9 +242,11 @@ __device__ __forceinline__ void ln_bwd_row(LnBwdRow<NV>& R, long long row, int C
 // Each warp walks its rows with a stride.  The operands of the next LNB_DEPTH - 1 rows (x, dy, residual gradient: 12 x 128-bit
 // loads per lane and row at C = 512) are kept in flight with cp.async into a per-warp shared-memory ring: every lane copies and
 // later reads only ITS OWN 16-byte slots, so the only synchronisation is cp.async.wait_group.  History: alternating load and
-// compute phases reached ~3 TB/s; a one-row register prefetch 2.6-2.9 TB/s at 183 registers (two resident CTAs per SM, ncu:
-// 2.3 long-scoreboard stall cycles per issued instruction, profiles/r01l_ncu_attn_ln_summary.txt); the ring needs registers for
-// one row only.
+// compute phases reached ~3 TB/s; a one-row register prefetch needed 183 registers (two resident CTAs per SM); the ring needs
+// registers for one row only (145, three CTAs per SM).  Measured: inside the training step the ring version is the faster one
+// (image-encoder backward 4.05 -> 3.95 ms, +1.3 % frames/s), but ISOLATED under ncu it is slower than the register prefetch
+// (43.2 vs 38.5 us at [12800, 512], long-scoreboard and end-of-kernel barrier stalls up; profiles/r01l_ncu_attn_ln_summary.txt):
+// the kernel still reaches only ~3 TB/s of its 131 MB and is a listed open item.
 constexpr int LNB_DEPTH = 3;
 
 __device__ __forceinline__ void ln_cp_async16(void* smem_dst, const void* gmem_src) {
