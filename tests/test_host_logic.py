@@ -256,8 +256,8 @@ def test_frame_ingestion_u8_bit_exact_and_model_equivalence(emu):
     assert torch.equal(c8, cf) and torch.equal(p8, pf)
 
 
-@pytest.mark.parametrize("layers,window,L_", [(1, 2, 5), (3, 3, 8)])
-def test_sequential_inference_matches_oracle(emu, layers, window, L_):
+@pytest.mark.parametrize("layers,window,L_,B_", [(1, 2, 5, 2), (3, 3, 8, 2), (2, 2, 4, 17)])  # 17 sequences: the step's GEMM path (> 16 rows)
+def test_sequential_inference_matches_oracle(emu, layers, window, L_, B_):
     """Rollout with action feedback through the incremental decoder (vc_seq_decode_step: one token per step against the key/value
     cache) against the oracle's O(T^2) recompute of the reference loop; three layers exercise the layer-output ping-pong, T >
     window the clipping of the cross-attention window."""
@@ -265,7 +265,7 @@ def test_sequential_inference_matches_oracle(emu, layers, window, L_):
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build_emu_model(emu, cfg)
     m.eval()
-    inp = to.model_inputs_from_batch(to.synthetic_batch(2, L_, 64))
+    inp = to.model_inputs_from_batch(to.synthetic_batch(B_, L_, 64))
     ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
     oc, op = to.rollout(sd, cfg, inp["frames"], inp["cad_image"], action=True)
     assert (ac - oc).abs().max() < 2e-4 and (ap - op).abs().max() < 2e-4
