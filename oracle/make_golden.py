@@ -42,6 +42,11 @@ CASES = {
     "fullres_small": dict(cfg=dict(hidden_size=256, nhead=4, num_decoder_layers=2, dim_feedforward=512, window_size=10,
                                    enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
                           B=1, T=3, S=224),
+    # BASELINE configs[1] model (C1: transformer_experiments.json "cad_past_10_actions_and_states_timestep_embedding" with
+    # hidden_size = dim_feedforward = 512, 8 layers, window 10) at full resolution, reduced batch
+    "c1_model": dict(cfg=dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,
+                              enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
+                     B=1, T=3, S=224),
     # multiview conditioning: two extra views through the CAD encoder, embed_multiview, 3-source image_projection
     "multiview": dict(cfg=dict(hidden_size=128, nhead=4, num_decoder_layers=2, dim_feedforward=128, window_size=2, num_views=2,
                                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
@@ -102,5 +107,7 @@ def run_case(name, case):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    only = sys.argv[1:]  # optional case names: generate only those (the committed fixtures of the others stay untouched)
     for n, c in CASES.items():
-        run_case(n, c)
+        if not only or n in only:
+            run_case(n, c)

@@ -13,7 +13,7 @@ from oracle import torch_oracle as to  # noqa: E402
 from videocad_b200 import AutoRegressiveTransformer  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview"]
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview", "c1_model"]
 
 # fp tolerance of the parity mode (3-pass split-bf16 GEMMs, fp32 everything else) against the reference's fp32
 # forward: BASELINE.json asks for 1e-3 max-abs on the logits; measured ~2e-5, asserted at 2e-4.

@@ -11,7 +11,7 @@ from oracle import torch_oracle as to
 from oracle import reference_model as rm
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview"]
+CASES = ["c0_shipped", "c0_states_actions", "states_only", "fullres_small", "multiview", "c1_model"]
 
 
 def load_case(name):
