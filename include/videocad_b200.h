@@ -299,6 +299,8 @@ typedef struct vc_vit_call {
   uint64_t seed; uint32_t site_base;
   const uint64_t* seed_dev;             /* optional device-resident seed (overrides `seed`; for CUDA-graph replay) */
   int passes;                           /* 3 = fp32-grade GEMMs (parity mode), 1 = bf16-grade */
+  int aux_streams;                      /* first of the TWO auxiliary-stream indices of the backward's weight-gradient GEMMs:
+                                         * 0 = default (2, 3); encoders that run concurrently must use different pairs (4 = 4, 5) */
   void* ws; size_t ws_bytes;            /* activation workspace, >= vc_vit_workspace_bytes(F, S) */
   float* cls_out;                       /* [F, 512] CLS embedding after the final LayerNorm */
 } vc_vit_call;

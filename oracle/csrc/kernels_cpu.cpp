@@ -636,9 +636,12 @@ LossWsC loss_carve(float* ws, int R, int NP) {
 void loss_window(const LossCfg& c, int i, float target, bool& valid, long long& t, long long& hi, float& count) {
   const long long tg = (long long)target;
   valid = tg != -1;
-  t = tg < 0 ? 0 : tg;
-  hi = t + (c.tolerance[i] - 1);
-  if (hi > c.NV - 1) hi = c.NV - 1;
+  // allowed classes = { clamp(target + o, 0, NV - 1) : 0 <= o < tolerance } (trainer.py:880-905): a contiguous window whose two
+  // ends are clamped separately, so an out-of-range target still has a one-class window (never empty, count >= 1)
+  const long long top = c.NV - 1;
+  t = tg < 0 ? 0 : (tg > top ? top : tg);
+  hi = tg + (c.tolerance[i] - 1);
+  hi = hi < 0 ? 0 : (hi > top ? top : hi);
   count = (float)(hi - t + 1);
 }
 }  // namespace

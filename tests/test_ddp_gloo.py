@@ -28,7 +28,7 @@ def _build(emu_path):
     from videocad_b200 import AutoRegressiveTransformer
     from videocad_b200 import lib as L
 
-    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, encoder="vit", dropout=0.0, **CFG)
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, encoder="vit", dropout=0.0, vit_dropout=0.0, **CFG)
     m.load_state_dict(to.seeded_state_dict(CFG, 0), strict=False)
     m._use_library_for_tests(L.load(emu_path, require_cuda_build=False))
     return m

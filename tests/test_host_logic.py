@@ -86,7 +86,7 @@ def test_module_contract_and_errors():
 
 
 def build_emu_model(emu, cfg, seed=0, dropout=0.1):
-    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, encoder="vit", **cfg)
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, vit_dropout=dropout, encoder="vit", **cfg)
     sd = to.seeded_state_dict(cfg, seed)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not missing and not unexpected
@@ -273,3 +273,39 @@ def test_sequential_inference_matches_oracle(emu, layers, window, L_, B_):
     zc, zp = m.sequential_inference(inp["frames"], inp["cad_image"], action=False)
     fc, fp = m(dict(inp, actions=torch.zeros_like(inp["actions"])))
     assert torch.equal(zc, fc.detach()) and torch.equal(zp, fp.detach())
+
+
+def test_clip_adam_step_is_seen_by_the_next_forward(emu):
+    """ClipAdam writes the parameters through raw pointers; the split-bf16 weight mirror every GEMM reads is refreshed when the
+    flat parameter's version counter moves.  After one step the drop-in must compute with the NEW weights everywhere
+    (without the version bump the GEMM weights stayed stale while LayerNorm / embed_action read the fresh fp32 values)."""
+    from videocad_b200.optim import ClipAdam
+
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2, **MODES[0])
+    inp = to.model_inputs_from_batch(to.synthetic_batch(2, 3, 64))
+    outs = []
+    for which in ("torch", "fused"):
+        m, _ = build_emu_model(emu, cfg, dropout=0.0)
+        m.train()
+        opt = (torch.optim.Adam(m.parameters(), lr=1e-2) if which == "torch"
+               else ClipAdam(m.parameters(), lr=1e-2, max_norm=1.0, _lib=emu))
+        for _ in range(2):
+            opt.zero_grad()
+            c, p = m(inp)
+            (c.sum() + p.sum() * 0.01).backward()
+            if which == "torch":
+                torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+        with torch.no_grad():
+            outs.append(m(inp))
+    assert (outs[0][0] - outs[1][0]).abs().max() < 1e-4 and (outs[0][1] - outs[1][1]).abs().max() < 1e-4
+
+
+def test_image_input_gradient_is_refused_loudly(emu):
+    cfg = dict(hidden_size=128, nhead=4, num_decoder_layers=1, dim_feedforward=128, window_size=2, **MODES[0])
+    m, _ = build_emu_model(emu, cfg, dropout=0.0)
+    m.eval()
+    inp = to.model_inputs_from_batch(to.synthetic_batch(1, 2, 64))
+    inp["cad_image"] = inp["cad_image"].clone().requires_grad_(True)  # trainer.generate_saliency_batch (trainer.py:621-645)
+    with pytest.raises(RuntimeError, match="input images"):
+        m(inp)

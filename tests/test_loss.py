@@ -26,8 +26,13 @@ def _case(R, seed, device, mode="mixed"):
                 params[b, 0, i, min(t + 1, 999)] = 50.0
     if mode == "empty":
         tgt[..., 1] = -1.0                                             # parameter 0: nothing selected -> contributes 0
-    if mode == "nan":
-        tgt[0, 0, 3] = 1000.0                                          # out-of-range target: count == 0 -> NaN term, dropped
+    if mode == "outrange":
+        # out-of-range labels: the reference clamps both window ends into [0, 999] (trainer.py:880-905), so the window is
+        # {999} for a target >= 1000 and starts at class 0 for a negative one (other than the ignore index -1)
+        tgt[0, 0, 3] = 1000.0
+        tgt[1, 1, 4] = 1700.0
+        tgt[2, 2, 5] = -3.0      # tolerance 500: window [0, 496]
+        tgt[3, 3, 1] = -7.0      # tolerance 2:   window {0}
     return cmds.to(device), params.to(device), tgt.to(device)
 
 
@@ -106,7 +111,7 @@ def test_fused_metrics_gpu(mode):
     _check_metrics(cm, pa, tg)
 
 
-@pytest.mark.parametrize("mode", ["dense", "mixed", "empty", "nan"])
+@pytest.mark.parametrize("mode", ["dense", "mixed", "empty", "outrange"])
 def test_fused_loss_cpu_restatement(mode):
     from oracle import build_emu
 
@@ -121,7 +126,7 @@ def test_fused_loss_refuses_cpu_tensors_without_the_test_hook():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["dense", "mixed", "empty", "nan"])
+@pytest.mark.parametrize("mode", ["dense", "mixed", "empty", "outrange"])
 def test_fused_loss_gpu(mode):
     _check(*_case(256, 5, "cuda", mode))
 

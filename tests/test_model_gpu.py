@@ -29,7 +29,7 @@ def load_case(name):
 
 
 def build(cfg, device="cuda", dropout=0.1, seed=0, **kw):
-    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, encoder="vit", **cfg, **kw)
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, dropout=dropout, vit_dropout=dropout, encoder="vit", **cfg, **kw)
     sd = to.seeded_state_dict(cfg, seed)
     missing, unexpected = m.load_state_dict(sd, strict=False)
     assert not missing and not unexpected, (missing, unexpected)

@@ -150,6 +150,14 @@ def test_loss_port_matches_reference_trainer(tmp_path, monkeypatch):
                 c = int(tgt[b, tt, 0].item())
                 if c >= 0:
                     cmds[b, tt, c] += 10
+    # out-of-range labels: both window ends are clamped into [0, 999] by the reference (trainer.py:880-905)
+    from videocad_b200.loss import flexible_cross_entropy as fce
+    g3 = torch.Generator().manual_seed(12)
+    lg = torch.randn(8, 1000, generator=g3)
+    for tol in (2, 50, 500):
+        tg3 = torch.tensor([1000, 1700, -3, -7, 999, 0, 998, -1])
+        want = t.flexible_cross_entropy(lg, tg3, 1000, tolerance=tol, above=[True])
+        assert abs(fce(lg, tg3, tol).item() - want.item()) < 1e-5 * abs(want.item()), tol
     lr, metrics_ref = t.compute_loss((cmds, params), tgt)
     lm = compute_loss((cmds, params), tgt)
     assert abs(lr.item() - lm.item()) < 1e-5 * abs(lr.item())

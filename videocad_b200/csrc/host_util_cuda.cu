@@ -72,23 +72,34 @@ int gemm_profile_read(double* total_ms, double* total_flops, long long* launches
 }
 
 namespace {
-constexpr int kSide = 4, kEvents = 128;  // 0,1: sequence transformer; 2,3: image encoders
-cudaStream_t g_side[kSide] = {nullptr, nullptr, nullptr, nullptr};
-cudaEvent_t g_ev[kEvents];
-bool g_side_init = false;
-int g_ev_next = 0;
-int side_init() {
-  if (g_side_init) return 0;
-  for (int i = 0; i < kSide; ++i)
-    if (cudaStreamCreateWithFlags(&g_side[i], cudaStreamNonBlocking) != cudaSuccess) return set_error("cudaStreamCreate failed");
-  for (int i = 0; i < kEvents; ++i)
-    if (cudaEventCreateWithFlags(&g_ev[i], cudaEventDisableTiming) != cudaSuccess) return set_error("cudaEventCreate failed");
-  g_side_init = true;
-  return 0;
+// Auxiliary streams and fork/join events, one pool PER DEVICE (created on first use while that device is current; the callers
+// launch in the device context of their tensors).  Indices 0,1: sequence transformer; 2,3: frame encoder; 4,5: CAD encoder
+// (the two encoders run concurrently on different torch streams and must not share side streams: false dependencies).
+constexpr int kSide = 6, kEvents = 256, kMaxDev = 64;
+struct SidePool {
+  cudaStream_t side[kSide];
+  cudaEvent_t ev[kEvents];
+  int ev_next;
+  bool init;
+};
+SidePool g_pools[kMaxDev] = {};
+SidePool* side_pool() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) { set_error("stream_fork: cannot query the current device"); return nullptr; }
+  SidePool& P = g_pools[dev];
+  if (!P.init) {
+    for (int i = 0; i < kSide; ++i)
+      if (cudaStreamCreateWithFlags(&P.side[i], cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return nullptr; }
+    for (int i = 0; i < kEvents; ++i)
+      if (cudaEventCreateWithFlags(&P.ev[i], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); return nullptr; }
+    P.ev_next = 0;
+    P.init = true;
+  }
+  return &P;
 }
-cudaEvent_t next_event() {
-  cudaEvent_t e = g_ev[g_ev_next];
-  g_ev_next = (g_ev_next + 1) % kEvents;
+cudaEvent_t next_event(SidePool& P) {
+  cudaEvent_t e = P.ev[P.ev_next];
+  P.ev_next = (P.ev_next + 1) % kEvents;
   return e;
 }
 }  // namespace
@@ -103,11 +114,12 @@ int stream_fork(void* main_s, int i, void** side) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (i < 0 || i >= kSide) return set_error("stream_fork: bad index");
   if (!g_side_enabled) { *side = main_s; return 0; }  // serialised mode (per-kernel timing): everything on the caller's stream
-  if (int rc = side_init()) return rc;
-  cudaEvent_t e = next_event();
+  SidePool* P = side_pool();
+  if (!P) return 1;
+  cudaEvent_t e = next_event(*P);
   if (cudaEventRecord(e, reinterpret_cast<cudaStream_t>(main_s)) != cudaSuccess) return set_error("stream_fork: event record failed");
-  if (cudaStreamWaitEvent(g_side[i], e, 0) != cudaSuccess) return set_error("stream_fork: wait failed");
-  *side = g_side[i];
+  if (cudaStreamWaitEvent(P->side[i], e, 0) != cudaSuccess) return set_error("stream_fork: wait failed");
+  *side = P->side[i];
   return 0;
 }
 
@@ -115,9 +127,10 @@ int stream_join(void* main_s, int i) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (i < 0 || i >= kSide) return set_error("stream_join: bad index");
   if (!g_side_enabled) return 0;
-  if (int rc = side_init()) return rc;
-  cudaEvent_t e = next_event();
-  if (cudaEventRecord(e, g_side[i]) != cudaSuccess) return set_error("stream_join: event record failed");
+  SidePool* P = side_pool();
+  if (!P) return 1;
+  cudaEvent_t e = next_event(*P);
+  if (cudaEventRecord(e, P->side[i]) != cudaSuccess) return set_error("stream_join: event record failed");
   if (cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(main_s), e, 0) != cudaSuccess) return set_error("stream_join: wait failed");
   return 0;
 }

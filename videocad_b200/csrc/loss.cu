@@ -59,9 +59,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __device__ __forceinline__ void window_of(const LossCfg& c, int i, float target, bool& valid, long long& t, long long& hi, float& count) {
   const long long tg = (long long)target;  // .long(): truncation
   valid = tg != -1;
-  t = tg < 0 ? 0 : tg;
-  hi = t + (c.tolerance[i] - 1);
-  if (hi > c.NV - 1) hi = c.NV - 1;
+  // allowed classes = { clamp(target + o, 0, NV - 1) : 0 <= o < tolerance } (trainer.py:880-905): a contiguous window whose two
+  // ends are clamped separately, so an out-of-range target still has a one-class window (never empty, count >= 1)
+  const long long top = c.NV - 1;
+  t = tg < 0 ? 0 : (tg > top ? top : tg);
+  hi = tg + (c.tolerance[i] - 1);
+  hi = hi < 0 ? 0 : (hi > top ? top : hi);
   count = (float)(hi - t + 1);
 }
 
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(LT) loss_rows_kernel(const LossCfg c, const fl
     const float lse = best.v + logf(se);
     const bool in_window = best.i >= t && best.i <= hi;
     const float sel = (valid && !in_window) ? 1.f : 0.f;
-    const float per_row = -(sw - nw * lse) / count;  // count == 0 -> NaN, which poisons (and thereby drops) the whole term
+    const float per_row = -(sw - nw * lse) / count;  // count >= 1 (window_of)
     const size_t o = (size_t)r * c.NP + i;
     w.lse[o] = lse;
     w.sel[o] = sel;

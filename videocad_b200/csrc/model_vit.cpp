@@ -203,6 +203,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
   if (!sa.ok()) return set_error("vit_backward: scratch too small");
   const float p = c->dropout_p;
   const uint32_t sb = c->site_base;
+  const int ax2 = c->aux_streams > 0 ? c->aux_streams : 2, ax3 = ax2 + 1;  // this encoder's pair of auxiliary streams
 
   // final LN (CLS rows only): every other row of d x[6] is zero
   VC_TRY(zero_f32(s.dxa, (int64_t)M * D, st));
@@ -223,7 +224,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
     // dgrad / attention / LayerNorm chain, and fill the SMs the chain's partial last waves leave idle.  Each is joined
     // before the scratch operand it reads (s.g, s.dpre, s.dqkvS) is overwritten.
     stream_t side2, side3;
-    VC_TRY(stream_fork(st, 2, &side2));
+    VC_TRY(stream_fork(st, ax2, &side2));
     VC_TRY(linear_wgrad(s.g, L.ud, M, D, VC_VIT_MLP, LW.fc2.dw, P, side2));
     {
       // d pre1 = (g W2) * mask(MLP hidden site) * gelu'(pre1): activation backward + fc1 bias gradient fused in the epilogue
@@ -234,7 +235,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       d.out_hi = s.dpre.hi; d.out_lo = s.dpre.lo; d.ldo_split = VC_VIT_MLP; d.colsum = LW.fc1.db;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(stream_fork(st, 3, &side3));
+    VC_TRY(stream_fork(st, ax3, &side3));
     VC_TRY(linear_wgrad(s.dpre, L.h2, M, VC_VIT_MLP, D, LW.fc1.dw, P, side3));
     {
       GemmDesc d;
@@ -242,12 +243,12 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       d.out_f32 = s.dh; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(stream_join(st, 2));  // fc2 wgrad has read s.g
+    VC_TRY(stream_join(st, ax2));  // fc2 wgrad has read s.g
     // d x2 = d x3 + LN2_bwd(dh); fused: s.g = split(d x2 * mask(to_out site)), to_out bias gradient
     VC_TRY(layernorm_bwd_fused(s.dh, D, L.x2, D, L.m2, L.r2, LW.ln2.w, M, D, cur, D, other, D, LW.ln2.dw, LW.ln2.db,
                                site_drop(p, c->training, c->seed, s0 + 1, c->seed_dev), s.g.hi, s.g.lo, D, LW.out.db, st));
     // ---- attention block (other = d x2)
-    VC_TRY(stream_fork(st, 2, &side2));
+    VC_TRY(stream_fork(st, ax2, &side2));
     VC_TRY(linear_wgrad(s.g, L.o, M, D, DI, LW.out.dw, P, side2));
     {
       GemmDesc d;
@@ -260,7 +261,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       VC_TRY(attention_bwd_split(a, L.o.hi, L.o.lo, DI, L.lse, nullptr, s.dOS.hi, s.dOS.lo, DI, s.dqkv, s.dqkvS.hi, s.dqkvS.lo, s.dqkvS.hi + DI,
                                  s.dqkvS.lo + DI, s.dqkvS.hi + 2 * DI, s.dqkvS.lo + 2 * DI, 3 * DI, st));
     }
-    VC_TRY(stream_fork(st, 3, &side3));
+    VC_TRY(stream_fork(st, ax3, &side3));
     VC_TRY(linear_wgrad(s.dqkvS, L.h1, M, 3 * DI, D, LW.qkv.dw, P, side3));
     {
       GemmDesc d;
@@ -268,7 +269,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
       d.out_f32 = s.dh; d.ldo = D;
       VC_TRY(gemm(d, st));
     }
-    VC_TRY(stream_join(st, 2));  // to_out wgrad has read s.g
+    VC_TRY(stream_join(st, ax2));  // to_out wgrad has read s.g
     if (l > 0) {
       // d x[l] = d x2 + LN1_bwd(dh); fused: s.g = split(d x[l] * mask(fc2 site of layer l-1)), fc2 bias gradient of layer l-1
       VC_TRY(layernorm_bwd_fused(s.dh, D, w.x[l], D, L.m1, L.r1, LW.ln1.w, M, D, other, D, cur, D, LW.ln1.dw, LW.ln1.db,
@@ -277,7 +278,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
     } else {
       VC_TRY(layernorm_bwd(s.dh, D, w.x[l], D, L.m1, L.r1, LW.ln1.w, M, D, other, D, cur, D, LW.ln1.dw, LW.ln1.db, st));
     }
-    VC_TRY(stream_join(st, 3));  // fc1 / to_qkv wgrads have read s.dpre / s.dqkvS (rewritten by the next layer's dgrad chain)
+    VC_TRY(stream_join(st, ax3));  // fc1 / to_qkv wgrads have read s.dpre / s.dqkvS (rewritten by the next layer's dgrad chain)
   }
   // ---- token assembly + patch embedding (cur = d x[0]); buffers reused: dh -> d e1, dud -> d e0, dO -> d pl
   float* de1 = s.dh;

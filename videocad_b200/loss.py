@@ -40,8 +40,10 @@ def flexible_cross_entropy(logits: torch.Tensor, targets: torch.Tensor, toleranc
     logits = logits.reshape(-1, num_classes)
     targets = targets.reshape(-1)
     valid_row = targets != ignore_index
-    t = targets.clamp(min=0)
-    hi = (t + (tolerance - 1)).clamp(max=num_classes - 1)        # window [t, hi], clamped like the reference
+    # allowed classes = {clamp(target + o, 0, C - 1) : 0 <= o < tolerance} (trainer.py:880-905): both ends clamped separately,
+    # so the window is never empty (an out-of-range target keeps the single class C - 1, a negative one the class 0)
+    t = targets.clamp(min=0, max=num_classes - 1)
+    hi = (targets + (tolerance - 1)).clamp(min=0, max=num_classes - 1)
     preds = logits.argmax(dim=1)
     in_window = (preds >= t) & (preds <= hi)
     select = valid_row & ~in_window
@@ -49,14 +51,11 @@ def flexible_cross_entropy(logits: torch.Tensor, targets: torch.Tensor, toleranc
     cls = torch.arange(num_classes, device=logits.device).unsqueeze(0)
     window = ((cls >= t.unsqueeze(1)) & (cls <= hi.unsqueeze(1))).to(logp.dtype)
     count = (hi - t + 1).to(logp.dtype)
-    # an out-of-range target (t == num_classes) has an empty window and count == 0: the reference's 0/0 makes the whole term
-    # NaN, which compute_loss then skips (trainer.py:959-960).  Same outcome here, without NaNs entering the backward.
-    poisoned = (count == 0).any()
-    per_row = -(logp * window).sum(dim=1) / torch.where(count == 0, torch.ones_like(count), count)
+    per_row = -(logp * window).sum(dim=1) / count
     sel = select.to(logp.dtype)
     n = sel.sum()
     val = (per_row * sel).sum() / n.clamp(min=1.0)
-    return torch.where(poisoned, torch.zeros_like(val), val)
+    return val
 
 
 _W_CACHE = {}

@@ -79,7 +79,7 @@ class _AttnParams(_NoForward):
         inner = heads * dim_head
         self.heads, self.scale = heads, dim_head ** -0.5
         self.norm = nn.LayerNorm(dim)
-        self.dropout = nn.Dropout(dropout)  # attribute kept for API parity (trainer.py:671 hooks it); never executed
+        self.dropout = nn.Dropout(dropout)  # part of the key/attribute schema only: these containers are discarded after init
         self.to_qkv = nn.Linear(dim, inner * 3, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner, dim), nn.Dropout(dropout))
 
@@ -357,6 +357,8 @@ class _VitRunner(_Segment):
         super().__init__(vit)
         self.site_base = site_base
         self.tag = "vit_frames" if site_base == _SITE_STATE_VIT else "vit_cad"
+        # the two encoders run concurrently (second torch stream): each gets its own pair of auxiliary streams inside the library
+        self.aux_streams = 2 if site_base == _SITE_STATE_VIT else 4
 
     def _weights(self, stream, gflat=None) -> A.VitWeights:
         self.ensure_split(stream)
@@ -399,6 +401,7 @@ class _VitRunner(_Segment):
             c.img, c.F, c.S = sl.img.data_ptr(), F_, S
             c.dropout_p, c.training = float(p), int(bool(training))
             c.seed, c.site_base, c.seed_dev, c.passes = 0, self.site_base, sl.seed_t.data_ptr(), passes
+            c.aux_streams = self.aux_streams
             c.ws, c.ws_bytes, c.cls_out = sl.ws.data_ptr(), sl.ws_bytes, sl.out.data_ptr()
             setattr(sl, name, c)
         return sl
@@ -448,6 +451,7 @@ class _VitRunner(_Segment):
         call.img, call.F, call.S = img.data_ptr(), F_, S
         call.dropout_p, call.training = float(p), int(bool(training))
         call.seed, call.site_base, call.passes = seed, self.site_base, passes
+        call.aux_streams = self.aux_streams
         call.ws, call.ws_bytes, call.cls_out = ws.data_ptr(), ws_bytes, out.data_ptr()
         L.check(lib.vc_vit_forward(C.byref(call), stream), lib)
         return out, (call, W, ws, img)
@@ -757,6 +761,12 @@ class _SeqRunner(_Segment):
 class _VitFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, training, p, seed, passes, img, flat):
+        if ctx.needs_input_grad[5]:
+            # trainer.generate_saliency_batch (trainer.py:621-645) asks for d loss / d cad_image; vc_vit_backward stops at the
+            # patch embedding's parameters (the image is a leaf of the training path).  Fail here, not with grad = None later.
+            raise RuntimeError("videocad_b200: the gradient with respect to the input images is not implemented (saliency / "
+                               "attention-rollout diagnostics of trainer.py:621-680 are out of scope, see DESIGN.md section 8); "
+                               "pass images that do not require grad")
         out, saved = runner.forward(img, training, p, seed, passes, need_grad=ctx.needs_input_grad[6])
         ctx.runner, ctx.saved = runner, saved
         return out
@@ -791,7 +801,7 @@ class AutoRegressiveTransformer(_FlatOwner):
                  enable_past_actions=False, enable_past_states=False, enable_timestep_embedding=False, num_classes=5,
                  num_params=6, num_params_values=1000, num_decoder_layers=8, dim_feedforward=512,
                  use_pretrained_cad_model=False, nhead=4, dropout=0.1, normalize=False, device=None, encoder="vit",
-                 num_views=0, window_size=1, precision: Optional[str] = None, **kwargs):
+                 num_views=0, window_size=1, precision: Optional[str] = None, vit_dropout: float = 0.1, **kwargs):
         super().__init__()
         if encoder != "vit":
             # trajectory_model.py:68-74: 'resnet' downloads ImageNet weights (no network here); anything else raises there too
@@ -817,13 +827,15 @@ class AutoRegressiveTransformer(_FlatOwner):
         self.precision = precision
 
         # --- parameters, in the reference's construction order and with its default initialisation ---
+        # the image encoders' dropout is hard-coded to 0.1 / 0.1 in the reference (trajectory_model.py:54-66), independent of
+        # the decoder's `dropout`; `vit_dropout` exists for tests that need a deterministic training-mode forward
         if state_dim > 0:
-            self.state_embedding_model = ViTParams()
+            self.state_embedding_model = ViTParams(vit_dropout, vit_dropout)
             self.state_embedding_model_size = A.VIT_DIM
         else:
             self.state_embedding_model = None
             self.state_embedding_model_size = 0
-        self.cad_embedding_model = ViTParams()
+        self.cad_embedding_model = ViTParams(vit_dropout, vit_dropout)
         self.cad_embedding_model_size = A.VIT_DIM
         self.num_decoder_layers = num_decoder_layers
         tmp = nn.Module()  # the reference's own sub-modules: built for default initialisation and key names, then discarded
@@ -910,13 +922,24 @@ class AutoRegressiveTransformer(_FlatOwner):
     @torch.compiler.disable
     def forward(self, inputs, attention_mask=None):
         """AutoRegressiveTransformer.forward (autoregressive_transformer.py:121-220)."""
+        dev = inputs["cad_image"].device
+        if dev.type == "cuda":
+            # the library launches on the CURRENT device and keeps per-device auxiliary streams: make the inputs' device current
+            # (autograd does the same for the backward nodes)
+            with torch.cuda.device(dev):
+                return self._forward(inputs)
+        return self._forward(inputs)
+
+    def _forward(self, inputs):
         ui_images, actions, cad_image = inputs["frames"], inputs["actions"], inputs["cad_image"]
         multiview_images = inputs.get("multiview_images", None)
         self._check_device(cad_image)
         st_r, cad_r, seq_r = self._get_runners()
         B, T = actions.shape[0], actions.shape[1]
         training, p, passes = self.training, self.dropout_p, self._passes
-        seed = self._draw_seed() if (training and p > 0) else 0
+        p_cad = cad_r.owner.dropout_p
+        p_st = st_r.owner.dropout_p if st_r is not None else 0.0
+        seed = self._draw_seed() if (training and max(p, p_cad, p_st) > 0) else 0
         if self.num_views > 0:
             # process_multiview_images (trajectory_model.py:77-87): every view goes through the CAD encoder
             if multiview_images is None:
@@ -925,11 +948,11 @@ class AutoRegressiveTransformer(_FlatOwner):
                 raise ValueError(f"expected {self.num_views} views, got {multiview_images.shape[1]}")
 
         def cad_branch():
-            cad_cls = _VitFn.apply(cad_r, training, p, seed, passes, cad_image, cad_r.flat)
+            cad_cls = _VitFn.apply(cad_r, training, p_cad, seed, passes, cad_image, cad_r.flat)
             mv_cls = None
             if self.num_views > 0:
                 views = multiview_images.reshape(-1, *multiview_images.shape[2:])
-                mv_cls = _VitFn.apply(cad_r, training, p, seed + 1 if seed else 0, passes, views, cad_r.flat)
+                mv_cls = _VitFn.apply(cad_r, training, p_cad, seed + 1 if seed else 0, passes, views, cad_r.flat)
             return cad_cls, mv_cls
 
         # The CAD encoder sees B images against the frame encoder's B*T: its kernels fill a fraction of the SMs and are
@@ -950,7 +973,7 @@ class AutoRegressiveTransformer(_FlatOwner):
             n_img = ui_images.numel() // (ui_images.shape[-1] * ui_images.shape[-2])
             if n_img != B * T:
                 raise ValueError(f"frames carry {n_img} images but actions are [{B},{T}]")
-            state_cls = _VitFn.apply(st_r, training, p, seed, passes, ui_images, st_r.flat)
+            state_cls = _VitFn.apply(st_r, training, p_st, seed, passes, ui_images, st_r.flat)
         if overlap:
             cur.wait_stream(side)
             cad_cls.record_stream(cur)
@@ -968,6 +991,9 @@ class AutoRegressiveTransformer(_FlatOwner):
         transformer is re-run on the growing prefix (forward is prefix-invariant).  `action=True`
         follows the intended feedback semantics (the shipped code raises IndexError)."""
         self._check_device(cad_image)
+        if cad_image.is_cuda and torch.cuda.current_device() != cad_image.device.index:
+            with torch.cuda.device(cad_image.device):
+                return self.sequential_inference(ui_images, cad_image, action)
         st_r, cad_r, seq_r = self._get_runners()
         B, T = ui_images.shape[:2]
         dev, passes = ui_images.device, self._passes

@@ -34,7 +34,8 @@ class VitWeights(C.Structure):
 
 class VitCall(C.Structure):
     _fields_ = [("w", C.POINTER(VitWeights)), ("img", vp), ("F", i32), ("S", i32), ("dropout_p", f32), ("training", i32),
-                ("seed", u64), ("site_base", u32), ("seed_dev", vp), ("passes", i32), ("ws", vp), ("ws_bytes", sz), ("cls_out", vp)]
+                ("seed", u64), ("site_base", u32), ("seed_dev", vp), ("passes", i32), ("aux_streams", i32), ("ws", vp), ("ws_bytes", sz),
+                ("cls_out", vp)]
 
 
 class DecLayer(C.Structure):

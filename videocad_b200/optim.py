@@ -73,4 +73,8 @@ class ClipAdam(torch.optim.Optimizer):
         max_norm = g0["max_norm"] if g0["max_norm"] is not None else 0.0
         L.check(lib.vc_clip_adam_step(arr, len(entries), float(g0["betas"][0]), float(g0["betas"][1]), float(g0["eps"]),
                                       float(max_norm), steps.pop(), self._scratch.data_ptr(), self.last_grad_norm.data_ptr(), stream), lib)
+        # the kernels wrote the parameters (and clipped the gradients) through raw pointers: bump the tensors' version counters
+        # as an in-place torch op would, so that everything keyed on `_version` (the model's split-bf16 weight mirror,
+        # autograd's saved-tensor checks) sees the update
+        torch._C._increment_version([p for p, _ in keep] + [p.grad for p, _ in keep])
         return loss
