@@ -15,9 +15,15 @@ the named shape; frames = B*T model frames per step, summed over ranks (weak sca
   roofline   the tcgen05 GEMM kernel (dominant kernel): algorithmic FLOPs (2*M*N*K per launch, counted by the library)
              / summed CUDA-event launch durations recorded around every launch on the launching stream during the timed
              region, against the measured bf16 tensor peak in MEASURED_PEAKS.json
-  cpu_baseline  the oracle's CPU port of the same training step on the host cores (bounded sample)
+  cpu_baseline  the reference's own trainer._process_batch around the reference's own model on the host cores (bounded sample;
+             "kind": "reference" when the staged reference sources are present -- oracle/build_ref.py -- else the oracle's port)
+  through_trainer  the UNMODIFIED reference trainer object (its compute_loss with the .item() syncs, torch clip + Adam) driving the
+             drop-in on the GPU: what a user of trainer.py gets without touching it
+  rollout    BASELINE config C4 on this GPU: 186-step action-feedback rollout of the H=1024 model, 8 sequences, with the decode
+             step's HBM roofline (weight + cache bytes per step / step time / measured copy bandwidth)
+  c3         (N > 1 only) BASELINE config C3 -- T=32, H=1024, 32 samples per GPU under DDP -- timed in the same launch
 
---impl reference times the CPU port only (rank 0), printing the same JSON line with "impl": "reference".
+--impl reference times the reference's CPU implementation only (rank 0), printing the same JSON line with "impl": "reference".
 """
 import argparse
 import ctypes as C
@@ -37,12 +43,14 @@ CONFIGS = {
     # BASELINE.json configs[1]: 1xB200, 8-frame context, 224x224, d_model=512, batch=32
     "c1": dict(model=dict(hidden_size=512, nhead=4, num_decoder_layers=8, dim_feedforward=512, window_size=10,
                           enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
-               B=32, T=8, S=224, cpu_B=2),
+               B=32, T=8, S=224, cpu_B=32),
     # BASELINE.json configs[3]: DDP, 32-frame context, H=1024, 32 samples per GPU
     "c3": dict(model=dict(hidden_size=1024, nhead=4, num_decoder_layers=8, dim_feedforward=1024, window_size=10,
                           enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True),
-               B=32, T=32, S=224, cpu_B=1),
+               B=32, T=32, S=224, cpu_B=4),
 }
+# BASELINE.json configs[4]: 186-step autoregressive rollout of the H=1024 model, 64 sequences over 8 GPUs = 8 per GPU
+ROLLOUT = dict(model=CONFIGS["c3"]["model"], B=8, T=186, S=224)
 NUM_BATCHES = 4  # distinct synthetic batches rotated through the timed region (4 x 58 MB of frames at c1 > 126 MB L2)
 
 
@@ -58,11 +66,16 @@ def fwd_flops_per_sample(cfg, T, S):
     return T * f_vit + f_vit + glue + dec + head
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE gemm_tc_pair_kernel launch (to_qkv forward, M=12800 N=3072 K=512), from the
-# `ncu --set full` capture summarised in profiles/ (see profiles/README.md); None until a capture exists
-PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH = 137445888
-PAIR_KERNEL_TRAFFIC_NOTE = ("profiles/r01m_ncu_gemm_pair_qkv_fwd_summary.txt: 32.9 MB read (= the split-bf16 operands, read once) + 104.5 MB written "
-                            "of the 157.3 MB fp32 output (the rest was still in L2 when the kernel ended); algorithmic bytes 189.8 MB")
+def pair_kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the `ncu --set full` capture
+    summarised under profiles/ (profiles/ncu_traffic.json names the capture it was read from); None until a capture exists."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)["gemm_tc_pair_kernel"]
+        return int(d["dram_bytes_per_launch"]), d.get("note", "")
+    except Exception:
+        return None, "no capture recorded in profiles/ncu_traffic.json"
 
 
 def measured_peaks():
@@ -70,8 +83,9 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1400.0, source="fallback (B200_PROFILING.md sustained figure)")
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), hbm_gbs=float(d.get("hbm_gbs", 6500.0)),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16 / copy bandwidth)")
+    return dict(tflops=1400.0, hbm_gbs=6500.0, source="fallback (B200_PROFILING.md sustained figures)")
 
 
 class ClockSampler:
@@ -127,19 +141,46 @@ def make_batches(B, T, S, rank, device=None, pinned=False):
     return out
 
 
+def workload_config(args, cfg, world):
+    """The `config` object of the JSON line: the same for both arms (they measure the same workload)."""
+    B, T, S = cfg["B"], cfg["T"], cfg["S"]
+    return dict(workload=f"{args.config}: {world} x (batch {B}, T={T}, {S}x{S} frames), H={cfg['model']['hidden_size']}, "
+                         f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0",
+                global_batch=world * B, parallelism=f"dp{world}" if world > 1 else "single",
+                l2="inputs rotate over 4 distinct batches (232 MB of frames at c1 > 126 MB L2); activations (>5 GB/step) stream through HBM",
+                fwd_gflop_per_sample=fwd_flops_per_sample(cfg["model"], T, S) / 1e9)
+
+
+def reference_available():
+    from oracle import reference_model as rm
+
+    return rm.available()
+
+
 def run_reference(args, cfg):
-    """The reference arm: the CPU implementation of the path (oracle port) on the host cores, rank 0 only."""
+    """The reference arm: the reference's OWN CPU implementation of the path -- the unmodified trainer._process_batch
+    (trainer.py:480-496) around the unmodified model (vit_pytorch shim) -- on the host cores, rank 0 only.  Falls back to the
+    oracle's port only if the reference sources were not staged (oracle/build_ref.py)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.train_port import CpuTrainStep, pick_threads
     from oracle import torch_oracle as to
 
     B, T, S = cfg["cpu_B"], cfg["T"], cfg["S"]
-    runner = CpuTrainStep(cfg["model"])
     batches = [to.synthetic_batch(B, T + 1, S, seed=100 + i) for i in range(2)]
+    if reference_available():
+        from oracle.ref_trainer import ReferenceTrainStep, pick_threads
+
+        runner, kind = ReferenceTrainStep(cfg["model"]), "reference"
+        what = "unmodified reference trainer._process_batch around the reference model (vit_pytorch shim)"
+    else:
+        from oracle.train_port import CpuTrainStep, pick_threads as _pt
+
+        runner, kind = CpuTrainStep(cfg["model"]), "port"
+        what = "oracle port of trainer._process_batch (reference sources not staged)"
+        pick_threads = lambda step, batch: _pt(runner, batch)  # noqa: E731
     runner.step(batches[0])
-    pick_threads(runner, batches[1])  # all the host threads that help (torchrun would pin OMP_NUM_THREADS=1)
+    pick_threads(runner.step, batches[1])  # all the host threads that help (torchrun would pin OMP_NUM_THREADS=1)
     for i in range(args.warmup):
         runner.step(batches[i % 2])
     t0 = time.perf_counter()
@@ -147,13 +188,12 @@ def run_reference(args, cfg):
         runner.step(batches[i % 2])
     dt = time.perf_counter() - t0
     fps = B * T * args.steps / dt
+    sample = (f"{args.steps} steps of the {what} at batch {B} x T={T} x {S}x{S}"
+              + ("" if B == cfg["B"] else f" (bounded sample of the {cfg['B']}-sample per-GPU batch)") + f", host_cpus={os.cpu_count()}")
     line = dict(metric="train frames/sec", value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1000 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", impl="reference",
-                config=dict(workload=f"{args.config}: CPU port of trainer._process_batch, batch {B} x T={T} x {S}x{S}, "
-                            f"H={cfg['model']['hidden_size']} (bounded sample of the {cfg['B']}-sample GPU batch)"),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=torch.get_num_threads(), kind="port",
-                                  sample=f"{args.steps} steps at batch {B}, host_cpus={os.cpu_count()}"),
+                data="synthetic", impl="reference", config=workload_config(args, cfg, args.gpus),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=torch.get_num_threads(), kind=kind, sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     emit(line)
 
@@ -177,6 +217,152 @@ def emit(line):
     out.flush()
 
 
+def measure_rollout(dev, peak, iters=3):
+    """BASELINE config C4 on one GPU: 8 sequences x 186 steps of action feedback through AutoRegressiveTransformer.sequential_inference
+    (every frame encoded once, one key/value-cached decode step per position).  HBM roofline of the decode step: the decoder and head
+    weights (read once per step) plus the self-attention cache rows read at step t, averaged over t."""
+    import videocad_b200.model as vmodel
+    from videocad_b200 import AutoRegressiveTransformer
+
+    cfg = ROLLOUT
+    B, T, S = cfg["B"], cfg["T"], cfg["S"]
+    mc = cfg["model"]
+    H, Ff, L = mc["hidden_size"], mc["dim_feedforward"], mc["num_decoder_layers"]
+    torch.manual_seed(0)
+    m = AutoRegressiveTransformer(state_dim=1644, act_dim=7, encoder="vit", **mc).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)
+    frames = torch.randn(B, T, 1, S, S, device=dev, generator=g).clamp_(-1, 1)
+    cad = torch.randn(B, 1, S, S, device=dev, generator=g).clamp_(-1, 1)
+    total, decode = [], []
+    for it in range(iters + 2):  # the first two calls run eagerly / capture the CUDA graphs
+        vmodel._ROLLOUT_EVENTS = []
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        cmds, params = m.sequential_inference(frames, cad, action=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if it > 1:
+            total.append(e0.elapsed_time(e1))
+            d0, d1 = vmodel._ROLLOUT_EVENTS[0]
+            decode.append(d0.elapsed_time(d1))
+    vmodel._ROLLOUT_EVENTS = None
+    assert cmds.shape == (B, T, 5) and params.shape == (B, T, 6, 1000) and bool(torch.isfinite(params).all())
+    ms = sorted(total)[len(total) // 2]
+    ms_dec = sorted(decode)[len(decode) // 2]
+    step_ms = ms_dec / T
+    w_bytes = 4 * (L * (6 * H * H + 2 * H * Ff) + 6005 * H)            # in_proj (3), out_proj, cross q, cross out, linear1/2; heads
+    kv_bytes = 4 * L * B * ((T + 1) / 2.0) * 2 * H                      # keys + values of the t+1 cached positions, mean over t
+    step_bytes = w_bytes + kv_bytes
+    gbs = step_bytes / (step_ms * 1e-3) / 1e9
+    del m, frames, cad
+    torch.cuda.empty_cache()
+    return dict(workload=f"c4: {B} sequences/GPU x {T} steps, H={H}, {S}x{S}, eval, argmax feedback (exact incremental decoding)",
+                ms_per_rollout=ms, frames_per_s=B * T / (ms / 1e3), ms_encode_frames=ms - ms_dec, ms_per_decode_step=step_ms,
+                roofline=dict(bound="hbm", kernel="decode step (all kernels of one position)", achieved=gbs, peak=peak["hbm_gbs"], unit="GB/s",
+                              frac=gbs / peak["hbm_gbs"], algorithmic_bytes_per_step=step_bytes,
+                              note="fp32 decoder + head weights read once per step plus the cached keys/values of the positions so far "
+                                   "(mean over the 186 steps); the step's time includes the full-length pass that builds the cache"))
+
+
+def measure_through_trainer(net, dev_batches, B, T, world, steps):
+    """frames/s of the UNMODIFIED reference trainer (oracle/_ref staged copy or /root/reference) driving the drop-in on the GPU:
+    trainer._process_batch = zero_grad -> prepare_batch -> model -> its own compute_loss (argmax metrics with ~30 .item() syncs) ->
+    backward -> torch clip_grad_norm_ -> torch Adam."""
+    if not reference_available():
+        return dict(unavailable="reference sources not staged (python -m oracle.build_ref in the build container)")
+    import torch.distributed as dist
+    from oracle import ref_trainer as rt
+
+    dev = dev_batches[0]["frames"].device
+    trainer = rt.make_trainer(net, dev, lr=1e-5)
+    for i in range(3):
+        trainer._process_batch(dev_batches[i % NUM_BATCHES])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        trainer._process_batch(dev_batches[i % NUM_BATCHES])
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    return dict(value=world * B * T * steps / (ms / 1e3), unit="frames/s", ms_per_step=ms / steps, steps=steps,
+                note="unmodified trainer._process_batch (trainer.py:480-496) around the drop-in: the reference's compute_loss with its "
+                     ".item() syncs, torch clip_grad_norm_ and torch Adam; inputs resident in HBM")
+
+
+def measure_c3(args, rank, world, local_rank, steps=10):
+    """BASELINE config C3 inside the same N-rank launch: T=32, H=Ff=1024, 32 samples per GPU, DDP gradient all-reduce (~508 MB).
+    Also times the same steps under no_sync() (no all-reduce): the difference is the all-reduce time the backward could not hide."""
+    import torch.distributed as dist
+    from videocad_b200 import AutoRegressiveTransformer
+    from videocad_b200 import loss as vloss
+    from videocad_b200.optim import ClipAdam
+
+    cfg = CONFIGS["c3"]
+    B, T, S = cfg["B"], cfg["T"], cfg["S"]
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(0)
+    model = AutoRegressiveTransformer(state_dim=1644, act_dim=7, encoder="vit", precision=args.precision, **cfg["model"]).to(dev)
+    model.train()
+    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], output_device=local_rank,
+                                                    find_unused_parameters=True) if world > 1 else model
+    opt = ClipAdam(model.parameters(), lr=1e-5, max_norm=1.0)
+    from videocad_b200.synthetic import synthetic_batch
+
+    batches = [{k: v.to(dev) for k, v in synthetic_batch(B, T + 1, S, seed=4321 + 1000 * rank + i).items()} for i in range(2)]
+
+    def step(i):
+        opt.zero_grad()
+        b = batches[i % 2]
+        inputs = {"frames": b["frames"][:, :-1], "actions": model.normalize_actions(b["actions"][:, :-1].clone()), "cad_image": b["cad_image"]}
+        loss = vloss.compute_loss_fused(net(inputs), b["actions"][:, 1:])
+        loss.backward()
+        opt.step()
+
+    def timed(n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item() / n
+
+    for i in range(3):
+        step(i)
+    ms = timed(steps)
+    ms_nosync = None
+    if world > 1:
+        with net.no_sync():
+            step(0)
+            ms_nosync = timed(steps)
+    grad_bytes = 4 * sum(p.numel() for p in model.parameters())
+    f_fwd = fwd_flops_per_sample(cfg["model"], T, S)
+    out = dict(workload=f"c3: {world} x (batch {B}, T={T}, {S}x{S} frames), H=1024, DDP gradient all-reduce of {grad_bytes / 1e6:.0f} MB",
+               global_batch=world * B, steps=steps, ms_per_step=ms, value=world * B * T / (ms / 1e3), unit="frames/s",
+               ms_per_step_without_allreduce=ms_nosync, exposed_allreduce_ms=(ms - ms_nosync) if ms_nosync is not None else None,
+               grad_bytes_per_step=grad_bytes, whole_step_algorithmic_tflops_per_gpu=B * T / (ms / 1e3) * 3.0 * f_fwd / T / 1e12)
+    del model, net, opt, batches
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     protect_stdout()
     ap = argparse.ArgumentParser()
@@ -192,6 +378,7 @@ def main():
                     help="clip_grad_norm_(1.0) + Adam: the native fused step (videocad_b200.optim.ClipAdam, default) or the two "
                          "torch calls of the reference trainer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the C4 rollout leg")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -324,6 +511,16 @@ def main():
     if not graphs_were_on:
         launches = launches_inst
 
+    # ---------------- the same steps without the gradient all-reduce (DDP no_sync): what the backward could not hide
+    ms_nosync = None
+    if world > 1:
+        with net.no_sync():
+            train_step(dev_batches[0])
+            ms_nosync, _ = timed(lambda i: train_step(dev_batches[i % NUM_BATCHES]), args.steps)
+
+    # ---------------- through the unmodified reference trainer object (its own loss / metrics / clip / Adam)
+    through_trainer = measure_through_trainer(net, dev_batches, B, T, world, max(5, args.steps // 2))
+
     # ---------------- e2e: host (pinned) inputs, H2D + loss read-back inside the timed region
     del dev_batches
     host_batches = make_batches(B, T, S, rank, pinned=True)
@@ -360,12 +557,20 @@ def main():
     pending.clear()
     e2e_value = frames_per_step * args.steps / (ms_e2e / 1000.0)
 
+    peak = measured_peaks()
+    # ---------------- BASELINE's other GPU configs, measured in the same launch
+    del host_batches
+    pending.clear()
+    torch.cuda.empty_cache()
+    c3 = measure_c3(args, rank, world, local_rank) if (world > 1 and args.config == "c1") else None
+    rollout = measure_rollout(dev, peak) if (rank == 0 and args.config == "c1" and not args.no_rollout) else None
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    peak = measured_peaks()
     f_fwd = fwd_flops_per_sample(cfg["model"], T, S)
     gemm_tflops = (g_fl.value / 1e12) / (g_ms.value / 1e3) if g_ms.value > 0 else 0.0
     step_tflops = value / world * 3.0 * f_fwd / T / 1e12  # per GPU, whole step (fwd + 2x bwd) algorithmic
@@ -373,9 +578,10 @@ def main():
     big_tflops = (b_fl.value / 1e12) / (b_ms.value / 1e3) if b_ms.value > 0 else 0.0
     pair_launches = lib.vc_gemm_pair_launch_count()
     # dominant kernel: the 2-SM 256x256 GEMM (gemm_tc_pair_kernel) that runs every image-encoder GEMM of >= 5 GFLOP
+    traffic, traffic_note = pair_kernel_traffic()
     roofline = dict(bound="tensor", kernel="gemm_tc_pair_kernel (tcgen05 cta_group::2, 256x256 tiles, split-bf16 x3)",
                     achieved=big_tflops, peak=peak["tflops"], unit="TFLOP/s", frac=big_tflops / peak["tflops"],
-                    traffic=PAIR_KERNEL_DRAM_BYTES_PER_LAUNCH, traffic_note=PAIR_KERNEL_TRAFFIC_NOTE,
+                    traffic=traffic, traffic_note=traffic_note,
                     peak_source=peak["source"], mma_passes_per_flop=passes, mma_issue_frac=passes * big_tflops / peak["tflops"],
                     launches_per_step=b_n.value / args.steps, ms_per_step=b_ms.value / args.steps,
                     share_of_step=(b_ms.value / args.steps) / (ms_inst / args.steps),
@@ -392,26 +598,30 @@ def main():
                     whole_step_algorithmic_tflops_per_gpu=step_tflops, whole_step_frac=step_tflops / peak["tflops"])
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        from oracle.train_port import time_cpu_train
+        if reference_available():
+            from oracle.ref_trainer import time_reference_train
 
-        cpu_baseline = time_cpu_train(cfg["model"], cfg["cpu_B"], T, S, steps=6, warmup=1)
+            cpu_baseline = time_reference_train(cfg["model"], cfg["cpu_B"], T, S, steps=3, warmup=1)
+        else:
+            from oracle.train_port import time_cpu_train
+
+            cpu_baseline = time_cpu_train(cfg["model"], min(cfg["cpu_B"], 2), T, S, steps=6, warmup=1)
     line = dict(metric="train frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32 (3-pass split-bf16 tensor-core GEMMs, fp32 accumulate)" if passes == 3 else "bf16",
                 data="synthetic", impl="native",
-                config=dict(workload=f"{args.config}: {world} x (batch {B}, T={T}, {S}x{S} frames), H={cfg['model']['hidden_size']}, "
-                            f"8 decoder layers, window 10, dropout 0.1, Adam lr 1e-5, clip 1.0, {args.loss} loss, {args.optimizer} clip+Adam",
-                            global_batch=world * B, parallelism=f"dp{world}" if world > 1 else "single",
-                            l2="inputs rotate over 4 distinct batches (232 MB of frames at c1 > 126 MB L2); activations (>5 GB/step) stream through HBM",
-                            fwd_gflop_per_sample=f_fwd / 1e9),
+                config=workload_config(args, cfg, world), step_impl=f"{args.loss} loss, {args.optimizer} clip+Adam",
                 clocks=clocks, e2e=dict(value=e2e_value, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                                         ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches_inst, gpu_launches_note="native kernels per %d steps (%d per step); with CUDA-graph replay "
                 "the same kernels run from 6 graph launches per step" % (args.steps, launches_inst // max(args.steps, 1)),
                 cuda_graphs=bool(graphs_were_on), segments_ms_per_step=segments, roofline=roofline,
-                cpu_baseline=cpu_baseline)
+                cpu_baseline=cpu_baseline, through_trainer=through_trainer, rollout=rollout, c3=c3,
+                ms_per_step_without_allreduce=(ms_nosync / args.steps) if ms_nosync is not None else None,
+                exposed_allreduce_ms=((ms - ms_nosync) / args.steps) if ms_nosync is not None else None)
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

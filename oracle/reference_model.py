@@ -1,18 +1,33 @@
 """Import the UNMODIFIED reference model from /root/reference (TEST INFRASTRUCTURE ONLY).
 
-Works only where /root/reference exists (the build container).  `vit_pytorch` and `timm` are not
-installed in this image, so the restatement/stub under oracle/shims/ is put on sys.path first
-(SURVEY.md 8(c)).  Nothing is copied from, or written to, /root/reference.
+Source: /root/reference where it exists (the build container), else the byte-for-byte copies staged under oracle/_ref/ by
+oracle/build_ref.py (git-ignored, shipped to the GPU box like a built .so).  `vit_pytorch` and `timm` are not installed in this
+image, so the restatement/stub under oracle/shims/ is put on sys.path first.  Nothing is written to
+/root/reference and no reference source enters the repository's history.
 """
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("VIDEOCAD_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+_STAGED = os.path.join(_HERE, "_ref")  # byte-for-byte copies made by oracle/build_ref.py (git-ignored; travels with gpurun)
+
+
+def _pick_root() -> str:
+    env = os.environ.get("VIDEOCAD_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "model", "autoregressive_transformer.py")):
+        return "/root/reference"
+    return _STAGED
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "autoregressive_transformer.py"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model", "autoregressive_transformer.py")) and \
+        os.path.isfile(os.path.join(REFERENCE_ROOT, "trainer.py"))
 
 
 def _prepare_path():

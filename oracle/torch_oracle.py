@@ -346,10 +346,10 @@ def apply_action_mask(cmd_pred: torch.Tensor, param_pred: torch.Tensor) -> torch
 def rollout(sd: dict, cfg: dict, frames: torch.Tensor, cad: torch.Tensor, action: bool = True):
     """sequential_inference (autoregressive_transformer.py:222-275) by full recompute -- O(T^2)."""
     B, T = frames.shape[:2]
-    acts = torch.zeros(B, 1, 7, dtype=frames.dtype)
+    acts = torch.zeros(B, 1, 7, dtype=frames.dtype, device=frames.device)
     out_c, out_p = [], []
     for t in range(T):
-        a_in = acts if action else torch.zeros(B, t + 1, 7, dtype=frames.dtype)
+        a_in = acts if action else torch.zeros(B, t + 1, 7, dtype=frames.dtype, device=frames.device)
         cmd, par = forward(sd, cfg, {"frames": frames[:, : t + 1], "actions": a_in, "cad_image": cad})
         out_c.append(cmd[:, -1])
         out_p.append(par[:, -1])

@@ -5,8 +5,9 @@
     python scripts/rollout_bench.py [--batch 8] [--steps 186] [--iters 2]
 
 Reports frames/s of AutoRegressiveTransformer.sequential_inference for action=False (one pass) and action=True (argmax feedback:
-one sequence-transformer pass per step on the growing prefix; every frame is encoded ONCE -- the reference re-encodes the whole
-prefix at every step, 17 577 encoder passes per sample instead of 187)."""
+every frame is encoded ONCE, one full-length pass builds the cross-attention keys/values, then one key/value-cached decode step per
+position -- the reference re-runs the whole forward, all encoder passes included, on the growing prefix at every step: 17 577 encoder
+passes per sample instead of 187).  bench.py reports the same measurement under its `rollout` key."""
 import argparse
 import json
 import os
@@ -24,6 +25,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--steps", type=int, default=186)
     ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--only-feedback", action="store_true", help="skip the action=False single pass")
+    ap.add_argument("--calls", type=int, default=0, help="> 0: exactly this many untimed-warm-up-free calls (profiling under ncu)")
     args = ap.parse_args()
     cfg = dict(hidden_size=1024, nhead=4, num_decoder_layers=8, dim_feedforward=1024, window_size=10,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
@@ -34,16 +37,16 @@ def main():
     frames = torch.randn(B, T, 1, S, S, device="cuda", generator=g).clamp_(-1, 1)
     cad = torch.randn(B, 1, S, S, device="cuda", generator=g).clamp_(-1, 1)
     out = {}
-    for action in (False, True):
+    for action in ((True,) if args.only_feedback else (False, True)):
         ts = []
-        for it in range(args.iters + 2):  # the first two calls run eagerly / capture the CUDA graphs
+        for it in range(args.calls if args.calls > 0 else args.iters + 2):  # the first two calls run eagerly / capture the CUDA graphs
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             cmds, params = m.sequential_inference(frames, cad, action=action)
             e1.record()
             torch.cuda.synchronize()
-            if it > 1:
+            if it > 1 or args.calls > 0:
                 ts.append(e0.elapsed_time(e1))
         ms = sorted(ts)[len(ts) // 2] if ts else float('nan')
         assert cmds.shape == (B, T, 5) and params.shape == (B, T, 6, 1000) and torch.isfinite(params).all()

@@ -37,6 +37,7 @@ _MAX_INFER_SLOTS = 12  # forward-only slots (no gradient arena): the rollout's p
 # run the CAD image encoder on a second stream, concurrently with the frame encoder ("0" disables)
 _OVERLAP = os.environ.get("VIDEOCAD_B200_OVERLAP", "1") != "0"
 _TIMING = None  # bench.py: list of (segment.direction, start event, end event) around every CUDA-graph replay
+_ROLLOUT_EVENTS = None  # bench.py: list receiving the (frames encoded, done) CUDA events of every action-feedback rollout
 
 
 def timing_begin():
@@ -986,10 +987,12 @@ class AutoRegressiveTransformer(_FlatOwner):
 
     @torch.no_grad()
     def sequential_inference(self, ui_images, cad_image, action=False):
-        """sequential_inference (autoregressive_transformer.py:222-275) with exact caching of the image encoders:
-        every frame is encoded once (187 ViT passes per 186-step sample instead of 17 577), then the cheap sequence
-        transformer is re-run on the growing prefix (forward is prefix-invariant).  `action=True`
-        follows the intended feedback semantics (the shipped code raises IndexError)."""
+        """sequential_inference (autoregressive_transformer.py:222-275) without the reference's O(T^2) recompute: every frame is
+        encoded ONCE (187 ViT passes per 186-step sample instead of 17 577), one full-length pass of the sequence transformer
+        builds the memory tokens and the cross-attention keys/values of every layer, and each step then pushes ONE token per
+        sequence through the decoder against the self-attention key/value cache (vc_seq_decode_step).  Exact: the forward is
+        prefix-invariant.  `action=True` follows the intended feedback semantics (the shipped code raises
+        IndexError)."""
         self._check_device(cad_image)
         if cad_image.is_cuda and torch.cuda.current_device() != cad_image.device.index:
             with torch.cuda.device(cad_image.device):
@@ -1016,6 +1019,10 @@ class AutoRegressiveTransformer(_FlatOwner):
         # Incremental decoding: ONE full-length pass builds the memory tokens and the cross-attention keys/values of every layer
         # (they do not depend on the actions); each step then pushes one token per sequence through the decoder against the
         # key/value cache (vc_seq_decode_step) -- 186 single-token steps instead of 186 passes over the growing prefix.
+        ev = None
+        if _ROLLOUT_EVENTS is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
         dec = seq_r.decode_begin(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, B, T, passes)
         action_t = torch.zeros(B, self.act_dim, device=dev)
         out_c, out_p = [], []
@@ -1028,4 +1035,7 @@ class AutoRegressiveTransformer(_FlatOwner):
             nxt = self.apply_action_mask(cmd_pred.unsqueeze(1), par_pred.unsqueeze(1)).float()
             nxt = torch.cat([cmd_pred.reshape(B, 1, 1).float(), nxt], dim=2)
             action_t = self.normalize_actions(nxt)[:, 0].contiguous()
+        if ev is not None:
+            ev[1].record()
+            _ROLLOUT_EVENTS.append(tuple(ev))
         return torch.stack(out_c, 1), torch.stack(out_p, 1)
