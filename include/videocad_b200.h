@@ -357,6 +357,18 @@ int vc_seq_forward(const vc_seq_call* c, void* stream);
 size_t vc_seq_decode_scratch_bytes(int B, int H, int Ff, int nhead);
 int vc_seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* scratch, size_t scratch_bytes, float* cmds_t,
                        float* params_t, void* stream);
+/* The same step with the position and the action feedback ON THE DEVICE, for B <= 16 sequences (the rollout of BASELINE config C4:
+ * 8 per GPU): *t_dev (device int, 0 before the first step) selects the position and is incremented by the call; actions_io
+ * [B, act_dim] (device, zeros before the first step) holds the normalised action of position *t_dev on entry and receives
+ * normalize_actions(apply_action_mask(argmax cmd, argmax params)) of this position (autoregressive_transformer.py:91-118, 256-266)
+ * on exit; the logits of the position go to row (b, t) of cmds_all [B, T, num_cmd] / params_all [B, T, num_param_out].  The launch
+ * sequence does not depend on the position: one captured CUDA graph serves all T steps and the host is never consulted.
+ * Every kernel is bound by reading its weights once (TMA bulk copies issued ahead of the dependency wait).
+ * vc_seq_decode_dev_supported() != 0 tells whether the configuration is covered (otherwise use vc_seq_decode_step). */
+int vc_seq_decode_dev_supported(const vc_seq_call* c);
+size_t vc_seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nhead);
+int vc_seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
+                           float* params_all, void* stream);
 /* dcmds [B*T,num_cmd], dparams [B*T,num_param_out]; d_state_cls [B*T,512] (may be null unless past_states),
  * d_cad_cls [B,512] and d_mv_cls [B*num_views,512] (may be null when num_views == 0) are OVERWRITTEN */
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,

@@ -781,6 +781,137 @@ int head_small_bwd(const float* dout, const float* x, int64_t R, int H, const fl
   return 0;
 }
 
+// ---- decode-step kernels (CPU twins of videocad_b200/csrc/decode.cu; contracts in kernels.h) ----
+int dec_gemv(const DecGemv& g, stream_t) {
+  if (g.M <= 0 || g.M > 16 || g.K <= 0 || g.N <= 0 || !g.W || !g.out) return set_error("dec_gemv: bad arguments");
+  const int M = g.M, K = g.K, t = g.t_ptr ? *g.t_ptr : 0;
+  std::vector<double> x((size_t)M * K, 0.0);
+  for (int m = 0; m < M; ++m) {
+    double* xr = x.data() + (size_t)m * K;
+    if (g.in_mode == VC_DEC_IN_PLAIN) {
+      for (int k = 0; k < K; ++k) xr[k] = g.x[(size_t)m * g.ldx + k];
+    } else if (g.in_mode == VC_DEC_IN_LN) {
+      double mean = 0.0, var = 0.0;
+      for (int k = 0; k < K; ++k) mean += g.x[(size_t)m * g.ldx + k];
+      mean /= K;
+      for (int k = 0; k < K; ++k) { const double d = g.x[(size_t)m * g.ldx + k] - mean; var += d * d; }
+      const double rstd = 1.0 / sqrt(var / K + 1e-5);
+      for (int k = 0; k < K; ++k) xr[k] = (g.x[(size_t)m * g.ldx + k] - mean) * rstd * g.gamma[k] + g.beta[k];
+    } else if (g.in_mode == VC_DEC_IN_EMBED) {
+      for (int k = 0; k < K; ++k) {
+        double acc = g.emb_b[k];
+        for (int i = 0; i < g.act_dim; ++i) acc += (double)g.actions[(size_t)m * g.act_dim + i] * g.emb_W[(size_t)k * g.act_dim + i];
+        if (g.emb_E) acc += g.emb_E[(size_t)t * K + k];
+        xr[k] = tanh(acc);
+      }
+    } else {
+      for (int h = 0; h < g.nh; ++h) {
+        const size_t base = ((size_t)m * g.nh + h) * g.nsplit;
+        double mx = -INFINITY, den = 0.0;
+        for (int s2 = 0; s2 < g.nsplit; ++s2) mx = fmax(mx, (double)g.part_ml[(base + s2) * 2]);
+        for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] = 0.0;
+        for (int s2 = 0; s2 < g.nsplit; ++s2) {
+          const double ms = g.part_ml[(base + s2) * 2];
+          if (ms == -INFINITY) continue;
+          const double w = exp(ms - mx);
+          den += w * g.part_ml[(base + s2) * 2 + 1];
+          for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] += w * g.part_o[(base + s2) * g.dh + d];
+        }
+        for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] /= den;
+      }
+    }
+    if (g.x_out) for (int k = 0; k < K; ++k) g.x_out[(size_t)m * K + k] = (float)xr[k];
+  }
+#pragma omp parallel for
+  for (int n = 0; n < g.N; ++n) {
+    for (int m = 0; m < M; ++m) {
+      double acc = 0.0;
+      const float* wr = g.W + (size_t)n * K;
+      const double* xr = x.data() + (size_t)m * K;
+      for (int k = 0; k < K; ++k) acc += xr[k] * wr[k];
+      float v = (float)(acc + (g.bias ? g.bias[n] : 0.f));
+      if (g.act == VC_ACT_RELU) v = v > 0.f ? v : 0.f;
+      else if (g.act == VC_ACT_TANH) v = tanhf(v);
+      else if (g.act == VC_ACT_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+      if (g.residual) v += g.residual[(size_t)m * g.ld_res + n];
+      g.out[(size_t)m * g.out_row_stride + (size_t)t * g.out_t_stride + n] = v;
+    }
+  }
+  return 0;
+}
+
+int dec_attn(const DecAttn& a, int B, stream_t) {
+  if (B <= 0 || !a.q || !a.k || !a.v || !a.part_o || !a.part_ml || !a.t_ptr || a.nsplit < 1) return set_error("dec_attn: bad arguments");
+  const int t = *a.t_ptr;
+  const int j_lo = a.window > 0 ? (t - a.window + 1 > 0 ? t - a.window + 1 : 0) : 0;
+  const int nkeys = t - j_lo + 1;
+  for (int b = 0; b < B; ++b)
+    for (int h = 0; h < a.nh; ++h)
+      for (int s2 = 0; s2 < a.nsplit; ++s2) {
+        const float* q = a.q + (size_t)b * a.q_bstride + (size_t)t * a.q_tstride + h * a.dh;
+        std::vector<double> sc;
+        std::vector<int> js;
+        for (int i = s2; i < nkeys; i += a.nsplit) {  // any partition of the keys is valid: the merge is exact
+          const float* kr = a.k + (size_t)b * a.kv_bstride + (size_t)(j_lo + i) * a.kv_rstride + h * a.dh;
+          double d = 0.0;
+          for (int e = 0; e < a.dh; ++e) d += (double)q[e] * a.scale * kr[e];
+          sc.push_back(d);
+          js.push_back(j_lo + i);
+        }
+        const size_t pb = ((size_t)b * a.nh + h) * a.nsplit + s2;
+        double mx = -INFINITY, l = 0.0;
+        for (double v : sc) mx = fmax(mx, v);
+        std::vector<double> o(a.dh, 0.0);
+        for (size_t i = 0; i < sc.size(); ++i) {
+          const double p = exp(sc[i] - mx);
+          l += p;
+          const float* vr = a.v + (size_t)b * a.kv_bstride + (size_t)js[i] * a.kv_rstride + h * a.dh;
+          for (int e = 0; e < a.dh; ++e) o[e] += p * vr[e];
+        }
+        a.part_ml[pb * 2] = (float)mx;
+        a.part_ml[pb * 2 + 1] = (float)l;
+        for (int e = 0; e < a.dh; ++e) a.part_o[pb * a.dh + e] = (float)o[e];
+      }
+  return 0;
+}
+
+int dec_select(const DecSelect& a, stream_t) {
+  static const int kMask[5][6] = {{1, 1, 0, 0, 0, 0}, {0, 0, 1, 1, 0, 0}, {0, 0, 0, 0, 1, 0}, {0, 0, 0, 0, 0, 1}, {0, 0, 0, 0, 0, 0}};
+  if (a.B <= 0 || a.NC < 1 || a.NC > 8 || a.NPAR > 8 || !a.y || !a.t_ptr) return set_error("dec_select: bad arguments");
+  const int t = *a.t_ptr, H = a.H;
+  for (int b = 0; b < a.B; ++b) {
+    const float* y = a.y + (size_t)b * H;
+    double mean = 0.0, var = 0.0;
+    for (int k = 0; k < H; ++k) mean += y[k];
+    mean /= H;
+    for (int k = 0; k < H; ++k) { const double d = y[k] - mean; var += d * d; }
+    const double rstd = 1.0 / sqrt(var / H + 1e-5);
+    int cmd = 0;
+    float best = -INFINITY;
+    for (int c = 0; c < a.NC; ++c) {
+      double acc = a.bc[c];
+      for (int k = 0; k < H; ++k) acc += ((y[k] - mean) * rstd * a.gamma[k] + a.beta[k]) * a.Wc[(size_t)c * H + k];
+      const float v = (float)acc;
+      a.cmds_all[((size_t)b * a.T + t) * a.NC + c] = v;
+      if (v > best) { best = v; cmd = c; }
+    }
+    if (!a.action_next) continue;
+    float par[8];
+    for (int i = 0; i < a.NPAR; ++i) {
+      const float* z = a.params_all + ((size_t)b * a.T + t) * ((size_t)a.NPAR * a.NV) + (size_t)i * a.NV;
+      int bi = 0;
+      for (int k = 1; k < a.NV; ++k) if (z[k] > z[bi]) bi = k;
+      par[i] = (cmd < 5 && i < 6 && kMask[cmd][i]) ? (float)bi : -1.0f;
+    }
+    if (a.NPAR > 3 && !(par[2] >= 200.f && par[2] < 250.f)) par[3] = -1.0f;
+    float* out = a.action_next + (size_t)b * (1 + a.NPAR);
+    out[0] = (float)cmd / 4.0f;
+    for (int i = 0; i < a.NPAR; ++i) out[1 + i] = par[i] / 1000.0f;
+  }
+  *a.t_ptr = t + 1;
+  return 0;
+}
+
 int stream_fork(stream_t main, int, stream_t* side) { *side = main; return 0; }
 int stream_join(stream_t, int) { return 0; }
 void side_streams_enable(int) {}

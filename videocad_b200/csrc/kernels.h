@@ -170,6 +170,56 @@ int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int6
                     int K, int act, const float* residual, int64_t ld_res, float* out_f32, int64_t ldo, bf16_t* out_hi, bf16_t* out_lo,
                     int64_t ldo_split, stream_t s);
 
+// ---- one position of the key/value-cached rollout for B <= 16 sequences (decode.cu; CPU twin in oracle/csrc/kernels_cpu.cpp) ----
+// out[m, n] = act(sum_k x[m, k] W[n, k] + bias[n]) + residual[m, n], stored at out[m * out_row_stride + t * out_t_stride + n]
+// with t = *t_ptr (0 if null).  The input rows x [M, K] are built on load according to in_mode:
+//   PLAIN  x = rows of `x` (ldx)                                   LN     x = LayerNorm(rows of `x`; gamma, beta, eps 1e-5)
+//   EMBED  x = tanh(actions[M, act_dim] emb_W^T + emb_b + emb_E[t])  (K = hidden size, emb_W [K, act_dim], emb_E [*, K] or null)
+//   ATTN   x[m, h*dh + d] = softmax-merge over the nsplit partials written by dec_attn (K = nh * dh)
+// x_out (optional, [M, K]): receives the rows that were built (the residual operand of a later call).
+enum { VC_DEC_IN_PLAIN = 0, VC_DEC_IN_LN = 1, VC_DEC_IN_EMBED = 2, VC_DEC_IN_ATTN = 3 };
+struct DecGemv {
+  int in_mode;
+  const float* x; long long ldx;
+  const float* gamma; const float* beta;
+  float* x_out;
+  const float* actions; int act_dim; const float* emb_W; const float* emb_b; const float* emb_E;
+  const float* part_o; const float* part_ml; int nsplit; int nh; int dh;
+  int M, N, K;
+  const float* W; const float* bias;
+  int act;
+  const float* residual; long long ld_res;
+  float* out; long long out_row_stride; long long out_t_stride;
+  const int* t_ptr;
+  int cols_per_cta;  // chosen by the launcher
+};
+int dec_gemv(const DecGemv& g, stream_t s);
+// attention of ONE query row per (sequence b, head h) at position t = *t_ptr against keys j in [0, t] (window == 0) or
+// (t - window, t] (window > 0):  q row = q + b*q_bstride + t*q_tstride, key/value row j = k|v + b*kv_bstride + j*kv_rstride, head h =
+// columns [h*dh, (h+1)*dh).  The keys are split over nsplit parts; part s writes its running max / sum to part_ml[b, h, s, 0:2] and
+// its unnormalised accumulator to part_o[b, h, s, 0:dh] (merged by dec_gemv's ATTN input mode).
+struct DecAttn {
+  const float* q; long long q_bstride; long long q_tstride;
+  const float* k; const float* v; long long kv_bstride; long long kv_rstride;
+  int nh, dh, nsplit, window;
+  float scale;
+  const int* t_ptr;
+  float* part_o; float* part_ml;
+};
+int dec_attn(const DecAttn& a, int B, stream_t s);
+// end of a step: x = LayerNorm(y[b]; gamma, beta); cmds_all[b, t, :] = x Wc^T + bc; argmax of the command logits and of the NPAR
+// parameter heads (params_all[b, t, i, :], already written); apply_action_mask + normalize_actions
+// (/root/reference/model/autoregressive_transformer.py:91-118) -> action_next[b, 0:1+NPAR]; finally *t_ptr += 1.
+struct DecSelect {
+  const float* y; const float* gamma; const float* beta;
+  const float* Wc; const float* bc; int NC;
+  int H, B, NPAR, NV, T;
+  float* cmds_all; float* params_all;
+  float* action_next;
+  int* t_ptr; unsigned int* done_ctr;
+};
+int dec_select(const DecSelect& a, stream_t s);
+
 // frame ingestion: uint8 grey-level frames -> the fp32 tensor the reference's loader hands the model,
 // i.e. torchvision ToTensor (u / 255) followed by Normalize(mean, std) (/root/reference/main.py:103-110: mean = std = 0.5):
 // dst[i] = (float(src[i]) / 255 - mean) / std, evaluated with the same fp32 operations in the same order (bit-exact)

@@ -440,6 +440,153 @@ int seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* s
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same step for a handful of sequences (B <= 16), bound by reading every weight once: 8 launches per layer (decode.cu) --
+//   K1 q|k|v of the new token (input rows built on load: token embedding for layer 0, LayerNorm3 of the previous layer
+//      otherwise) -> cache row (b, t)            K2 self-attention over cache rows [0, t], keys split over 4 CTAs per head
+//   K3 out_proj(merge of K2's partials) + x       K4 cross-attention query = W_q LayerNorm1(.)
+//   K5 cross-attention over the memory window     K6 out_proj(.) + x1
+//   K7 relu(linear1(LayerNorm2(.)))               K8 linear2(.) + x2
+// then the parameter head (LayerNorm3 on load) writes row (b, t) of params_all and dec_select_kernel finishes the step on the
+// device: command head, both argmaxes, action mask, normalisation -> actions_io (the next step's input), *t_dev += 1.
+// Nothing depends on the host: the launch sequence is identical for every position (the position is read from *t_dev), so one
+// captured CUDA graph replays for all T steps.  Same contract as seq_decode_step otherwise (one seq_forward first; eval mode).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr int DEC_SPLITS = 4;
+struct DevStepWs {
+  float *xn0, *xn1, *xn2, *y1, *y2, *y3, *q2, *f;
+  float *sa_o, *sa_ml, *ca_o, *ca_ml;
+  unsigned int* done;
+};
+void dev_step_carve(Arena& a, int B, int H, int Ff, int nh, DevStepWs& s) {
+  const size_t BH = (size_t)B * H;
+  s.xn0 = a.alloc<float>(BH); s.xn1 = a.alloc<float>(BH); s.xn2 = a.alloc<float>(BH);
+  s.y1 = a.alloc<float>(BH); s.y2 = a.alloc<float>(BH); s.y3 = a.alloc<float>(BH);
+  s.q2 = a.alloc<float>(BH); s.f = a.alloc<float>((size_t)B * Ff);
+  s.sa_o = a.alloc<float>(BH * DEC_SPLITS); s.sa_ml = a.alloc<float>((size_t)B * nh * DEC_SPLITS * 2);
+  s.ca_o = a.alloc<float>(BH); s.ca_ml = a.alloc<float>((size_t)B * nh * 2);
+  s.done = a.alloc<unsigned int>(64);
+}
+}  // namespace
+
+int seq_decode_dev_supported(const vc_seq_call* c) {
+  if (check_call(c)) return 0;
+  const int dh = c->H / c->nhead;
+  return c->past_actions && !c->training && c->B <= 16 && c->H % 128 == 0 && c->H <= 1024 && c->Ff % 128 == 0 && c->Ff <= 1024 &&
+         (dh == 64 || dh == 128 || dh == 256) && c->num_cmd <= 5 && c->num_param_out % 1000 == 0 && c->num_param_out / 1000 <= 6 &&
+         c->act_dim == 1 + c->num_param_out / 1000;
+}
+
+size_t seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nh) {
+  Arena a(nullptr, 0);
+  DevStepWs s;
+  dev_step_carve(a, B, H, Ff, nh, s);
+  return a.used();
+}
+
+int seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
+                        float* params_all, stream_t st) {
+  VC_TRY(check_call(c));
+  if (!t_dev || !actions_io || !scratch || !cmds_all || !params_all) return set_error("seq_decode_step_dev: null argument");
+  if (!seq_decode_dev_supported(c)) return set_error("seq_decode_step_dev: unsupported configuration (use vc_seq_decode_step)");
+  const vc_seq_weights& W = *c->w;
+  const Dims d = dims_of(c);
+  const int B = d.B, T = d.T, H = d.H, Ff = d.Ff;
+  Arena arena(c->ws, c->ws_bytes);
+  SeqWs w;
+  seq_carve(arena, B, T, H, Ff, d.L, d.nh, d.nv, w);
+  if (!arena.ok()) return set_error("seq_decode_step_dev: workspace too small");
+  Arena sa(scratch, scratch_bytes);
+  DevStepWs s;
+  dev_step_carve(sa, B, H, Ff, d.nh, s);
+  if (!sa.ok()) return set_error("seq_decode_step_dev: scratch too small");
+  const float scale = 1.0f / sqrtf((float)d.dh);
+
+  auto gemv = [&](DecGemv& g, const vc_linear& Lw, int64_t row0, int N, int K, float* out, int64_t row_stride, int64_t t_stride) -> int {
+    g.M = B; g.N = N; g.K = K;
+    g.W = Lw.w + row0 * K; g.bias = Lw.b ? Lw.b + row0 : nullptr;
+    g.out = out; g.out_row_stride = row_stride; g.out_t_stride = t_stride; g.t_ptr = t_dev;
+    return dec_gemv(g, st);
+  };
+  for (int l = 0; l < d.L; ++l) {
+    const vc_dec_layer& LW = W.layers[l];
+    SeqWs::Layer& Y = w.l[l];
+    {  // K1
+      DecGemv g = {};
+      if (l == 0) {
+        g.in_mode = VC_DEC_IN_EMBED; g.actions = actions_io; g.act_dim = c->act_dim;
+        g.emb_W = W.embed_action_w; g.emb_b = W.embed_action_b; g.emb_E = W.timestep_emb;
+      } else {
+        g.in_mode = VC_DEC_IN_LN; g.x = s.y3; g.ldx = H; g.gamma = W.layers[l - 1].n3.w; g.beta = W.layers[l - 1].n3.b;
+      }
+      g.x_out = s.xn0;
+      VC_TRY(gemv(g, LW.sa_in, 0, 3 * H, H, Y.qkv, (int64_t)T * 3 * H, 3 * H));
+    }
+    {  // K2
+      DecAttn a = {};
+      a.q = Y.qkv; a.q_bstride = (int64_t)T * 3 * H; a.q_tstride = 3 * H;
+      a.k = Y.qkv + H; a.v = Y.qkv + 2 * H; a.kv_bstride = (int64_t)T * 3 * H; a.kv_rstride = 3 * H;
+      a.nh = d.nh; a.dh = d.dh; a.nsplit = DEC_SPLITS; a.window = 0; a.scale = scale; a.t_ptr = t_dev;
+      a.part_o = s.sa_o; a.part_ml = s.sa_ml;
+      VC_TRY(dec_attn(a, B, st));
+    }
+    {  // K3
+      DecGemv g = {};
+      g.in_mode = VC_DEC_IN_ATTN; g.part_o = s.sa_o; g.part_ml = s.sa_ml; g.nsplit = DEC_SPLITS; g.nh = d.nh; g.dh = d.dh;
+      g.residual = s.xn0; g.ld_res = H;
+      VC_TRY(gemv(g, LW.sa_out, 0, H, H, s.y1, H, 0));
+    }
+    {  // K4
+      DecGemv g = {};
+      g.in_mode = VC_DEC_IN_LN; g.x = s.y1; g.ldx = H; g.gamma = LW.n1.w; g.beta = LW.n1.b; g.x_out = s.xn1;
+      VC_TRY(gemv(g, LW.ca_in, 0, H, H, s.q2, H, 0));
+    }
+    {  // K5
+      DecAttn a = {};
+      a.q = s.q2; a.q_bstride = H; a.q_tstride = 0;
+      a.k = Y.kv2; a.v = Y.kv2 + H; a.kv_bstride = (int64_t)T * 2 * H; a.kv_rstride = 2 * H;
+      a.nh = d.nh; a.dh = d.dh; a.nsplit = 1; a.window = c->window; a.scale = scale; a.t_ptr = t_dev;
+      a.part_o = s.ca_o; a.part_ml = s.ca_ml;
+      VC_TRY(dec_attn(a, B, st));
+    }
+    {  // K6
+      DecGemv g = {};
+      g.in_mode = VC_DEC_IN_ATTN; g.part_o = s.ca_o; g.part_ml = s.ca_ml; g.nsplit = 1; g.nh = d.nh; g.dh = d.dh;
+      g.residual = s.xn1; g.ld_res = H;
+      VC_TRY(gemv(g, LW.ca_out, 0, H, H, s.y2, H, 0));
+    }
+    {  // K7
+      DecGemv g = {};
+      g.in_mode = VC_DEC_IN_LN; g.x = s.y2; g.ldx = H; g.gamma = LW.n2.w; g.beta = LW.n2.b; g.x_out = s.xn2;
+      g.act = VC_ACT_RELU;
+      VC_TRY(gemv(g, LW.lin1, 0, Ff, H, s.f, Ff, 0));
+    }
+    {  // K8
+      DecGemv g = {};
+      g.in_mode = VC_DEC_IN_PLAIN; g.x = s.f; g.ldx = Ff;
+      g.residual = s.xn2; g.ld_res = H;
+      VC_TRY(gemv(g, LW.lin2, 0, H, Ff, s.y3, H, 0));
+    }
+  }
+  const vc_dec_layer& last = W.layers[d.L - 1];
+  {
+    DecGemv g = {};
+    g.in_mode = VC_DEC_IN_LN; g.x = s.y3; g.ldx = H; g.gamma = last.n3.w; g.beta = last.n3.b;
+    VC_TRY(gemv(g, W.head_params, 0, d.NP, H, params_all, (int64_t)T * d.NP, d.NP));
+  }
+  {
+    DecSelect a = {};
+    a.y = s.y3; a.gamma = last.n3.w; a.beta = last.n3.b;
+    a.Wc = W.head_cmd_w; a.bc = W.head_cmd_b; a.NC = d.NC;
+    a.H = H; a.B = B; a.NPAR = d.NP / 1000; a.NV = 1000; a.T = T;
+    a.cmds_all = cmds_all; a.params_all = params_all; a.action_next = actions_io;
+    a.t_ptr = t_dev; a.done_ctr = s.done;
+    VC_TRY(dec_select(a, st));
+  }
+  return 0;
+}
+
 int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                  float* d_mv_cls, void* scratch, size_t scratch_bytes, stream_t st) {
   VC_TRY(check_call(c));
@@ -654,6 +801,12 @@ size_t vc_seq_decode_scratch_bytes(int B, int H, int Ff, int nhead) { return vck
 int vc_seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* scratch, size_t scratch_bytes, float* cmds_t,
                        float* params_t, void* stream) {
   return vck::seq_decode_step(c, t, actions_t, scratch, scratch_bytes, cmds_t, params_t, stream);
+}
+int vc_seq_decode_dev_supported(const vc_seq_call* c) { return vck::seq_decode_dev_supported(c); }
+size_t vc_seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nhead) { return vck::seq_decode_dev_scratch_bytes(B, H, Ff, nhead); }
+int vc_seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
+                           float* params_all, void* stream) {
+  return vck::seq_decode_step_dev(c, t_dev, actions_io, scratch, scratch_bytes, cmds_all, params_all, stream);
 }
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                     float* d_mv_cls, void* scratch, size_t scratch_bytes, void* stream) {

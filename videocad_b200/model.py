@@ -678,6 +678,15 @@ class _SeqRunner(_Segment):
             c.dropout_p, c.training, c.seed, c.site_base, c.passes = 0.0, 0, 0, _SITE_SEQ, passes
             c.ws, c.ws_bytes, c.cmds, c.params = dec["ws"].data_ptr(), dec["ws_bytes"], dec["cmds_full"].data_ptr(), dec["params_full"].data_ptr()
             dec["call"], dec["W"], dec["arr"] = c, W, arr
+            # B <= 16 sequences: the whole step, action feedback included, runs on the device (vc_seq_decode_step_dev)
+            dec["fused"] = bool(lib.vc_seq_decode_dev_supported(C.byref(c))) and os.environ.get("VIDEOCAD_B200_DECODE_DEV", "1") != "0"
+            if dec["fused"]:
+                dec["t_dev"] = torch.zeros(1, dtype=torch.int32, device=dev)
+                dec["actions_io"] = torch.zeros(B, m.act_dim, **f32)
+                dec["cmds_all"], dec["params_all"] = torch.empty(B, T, NC, **f32), torch.empty(B, T, NP, **f32)
+                dec["dsc_bytes"] = lib.vc_seq_decode_dev_scratch_bytes(B, H, Ff, nh)
+                dec["dscratch"] = torch.zeros(dec["dsc_bytes"], dtype=torch.uint8, device=dev)
+                dec["dgraph"], dec["duses"] = None, 0
             if persistent:
                 if len(self._dstates) >= 2:
                     self._dstates.pop(next(iter(self._dstates)))
@@ -689,6 +698,35 @@ class _SeqRunner(_Segment):
         self.ensure_split(stream)  # the split-bf16 mirror follows the fp32 weights (refreshed in place when they changed)
         L.check(lib.vc_seq_forward(C.byref(dec["call"]), stream), lib)
         return dec
+
+    def decode_run(self, dec, T):
+        """All T positions of a rollout on the device: the step's launch sequence does not depend on the position (it is read from
+        a device counter the last kernel of a step advances), so ONE captured CUDA graph is replayed T times; the host only
+        enqueues.  -> (cmds [B, T, NC], params [B, T, NP])"""
+        lib = self.lib()
+        dec["t_dev"].zero_()
+        dec["actions_io"].zero_()
+
+        def body():
+            st = _stream_of(dec["cmds_all"])
+            L.check(lib.vc_seq_decode_step_dev(C.byref(dec["call"]), dec["t_dev"].data_ptr(), dec["actions_io"].data_ptr(),
+                                               dec["dscratch"].data_ptr(), dec["dsc_bytes"], dec["cmds_all"].data_ptr(),
+                                               dec["params_all"].data_ptr(), st), lib)
+
+        for t in range(T):
+            g = dec["dgraph"]
+            if g is not None:
+                g.replay()
+            elif dec["persistent"] and dec["duses"] >= 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    body()
+                dec["dgraph"] = g
+                g.replay()
+            else:
+                body()
+                dec["duses"] += 1
+        return dec["cmds_all"].clone(), dec["params_all"].clone()
 
     def decode_step(self, dec, t, action_t):
         lib = self.lib()
@@ -1024,6 +1062,12 @@ class AutoRegressiveTransformer(_FlatOwner):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
             ev[0].record()
         dec = seq_r.decode_begin(state_cls.reshape(B * T, -1) if state_cls is not None else None, cad_cls, B, T, passes)
+        if dec.get("fused"):
+            cmds, params = seq_r.decode_run(dec, T)
+            if ev is not None:
+                ev[1].record()
+                _ROLLOUT_EVENTS.append(tuple(ev))
+            return cmds, params.view(B, T, self.num_params, self.num_params_values)
         action_t = torch.zeros(B, self.act_dim, device=dev)
         out_c, out_p = [], []
         for t in range(T):
