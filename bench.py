@@ -217,7 +217,7 @@ def emit(line):
     out.flush()
 
 
-def measure_rollout(dev, peak, iters=3):
+def measure_rollout(dev, peak, world=1, iters=3):
     """BASELINE config C4 on one GPU: 8 sequences x 186 steps of action feedback through AutoRegressiveTransformer.sequential_inference
     (every frame encoded once, one key/value-cached decode step per position).  HBM roofline of the decode step: the decoder and head
     weights (read once per step) plus the self-attention cache rows read at step t, averaged over t."""
@@ -250,6 +250,12 @@ def measure_rollout(dev, peak, iters=3):
     assert cmds.shape == (B, T, 5) and params.shape == (B, T, 6, 1000) and bool(torch.isfinite(params).all())
     ms = sorted(total)[len(total) // 2]
     ms_dec = sorted(decode)[len(decode) // 2]
+    if world > 1:  # every rank rolls out its own 8 sequences (no communication): the job finishes with the slowest rank
+        import torch.distributed as dist
+
+        both = torch.tensor([ms, ms_dec], device=dev)
+        dist.all_reduce(both, op=dist.ReduceOp.MAX)
+        ms, ms_dec = both[0].item(), both[1].item()
     step_ms = ms_dec / T
     w_bytes = 4 * (L * (6 * H * H + 2 * H * Ff) + 6005 * H)            # in_proj (3), out_proj, cross q, cross out, linear1/2; heads
     kv_bytes = 4 * L * B * ((T + 1) / 2.0) * 2 * H                      # keys + values of the t+1 cached positions, mean over t
@@ -257,8 +263,9 @@ def measure_rollout(dev, peak, iters=3):
     gbs = step_bytes / (step_ms * 1e-3) / 1e9
     del m, frames, cad
     torch.cuda.empty_cache()
-    return dict(workload=f"c4: {B} sequences/GPU x {T} steps, H={H}, {S}x{S}, eval, argmax feedback (exact incremental decoding)",
-                ms_per_rollout=ms, frames_per_s=B * T / (ms / 1e3), ms_encode_frames=ms - ms_dec, ms_per_decode_step=step_ms,
+    return dict(workload=f"c4: {world} x ({B} sequences x {T} steps), H={H}, {S}x{S}, eval, argmax feedback (exact incremental decoding)",
+                n_gpus=world, sequences=world * B, ms_per_rollout=ms, frames_per_s=world * B * T / (ms / 1e3),
+                ms_encode_frames=ms - ms_dec, ms_per_decode_step=step_ms,
                 roofline=dict(bound="hbm", kernel="decode step (all kernels of one position)", achieved=gbs, peak=peak["hbm_gbs"], unit="GB/s",
                               frac=gbs / peak["hbm_gbs"], algorithmic_bytes_per_step=step_bytes,
                               note="fp32 decoder + head weights read once per step plus the cached keys/values of the positions so far "
@@ -563,7 +570,7 @@ def main():
     pending.clear()
     torch.cuda.empty_cache()
     c3 = measure_c3(args, rank, world, local_rank) if (world > 1 and args.config == "c1") else None
-    rollout = measure_rollout(dev, peak) if (rank == 0 and args.config == "c1" and not args.no_rollout) else None
+    rollout = measure_rollout(dev, peak, world) if (args.config == "c1" and not args.no_rollout) else None
 
     if rank != 0:
         if world > 1:
