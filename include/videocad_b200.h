@@ -245,6 +245,15 @@ int vc_linear_rows_fwd(const float* x, const vc_bf16* x_hi, const vc_bf16* x_lo,
  * dst[i] = (float(src[i]) / 255 - mean) / std with the same fp32 operations in the same order (bit-exact).
  * src and dst 16-byte aligned, n = number of pixels. */
 int vc_frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, void* stream);
+/* The whole frame transform of the reference's loader on the device: uint8 RGB frames [n, Hin, Win, 3], exactly as the dataset
+ * stores them (generate_dataset.py:194-199), -> the encoder's fp32 input [n, 1, Hout, Wout]; replaces
+ * Resize((224, 224)) -> Grayscale(1) -> ToTensor() -> Normalize([0.5], [0.5]) (main.py:103-108; per frame, through PIL, in
+ * DatasetBase.__getitem__, data_loader/data_loader.py:434-446).  Bit-exact with Pillow's 8-bit resampling / rgb2l arithmetic.
+ * kk_h / kk_v: Pillow's fixed-point bilinear coefficients [out, ks] (22 fractional bits), bounds_*: (first tap, tap count) [out, 2],
+ * both on the device (videocad_b200.ingest.resample_coeffs computes them); an axis whose size does not change needs none.
+ * tmp: uint8 [n, Hin, Wout, 3] when Win != Wout.  src 4-byte aligned, dst 16-byte aligned. */
+int vc_frames_rgb_u8_ingest(const uint8_t* src, int64_t n, int Hin, int Win, int Hout, int Wout, const int* kk_h, const int* bounds_h, int ks_h,
+                            const int* kk_v, const int* bounds_v, int ks_v, uint8_t* tmp, float mean, float std, float* dst, void* stream);
 int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
 int vc_zero_f32(float* x, int64_t n, void* stream);
 int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream);
@@ -364,6 +373,8 @@ int vc_seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void
  * on exit; the logits of the position go to row (b, t) of cmds_all [B, T, num_cmd] / params_all [B, T, num_param_out].  The launch
  * sequence does not depend on the position: one captured CUDA graph serves all T steps and the host is never consulted.
  * Every kernel is bound by reading its weights once (TMA bulk copies issued ahead of the dependency wait).
+ * scratch (>= vc_seq_decode_dev_scratch_bytes) must be ZERO-FILLED before the first step of the first rollout (it holds the arrival
+ * counters of the kernels, which every call leaves at zero again).
  * vc_seq_decode_dev_supported() != 0 tells whether the configuration is covered (otherwise use vc_seq_decode_step). */
 int vc_seq_decode_dev_supported(const vc_seq_call* c);
 size_t vc_seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nhead);

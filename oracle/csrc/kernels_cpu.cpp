@@ -521,6 +521,45 @@ int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int6
   return 0;
 }
 
+int frames_rgb_u8_ingest(const uint8_t* src, int64_t n, int Hin, int Win, int Hout, int Wout, const int* kk_h, const int* bounds_h, int ks_h,
+                         const int* kk_v, const int* bounds_v, int ks_v, uint8_t* tmp, float mean, float std, float* dst, stream_t) {
+  if (!src || !dst || n <= 0 || Hin <= 0 || Win <= 0 || Hout <= 0 || Wout <= 0) return set_error("frames_rgb_u8_ingest: bad arguments");
+  if (!(std != 0.f)) return set_error("frames_rgb_u8_ingest: std must be non-zero");
+  auto clip8 = [](int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); };
+  const uint8_t* cur = src;
+  if (Win != Wout) {
+    if (!kk_h || !bounds_h || !tmp) return set_error("frames_rgb_u8_ingest: horizontal pass needs coefficients and a temporary");
+    for (int64_t row = 0; row < n * Hin; ++row)
+      for (int xx = 0; xx < Wout; ++xx)
+        for (int c = 0; c < 3; ++c) {
+          int acc = 1 << 21;
+          for (int x = 0; x < bounds_h[2 * xx + 1]; ++x) acc += (int)src[(row * Win + bounds_h[2 * xx] + x) * 3 + c] * kk_h[(int64_t)xx * ks_h + x];
+          tmp[(row * Wout + xx) * 3 + c] = (uint8_t)clip8(acc >> 22);
+        }
+    cur = tmp;
+  }
+  for (int64_t f = 0; f < n; ++f)
+    for (int yy = 0; yy < Hout; ++yy)
+      for (int x = 0; x < Wout; ++x) {
+        int rgb[3];
+        for (int c = 0; c < 3; ++c) {
+          if (Hin != Hout) {
+            if (!kk_v || !bounds_v) return set_error("frames_rgb_u8_ingest: vertical pass needs coefficients");
+            int acc = 1 << 21;
+            for (int y = 0; y < bounds_v[2 * yy + 1]; ++y) acc += (int)cur[((f * Hin + bounds_v[2 * yy] + y) * Wout + x) * 3 + c] * kk_v[(int64_t)yy * ks_v + y];
+            rgb[c] = clip8(acc >> 22);
+          } else {
+            rgb[c] = cur[((f * Hin + yy) * Wout + x) * 3 + c];
+          }
+        }
+        const unsigned l = ((unsigned)rgb[0] * 19595u + (unsigned)rgb[1] * 38470u + (unsigned)rgb[2] * 7471u + 0x8000u) >> 16;
+        volatile float v = (float)l / 255.0f;
+        volatile float w = v - mean;
+        dst[(f * Hout + yy) * Wout + x] = w / std;
+      }
+  return 0;
+}
+
 int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t) {
   if (n > 0 && (!src || !dst)) return set_error("frames_u8_normalize: null pointer");
   if (!(std != 0.f)) return set_error("frames_u8_normalize: std must be non-zero");
@@ -804,21 +843,6 @@ int dec_gemv(const DecGemv& g, stream_t) {
         if (g.emb_E) acc += g.emb_E[(size_t)t * K + k];
         xr[k] = tanh(acc);
       }
-    } else {
-      for (int h = 0; h < g.nh; ++h) {
-        const size_t base = ((size_t)m * g.nh + h) * g.nsplit;
-        double mx = -INFINITY, den = 0.0;
-        for (int s2 = 0; s2 < g.nsplit; ++s2) mx = fmax(mx, (double)g.part_ml[(base + s2) * 2]);
-        for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] = 0.0;
-        for (int s2 = 0; s2 < g.nsplit; ++s2) {
-          const double ms = g.part_ml[(base + s2) * 2];
-          if (ms == -INFINITY) continue;
-          const double w = exp(ms - mx);
-          den += w * g.part_ml[(base + s2) * 2 + 1];
-          for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] += w * g.part_o[(base + s2) * g.dh + d];
-        }
-        for (int d = 0; d < g.dh; ++d) xr[h * g.dh + d] /= den;
-      }
     }
     if (g.x_out) for (int k = 0; k < K; ++k) g.x_out[(size_t)m * K + k] = (float)xr[k];
   }
@@ -841,37 +865,31 @@ int dec_gemv(const DecGemv& g, stream_t) {
 }
 
 int dec_attn(const DecAttn& a, int B, stream_t) {
-  if (B <= 0 || !a.q || !a.k || !a.v || !a.part_o || !a.part_ml || !a.t_ptr || a.nsplit < 1) return set_error("dec_attn: bad arguments");
+  if (B <= 0 || !a.q || !a.k || !a.v || !a.out || !a.t_ptr || a.nsplit < 1) return set_error("dec_attn: bad arguments");
   const int t = *a.t_ptr;
   const int j_lo = a.window > 0 ? (t - a.window + 1 > 0 ? t - a.window + 1 : 0) : 0;
   const int nkeys = t - j_lo + 1;
   for (int b = 0; b < B; ++b)
-    for (int h = 0; h < a.nh; ++h)
-      for (int s2 = 0; s2 < a.nsplit; ++s2) {
-        const float* q = a.q + (size_t)b * a.q_bstride + (size_t)t * a.q_tstride + h * a.dh;
-        std::vector<double> sc;
-        std::vector<int> js;
-        for (int i = s2; i < nkeys; i += a.nsplit) {  // any partition of the keys is valid: the merge is exact
-          const float* kr = a.k + (size_t)b * a.kv_bstride + (size_t)(j_lo + i) * a.kv_rstride + h * a.dh;
-          double d = 0.0;
-          for (int e = 0; e < a.dh; ++e) d += (double)q[e] * a.scale * kr[e];
-          sc.push_back(d);
-          js.push_back(j_lo + i);
-        }
-        const size_t pb = ((size_t)b * a.nh + h) * a.nsplit + s2;
-        double mx = -INFINITY, l = 0.0;
-        for (double v : sc) mx = fmax(mx, v);
-        std::vector<double> o(a.dh, 0.0);
-        for (size_t i = 0; i < sc.size(); ++i) {
-          const double p = exp(sc[i] - mx);
-          l += p;
-          const float* vr = a.v + (size_t)b * a.kv_bstride + (size_t)js[i] * a.kv_rstride + h * a.dh;
-          for (int e = 0; e < a.dh; ++e) o[e] += p * vr[e];
-        }
-        a.part_ml[pb * 2] = (float)mx;
-        a.part_ml[pb * 2 + 1] = (float)l;
-        for (int e = 0; e < a.dh; ++e) a.part_o[pb * a.dh + e] = (float)o[e];
+    for (int h = 0; h < a.nh; ++h) {
+      const float* q = a.q + (size_t)b * a.q_bstride + (size_t)t * a.q_tstride + h * a.dh;
+      std::vector<double> sc(nkeys);
+      double mx = -INFINITY, l = 0.0;
+      for (int i = 0; i < nkeys; ++i) {
+        const float* kr = a.k + (size_t)b * a.kv_bstride + (size_t)(j_lo + i) * a.kv_rstride + h * a.dh;
+        double d = 0.0;
+        for (int e = 0; e < a.dh; ++e) d += (double)q[e] * a.scale * kr[e];
+        sc[i] = d;
+        mx = fmax(mx, d);
       }
+      std::vector<double> o(a.dh, 0.0);
+      for (int i = 0; i < nkeys; ++i) {
+        const double p = exp(sc[i] - mx);
+        l += p;
+        const float* vr = a.v + (size_t)b * a.kv_bstride + (size_t)(j_lo + i) * a.kv_rstride + h * a.dh;
+        for (int e = 0; e < a.dh; ++e) o[e] += p * vr[e];
+      }
+      for (int e = 0; e < a.dh; ++e) a.out[(size_t)b * a.ld_out + h * a.dh + e] = (float)(o[e] / l);
+    }
   return 0;
 }
 

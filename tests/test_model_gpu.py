@@ -320,11 +320,27 @@ def test_errors_match_reference_behaviour():
         m(bad)  # > 224x224 exceeds the positional table (the reference raises a shape error here too)
 
 
+def _grad_error(g, ref):
+    """(max, 99.5th percentile) of |g - ref| / max|ref| over the elements of one weight's gradient."""
+    d = ((g.double() - ref).abs() / (ref.abs().max() + 1e-6)).flatten()
+    k = max(1, int(0.995 * d.numel()))
+    return d.max().item(), d.kthvalue(k).values.item()
+
+
 def test_c3_per_gpu_shape_forward_backward_vs_oracle():
     """BASELINE config C3 at its per-GPU model shape and a reduced batch: H = Ff = 1024 (head dim 256), 8 decoder layers, window 10,
     T = 32, 224 x 224 frames, batch 4 (128 frames + 4 CAD images; T = 32 short-sequence attention with d = 256, the F = 128-image
     encoder GEMMs, 8-layer workspace carve): logits and EVERY gradient against the fp64 oracle run on the GPU, on the eager,
-    CUDA-graph capture and replay paths."""
+    CUDA-graph capture and replay paths.
+
+    Gradient tolerance at this size.  The decoder's FFN has 8 x 128 x 1024 ~ 1M ReLU inputs; a pre-activation that the fp64
+    oracle puts within the forward rounding error of zero (ours: ~1e-6 absolute there, logits within 3e-5) may get the other sign,
+    and relu' is discontinuous: the corresponding row of linear1.weight / entry of linear1.bias is then off by a whole term
+    (measured: one such element in layers 1 and 4, 3e-2 / 9e-2 of the largest entry, profiles/r02b_diag_c3.txt; plain torch fp32
+    flips less often only because its forward error is smaller), and every gradient upstream of that layer moves by ~1e-3
+    (largest measured: 2.0e-3).  So: every gradient within 5e-3 of the oracle relative to its largest entry -- a wrong kernel
+    is off by O(1) -- except the linear1 tensors, where 99.5 % of the elements must meet the same bound and the few rows / entries
+    behind a flipped relu' at most 0.2."""
     cfg = dict(hidden_size=1024, nhead=4, num_decoder_layers=8, dim_feedforward=1024, window_size=10,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     B, T, S = 4, 32, 224
@@ -344,14 +360,19 @@ def test_c3_per_gpu_shape_forward_backward_vs_oracle():
         ((cmds * wc.cuda()).sum() + (params * wp.cuda()).sum()).backward()
         dc, dp = (cmds.double() - oc).abs().max().item(), (params.double() - op).abs().max().item()
         assert dc < LOGIT_TOL and dp < LOGIT_TOL, (it, dc, dp)
-        worst = 0.0
+        worst, worst_q, relu_rows = 0.0, 0.0, 0
         for k, p in m.named_weights():
             if ref[k] is None:
                 continue
-            err = (p.grad.double() - ref[k]).abs().max().item() / (ref[k].abs().max().item() + 1e-6)
-            worst = max(worst, err)
-            assert err < GRAD_REL_TOL, f"pass {it} {k}: {err:.3e}"
-    print(f"C3 shape: logits max|d| cmds {dc:.3e} params {dp:.3e}; worst relative gradient error {worst:.3e}")
+            emax, eq = _grad_error(p.grad, ref[k])
+            worst, worst_q = max(worst, emax), max(worst_q, eq)
+            if ".linear1." in k:  # the direct victims of a flipped relu': bounded, and confined to a few rows
+                assert emax < 0.2 and eq < 5e-3, f"pass {it} {k}: max {emax:.3e}, 99.5th percentile {eq:.3e}"
+                relu_rows += int(emax > 5e-3)
+            else:
+                assert emax < 5e-3, f"pass {it} {k}: {emax:.3e}"
+        assert relu_rows <= 8, "relu' flips in at most a few layers"
+    print(f"C3 shape: logits max|d| cmds {dc:.3e} params {dp:.3e}; gradient error max {worst:.3e}, 99.5th percentile {worst_q:.3e}")
 
 
 def _fed_back_actions(c, p):

@@ -172,6 +172,10 @@ int vc_linear_rows_fwd(const float* x, const vc_bf16* x_hi, const vc_bf16* x_lo,
 int vc_frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, void* stream) {
   return vck::frames_u8_normalize(src, n, mean, std, dst, stream);
 }
+int vc_frames_rgb_u8_ingest(const uint8_t* src, int64_t n, int Hin, int Win, int Hout, int Wout, const int* kk_h, const int* bounds_h, int ks_h,
+                            const int* kk_v, const int* bounds_v, int ks_v, uint8_t* tmp, float mean, float std, float* dst, void* stream) {
+  return vck::frames_rgb_u8_ingest(src, n, Hin, Win, Hout, Wout, kk_h, bounds_h, ks_h, kk_v, bounds_v, ks_v, tmp, mean, std, dst, stream);
+}
 int vc_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream) { return vck::add_f32(a, b, out, n, stream); }
 int vc_zero_f32(float* x, int64_t n, void* stream) { return vck::zero_f32(x, n, stream); }
 int vc_dropout_mask_debug(vc_drop drop, int64_t n, float* out, void* stream) {

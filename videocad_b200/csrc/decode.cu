@@ -12,11 +12,11 @@
 //     of the chain is still running (programmatic dependent launch).  Each thread owns one float4 slot of the K dimension for all
 //     B rows (x lives in registers); a halving butterfly reduces the B partial sums of a column with log-many shuffles.
 //     The input rows are built on load: plain rows, LayerNorm of the previous sub-layer's sum (two-pass statistics, as
-//     ln_fwd_kernel), tanh(embed_action(a) + E[t]) for the first layer, or the merge of the attention kernel's split partials
-//     -- so LayerNorm, the token embedding and the softmax merge cost no launches of their own.
+//     ln_fwd_kernel) or tanh(embed_action(a) + E[t]) for the first layer -- so LayerNorm and the token embedding cost no
+//     launches of their own.
 //   * dec_attn_kernel  one query row per (sequence, head) against the cached keys/values: the keys are split over `nsplit` CTAs
-//     and 8 warps each (online softmax per warp, merged in shared memory); partial (max, sum, acc) go to global and are merged by
-//     the consuming out-projection GEMV.
+//     and 8 warps each (online softmax per warp, merged in shared memory); each CTA leaves its partial (max, sum, acc) in global
+//     memory and the LAST one to arrive (atomic ticket) merges them into the attention output: no second launch.
 //   * dec_select_kernel  final LayerNorm + command head + argmax of both heads + action mask + normalisation: the next action is
 //     written on the device and the position counter advances there, so the 186-step loop never returns to the host and ONE
 //     captured CUDA graph serves every position.
@@ -193,40 +193,49 @@ __global__ void __launch_bounds__(DG_THREADS) dec_gemv_kernel(const DecGemv a) {
         }
       }
     }
-  } else {  // VC_DEC_IN_ATTN: merge the attention kernel's split partials (online-softmax combine), K = nh * dh
-    if (active) {
-      const int h = k0 / a.dh, d = k0 - h * a.dh;
-#pragma unroll
-      for (int m = 0; m < MM; ++m) {
-        if (m < M) {
-          const size_t base = ((size_t)m * a.nh + h) * a.nsplit;
-          float mx = -INFINITY;
-          for (int s = 0; s < a.nsplit; ++s) mx = fmaxf(mx, a.part_ml[(base + s) * 2]);
-          float den = 0.f;
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int s = 0; s < a.nsplit; ++s) {
-            const float ms = a.part_ml[(base + s) * 2];
-            if (ms == -INFINITY) continue;  // a split that saw no key
-            const float w = __expf(ms - mx);
-            den += w * a.part_ml[(base + s) * 2 + 1];
-            const float4 o = *reinterpret_cast<const float4*>(a.part_o + (base + s) * a.dh + d);
-            acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
-          }
-          const float inv = 1.0f / den;
-          x[m] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-        }
-      }
-    }
   }
   if (a.x_out != nullptr && blockIdx.x == 0 && active) {  // the rows just built are the residual operand of a later kernel
 #pragma unroll
     for (int m = 0; m < MM; ++m)
       if (m < M) *reinterpret_cast<float4*>(a.x_out + (size_t)m * K + k0) = x[m];
   }
+  // ---------------------------------------------------------------- epilogue operands do not depend on the dot products: request them now
+  const int e_m = tid / cols, e_c = tid - e_m * cols;
+  const bool e_on = tid < cols * M;
+  float e_bias = 0.f, e_res = 0.f;
+  if (e_on) {
+    if (a.bias) e_bias = __ldg(a.bias + n0 + e_c);
+    if (a.residual) e_res = a.residual[(size_t)e_m * a.ld_res + n0 + e_c];
+  }
   // ---------------------------------------------------------------- dot products against the weight slab
   mbar_wait(bar, 0);
   constexpr int kShift = MM == 8 ? 2 : 1;
-  for (int c = 0; c < cols; ++c) {
+  int c = 0;
+  for (; c + 4 <= cols; c += 4) {  // four columns per iteration: four independent load / FMA / shuffle chains
+    float p0[MM], p1[MM], p2[MM], p3[MM];
+    if (active) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wsm + (size_t)(c + 0) * K + k0);
+      const float4 w1 = *reinterpret_cast<const float4*>(wsm + (size_t)(c + 1) * K + k0);
+      const float4 w2 = *reinterpret_cast<const float4*>(wsm + (size_t)(c + 2) * K + k0);
+      const float4 w3 = *reinterpret_cast<const float4*>(wsm + (size_t)(c + 3) * K + k0);
+#pragma unroll
+      for (int m = 0; m < MM; ++m) {
+        p0[m] = fmaf(w0.x, x[m].x, fmaf(w0.y, x[m].y, fmaf(w0.z, x[m].z, w0.w * x[m].w)));
+        p1[m] = fmaf(w1.x, x[m].x, fmaf(w1.y, x[m].y, fmaf(w1.z, x[m].z, w1.w * x[m].w)));
+        p2[m] = fmaf(w2.x, x[m].x, fmaf(w2.y, x[m].y, fmaf(w2.z, x[m].z, w2.w * x[m].w)));
+        p3[m] = fmaf(w3.x, x[m].x, fmaf(w3.y, x[m].y, fmaf(w3.z, x[m].z, w3.w * x[m].w)));
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < MM; ++m) p0[m] = p1[m] = p2[m] = p3[m] = 0.f;
+    }
+    const float r0 = reduce_rows<MM>(p0, lane), r1 = reduce_rows<MM>(p1, lane), r2 = reduce_rows<MM>(p2, lane), r3 = reduce_rows<MM>(p3, lane);
+    if ((lane & ((1 << kShift) - 1)) == 0) {
+      float* dst = part + ((size_t)c * DG_WARPS + warp) * MM + (lane >> kShift);
+      dst[0] = r0; dst[DG_WARPS * MM] = r1; dst[2 * DG_WARPS * MM] = r2; dst[3 * DG_WARPS * MM] = r3;
+    }
+  }
+  for (; c < cols; ++c) {
     float p[MM];
     if (active) {
       const float4 w4 = *reinterpret_cast<const float4*>(wsm + (size_t)c * K + k0);
@@ -242,24 +251,49 @@ __global__ void __launch_bounds__(DG_THREADS) dec_gemv_kernel(const DecGemv a) {
   __syncthreads();
   // ---------------------------------------------------------------- epilogue: consecutive threads <-> consecutive columns
   for (int idx = tid; idx < cols * M; idx += DG_THREADS) {
-    const int m = idx / cols, c = idx - m * cols;
-    const int n = n0 + c;
+    const int m = idx / cols, cc = idx - m * cols;
+    const int n = n0 + cc;
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < DG_WARPS; ++w) v += part[((size_t)c * DG_WARPS + w) * MM + m];
-    if (a.bias) v += __ldg(a.bias + n);
+    for (int w = 0; w < DG_WARPS; ++w) v += part[((size_t)cc * DG_WARPS + w) * MM + m];
+    const bool first = idx == tid;  // operands of the first round were requested before the dot products
+    if (a.bias) v += first ? e_bias : __ldg(a.bias + n);
     v = apply_act(v, a.act);
-    if (a.residual) v += a.residual[(size_t)m * a.ld_res + n];
+    if (a.residual) v += first ? e_res : a.residual[(size_t)m * a.ld_res + n];
     a.out[(size_t)m * a.out_row_stride + (size_t)t * a.out_t_stride + n] = v;
   }
 }
 
 // ------------------------------------------------------------------------------------------------- attention of one query row
 template <int DPL>
+struct VecLd;
+template <>
+struct VecLd<2> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+};
+template <>
+struct VecLd<4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <>
+struct VecLd<8> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[8]) {
+    const float4 t = *reinterpret_cast<const float4*>(p), u = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; v[4] = u.x; v[5] = u.y; v[6] = u.z; v[7] = u.w;
+  }
+};
+
+constexpr int DA_KEYS = 4;  // keys per warp iteration: all their key / value rows are requested before the first reduction
+
+template <int DPL>
 __global__ void __launch_bounds__(DG_THREADS) dec_attn_kernel(const DecAttn a) {
   pdl_grid_sync();
   __shared__ float sm_m[DG_WARPS], sm_l[DG_WARPS];
   __shared__ float sm_acc[DG_WARPS][32 * DPL];
+  __shared__ unsigned int sm_ticket;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int t = *a.t_ptr;
@@ -267,68 +301,94 @@ __global__ void __launch_bounds__(DG_THREADS) dec_attn_kernel(const DecAttn a) {
   const int nkeys = t - j_lo + 1;
   const int d0 = h * a.dh + lane * DPL;
   float q[DPL];
-  {
-    const float* qp = a.q + (size_t)b * a.q_bstride + (size_t)t * a.q_tstride + d0;
+  VecLd<DPL>::ld(a.q + (size_t)b * a.q_bstride + (size_t)t * a.q_tstride + d0, q);
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) q[i] = qp[i] * a.scale;
-  }
+  for (int i = 0; i < DPL; ++i) q[i] *= a.scale;
   float mrun = -INFINITY, lrun = 0.f, acc[DPL];
 #pragma unroll
   for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
   const float* kb = a.k + (size_t)b * a.kv_bstride + d0;
   const float* vb = a.v + (size_t)b * a.kv_bstride + d0;
   const int stride = a.nsplit * DG_WARPS;
-  for (int i = s * DG_WARPS + warp; i < nkeys; i += 2 * stride) {
-    // two keys per iteration: both keys' and values' loads are in flight before the first reduction
-    const int i1 = i + stride;
-    const bool has1 = i1 < nkeys;
-    const float* k0p = kb + (size_t)(j_lo + i) * a.kv_rstride;
-    const float* v0p = vb + (size_t)(j_lo + i) * a.kv_rstride;
-    const float* k1p = kb + (size_t)(j_lo + (has1 ? i1 : i)) * a.kv_rstride;
-    const float* v1p = vb + (size_t)(j_lo + (has1 ? i1 : i)) * a.kv_rstride;
-    float k0[DPL], k1[DPL], v0[DPL], v1[DPL];
+  for (int i = s * DG_WARPS + warp; i < nkeys; i += DA_KEYS * stride) {
+    float kk[DA_KEYS][DPL], vv[DA_KEYS][DPL], sc[DA_KEYS];
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) { k0[e] = k0p[e]; k1[e] = k1p[e]; }
+    for (int u = 0; u < DA_KEYS; ++u) {
+      const int iu = i + u * stride;
+      const size_t row = (size_t)(j_lo + (iu < nkeys ? iu : i)) * a.kv_rstride;  // past the end: re-read a valid row, weight 0
+      VecLd<DPL>::ld(kb + row, kk[u]);
+      VecLd<DPL>::ld(vb + row, vv[u]);
+    }
+    float mnew = mrun;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) { v0[e] = v0p[e]; v1[e] = v1p[e]; }
-    float s0 = 0.f, s1 = 0.f;
+    for (int u = 0; u < DA_KEYS; ++u) {
+      float d = 0.f;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) { s0 = fmaf(q[e], k0[e], s0); s1 = fmaf(q[e], k1[e], s1); }
-    s0 = warp_sum(s0);
-    s1 = has1 ? warp_sum(s1) : -INFINITY;  // has1 is warp-uniform
-    const float mnew = fmaxf(mrun, fmaxf(s0, s1));
-    const float corr = __expf(mrun - mnew), p0 = __expf(s0 - mnew), p1 = has1 ? __expf(s1 - mnew) : 0.f;
-    lrun = lrun * corr + p0 + p1;
+      for (int e = 0; e < DPL; ++e) d = fmaf(q[e], kk[u][e], d);
+      d = warp_sum(d);
+      sc[u] = (i + u * stride < nkeys) ? d : -INFINITY;  // warp-uniform
+      mnew = fmaxf(mnew, sc[u]);
+    }
+    const float corr = __expf(mrun - mnew);  // mnew is finite: key i exists
+    lrun *= corr;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) acc[e] = acc[e] * corr + p0 * v0[e] + p1 * v1[e];
+    for (int e = 0; e < DPL; ++e) acc[e] *= corr;
+#pragma unroll
+    for (int u = 0; u < DA_KEYS; ++u) {
+      const float p = __expf(sc[u] - mnew);  // exp(-inf) = 0 for the keys past the end
+      lrun += p;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[e] = fmaf(p, vv[u][e], acc[e]);
+    }
     mrun = mnew;
   }
   if (lane == 0) { sm_m[warp] = mrun; sm_l[warp] = lrun; }
 #pragma unroll
   for (int e = 0; e < DPL; ++e) sm_acc[warp][lane * DPL + e] = acc[e];
   __syncthreads();
-  const size_t pbase = ((size_t)b * a.nh + h) * a.nsplit + s;
+  // merge the 8 warps of this CTA
   float mx = -INFINITY;
 #pragma unroll
   for (int w = 0; w < DG_WARPS; ++w) mx = fmaxf(mx, sm_m[w]);
-  if (tid < a.dh) {
-    float o = 0.f;
-    if (mx != -INFINITY) {
+  float o = 0.f, l = 0.f;
+  if (mx != -INFINITY) {
 #pragma unroll
-      for (int w = 0; w < DG_WARPS; ++w)
-        if (sm_m[w] != -INFINITY) o += __expf(sm_m[w] - mx) * sm_acc[w][tid];
+    for (int w = 0; w < DG_WARPS; ++w) {
+      if (sm_m[w] != -INFINITY) {
+        const float e = __expf(sm_m[w] - mx);
+        l += e * sm_l[w];
+        if (tid < a.dh) o += e * sm_acc[w][tid];
+      }
     }
-    a.part_o[pbase * a.dh + tid] = o;
   }
-  if (tid == 0) {
-    float l = 0.f;
-    if (mx != -INFINITY) {
-#pragma unroll
-      for (int w = 0; w < DG_WARPS; ++w)
-        if (sm_m[w] != -INFINITY) l += __expf(sm_m[w] - mx) * sm_l[w];
+  float* outp = a.out + (size_t)b * a.ld_out + h * a.dh;
+  if (a.nsplit == 1) {  // a single part: finished
+    if (tid < a.dh) outp[tid] = o / l;
+    return;
+  }
+  const size_t pbase = ((size_t)b * a.nh + h) * a.nsplit;
+  if (tid < a.dh) a.part_o[(pbase + s) * a.dh + tid] = o;
+  if (tid == 0) { a.part_ml[(pbase + s) * 2] = mx; a.part_ml[(pbase + s) * 2 + 1] = l; }
+  // the last part of this (sequence, head) to arrive merges all of them (no second launch, no extra pass in the consumer)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sm_ticket = atomicAdd(a.counters + (size_t)b * a.nh + h, 1u);
+  __syncthreads();
+  if (sm_ticket != (unsigned int)(a.nsplit - 1)) return;
+  __threadfence();
+  if (tid == 0) a.counters[(size_t)b * a.nh + h] = 0u;  // ready for the next launch
+  float gm = -INFINITY;
+  for (int s2 = 0; s2 < a.nsplit; ++s2) gm = fmaxf(gm, __ldcg(a.part_ml + (pbase + s2) * 2));
+  if (tid < a.dh) {
+    float den = 0.f, num = 0.f;
+    for (int s2 = 0; s2 < a.nsplit; ++s2) {
+      const float ms = __ldcg(a.part_ml + (pbase + s2) * 2);
+      if (ms == -INFINITY) continue;  // a part that saw no key
+      const float w = __expf(ms - gm);
+      den += w * __ldcg(a.part_ml + (pbase + s2) * 2 + 1);
+      num += w * __ldcg(a.part_o + (pbase + s2) * a.dh + tid);
     }
-    a.part_ml[pbase * 2] = mx;
-    a.part_ml[pbase * 2 + 1] = l;
+    outp[tid] = num / den;
   }
 }
 
@@ -430,8 +490,6 @@ int dec_gemv(const DecGemv& g, stream_t s) {
   if (g.M <= 0 || g.M > 16) return set_error("dec_gemv: 1..16 rows");
   if (g.K <= 0 || g.K % 128 != 0 || g.K > 4 * DG_THREADS) return set_error("dec_gemv: K must be a multiple of 128 and <= 1024");
   if (g.N <= 0 || !g.W || !g.out) return set_error("dec_gemv: null weight / output or empty problem");
-  if (g.in_mode == VC_DEC_IN_ATTN && (g.nh * g.dh != g.K || g.dh % 4 != 0 || !g.part_o || !g.part_ml || g.nsplit < 1))
-    return set_error("dec_gemv: bad attention-partial input");
   if ((g.in_mode == VC_DEC_IN_PLAIN || g.in_mode == VC_DEC_IN_LN) && (!g.x || g.ldx % 4 != 0)) return set_error("dec_gemv: bad input rows");
   if (g.in_mode == VC_DEC_IN_LN && (!g.gamma || !g.beta)) return set_error("dec_gemv: LayerNorm input needs gamma / beta");
   if (g.in_mode == VC_DEC_IN_EMBED && (!g.actions || !g.emb_W || !g.emb_b)) return set_error("dec_gemv: bad embedding input");
@@ -459,7 +517,9 @@ int dec_gemv(const DecGemv& g, stream_t s) {
 }
 
 int dec_attn(const DecAttn& a, int B, stream_t s) {
-  if (B <= 0 || a.nh <= 0 || a.nsplit < 1 || !a.q || !a.k || !a.v || !a.part_o || !a.part_ml || !a.t_ptr) return set_error("dec_attn: bad arguments");
+  if (B <= 0 || a.nh <= 0 || a.nsplit < 1 || !a.q || !a.k || !a.v || !a.out || !a.t_ptr) return set_error("dec_attn: bad arguments");
+  if (a.nsplit > 1 && (!a.part_o || !a.part_ml || !a.counters)) return set_error("dec_attn: split keys need the partial buffers and counters");
+  if (a.q_bstride % 4 != 0 || a.q_tstride % 4 != 0 || a.kv_bstride % 4 != 0 || a.kv_rstride % 4 != 0) return set_error("dec_attn: strides must be multiples of 4");
   if (a.dh != 64 && a.dh != 128 && a.dh != 256) return set_error("dec_attn: head dim must be 64, 128 or 256");
   const dim3 grid(a.nsplit, a.nh, B);
   if (a.dh == 64) VC_LAUNCH((dec_attn_kernel<2>), grid, DG_THREADS, 0, cs(s), a);

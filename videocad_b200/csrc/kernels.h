@@ -175,16 +175,14 @@ int linear_rows_fwd(const float* x, const bf16_t* x_hi, const bf16_t* x_lo, int6
 // with t = *t_ptr (0 if null).  The input rows x [M, K] are built on load according to in_mode:
 //   PLAIN  x = rows of `x` (ldx)                                   LN     x = LayerNorm(rows of `x`; gamma, beta, eps 1e-5)
 //   EMBED  x = tanh(actions[M, act_dim] emb_W^T + emb_b + emb_E[t])  (K = hidden size, emb_W [K, act_dim], emb_E [*, K] or null)
-//   ATTN   x[m, h*dh + d] = softmax-merge over the nsplit partials written by dec_attn (K = nh * dh)
 // x_out (optional, [M, K]): receives the rows that were built (the residual operand of a later call).
-enum { VC_DEC_IN_PLAIN = 0, VC_DEC_IN_LN = 1, VC_DEC_IN_EMBED = 2, VC_DEC_IN_ATTN = 3 };
+enum { VC_DEC_IN_PLAIN = 0, VC_DEC_IN_LN = 1, VC_DEC_IN_EMBED = 2 };
 struct DecGemv {
   int in_mode;
   const float* x; long long ldx;
   const float* gamma; const float* beta;
   float* x_out;
   const float* actions; int act_dim; const float* emb_W; const float* emb_b; const float* emb_E;
-  const float* part_o; const float* part_ml; int nsplit; int nh; int dh;
   int M, N, K;
   const float* W; const float* bias;
   int act;
@@ -196,15 +194,17 @@ struct DecGemv {
 int dec_gemv(const DecGemv& g, stream_t s);
 // attention of ONE query row per (sequence b, head h) at position t = *t_ptr against keys j in [0, t] (window == 0) or
 // (t - window, t] (window > 0):  q row = q + b*q_bstride + t*q_tstride, key/value row j = k|v + b*kv_bstride + j*kv_rstride, head h =
-// columns [h*dh, (h+1)*dh).  The keys are split over nsplit parts; part s writes its running max / sum to part_ml[b, h, s, 0:2] and
-// its unnormalised accumulator to part_o[b, h, s, 0:dh] (merged by dec_gemv's ATTN input mode).
+// columns [h*dh, (h+1)*dh).  out[b*ld_out + h*dh + d] receives softmax(q k^T) v.  The keys may be split over nsplit parts that run
+// concurrently; they meet through part_o [B, nh, nsplit, dh] / part_ml [B, nh, nsplit, 2] / counters [B, nh] (zero before the first
+// call, left zero by every call).
 struct DecAttn {
   const float* q; long long q_bstride; long long q_tstride;
   const float* k; const float* v; long long kv_bstride; long long kv_rstride;
   int nh, dh, nsplit, window;
   float scale;
   const int* t_ptr;
-  float* part_o; float* part_ml;
+  float* out; long long ld_out;
+  float* part_o; float* part_ml; unsigned int* counters;
 };
 int dec_attn(const DecAttn& a, int B, stream_t s);
 // end of a step: x = LayerNorm(y[b]; gamma, beta); cmds_all[b, t, :] = x Wc^T + bc; argmax of the command logits and of the NPAR
@@ -224,6 +224,13 @@ int dec_select(const DecSelect& a, stream_t s);
 // i.e. torchvision ToTensor (u / 255) followed by Normalize(mean, std) (/root/reference/main.py:103-110: mean = std = 0.5):
 // dst[i] = (float(src[i]) / 255 - mean) / std, evaluated with the same fp32 operations in the same order (bit-exact)
 int frames_u8_normalize(const uint8_t* src, int64_t n, float mean, float std, float* dst, stream_t s);
+// uint8 RGB frames [n, Hin, Win, 3] (as stored in the dataset) -> fp32 [n, 1, Hout, Wout]: the whole frame transform of the reference's
+// loader, Resize((Hout, Wout)) -> Grayscale(1) -> ToTensor -> Normalize(mean, std) (main.py:103-108), bit-exact with Pillow's
+// 8-bit arithmetic (ingest.cu).  kk_* / bounds_*: Pillow's fixed-point resampling coefficients [out, ks] and (first tap, tap count)
+// pairs [out, 2] per axis, device-resident, needed only for an axis whose size changes; tmp: uint8 [n, Hin, Wout, 3], needed only
+// when the width changes.
+int frames_rgb_u8_ingest(const uint8_t* src, int64_t n, int Hin, int Win, int Hout, int Wout, const int* kk_h, const int* bounds_h, int ks_h,
+                         const int* kk_v, const int* bounds_v, int ks_v, uint8_t* tmp, float mean, float std, float* dst, stream_t s);
 
 // misc
 int add_f32(const float* a, const float* b, float* out, int64_t n, stream_t s);  // out = a + b (b may alias out)

@@ -443,8 +443,8 @@ int seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* s
 // ---------------------------------------------------------------------------------------------------------------------
 // The same step for a handful of sequences (B <= 16), bound by reading every weight once: 8 launches per layer (decode.cu) --
 //   K1 q|k|v of the new token (input rows built on load: token embedding for layer 0, LayerNorm3 of the previous layer
-//      otherwise) -> cache row (b, t)            K2 self-attention over cache rows [0, t], keys split over 4 CTAs per head
-//   K3 out_proj(merge of K2's partials) + x       K4 cross-attention query = W_q LayerNorm1(.)
+//      otherwise) -> cache row (b, t)            K2 self-attention over cache rows [0, t], keys split over 8 CTAs per head
+//   K3 out_proj(.) + x                            K4 cross-attention query = W_q LayerNorm1(.)
 //   K5 cross-attention over the memory window     K6 out_proj(.) + x1
 //   K7 relu(linear1(LayerNorm2(.)))               K8 linear2(.) + x2
 // then the parameter head (LayerNorm3 on load) writes row (b, t) of params_all and dec_select_kernel finishes the step on the
@@ -453,20 +453,21 @@ int seq_decode_step(const vc_seq_call* c, int t, const float* actions_t, void* s
 // captured CUDA graph replays for all T steps.  Same contract as seq_decode_step otherwise (one seq_forward first; eval mode).
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
-constexpr int DEC_SPLITS = 4;
+constexpr int DEC_SPLITS = 8;  // self-attention keys of one (sequence, head) are split over this many CTAs
 struct DevStepWs {
-  float *xn0, *xn1, *xn2, *y1, *y2, *y3, *q2, *f;
-  float *sa_o, *sa_ml, *ca_o, *ca_ml;
-  unsigned int* done;
+  float *xn0, *xn1, *xn2, *y1, *y2, *y3, *q2, *f, *sa, *ca;
+  float *part_o, *part_ml;
+  unsigned int *counters, *done;
 };
 void dev_step_carve(Arena& a, int B, int H, int Ff, int nh, DevStepWs& s) {
   const size_t BH = (size_t)B * H;
+  s.counters = a.alloc<unsigned int>((size_t)B * nh);  // zero before the first step, left zero by every kernel
+  s.done = a.alloc<unsigned int>(64);                  // likewise
   s.xn0 = a.alloc<float>(BH); s.xn1 = a.alloc<float>(BH); s.xn2 = a.alloc<float>(BH);
   s.y1 = a.alloc<float>(BH); s.y2 = a.alloc<float>(BH); s.y3 = a.alloc<float>(BH);
   s.q2 = a.alloc<float>(BH); s.f = a.alloc<float>((size_t)B * Ff);
-  s.sa_o = a.alloc<float>(BH * DEC_SPLITS); s.sa_ml = a.alloc<float>((size_t)B * nh * DEC_SPLITS * 2);
-  s.ca_o = a.alloc<float>(BH); s.ca_ml = a.alloc<float>((size_t)B * nh * 2);
-  s.done = a.alloc<unsigned int>(64);
+  s.sa = a.alloc<float>(BH); s.ca = a.alloc<float>(BH);
+  s.part_o = a.alloc<float>(BH * DEC_SPLITS); s.part_ml = a.alloc<float>((size_t)B * nh * DEC_SPLITS * 2);
 }
 }  // namespace
 
@@ -528,12 +529,12 @@ int seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, voi
       a.q = Y.qkv; a.q_bstride = (int64_t)T * 3 * H; a.q_tstride = 3 * H;
       a.k = Y.qkv + H; a.v = Y.qkv + 2 * H; a.kv_bstride = (int64_t)T * 3 * H; a.kv_rstride = 3 * H;
       a.nh = d.nh; a.dh = d.dh; a.nsplit = DEC_SPLITS; a.window = 0; a.scale = scale; a.t_ptr = t_dev;
-      a.part_o = s.sa_o; a.part_ml = s.sa_ml;
+      a.out = s.sa; a.ld_out = H; a.part_o = s.part_o; a.part_ml = s.part_ml; a.counters = s.counters;
       VC_TRY(dec_attn(a, B, st));
     }
     {  // K3
       DecGemv g = {};
-      g.in_mode = VC_DEC_IN_ATTN; g.part_o = s.sa_o; g.part_ml = s.sa_ml; g.nsplit = DEC_SPLITS; g.nh = d.nh; g.dh = d.dh;
+      g.in_mode = VC_DEC_IN_PLAIN; g.x = s.sa; g.ldx = H;
       g.residual = s.xn0; g.ld_res = H;
       VC_TRY(gemv(g, LW.sa_out, 0, H, H, s.y1, H, 0));
     }
@@ -547,12 +548,12 @@ int seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, voi
       a.q = s.q2; a.q_bstride = H; a.q_tstride = 0;
       a.k = Y.kv2; a.v = Y.kv2 + H; a.kv_bstride = (int64_t)T * 2 * H; a.kv_rstride = 2 * H;
       a.nh = d.nh; a.dh = d.dh; a.nsplit = 1; a.window = c->window; a.scale = scale; a.t_ptr = t_dev;
-      a.part_o = s.ca_o; a.part_ml = s.ca_ml;
+      a.out = s.ca; a.ld_out = H;
       VC_TRY(dec_attn(a, B, st));
     }
     {  // K6
       DecGemv g = {};
-      g.in_mode = VC_DEC_IN_ATTN; g.part_o = s.ca_o; g.part_ml = s.ca_ml; g.nsplit = 1; g.nh = d.nh; g.dh = d.dh;
+      g.in_mode = VC_DEC_IN_PLAIN; g.x = s.ca; g.ldx = H;
       g.residual = s.xn1; g.ld_res = H;
       VC_TRY(gemv(g, LW.ca_out, 0, H, H, s.y2, H, 0));
     }

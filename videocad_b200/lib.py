@@ -120,6 +120,7 @@ _PROTOS = {
     "vc_head_small_bwd": ([vp, vp, i64, i32, vp, i32, vp, i32, vp, vp, vp], i32),
     "vc_linear_rows_fwd": ([vp, vp, vp, i64, i32, vp, vp, i32, i32, i32, vp, i64, vp, i64, vp, vp, i64, vp], i32),
     "vc_frames_u8_normalize": ([vp, i64, f32, f32, vp, vp], i32),
+    "vc_frames_rgb_u8_ingest": ([vp, i64, i32, i32, i32, i32, vp, vp, i32, vp, vp, i32, vp, f32, f32, vp, vp], i32),
     "vc_add_f32": ([vp, vp, vp, i64, vp], i32),
     "vc_zero_f32": ([vp, i64, vp], i32),
     "vc_dropout_mask_debug": ([Drop, i64, vp, vp], i32),
