@@ -116,14 +116,18 @@ __global__ void __launch_bounds__(DG_THREADS) dec_gemv_kernel(const DecGemv a) {
   const int n0 = blockIdx.x * a.cols_per_cta;
   const int cols = min(a.cols_per_cta, a.N - n0);
   const int K = a.K, M = a.M;
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-    // the CTA's weight rows [n0, n0 + cols) x K are contiguous in the row-major [N, K] weight: one bulk copy.  Issued before the
+  if (warp == 0) {
+    // The CTA's weight rows [n0, n0 + cols) x K are one contiguous slab of the row-major [N, K] weight.  It is fetched as one TMA
+    // bulk copy PER ROW, issued by the lanes of warp 0: a single 96 KB copy is processed as one serial request stream (measured:
+    // ~6 B/clk per SM, profiles/r02c_rollout_launches.csv), many 2-4 KB copies are in flight together.  Issued before the
     // dependency wait: weights are constants of the rollout.
-    const uint32_t bytes = (uint32_t)cols * (uint32_t)K * 4u;
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(wsm, a.W + (size_t)n0 * K, bytes, bar);
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      fence_barrier_init();
+      mbar_expect_tx(bar, (uint32_t)cols * (uint32_t)K * 4u);
+    }
+    __syncwarp();
+    for (int c = lane; c < cols; c += 32) bulk_g2s(wsm + (size_t)c * K, a.W + (size_t)(n0 + c) * K, (uint32_t)K * 4u, bar);
   }
   __syncthreads();  // the initialised barrier is visible to every thread that will wait on it
   pdl_wait();

@@ -593,6 +593,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   using C = PCfg<PBN>;
   constexpr int P_STAGES = C::STAGES, P_STAGE_BYTES = C::STAGE_BYTES, P_BN = PBN;
+  __shared__ long long ptl[16];  // VC_GEMM_DEBUG & 8: clock64 timeline of the leader CTA of cluster 0 (experiment)
+  const bool ptlon = (p.debug & 8) && blockIdx.x == 0;
+  if (ptlon && threadIdx.x == 0) { for (int i = 0; i < 16; ++i) ptl[i] = 0; ptl[0] = clock64(); }
   extern __shared__ uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);  // used in the leader CTA only
   uint64_t* empty_bar = full_bar + P_STAGES;
@@ -632,6 +635,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (ptlon && threadIdx.x == 0) ptl[1] = clock64();
   pdl_wait();
 
   const int num_m = (p.M + P_BM - 1) / P_BM;
@@ -719,6 +723,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           const uint32_t ph = (it / P_STAGES) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (ptlon && lane == 0 && kb == kb0 && acc_it < 2) ptl[2 + 4 * acc_it] = clock64();  // first stage of the tile landed
           const uint32_t sA_hi = smem_u32(tiles + s * P_STAGE_BYTES);
           const uint32_t sA_lo = sA_hi + P_TILE_BYTES;
           const uint32_t sB_hi = sA_hi + 2 * P_TILE_BYTES;
@@ -743,6 +748,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         if (elect_one()) umma_commit_pair(&tfull_bar[a]);  // accumulator complete -> both CTAs' epilogue warps
         __syncwarp();
+        if (ptlon && lane == 0 && acc_it < 2) ptl[3 + 4 * acc_it] = clock64();  // last MMA of the tile issued
       }
     }
     __syncwarp();
@@ -766,6 +772,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       const uint32_t aph = (acc_it >> 1) & 1u;
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
+      if (ptlon && warp == 2 && lane == 0 && acc_it < 2) ptl[4 + 4 * acc_it] = clock64();  // accumulator ready
       constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
       for (int c = 0; c < kCols / P_CW; ++c) {
@@ -848,11 +855,19 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         __syncwarp();
       }
+      if (ptlon && warp == 2 && lane == 0 && acc_it < 2) ptl[5 + 4 * acc_it] = clock64();  // this warp's epilogue of the tile done
     }
   }
 
   tc_fence_before();
   cluster_sync_all();
+  if (ptlon && threadIdx.x == 0) {
+    const long long z = ptl[0];
+    printf("pair timeline M%d N%d K%d BN%d (cycles since entry): setup %lld | tile0: first stage %lld, MMAs issued %lld, acc ready %lld, epilogue done %lld | "
+           "tile1: first stage %lld, MMAs issued %lld, acc ready %lld, epilogue done %lld | all done %lld\n",
+           p.M, p.N, p.K, PBN, ptl[1] - z, ptl[2] - z, ptl[3] - z, ptl[4] - z, ptl[5] - z, ptl[6] ? ptl[6] - z : 0, ptl[7] ? ptl[7] - z : 0,
+           ptl[8] ? ptl[8] - z : 0, ptl[9] ? ptl[9] - z : 0, clock64() - z);
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
