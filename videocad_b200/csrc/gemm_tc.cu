@@ -761,6 +761,40 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
     const DropKey seed = epilogue_seed<F>(p);
+    // Operands of the epilogue that do not depend on the accumulator (residual, activation-backward operand) are requested ONE
+    // 16-column chunk ahead: the first chunk of a tile before the wait for its accumulator (they fly during the MMAs), every other
+    // chunk while the previous one is read from TMEM, computed and stored.  Requested at the top of their own chunk, every
+    // chunk began with an exposed L2 / HBM round trip: 11-13 k cycles per 128 x 256 tile for the loads alone -- as long as the
+    // tile's MMAs (clock64 timeline, profiles/r02d_pair_timeline.txt).
+    constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
+    struct Pre {
+      float4 res[kPreRes ? 4 : 1];
+      float4 aux[kPreAux ? 4 : 1];
+    };
+    bool has_res = false, has_aux = false;
+    if constexpr (kPreRes) has_res = p.residual != nullptr;
+    if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+    auto preload = [&](Pre& P, int m0, int col0) {
+      const int pcol = col0 + 4 * (lane & 3);
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
+        const bool ok = prow < p.M && pcol < p.N;
+        if constexpr (kPreRes) {
+          P.res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res && ok) P.res[it] = *reinterpret_cast<const float4*>(p.residual + prow * p.ld_res + pcol);
+        }
+        if constexpr (kPreAux) {
+          P.aux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_aux && ok) P.aux[it] = *reinterpret_cast<const float4*>(p.act_aux + prow * p.ld_act_aux + pcol);
+        }
+      }
+    };
+    Pre nxt;
+    if (cluster_id < total_tiles) {
+      const int t2 = cluster_id / num_n;
+      preload(nxt, (t2 % num_m) * P_BM + (int)rank * 128, (cluster_id % num_n) * P_BN + hc * kCols);
+    }
     uint32_t acc_it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
       const int n_idx = tile % num_n;
@@ -776,27 +810,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
       for (int c = 0; c < kCols / P_CW; ++c) {
-        // The epilogue is latency-bound (4 warps per scheduler, each iteration behind a global load): issue this chunk's
-        // residual / activation-backward operand loads first, so that they fly during the TMEM read and the staging.
-        constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
-        float4 pres[kPreRes ? 4 : 1], paux[kPreAux ? 4 : 1];
-        bool has_res = false, has_aux = false;
-        {
-          const int pcol = n0 + c * P_CW + 4 * (lane & 3);
-          if constexpr (kPreRes) has_res = p.residual != nullptr;
-          if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
-            const bool ok = prow < p.M && pcol < p.N;
-            if constexpr (kPreRes) {
-              pres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (has_res && ok) pres[it] = *reinterpret_cast<const float4*>(p.residual + prow * p.ld_res + pcol);
-            }
-            if constexpr (kPreAux) {
-              paux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (has_aux && ok) paux[it] = *reinterpret_cast<const float4*>(p.act_aux + prow * p.ld_act_aux + pcol);
-            }
+        const Pre cur = nxt;
+        if (c + 1 < kCols / P_CW) {
+          preload(nxt, m0, n0 + (c + 1) * P_CW);
+        } else {
+          const int ntile = tile + num_clusters;
+          if (ntile < total_tiles) {  // first chunk of this cluster's next tile
+            const int nt2 = ntile / num_n;
+            preload(nxt, (nt2 % num_m) * P_BM + (int)rank * 128, (ntile % num_n) * P_BN + hc * kCols);
           }
         }
         uint32_t r[P_CW];
@@ -833,8 +854,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             if (p.debug & 1) {  // VC_GEMM_DEBUG = 1: no epilogue math, no global stores
               if (v[0] == 123.456f) p.out_f32[0] = v[1];
             } else {
-              epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
-                               paux[kPreAux ? it : 0]);
+              epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, cur.res[kPreRes ? it : 0], kPreAux && has_aux,
+                               cur.aux[kPreAux ? it : 0]);
             }
             if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
           }
