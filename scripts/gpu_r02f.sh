@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x > gpurun_out/r02f_pytest.txt 2>&1
+tail -3 gpurun_out/r02f_pytest.txt
+VC_GEMM_DEBUG=8 timeout 300 python scripts/gemm_bench.py --only "epi fc2 fwd,epi out fwd,epi fc2 dgrad" --iters 1 > gpurun_out/r02f_pair_timeline.txt 2>&1
+timeout 300 python scripts/gemm_bench.py --only "epi" > gpurun_out/r02f_gemm_bench.txt 2>&1
+cat gpurun_out/r02f_gemm_bench.txt
+VC_GEMM_L2PRE=0 timeout 300 python scripts/gemm_bench.py --only "epi" > gpurun_out/r02f_gemm_bench_nopre.txt 2>&1
+cat gpurun_out/r02f_gemm_bench_nopre.txt
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-rollout > gpurun_out/r02f_bench_c1.json 2> gpurun_out/r02f_bench_c1.err
+python -c "import json; d=json.load(open('gpurun_out/r02f_bench_c1.json')); print(d['value'], d['ms_per_step'], d['segments_ms_per_step'], d['roofline']['frac'])"
+VC_GEMM_L2PRE=0 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-rollout > gpurun_out/r02f_bench_c1_nopre.json 2> gpurun_out/r02f_bench_c1_nopre.err
+python -c "import json; d=json.load(open('gpurun_out/r02f_bench_c1_nopre.json')); print(d['value'], d['ms_per_step'], d['segments_ms_per_step'], d['roofline']['frac'])"

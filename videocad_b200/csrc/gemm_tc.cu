@@ -53,6 +53,7 @@ struct GemmParams {
   const __nv_bfloat16* act_aux_hi; long long ld_act_aux_hi;
   float* colsum;
   int debug;  // VC_GEMM_DEBUG (profiling experiments only): 1 = no global stores, 2 = TMEM loads only, 4 = no TMEM loads
+  int pre_l2;  // pair kernel: the residual / activation-backward operand has a tensor map (tmE): prefetch each tile's slab into L2
 };
 
 template <int BN>
@@ -585,11 +586,16 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
+// asynchronous prefetch of a 2-D box into L2 (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+
 template <uint32_t F, int EW, int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmE, const GemmParams p) {
   pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   using C = PCfg<PBN>;
   constexpr int P_STAGES = C::STAGES, P_STAGE_BYTES = C::STAGE_BYTES, P_BN = PBN;
@@ -656,6 +662,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + (int)rank * C::B_ROWS;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        if constexpr ((F & (EF_RES | EF_ACTBWD)) != 0) {
+          // The epilogue of this tile will read this CTA's 128 x PBN fp32 slab of the residual (or of the activation-backward
+          // operand) with ordinary loads, whose throughput is in-flight capacity / latency: pull the slab into L2 now, while the
+          // tile's MMAs run, so that those loads pay an L2 hit instead of an HBM round trip (the operand was written several
+          // kernels ago and has usually been evicted).  One asynchronous TMA prefetch per 128-byte-wide box, no destination.
+          if (p.pre_l2 && elect_one()) {
+#pragma unroll
+            for (int j = 0; j < P_BN / 32; ++j) tma_prefetch_l2_2d(&tmE, n_idx * P_BN + 32 * j, m0);
+          }
+          __syncwarp();
+        }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1u;
@@ -918,7 +935,7 @@ PFN_encodeTiled get_encode_fn() {
 // cuTensorMapEncodeTiled costs a few microseconds of host time; the same (buffer, shape) pairs recur every training step
 // (weights, persistent workspaces), so encoded maps are cached.
 struct TmapKey {
-  const void* base; int64_t rows, cols, ld; int box_cols, box_rows;
+  const void* base; int64_t rows, cols, ld; int box_cols, box_rows;  // box_rows < 0: fp32 map without swizzle (L2 prefetch boxes)
   bool operator==(const TmapKey& o) const {
     return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows;
   }
@@ -947,6 +964,28 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int
   if (int rc = make_tmap_uncached(tm, base, rows, cols, ld, box_cols, box_rows)) return rc;
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *tm);
+  return 0;
+}
+
+// fp32 matrix [rows, cols] (leading dimension ld), box = {box_cols, box_rows}, no swizzle: used for L2 prefetch boxes only
+int make_tmap_f32(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  TmapKey key{base, rows, cols, ld, box_cols, -box_rows};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *tm = it->second; return 0; }
+  }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (fp32) failed");
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
   g_tmap_cache.emplace(key, *tm);
   return 0;
 }
@@ -1157,6 +1196,18 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   fill_params(p, d, splitk);
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, C::B_ROWS)) return rc;  // each CTA stages half of the tile's B rows
+  CUtensorMap tE = tA_hi;  // placeholder when the epilogue has no fp32 operand to prefetch
+  {
+    static int l2pre = -1;
+    if (l2pre < 0) { const char* e = getenv("VC_GEMM_L2PRE"); l2pre = e ? atoi(e) : 1; }
+    const float* eop = nullptr; long long eld = 0;
+    if ((F & EF_RES) != 0 && d.residual) { eop = d.residual; eld = d.ld_res; }
+    else if ((F & EF_ACTBWD) != 0 && d.act_backward && d.act_aux) { eop = d.act_aux; eld = d.ld_act_aux; }
+    if (l2pre && eop && (reinterpret_cast<uintptr_t>(eop) & 15) == 0 && eld % 4 == 0 && d.N % 32 == 0) {
+      if (int rc = make_tmap_f32(&tE, eop, d.M, d.N, eld, 32, 128)) return rc;
+      p.pre_l2 = 1;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F, EW, PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
@@ -1171,7 +1222,7 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act, PBN);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  VC_LAUNCH((gemm_tc_pair_kernel<F, EW, PBN>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
+  VC_LAUNCH((gemm_tc_pair_kernel<F, EW, PBN>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, tE, p);
   count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_pair_kernel");
