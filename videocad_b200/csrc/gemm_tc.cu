@@ -557,9 +557,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 constexpr int P_BM = 256;
 constexpr int P_MAX_EW = 16;                         // epilogue warps per CTA (template parameter EW: 8 or 16)
 constexpr int P_TILE_BYTES = 128 * BK * 2;           // 16 KiB: one 128-row operand tile (hi or lo)
-constexpr int P_CW = 16;                             // epilogue chunk width (columns)
-constexpr int P_STG_LD = 16;                         // floats per staged row: unpadded, float4 slots XOR-swizzled by (row >> 1) & 3
-constexpr int P_STG_BYTES = P_MAX_EW * 32 * P_STG_LD * 4;
+// epilogue chunk width (columns) per warp pass: 16 with 16 epilogue warps, 32 with 8 (the per-warp 32 x CW fp32 staging buffers
+// share 32 KiB either way).  With 32 columns every row segment a warp loads / stores is a full 128-byte line.
+template <int EW>
+struct PEpi {
+  static constexpr int CW = EW == 16 ? 16 : 32;
+  static constexpr int LPR = CW / 4;        // lanes per row in the coalesced phase (one float4 each)
+  static constexpr int RPI = 32 / LPR;      // rows per warp instruction
+  static constexpr int ITS = 32 / RPI;      // iterations over the chunk's 32 rows
+};
+constexpr int P_STG_BYTES = 32 * 1024;
 constexpr int P_BAR_BYTES = 256;
 // Tile width PBN (template parameter): 256, or 128 for problems whose 256-wide tiling leaves the last wave mostly empty.
 // The N = 512 image-encoder GEMMs at C1 are 100 tiles of 256 x 256 on 74 SM pairs: two waves for 1.35 waves of work, and
@@ -662,17 +669,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         const int m0 = m_idx * P_BM + (int)rank * 128, n0 = n_idx * P_BN + (int)rank * C::B_ROWS;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        if constexpr ((F & (EF_RES | EF_ACTBWD)) != 0) {
-          // The epilogue of this tile will read this CTA's 128 x PBN fp32 slab of the residual (or of the activation-backward
-          // operand) with ordinary loads, whose throughput is in-flight capacity / latency: pull the slab into L2 now, while the
-          // tile's MMAs run, so that those loads pay an L2 hit instead of an HBM round trip (the operand was written several
-          // kernels ago and has usually been evicted).  One asynchronous TMA prefetch per 128-byte-wide box, no destination.
-          if (p.pre_l2 && elect_one()) {
-#pragma unroll
-            for (int j = 0; j < P_BN / 32; ++j) tma_prefetch_l2_2d(&tmE, n_idx * P_BN + 32 * j, m0);
-          }
-          __syncwarp();
-        }
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % P_STAGES;
           const uint32_t ph = (it / P_STAGES) & 1u;
@@ -704,6 +700,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
             for (int j = 0; j < C::B_ROWS / 64; ++j) {
               tma_load_2d_pair(sB_hi + j * 8192, &tmB_hi, fb, n0 + 64 * j, k0);
               if (p.passes == 3) tma_load_2d_pair(sB_lo + j * 8192, &tmB_lo, fb, n0 + 64 * j, k0);
+            }
+          }
+          if constexpr ((F & (EF_RES | EF_ACTBWD)) != 0) {
+            // The epilogue of this tile will read this CTA's 128 x PBN fp32 slab of the residual (or of the activation-backward
+            // operand) with ordinary loads, whose throughput is in-flight capacity / latency: pull the slab into L2 while the
+            // tile's MMAs run, so that those loads pay an L2 hit instead of an HBM round trip (the operand was written several
+            // kernels ago and has usually been evicted).  Asynchronous TMA prefetches without destination, queued behind the
+            // first operand stages so that they do not delay the start of the main loop.
+            if (p.pre_l2 && kb == min(kb0 + 2, kb1 - 1)) {
+#pragma unroll
+              for (int j = 0; j < P_BN / 32; ++j) tma_prefetch_l2_2d(&tmE, n_idx * P_BN + 32 * j, m_idx * P_BM + (int)rank * 128);
             }
           }
         }
@@ -776,6 +783,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int kCols = P_BN * 4 / EW;  // columns per epilogue warp: 128 (EW = 8) or 64 (EW = 16)
     const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
+    using E = PEpi<EW>;
+    constexpr int P_CW = E::CW, P_STG_LD = E::CW, LPR = E::LPR, RPI = E::RPI, ITS = E::ITS;
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
     const DropKey seed = epilogue_seed<F>(p);
     // Operands of the epilogue that do not depend on the accumulator (residual, activation-backward operand) are requested ONE
@@ -785,17 +794,17 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     // tile's MMAs (clock64 timeline, profiles/r02d_pair_timeline.txt).
     constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
     struct Pre {
-      float4 res[kPreRes ? 4 : 1];
-      float4 aux[kPreAux ? 4 : 1];
+      float4 res[kPreRes ? ITS : 1];
+      float4 aux[kPreAux ? ITS : 1];
     };
     bool has_res = false, has_aux = false;
     if constexpr (kPreRes) has_res = p.residual != nullptr;
     if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
     auto preload = [&](Pre& P, int m0, int col0) {
-      const int pcol = col0 + 4 * (lane & 3);
+      const int pcol = col0 + 4 * (lane % LPR);
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
+      for (int it = 0; it < ITS; ++it) {
+        const long long prow = (long long)m0 + g * 32 + it * RPI + (lane / LPR);
         const bool ok = prow < p.M && pcol < p.N;
         if constexpr (kPreRes) {
           P.res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -824,7 +833,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       if (ptlon && warp == 2 && lane == 0 && acc_it < 2) ptl[4 + 4 * acc_it] = clock64();  // accumulator ready
-      constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
+      constexpr int kUnrollIt = ITS;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
       for (int c = 0; c < kCols / P_CW; ++c) {
         const Pre cur = nxt;
@@ -839,7 +848,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         }
         uint32_t r[P_CW];
         if (!(p.debug & 4)) {
-          tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW, r);
+          const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW;
+          if constexpr (P_CW == 16) tmem_ld_32x16(taddr, r); else tmem_ld_32x32(taddr, r);
           tmem_ld_wait();
         }
         if (c == kCols / P_CW - 1) {
@@ -852,21 +862,25 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           continue;
         }
         const int col0 = n0 + c * P_CW;
+        // staging: thread = accumulator row; the row's float4 slots are XOR-swizzled so that both the row-wise writes and the
+        // coalesced reads below are bank-conflict free (16 columns: 4 slots, key (row >> 1) & 3; 32 columns: 8 slots, key row & 7)
         float* myrow = stg + lane * P_STG_LD;
+        const int wkey = P_CW == 16 ? ((lane >> 1) & 3) : (lane & 7);
 #pragma unroll
         for (int q = 0; q < P_CW / 4; ++q)
-          *reinterpret_cast<float4*>(myrow + 4 * (q ^ ((lane >> 1) & 3))) =
+          *reinterpret_cast<float4*>(myrow + 4 * (q ^ wkey)) =
               make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         __syncwarp();
-        const int q = lane & 3;
+        const int q = lane % LPR;
         const int col = col0 + 4 * q;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll kUnrollIt
-        for (int it = 0; it < 4; ++it) {
-          const int rr = it * 8 + (lane >> 2);
+        for (int it = 0; it < ITS; ++it) {
+          const int rr = it * RPI + (lane / LPR);
           const long long row = (long long)m0 + g * 32 + rr;
           if (row < p.M && col < p.N) {
-            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ ((rr >> 1) & 3)));
+            const int rkey = P_CW == 16 ? ((rr >> 1) & 3) : (rr & 7);
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ rkey));
             float v[4] = {t4.x, t4.y, t4.z, t4.w};
             if (p.debug & 1) {  // VC_GEMM_DEBUG = 1: no epilogue math, no global stores
               if (v[0] == 123.456f) p.out_f32[0] = v[1];
@@ -878,14 +892,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           }
         }
         if constexpr ((F & EF_COLSUM) != 0) {
-          if (p.colsum != nullptr) {  // combine the 8 lanes that share a column quad
+          if (p.colsum != nullptr) {  // combine the lanes that share a column quad (lane % LPR)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+              if constexpr (LPR == 4) cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
               cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
               cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
             }
-            if (lane < 4 && col < p.N) {
+            if (lane < LPR && col < p.N) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
             }
