@@ -53,7 +53,6 @@ struct GemmParams {
   const __nv_bfloat16* act_aux_hi; long long ld_act_aux_hi;
   float* colsum;
   int debug;  // VC_GEMM_DEBUG (profiling experiments only): 1 = no global stores, 2 = TMEM loads only, 4 = no TMEM loads
-  int pre_l2;  // pair kernel: the residual / activation-backward operand has a tensor map (tmE): prefetch each tile's slab into L2
 };
 
 template <int BN>
@@ -557,16 +556,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 constexpr int P_BM = 256;
 constexpr int P_MAX_EW = 16;                         // epilogue warps per CTA (template parameter EW: 8 or 16)
 constexpr int P_TILE_BYTES = 128 * BK * 2;           // 16 KiB: one 128-row operand tile (hi or lo)
-// epilogue chunk width (columns) per warp pass: 16 with 16 epilogue warps, 32 with 8 (the per-warp 32 x CW fp32 staging buffers
-// share 32 KiB either way).  With 32 columns every row segment a warp loads / stores is a full 128-byte line.
-template <int EW>
-struct PEpi {
-  static constexpr int CW = EW == 16 ? 16 : 32;
-  static constexpr int LPR = CW / 4;        // lanes per row in the coalesced phase (one float4 each)
-  static constexpr int RPI = 32 / LPR;      // rows per warp instruction
-  static constexpr int ITS = 32 / RPI;      // iterations over the chunk's 32 rows
-};
-constexpr int P_STG_BYTES = 32 * 1024;
+constexpr int P_CW = 16;                             // epilogue chunk width (columns)
+constexpr int P_STG_LD = 16;                         // floats per staged row: unpadded, float4 slots XOR-swizzled by (row >> 1) & 3
+constexpr int P_STG_BYTES = P_MAX_EW * 32 * P_STG_LD * 4;
 constexpr int P_BAR_BYTES = 256;
 // Tile width PBN (template parameter): 256, or 128 for problems whose 256-wide tiling leaves the last wave mostly empty.
 // The N = 512 image-encoder GEMMs at C1 are 100 tiles of 256 x 256 on 74 SM pairs: two waves for 1.35 waves of work, and
@@ -593,16 +585,11 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "memory");
 }
 
-// asynchronous prefetch of a 2-D box into L2 (no shared-memory destination, no completion to wait for)
-__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
-}
-
 template <uint32_t F, int EW, int PBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                     const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                    const __grid_constant__ CUtensorMap tmE, const GemmParams p) {
+                    const GemmParams p) {
   pdl_trigger();  // the wait follows the barrier / TMEM set-up, which touches no global memory
   using C = PCfg<PBN>;
   constexpr int P_STAGES = C::STAGES, P_STAGE_BYTES = C::STAGE_BYTES, P_BN = PBN;
@@ -702,17 +689,6 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
               if (p.passes == 3) tma_load_2d_pair(sB_lo + j * 8192, &tmB_lo, fb, n0 + 64 * j, k0);
             }
           }
-          if constexpr ((F & (EF_RES | EF_ACTBWD)) != 0) {
-            // The epilogue of this tile will read this CTA's 128 x PBN fp32 slab of the residual (or of the activation-backward
-            // operand) with ordinary loads, whose throughput is in-flight capacity / latency: pull the slab into L2 while the
-            // tile's MMAs run, so that those loads pay an L2 hit instead of an HBM round trip (the operand was written several
-            // kernels ago and has usually been evicted).  Asynchronous TMA prefetches without destination, queued behind the
-            // first operand stages so that they do not delay the start of the main loop.
-            if (p.pre_l2 && kb == min(kb0 + 2, kb1 - 1)) {
-#pragma unroll
-              for (int j = 0; j < P_BN / 32; ++j) tma_prefetch_l2_2d(&tmE, n_idx * P_BN + 32 * j, m_idx * P_BM + (int)rank * 128);
-            }
-          }
         }
       }
       // tail: wait until every stage-free arrival the leader's MMA commits multicast to this CTA has landed, so that no
@@ -783,44 +759,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
     constexpr int kCols = P_BN * 4 / EW;  // columns per epilogue warp: 128 (EW = 8) or 64 (EW = 16)
     const uint32_t tempty_remote0 = mapa_shared(smem_u32(&tempty_bar[0]), 0);
     const uint32_t tempty_remote1 = mapa_shared(smem_u32(&tempty_bar[1]), 0);
-    using E = PEpi<EW>;
-    constexpr int P_CW = E::CW, P_STG_LD = E::CW, LPR = E::LPR, RPI = E::RPI, ITS = E::ITS;
     float* stg = reinterpret_cast<float*>(tiles + P_STAGES * P_STAGE_BYTES) + (warp - 2) * 32 * P_STG_LD;
     const DropKey seed = epilogue_seed<F>(p);
-    // Operands of the epilogue that do not depend on the accumulator (residual, activation-backward operand) are requested ONE
-    // 16-column chunk ahead: the first chunk of a tile before the wait for its accumulator (they fly during the MMAs), every other
-    // chunk while the previous one is read from TMEM, computed and stored.  Requested at the top of their own chunk, every
-    // chunk began with an exposed L2 / HBM round trip: 11-13 k cycles per 128 x 256 tile for the loads alone -- as long as the
-    // tile's MMAs (clock64 timeline, profiles/r02d_pair_timeline.txt).
-    constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
-    struct Pre {
-      float4 res[kPreRes ? ITS : 1];
-      float4 aux[kPreAux ? ITS : 1];
-    };
-    bool has_res = false, has_aux = false;
-    if constexpr (kPreRes) has_res = p.residual != nullptr;
-    if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
-    auto preload = [&](Pre& P, int m0, int col0) {
-      const int pcol = col0 + 4 * (lane % LPR);
-#pragma unroll
-      for (int it = 0; it < ITS; ++it) {
-        const long long prow = (long long)m0 + g * 32 + it * RPI + (lane / LPR);
-        const bool ok = prow < p.M && pcol < p.N;
-        if constexpr (kPreRes) {
-          P.res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res && ok) P.res[it] = *reinterpret_cast<const float4*>(p.residual + prow * p.ld_res + pcol);
-        }
-        if constexpr (kPreAux) {
-          P.aux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_aux && ok) P.aux[it] = *reinterpret_cast<const float4*>(p.act_aux + prow * p.ld_act_aux + pcol);
-        }
-      }
-    };
-    Pre nxt;
-    if (cluster_id < total_tiles) {
-      const int t2 = cluster_id / num_n;
-      preload(nxt, (t2 % num_m) * P_BM + (int)rank * 128, (cluster_id % num_n) * P_BN + hc * kCols);
-    }
     uint32_t acc_it = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters, ++acc_it) {
       const int n_idx = tile % num_n;
@@ -833,23 +773,35 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       if (ptlon && warp == 2 && lane == 0 && acc_it < 2) ptl[4 + 4 * acc_it] = clock64();  // accumulator ready
-      constexpr int kUnrollIt = ITS;  // fully unrolled: the preloaded operands are indexed by `it`
+      constexpr int kUnrollIt = 4;  // fully unrolled: the preloaded operands are indexed by `it`
 #pragma unroll 1
       for (int c = 0; c < kCols / P_CW; ++c) {
-        const Pre cur = nxt;
-        if (c + 1 < kCols / P_CW) {
-          preload(nxt, m0, n0 + (c + 1) * P_CW);
-        } else {
-          const int ntile = tile + num_clusters;
-          if (ntile < total_tiles) {  // first chunk of this cluster's next tile
-            const int nt2 = ntile / num_n;
-            preload(nxt, (nt2 % num_m) * P_BM + (int)rank * 128, (ntile % num_n) * P_BN + hc * kCols);
+        // The epilogue is latency-bound (4 warps per scheduler, each iteration behind a global load): issue this chunk's
+        // residual / activation-backward operand loads first, so that they fly during the TMEM read and the staging.
+        constexpr bool kPreRes = (F & EF_RES) != 0, kPreAux = (F & EF_ACTBWD) != 0;
+        float4 pres[kPreRes ? 4 : 1], paux[kPreAux ? 4 : 1];
+        bool has_res = false, has_aux = false;
+        {
+          const int pcol = n0 + c * P_CW + 4 * (lane & 3);
+          if constexpr (kPreRes) has_res = p.residual != nullptr;
+          if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
+            const bool ok = prow < p.M && pcol < p.N;
+            if constexpr (kPreRes) {
+              pres[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_res && ok) pres[it] = *reinterpret_cast<const float4*>(p.residual + prow * p.ld_res + pcol);
+            }
+            if constexpr (kPreAux) {
+              paux[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (has_aux && ok) paux[it] = *reinterpret_cast<const float4*>(p.act_aux + prow * p.ld_act_aux + pcol);
+            }
           }
         }
         uint32_t r[P_CW];
         if (!(p.debug & 4)) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW;
-          if constexpr (P_CW == 16) tmem_ld_32x16(taddr, r); else tmem_ld_32x32(taddr, r);
+          tmem_ld_32x16(tmem_base + ((uint32_t)(g * 32) << 16) + a * P_BN + hc * kCols + c * P_CW, r);
           tmem_ld_wait();
         }
         if (c == kCols / P_CW - 1) {
@@ -862,44 +814,40 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
           continue;
         }
         const int col0 = n0 + c * P_CW;
-        // staging: thread = accumulator row; the row's float4 slots are XOR-swizzled so that both the row-wise writes and the
-        // coalesced reads below are bank-conflict free (16 columns: 4 slots, key (row >> 1) & 3; 32 columns: 8 slots, key row & 7)
         float* myrow = stg + lane * P_STG_LD;
-        const int wkey = P_CW == 16 ? ((lane >> 1) & 3) : (lane & 7);
 #pragma unroll
         for (int q = 0; q < P_CW / 4; ++q)
-          *reinterpret_cast<float4*>(myrow + 4 * (q ^ wkey)) =
+          *reinterpret_cast<float4*>(myrow + 4 * (q ^ ((lane >> 1) & 3))) =
               make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
         __syncwarp();
-        const int q = lane % LPR;
+        const int q = lane & 3;
         const int col = col0 + 4 * q;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll kUnrollIt
-        for (int it = 0; it < ITS; ++it) {
-          const int rr = it * RPI + (lane / LPR);
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane >> 2);
           const long long row = (long long)m0 + g * 32 + rr;
           if (row < p.M && col < p.N) {
-            const int rkey = P_CW == 16 ? ((rr >> 1) & 3) : (rr & 7);
-            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ rkey));
+            const float4 t4 = *reinterpret_cast<const float4*>(stg + rr * P_STG_LD + 4 * (q ^ ((rr >> 1) & 3)));
             float v[4] = {t4.x, t4.y, t4.z, t4.w};
             if (p.debug & 1) {  // VC_GEMM_DEBUG = 1: no epilogue math, no global stores
               if (v[0] == 123.456f) p.out_f32[0] = v[1];
             } else {
-              epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, cur.res[kPreRes ? it : 0], kPreAux && has_aux,
-                               cur.aux[kPreAux ? it : 0]);
+              epilogue_quad<F>(p, v, row, col, split == 0, seed, kPreRes && has_res, pres[kPreRes ? it : 0], kPreAux && has_aux,
+                               paux[kPreAux ? it : 0]);
             }
             if constexpr ((F & EF_COLSUM) != 0) { cs[0] += v[0]; cs[1] += v[1]; cs[2] += v[2]; cs[3] += v[3]; }
           }
         }
         if constexpr ((F & EF_COLSUM) != 0) {
-          if (p.colsum != nullptr) {  // combine the lanes that share a column quad (lane % LPR)
+          if (p.colsum != nullptr) {  // combine the 8 lanes that share a column quad
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if constexpr (LPR == 4) cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+              cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
               cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
               cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
             }
-            if (lane < LPR && col < p.N) {
+            if (lane < 4 && col < p.N) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) atomicAdd(p.colsum + col + i, cs[i]);
             }
@@ -949,7 +897,7 @@ PFN_encodeTiled get_encode_fn() {
 // cuTensorMapEncodeTiled costs a few microseconds of host time; the same (buffer, shape) pairs recur every training step
 // (weights, persistent workspaces), so encoded maps are cached.
 struct TmapKey {
-  const void* base; int64_t rows, cols, ld; int box_cols, box_rows;  // box_rows < 0: fp32 map without swizzle (L2 prefetch boxes)
+  const void* base; int64_t rows, cols, ld; int box_cols, box_rows;
   bool operator==(const TmapKey& o) const {
     return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_cols == o.box_cols && box_rows == o.box_rows;
   }
@@ -978,28 +926,6 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int
   if (int rc = make_tmap_uncached(tm, base, rows, cols, ld, box_cols, box_rows)) return rc;
   std::lock_guard<std::mutex> lk(g_tmap_mu);
   if (g_tmap_cache.size() > 16384) g_tmap_cache.clear();
-  g_tmap_cache.emplace(key, *tm);
-  return 0;
-}
-
-// fp32 matrix [rows, cols] (leading dimension ld), box = {box_cols, box_rows}, no swizzle: used for L2 prefetch boxes only
-int make_tmap_f32(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
-  TmapKey key{base, rows, cols, ld, box_cols, -box_rows};
-  {
-    std::lock_guard<std::mutex> lk(g_tmap_mu);
-    auto it = g_tmap_cache.find(key);
-    if (it != g_tmap_cache.end()) { *tm = it->second; return 0; }
-  }
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return set_error("cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return set_error("cuTensorMapEncodeTiled (fp32) failed");
-  std::lock_guard<std::mutex> lk(g_tmap_mu);
   g_tmap_cache.emplace(key, *tm);
   return 0;
 }
@@ -1210,18 +1136,6 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   fill_params(p, d, splitk);
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   if (int rc = make_operand_maps(d, tA_hi, tA_lo, tB_hi, tB_lo, C::B_ROWS)) return rc;  // each CTA stages half of the tile's B rows
-  CUtensorMap tE = tA_hi;  // placeholder when the epilogue has no fp32 operand to prefetch
-  {
-    static int l2pre = -1;
-    if (l2pre < 0) { const char* e = getenv("VC_GEMM_L2PRE"); l2pre = e ? atoi(e) : 1; }
-    const float* eop = nullptr; long long eld = 0;
-    if ((F & EF_RES) != 0 && d.residual) { eop = d.residual; eld = d.ld_res; }
-    else if ((F & EF_ACTBWD) != 0 && d.act_backward && d.act_aux) { eop = d.act_aux; eld = d.ld_act_aux; }
-    if (l2pre && eop && (reinterpret_cast<uintptr_t>(eop) & 15) == 0 && eld % 4 == 0 && d.N % 32 == 0) {
-      if (int rc = make_tmap_f32(&tE, eop, d.M, d.N, eld, 32, 128)) return rc;
-      p.pre_l2 = 1;
-    }
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_pair_kernel<F, EW, PBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
@@ -1236,7 +1150,7 @@ int launch_gemm_pair_ew(const GemmDesc& d, int splitk, cudaStream_t stream) {
   snprintf(tag, sizeof tag, "M%d N%d K%d a%d b%d s%d p%d e%d%d%d%d P%d", d.M, d.N, d.K, p.a_mn, p.b_mn, p.splitk, p.passes,
            d.out_f32 ? 1 : 0, d.out_hi ? 1 : 0, d.residual ? 1 : 0, d.act, PBN);
   const bool prof = gemm_profile_begin(stream, 2.0 * (double)d.M * (double)d.N * (double)d.K, &slot, tag);
-  VC_LAUNCH((gemm_tc_pair_kernel<F, EW, PBN>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, tE, p);
+  VC_LAUNCH((gemm_tc_pair_kernel<F, EW, PBN>), grid, 64 + 32 * EW, P_SMEM_BYTES, stream, tA_hi, tA_lo, tB_hi, tB_lo, p);
   count_pair_launch();
   if (prof) gemm_profile_end(stream, slot);
   return check_launch("gemm_tc_pair_kernel");
