@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_model_gpu.py -m gpu -q -x 2>&1 | tail -3
+timeout 300 python scripts/attn_bench.py > gpurun_out/r02h_attn_bench.txt 2>&1
+cat gpurun_out/r02h_attn_bench.txt
+VC_VIT_ATTN_PIPE=0 timeout 300 python scripts/attn_bench.py > gpurun_out/r02h_attn_bench_old.txt 2>&1
+head -3 gpurun_out/r02h_attn_bench_old.txt
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-rollout > gpurun_out/r02h_bench_c1.json 2> gpurun_out/r02h_bench_c1.err
+python -c "import json; d=json.load(open('gpurun_out/r02h_bench_c1.json')); print(d['value'], d['ms_per_step'], d['segments_ms_per_step'], d['roofline']['frac'])"
