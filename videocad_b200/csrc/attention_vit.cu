@@ -149,23 +149,36 @@ __device__ __forceinline__ void load_a_global(const float* base, long long ld, i
   }
 }
 
-// acc[8][4] (16 x 64) += A(16 x 64, split regs) * B^T where B is a [64 x 64] split smem tile stored [n][k] (non-transposed read)
+// acc[8][4] (16 x 64) += A(16 x 64, split regs) * B^T where B is a [64 x 64] split smem tile stored [n][k] (non-transposed read).
+// Per k16 step the B fragments of all four column pairs are fetched first and the three passes (hi*hi, lo*hi, hi*lo) are issued
+// pass by pass over the eight accumulators: consecutive mma.sync instructions never accumulate into the same registers (issuing
+// the three passes of one accumulator back to back left only two independent chains in flight: the mma.sync pipe was 37 % busy,
+// stall reason `wait`).  Each accumulator still receives its products in the same order, so results are bit-identical.
 __device__ __forceinline__ void mma_ABt(float (&acc)[8][4], const uint32_t (&ah)[4][4], const uint32_t (&al)[4][4],
                                         const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int lane) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    uint32_t bh[4][4], bl[4][4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       const int row = jp * 16 + (lane & 7) + (lane >> 4) * 8, col = kk * 16 + ((lane >> 3) & 1) * 8;
-      uint32_t bh[4], bl[4];
-      ldsm_x4(bh, Bh + row * LDH + col);
-      ldsm_x4(bl, Bl + row * LDH + col);
-      mma16816(acc[2 * jp], ah[kk], bh[0], bh[1]);
-      mma16816(acc[2 * jp + 1], ah[kk], bh[2], bh[3]);
-      mma16816(acc[2 * jp], al[kk], bh[0], bh[1]);
-      mma16816(acc[2 * jp + 1], al[kk], bh[2], bh[3]);
-      mma16816(acc[2 * jp], ah[kk], bl[0], bl[1]);
-      mma16816(acc[2 * jp + 1], ah[kk], bl[2], bl[3]);
+      ldsm_x4(bh[jp], Bh + row * LDH + col);
+      ldsm_x4(bl[jp], Bl + row * LDH + col);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], ah[kk], bh[jp][0], bh[jp][1]);
+      mma16816(acc[2 * jp + 1], ah[kk], bh[jp][2], bh[jp][3]);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], al[kk], bh[jp][0], bh[jp][1]);
+      mma16816(acc[2 * jp + 1], al[kk], bh[jp][2], bh[jp][3]);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], ah[kk], bl[jp][0], bl[jp][1]);
+      mma16816(acc[2 * jp + 1], ah[kk], bl[jp][2], bl[jp][3]);
     }
   }
 }
@@ -175,18 +188,27 @@ __device__ __forceinline__ void mma_AB(float (&acc)[8][4], const uint32_t (&ah)[
                                        const __nv_bfloat16* Bh, const __nv_bfloat16* Bl, int lane) {
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
+    uint32_t bh[4][4], bl[4][4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) {
       const int row = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, col = jp * 16 + (lane >> 4) * 8;
-      uint32_t bh[4], bl[4];
-      ldsm_x4_t(bh, Bh + row * LDH + col);
-      ldsm_x4_t(bl, Bl + row * LDH + col);
-      mma16816(acc[2 * jp], ah[kk], bh[0], bh[1]);
-      mma16816(acc[2 * jp + 1], ah[kk], bh[2], bh[3]);
-      mma16816(acc[2 * jp], al[kk], bh[0], bh[1]);
-      mma16816(acc[2 * jp + 1], al[kk], bh[2], bh[3]);
-      mma16816(acc[2 * jp], ah[kk], bl[0], bl[1]);
-      mma16816(acc[2 * jp + 1], ah[kk], bl[2], bl[3]);
+      ldsm_x4_t(bh[jp], Bh + row * LDH + col);
+      ldsm_x4_t(bl[jp], Bl + row * LDH + col);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], ah[kk], bh[jp][0], bh[jp][1]);
+      mma16816(acc[2 * jp + 1], ah[kk], bh[jp][2], bh[jp][3]);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], al[kk], bh[jp][0], bh[jp][1]);
+      mma16816(acc[2 * jp + 1], al[kk], bh[jp][2], bh[jp][3]);
+    }
+#pragma unroll
+    for (int jp = 0; jp < 4; ++jp) {
+      mma16816(acc[2 * jp], ah[kk], bl[jp][0], bl[jp][1]);
+      mma16816(acc[2 * jp + 1], ah[kk], bl[jp][2], bl[jp][3]);
     }
   }
 }
@@ -299,138 +321,6 @@ vit_attn_fwd_mma_kernel(const VitAttnP p, __nv_bfloat16* __restrict__ o_hi, __nv
       }
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Forward, split-bf16 inputs (the training path): persistent CTAs with a two-stage cp.async pipeline.  The one-tile-per-CTA
-// kernel above alternates a load phase and a compute phase; with five resident CTAs per SM the loads in flight averaged ~20 KB per
-// SM (2.8 TB/s, profiles/r01l_ncu_attn_ln_summary.txt: 28 % of the warp slots active, issue slots 45 %).  Here every CTA walks
-// (image, head) tiles and requests tile i + 1 -- K and V into the other shared-memory stage, its 16 query rows per warp into
-// registers -- BEFORE it computes tile i, so that three resident CTAs keep ~115 KB per SM in flight all the time.  The output
-// tile is staged through the (dead) K rows of the warp and leaves as 16-byte row-contiguous stores (128 B per row) instead of
-// 4-byte fragments.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int FWD_STAGE_ELEMS = 4 * NT * LDH;  // Kh, Kl, Vh, Vl
-
-__global__ void __launch_bounds__(VA_THREADS)
-vit_attn_fwd_pipe_kernel(const VitAttnP p, int total_tiles, __nv_bfloat16* __restrict__ o_hi, __nv_bfloat16* __restrict__ o_lo, long long ldo,
-                         float* __restrict__ lse_out) {
-  pdl_grid_sync();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16* stage0 = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  const int n = p.n;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const DropKey dkey = drop_key_of(p.drop);
-
-  auto issue = [&](int tile, int buf, uint32_t (&qh)[4][4], uint32_t (&ql)[4][4]) {
-    const int h = tile % p.nh, b = tile / p.nh;
-    const long long rowbase = (long long)b * n;
-    __nv_bfloat16* st = stage0 + buf * FWD_STAGE_ELEMS;
-    stage_copy(p.kh + rowbase * p.ldk + (long long)h * HD, p.kl + rowbase * p.ldk + (long long)h * HD, p.ldk, n, st, st + NT * LDH);
-    stage_copy(p.vh + rowbase * p.ldv + (long long)h * HD, p.vl + rowbase * p.ldv + (long long)h * HD, p.ldv, n, st + 2 * NT * LDH, st + 3 * NT * LDH);
-    cp_async_commit();
-    load_a_global_split(p.qh + rowbase * p.ldq + (long long)h * HD, p.ql + rowbase * p.ldq + (long long)h * HD, p.ldq, warp * 16, n, g, t, qh, ql);
-  };
-
-  uint32_t qh[4][4], ql[4][4], qh_n[4][4], ql_n[4][4];
-  int tile = blockIdx.x, buf = 0;
-  if (tile < total_tiles) issue(tile, 0, qh, ql);
-  for (; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
-    const int next = tile + gridDim.x;
-    if (next < total_tiles) issue(next, buf ^ 1, qh_n, ql_n); else cp_async_commit();  // one group per iteration: the wait counts groups
-    cp_async_wait_group<1>();  // this tile's K / V have landed (the next tile's group may still be in flight)
-    __syncthreads();
-    const int h = tile % p.nh, b = tile / p.nh;
-    const long long rowbase = (long long)b * n;
-    __nv_bfloat16* Kh = stage0 + buf * FWD_STAGE_ELEMS;
-    __nv_bfloat16 *Kl = Kh + NT * LDH, *Vh = Kl + NT * LDH, *Vl = Vh + NT * LDH;
-
-    float s[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-    mma_ABt(s, qh, ql, Kh, Kl, lane);
-    __syncthreads();  // every warp has read K: its rows become the output staging area of the warp that owns them
-
-    // softmax over the n valid keys, rows r0 = warp*16+g (regs [0],[1]) and r1 = r0+8 (regs [2],[3])
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = warp * 16 + g + rr * 8;
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = 8 * j + 2 * t + e;
-          float v = s[j][rr * 2 + e] * p.scale;
-          if (col >= n) v = -INFINITY;
-          s[j][rr * 2 + e] = v;
-          m = fmaxf(m, v);
-        }
-      }
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-      float sum = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float pv = __expf(s[j][rr * 2 + e] - m);
-          s[j][rr * 2 + e] = pv;
-          sum += pv;
-        }
-      }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      const float inv = 1.0f / sum;
-      const unsigned long long base = (((unsigned long long)b * p.nh + h) * n + (unsigned long long)(row < n ? row : 0)) * (unsigned long long)n;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = 8 * j + 2 * t;
-        float f0 = 1.f, f1 = 1.f;
-        if (col < n) drop_pair(p, dkey, base + col, f0, f1);  // f1 is unused when col + 1 == n (its probability is 0)
-        s[j][rr * 2 + 0] *= inv * f0;
-        s[j][rr * 2 + 1] *= inv * f1;
-      }
-      if (row < n && t == 0) lse_out[((long long)b * p.nh + h) * n + row] = m + __logf(sum);
-    }
-
-    uint32_t ph[4][4], pl[4][4];
-    c_to_a(s, ph, pl);
-    float o[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-    mma_AB(o, ph, pl, Vh, Vl, lane);
-
-    // output: fragments -> this warp's 16 rows of the K tiles -> 16-byte row-contiguous global stores
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-      const int row = warp * 16 + g + rr * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t hi, lo;
-        split2(o[j][rr * 2], o[j][rr * 2 + 1], hi, lo);
-        *reinterpret_cast<uint32_t*>(Kh + row * LDH + 8 * j + 2 * t) = hi;
-        *reinterpret_cast<uint32_t*>(Kl + row * LDH + 8 * j + 2 * t) = lo;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int row = warp * 16 + it * 4 + (lane >> 3), c8 = (lane & 7) * 8;
-      if (row < n) {
-        const long long off = (rowbase + row) * ldo + (long long)h * HD + c8;
-        *reinterpret_cast<uint4*>(o_hi + off) = *reinterpret_cast<const uint4*>(Kh + row * LDH + c8);
-        if (o_lo) *reinterpret_cast<uint4*>(o_lo + off) = *reinterpret_cast<const uint4*>(Kl + row * LDH + c8);
-      }
-    }
-    __syncthreads();  // this stage may be refilled by the next iteration's request
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { qh[kk][i] = qh_n[kk][i]; ql[kk][i] = ql_n[kk][i]; }
-    }
-  }
-  cp_async_wait_all();
 }
 
 __device__ __forceinline__ void store_pair(const VitBwdOut& out, int which, long long row, int col, float x, float y) {
@@ -641,27 +531,6 @@ bool vit_attention_eligible(const AttnDesc& a) {
 
 int vit_attention_fwd(const AttnDesc& a, bf16_t* o_hi, bf16_t* o_lo, int64_t ldo, float* lse, stream_t s) {
   if (ldo % 2 != 0) return set_error("vit_attention_fwd: ldo must be even");
-  static int use_pipe = -1;
-  if (use_pipe < 0) { const char* e = getenv("VC_VIT_ATTN_PIPE"); use_pipe = e ? atoi(e) : 1; }
-  if (use_pipe && a.q_hi != nullptr && ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o_hi) & 15) == 0 &&
-      (o_lo == nullptr || (reinterpret_cast<uintptr_t>(o_lo) & 15) == 0)) {
-    constexpr size_t PIPE_SMEM = (size_t)2 * FWD_STAGE_ELEMS * 2;
-    static bool pipe_configured = false;
-    static int sms = 148;
-    if (!pipe_configured) {
-      cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PIPE_SMEM);
-      if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-      pipe_configured = true;
-    }
-    const int total = a.B * a.nh;
-    const int grid = total < 3 * sms ? total : 3 * sms;  // three resident CTAs per SM (2 x 36.9 KB of shared memory each)
-    VC_LAUNCH((vit_attn_fwd_pipe_kernel), grid, VA_THREADS, PIPE_SMEM, reinterpret_cast<cudaStream_t>(s), make_p(a), total,
-              reinterpret_cast<__nv_bfloat16*>(o_hi), reinterpret_cast<__nv_bfloat16*>(o_lo), ldo, lse);
-    return check_launch("vit_attn_fwd_pipe_kernel");
-  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(vit_attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM);
