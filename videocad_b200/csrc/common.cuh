@@ -42,27 +42,11 @@ __device__ __forceinline__ void split4(const float v[4], uint2& hi, uint2& lo) {
 // ---------------------------------------------------------------------------------------------
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
-// Standard normal CDF Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and e = exp(-x^2 / 2), branch-free: erfc(z) = t (a1 + t (a2 + ...)) exp(-z^2),
-// t = 1 / (1 + p z) (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7), evaluated on z = |x| / sqrt 2 and reflected for x < 0 without
-// cancellation.  Measured over [-12, 12] in fp32: |Phi - exact| <= 3.0e-7, |gelu - exact| <= 4.7e-7, |gelu' - exact| <= 3.3e-7 -- the
-// same absolute accuracy as the fp32 erff formulation (4.5e-7), at ~16 instructions instead of ~40 with a divergent branch: the GELU
-// epilogues of the image-encoder GEMMs are instruction-issue bound (profiles/r02_pair_epilogue_experiments.md).
-__device__ __forceinline__ float norm_cdf_e(float x, float& e) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);
-  const float poly = ((((1.061405429f * t - 1.453152027f) * t + 1.421413741f) * t - 0.284496736f) * t + 0.254829592f) * t;
-  const float tail = 0.5f * poly * e;  // Phi(-|x|)
-  return x >= 0.f ? 1.0f - tail : tail;
-}
-__device__ __forceinline__ float gelu_f(float x) {
-  float e;
-  return x * norm_cdf_e(x, e);
-}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  float e;
-  const float cdf = norm_cdf_e(x, e);
-  return fmaf(x, 0.39894228040143267794f * e, cdf);
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
 }
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
