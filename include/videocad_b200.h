@@ -319,6 +319,11 @@ size_t vc_vit_scratch_bytes(int F, int S);
 int vc_vit_forward(const vc_vit_call* c, void* stream);
 /* needs the SAME call struct (and untouched workspace) as the forward; dcls [F,512] */
 int vc_vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, void* stream);
+/* The same backward in pieces: encoder layers l_hi, l_hi - 1, ..., l_lo (0 <= l_lo <= l_hi <= 5).  The range with l_hi == 5 also runs the
+ * final LayerNorm (dcls required), the range with l_lo == 0 the token assembly and the patch embedding.  Ranges called in descending
+ * order on the SAME scratch equal one vc_vit_backward; after a range returns, the parameter gradients of its layers are final, so the
+ * host can hand them to the gradient all-reduce (DistributedDataParallel, experiment.py:104-109) while the lower layers still run. */
+int vc_vit_backward_layers(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, int l_hi, int l_lo, void* stream);
 
 typedef struct vc_dec_layer {
   vc_linear sa_in; vc_linear sa_out;    /* self_attn.in_proj [3H,H], out_proj [H,H] */

@@ -187,9 +187,16 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
   return 0;
 }
 
-int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, stream_t st) {
+// Backward of encoder layers l_hi, l_hi - 1, ..., l_lo (0 <= l_lo <= l_hi < depth).  l_hi == depth - 1 also runs the final
+// LayerNorm's backward (and needs dcls), l_lo == 0 also the token assembly / patch embedding.  Consecutive ranges called in
+// descending order on the same scratch equal one full backward: the running gradient of the residual stream (s.dxa) and the
+// masked split operand of the next fc2 (s.g) stay in the scratch between calls.  This lets the host hand the gradients of the
+// upper layers to the data-parallel all-reduce while the lower layers are still in their backward.
+int vit_backward_layers(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, int l_hi, int l_lo, stream_t st) {
   VC_TRY(check_call(c));
-  if (!dcls || !scratch) return set_error("vit_backward: null argument");
+  if (!scratch) return set_error("vit_backward: null argument");
+  if (l_lo < 0 || l_hi >= VC_VIT_DEPTH || l_lo > l_hi) return set_error("vit_backward_layers: bad layer range");
+  if (l_hi == VC_VIT_DEPTH - 1 && !dcls) return set_error("vit_backward: the top range needs dcls");
   const vc_vit_weights& W = *c->w;
   const int F = c->F, S = c->S, N = (S / VC_PATCH) * (S / VC_PATCH), n = N + 1;
   const int Mp = F * N, M = F * n, P = c->passes;
@@ -205,13 +212,15 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
   const uint32_t sb = c->site_base;
   const int ax2 = c->aux_streams > 0 ? c->aux_streams : 2, ax3 = ax2 + 1;  // this encoder's pair of auxiliary streams
 
-  // final LN (CLS rows only): every other row of d x[6] is zero
-  VC_TRY(zero_f32(s.dxa, (int64_t)M * D, st));
-  VC_TRY(layernorm_bwd(dcls, D, w.x[VC_VIT_DEPTH], (int64_t)n * D, w.fmean, w.frstd, W.norm.w, F, D, nullptr, 0, s.dxa,
-                       (int64_t)n * D, W.norm.dw, W.norm.db, st));
-  float* cur = s.dxa;
+  if (l_hi == VC_VIT_DEPTH - 1) {
+    // final LN (CLS rows only): every other row of d x[6] is zero
+    VC_TRY(zero_f32(s.dxa, (int64_t)M * D, st));
+    VC_TRY(layernorm_bwd(dcls, D, w.x[VC_VIT_DEPTH], (int64_t)n * D, w.fmean, w.frstd, W.norm.w, F, D, nullptr, 0, s.dxa,
+                         (int64_t)n * D, W.norm.dw, W.norm.db, st));
+  }
+  float* cur = s.dxa;  // d x[l + 1] at the top of every layer iteration (the two buffers swap twice per layer)
   float* other = s.dxb;
-  for (int l = VC_VIT_DEPTH - 1; l >= 0; --l) {
+  for (int l = l_hi; l >= l_lo; --l) {
     const vc_vit_layer& LW = W.layer[l];
     VitWs::Layer& L = w.l[l];
     const uint32_t s0 = sb + 1 + 4 * l;
@@ -280,6 +289,7 @@ int vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t 
     }
     VC_TRY(stream_join(st, ax3));  // fc1 / to_qkv wgrads have read s.dpre / s.dqkvS (rewritten by the next layer's dgrad chain)
   }
+  if (l_lo > 0) return 0;
   // ---- token assembly + patch embedding (cur = d x[0]); buffers reused: dh -> d e1, dud -> d e0, dO -> d pl
   float* de1 = s.dh;
   float* de0 = s.dud;
@@ -308,6 +318,9 @@ size_t vc_vit_workspace_bytes(int F, int S) { return vck::vit_workspace_bytes(F,
 size_t vc_vit_scratch_bytes(int F, int S) { return vck::vit_scratch_bytes(F, S); }
 int vc_vit_forward(const vc_vit_call* c, void* stream) { return vck::vit_forward(c, stream); }
 int vc_vit_backward(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, void* stream) {
-  return vck::vit_backward(c, dcls, scratch, scratch_bytes, stream);
+  return vck::vit_backward_layers(c, dcls, scratch, scratch_bytes, VC_VIT_DEPTH - 1, 0, stream);
+}
+int vc_vit_backward_layers(const vc_vit_call* c, const float* dcls, void* scratch, size_t scratch_bytes, int l_hi, int l_lo, void* stream) {
+  return vck::vit_backward_layers(c, dcls, scratch, scratch_bytes, l_hi, l_lo, stream);
 }
 }

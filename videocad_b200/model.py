@@ -116,23 +116,32 @@ class _ViTContainers(_NoForward):
 
 
 class _FlatSpec:
-    """Key names, shapes and (64-element aligned) offsets of one segment's weights inside its flat buffer."""
+    """Key names, shapes and (64-element aligned) offsets of one segment's weights.  The segment's storage is `n_parts` flat
+    buffers (one nn.Parameter each); `offs` are offsets into their CONCATENATION, which is the layout of the split-bf16 weight
+    mirror and of the gradient arena, `loffs` offsets inside the weight's own part."""
 
-    def __init__(self, named):
-        self.names, self.shapes, self.offs, self.numels = [], [], [], []
-        total = 0
+    def __init__(self, named, part_of=None, n_parts=1):
+        self.names, self.shapes, self.numels, self.parts, self.loffs = [], [], [], [], []
+        totals = [0] * n_parts
         for name, t in named:
+            k = part_of(name) if part_of is not None else 0
             self.names.append(name)
             self.shapes.append(tuple(t.shape))
-            self.offs.append(total)
             self.numels.append(t.numel())
-            total += (t.numel() + 63) // 64 * 64
-        self.total = total
+            self.parts.append(k)
+            self.loffs.append(totals[k])
+            totals[k] += (t.numel() + 63) // 64 * 64
+        self.n_parts = n_parts
+        self.part_totals = totals
+        self.part_base = [sum(totals[:k]) for k in range(n_parts)]
+        self.offs = [self.part_base[k] + o for k, o in zip(self.parts, self.loffs)]
+        self.total = sum(totals)
         self.index = {n: i for i, n in enumerate(self.names)}
 
-    def view(self, flat: torch.Tensor, name: str) -> torch.Tensor:
+    def view(self, flats, name: str) -> torch.Tensor:
+        """View of one weight inside the list of part buffers `flats`."""
         i = self.index[name]
-        return flat[self.offs[i]: self.offs[i] + self.numels[i]].view(self.shapes[i])
+        return flats[self.parts[i]][self.loffs[i]: self.loffs[i] + self.numels[i]].view(self.shapes[i])
 
 
 class WeightView:
@@ -143,20 +152,25 @@ class WeightView:
 
 
 class _FlatOwner(_NoForward):
-    """Module whose only registered parameter is `flat_params`; (de)serialises under the reference's key names."""
+    """Module whose only registered parameters are its flat part buffers (`flat_params`, `flat_params_1`, ...); (de)serialises
+    under the reference's key names."""
 
-    def _init_flat(self, named):
-        self._spec = _FlatSpec(named)
-        flat = torch.zeros(self._spec.total)
+    def _init_flat(self, named, part_of=None, n_parts=1):
+        self._spec = _FlatSpec(named, part_of, n_parts)
+        flats = [torch.zeros(n) for n in self._spec.part_totals]
         for name, t in named:
-            self._spec.view(flat, name).copy_(t.detach())
-        self.flat_params = nn.Parameter(flat)
+            self._spec.view(flats, name).copy_(t.detach())
+        self._flat_names = ["flat_params" if k == 0 else f"flat_params_{k}" for k in range(n_parts)]
+        for nm, f in zip(self._flat_names, flats):
+            setattr(self, nm, nn.Parameter(f))
 
-    def _own_named_views(self, grads=False):
-        flat = self.flat_params
-        src = flat.grad if grads else flat.detach()  # detach(): same storage AND version counter (in-place loads invalidate caches)
+    def flats(self):
+        return [getattr(self, nm) for nm in self._flat_names]
+
+    def _own_named_views(self):
+        src = [f.detach() for f in self.flats()]  # detach(): same storage AND version counter (in-place loads invalidate caches)
         for name in self._spec.names:
-            yield name, (self._spec.view(src, name) if src is not None else None)
+            yield name, self._spec.view(src, name)
 
     def _flat_children(self):
         return [(n, m) for n, m in self._modules.items() if isinstance(m, _FlatOwner)]
@@ -165,9 +179,11 @@ class _FlatOwner(_NoForward):
         """(reference key, WeightView) for every weight, children first (the reference's registration order)."""
         for cname, child in self._flat_children():
             yield from child.named_weights(prefix + cname + ".")
-        g = self.flat_params.grad
-        for name, v in self._own_named_views():
-            yield prefix + name, WeightView(v, self._spec.view(g, name) if g is not None else None)
+        grads = [f.grad for f in self.flats()]
+        for i, (name, v) in enumerate(self._own_named_views()):
+            g = grads[self._spec.parts[i]]
+            gv = g[self._spec.loffs[i]: self._spec.loffs[i] + self._spec.numels[i]].view(self._spec.shapes[i]) if g is not None else None
+            yield prefix + name, WeightView(v, gv)
 
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
         if len(args) > 0:  # legacy positional form (destination, prefix, keep_vars)
@@ -207,13 +223,28 @@ class _FlatOwner(_NoForward):
                     unexpected_keys.append(key)
 
 
+# The image encoders keep their weights in VIT_PARTS buffers, split by depth, so that the backward can hand the gradients of the
+# upper layers to DistributedDataParallel's all-reduce while the lower layers are still running (vc_vit_backward_layers):
+#   part 0: patch embedding, cls / pos, layers 0-1     part 1: layers 2-3     part 2: layers 4-5 + final LayerNorm
+VIT_PARTS = 3
+_VIT_PART_LAYERS = [(1, 0), (3, 2), (5, 4)]  # (l_hi, l_lo) of each part
+
+
+def _vit_part_of(name: str) -> int:
+    if name.startswith("transformer.layers."):
+        return int(name.split(".")[2]) // 2
+    if name.startswith("transformer.norm"):
+        return VIT_PARTS - 1
+    return 0
+
+
 class ViTParams(_FlatOwner):
     """Weights of one vit_pytorch.ViT image encoder (trajectory_model.py:54-67) in one flat parameter."""
 
     def __init__(self, dropout=0.1, emb_dropout=0.1):
         super().__init__()
         self.dropout_p = dropout
-        self._init_flat(list(_ViTContainers(dropout, emb_dropout).named_parameters()))
+        self._init_flat(list(_ViTContainers(dropout, emb_dropout).named_parameters()), _vit_part_of, VIT_PARTS)
 
 
 # =====================================================================================================
@@ -255,15 +286,15 @@ class _Segment:
         self._lib = None  # tests may inject the CPU emulation library; the product path loads the CUDA build
 
     @property
-    def flat(self) -> nn.Parameter:
-        return self.owner.flat_params
+    def flats(self):
+        return self.owner.flats()
 
     def graphs_enabled(self, t: torch.Tensor) -> bool:
         return _GRAPHS and t.is_cuda and self._lib is None
 
     def _check_storage(self):
         """Persistent structs and graphs bake parameter addresses: drop them if the flat parameter's storage moved (.to(), ...)."""
-        sig = self.flat.data_ptr()
+        sig = tuple(f.data_ptr() for f in self.flats)
         if sig != self._sig:
             self._sig, self._slots, self._islots, self._dstates, self._split = sig, {}, {}, {}, None
 
@@ -283,20 +314,26 @@ class _Segment:
         return slot
 
     def ensure_split(self, stream, force=False):
-        """split-bf16 (hi, lo) mirror of the flat parameter, refreshed with ONE launch when the fp32 values changed
-        (optimizer step, load_state_dict, .to()); the GEMM weights are slices of it at the same element offsets."""
-        flat = self.flat
+        """split-bf16 (hi, lo) mirror of the segment's weights (all parts, concatenated), refreshed with ONE launch per part when
+        the fp32 values changed (optimizer step, load_state_dict, .to()); the GEMM weights are slices of it at the weights' offsets."""
+        flats = self.flats
         ent = self._split
-        if ent is None or ent[1] != flat.data_ptr() or ent[2].device != flat.device:
-            hi = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
-            lo = torch.empty(self.total, dtype=torch.bfloat16, device=flat.device)
+        ptrs = tuple(f.data_ptr() for f in flats)
+        if ent is None or ent[1] != ptrs or ent[2].device != flats[0].device:
+            hi = torch.empty(self.total, dtype=torch.bfloat16, device=flats[0].device)
+            lo = torch.empty(self.total, dtype=torch.bfloat16, device=flats[0].device)
             ent = None
         else:
             hi, lo = ent[2], ent[3]  # refreshed in place: captured graphs and cached structs keep these addresses
-        if force or ent is None or ent[0] != flat._version:
+        versions = tuple(f._version for f in flats)
+        if force or ent is None or ent[0] != versions:
             lib = self.lib()
-            L.check(lib.vc_split_f32(flat.data_ptr(), self.total, 1, self.total, hi.data_ptr(), lo.data_ptr(), self.total, stream), lib)
-            self._split = (flat._version, flat.data_ptr(), hi, lo)
+            for k, f in enumerate(flats):
+                if ent is not None and not force and ent[0][k] == versions[k]:
+                    continue
+                n, base = self.spec.part_totals[k], self.spec.part_base[k]
+                L.check(lib.vc_split_f32(f.data_ptr(), n, 1, n, hi.data_ptr() + 2 * base, lo.data_ptr() + 2 * base, n, stream), lib)
+            self._split = (versions, ptrs, hi, lo)
         return hi, lo
 
     def resplit_all(self, stream):
@@ -333,7 +370,8 @@ class _Segment:
         return self.spec.offs[self.spec.index[name]]
 
     def _ptr(self, name: str) -> int:
-        return self.flat.data_ptr() + 4 * self._off(name)
+        i = self.spec.index[name]
+        return self.flats[self.spec.parts[i]].data_ptr() + 4 * self.spec.loffs[i]
 
     def _gptr(self, gflat, name: str):
         return gflat.data_ptr() + 4 * self._off(name) if gflat is not None else None
@@ -455,7 +493,7 @@ class _VitRunner(_Segment):
         call.aux_streams = self.aux_streams
         call.ws, call.ws_bytes, call.cls_out = ws.data_ptr(), ws_bytes, out.data_ptr()
         L.check(lib.vc_vit_forward(C.byref(call), stream), lib)
-        return out, (call, W, ws, img)
+        return out, ("eager", dict(call=call, W=W, ws=ws, img=img))
 
     def _normalize_u8(self, img_u8: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
         lib = self.lib()
@@ -463,36 +501,45 @@ class _VitRunner(_Segment):
         L.check(lib.vc_frames_u8_normalize(src.data_ptr(), src.numel(), 0.5, 0.5, dst.data_ptr(), _stream_of(dst)), lib)
         return dst
 
-    def backward(self, saved, dcls: torch.Tensor):
-        """-> gradient of the flat parameter (one tensor, same layout)."""
+    def backward_part(self, saved, k: int, dcls: Optional[torch.Tensor]):
+        """Backward of the encoder layers of weight part k (parts are processed in DESCENDING order; the top part needs dcls)
+        -> gradient of that part's flat parameter.  After part k returns its layers' gradients are final: autograd hands them
+        to DistributedDataParallel, whose all-reduce then overlaps the backward of the lower parts."""
         lib = self.lib()
+        l_hi, l_lo = _VIT_PART_LAYERS[k]
+        base, n = self.spec.part_base[k], self.spec.part_totals[k]
+        top = k == VIT_PARTS - 1
         if saved[0] == "slot":
             _, sl, lease = saved
             dev = sl.img.device
             if sl.scratch is None:
                 sl.scratch = torch.empty(sl.sc_bytes, dtype=torch.uint8, device=dev)
-            sl.dcls.copy_(dcls)
+            if top:
+                sl.dcls.copy_(dcls)
 
             def body():
                 st = torch.cuda.current_stream(dev).cuda_stream
-                sl.gflat.zero_()
-                L.check(lib.vc_vit_backward(C.byref(sl.call_b), sl.dcls.data_ptr(), sl.scratch.data_ptr(), sl.sc_bytes, st), lib)
+                if top:
+                    sl.gflat.zero_()
+                L.check(lib.vc_vit_backward_layers(C.byref(sl.call_b), sl.dcls.data_ptr(), sl.scratch.data_ptr(), sl.sc_bytes, l_hi, l_lo, st), lib)
 
-            self._launch(sl, "bwd", body)
-            g = sl.gflat.clone()
-            if lease is not None:
+            self._launch(sl, f"bwd{k}", body)
+            g = sl.gflat[base: base + n].clone()
+            if k == 0 and lease is not None:
                 lease.release()
             return g
-        call, W, ws, img = saved
+        st8 = saved[1]  # eager path: per-call state shared by the parts
+        call, img = st8["call"], st8["img"]
         stream = _stream_of(img)
-        gflat = torch.zeros(self.total, dtype=torch.float32, device=img.device)
-        Wg = self._weights(stream, gflat)
-        call.w = C.pointer(Wg)
-        sc_bytes = lib.vc_vit_scratch_bytes(call.F, call.S)
-        scratch = torch.empty(sc_bytes, dtype=torch.uint8, device=img.device)
-        dcls = dcls.contiguous().float()
-        L.check(lib.vc_vit_backward(C.byref(call), dcls.data_ptr(), scratch.data_ptr(), sc_bytes, stream), lib)
-        return gflat
+        if top:
+            st8["gflat"] = torch.zeros(self.total, dtype=torch.float32, device=img.device)
+            st8["Wg"] = self._weights(stream, st8["gflat"])
+            call.w = C.pointer(st8["Wg"])
+            st8["sc_bytes"] = lib.vc_vit_scratch_bytes(call.F, call.S)
+            st8["scratch"] = torch.empty(st8["sc_bytes"], dtype=torch.uint8, device=img.device)
+            st8["dcls"] = dcls.contiguous().float()
+        L.check(lib.vc_vit_backward_layers(C.byref(call), st8["dcls"].data_ptr(), st8["scratch"].data_ptr(), st8["sc_bytes"], l_hi, l_lo, stream), lib)
+        return st8["gflat"][base: base + n].clone()
 
 
 class _SeqRunner(_Segment):
@@ -797,24 +844,45 @@ class _SeqRunner(_Segment):
         return d_state, d_cad, d_mv, gflat
 
 
-class _VitFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, runner, training, p, seed, passes, img, flat):
-        if ctx.needs_input_grad[5]:
-            # trainer.generate_saliency_batch (trainer.py:621-645) asks for d loss / d cad_image; vc_vit_backward stops at the
-            # patch embedding's parameters (the image is a leaf of the training path).  Fail here, not with grad = None later.
-            raise RuntimeError("videocad_b200: the gradient with respect to the input images is not implemented (saliency / "
-                               "attention-rollout diagnostics of trainer.py:621-680 are out of scope, see DESIGN.md section 8); "
-                               "pass images that do not require grad")
-        out, saved = runner.forward(img, training, p, seed, passes, need_grad=ctx.needs_input_grad[6])
-        ctx.runner, ctx.saved = runner, saved
-        return out
+class _VitPartFn(torch.autograd.Function):
+    """One of the VIT_PARTS autograd nodes of an image encoder (bottom part 0 ... top part VIT_PARTS - 1).  Node 0 runs the whole
+    native forward; every node's forward passes a tensor on to the next one (the top node returns the encoder's output), so that
+    the engine runs the backward nodes top-down, each returning the gradient of ITS flat parameter as soon as its layers are
+    done -- DistributedDataParallel starts that all-reduce while the lower parts still compute."""
 
     @staticmethod
-    def backward(ctx, dcls):
-        g = ctx.runner.backward(ctx.saved, dcls)
-        ctx.saved = None
-        return (None, None, None, None, None, None, g)
+    def forward(ctx, runner, k, box, carry, flat_k, training, p, seed, passes):
+        if k == 0:
+            if carry.requires_grad:
+                # trainer.generate_saliency_batch (trainer.py:621-645) asks for d loss / d cad_image; vc_vit_backward stops at the
+                # patch embedding's parameters (the image is a leaf of the training path).  Fail here, not with grad = None later.
+                raise RuntimeError("videocad_b200: the gradient with respect to the input images is not implemented (saliency / "
+                                   "attention-rollout diagnostics of trainer.py:621-680 are out of scope, see DESIGN.md section 8); "
+                                   "pass images that do not require grad")
+            box["out"], box["saved"] = runner.forward(carry, training, p, seed, passes, need_grad=box["need_grad"])
+        ctx.runner, ctx.k, ctx.box = runner, k, box
+        if k == VIT_PARTS - 1:
+            return box["out"]
+        return box["out"].new_zeros(1)  # carries only the dependency between the nodes
+
+    @staticmethod
+    def backward(ctx, d):
+        k, box = ctx.k, ctx.box
+        g = ctx.runner.backward_part(box["saved"], k, d if k == VIT_PARTS - 1 else None)
+        if k == 0:
+            box.clear()
+        d_carry = None if k == 0 else g.new_zeros(1)
+        return (None, None, None, d_carry, g, None, None, None, None)
+
+
+def _vit_apply(runner, training, p, seed, passes, img):
+    """Image encoder through its chain of autograd nodes -> CLS embeddings [F, 512]."""
+    flats = runner.flats
+    box = {"need_grad": torch.is_grad_enabled() and any(f.requires_grad for f in flats)}
+    carry = img
+    for k in range(VIT_PARTS):
+        carry = _VitPartFn.apply(runner, k, box, carry, flats[k], training, p, seed, passes)
+    return carry
 
 
 class _SeqFn(torch.autograd.Function):
@@ -987,11 +1055,11 @@ class AutoRegressiveTransformer(_FlatOwner):
                 raise ValueError(f"expected {self.num_views} views, got {multiview_images.shape[1]}")
 
         def cad_branch():
-            cad_cls = _VitFn.apply(cad_r, training, p_cad, seed, passes, cad_image, cad_r.flat)
+            cad_cls = _vit_apply(cad_r, training, p_cad, seed, passes, cad_image)
             mv_cls = None
             if self.num_views > 0:
                 views = multiview_images.reshape(-1, *multiview_images.shape[2:])
-                mv_cls = _VitFn.apply(cad_r, training, p_cad, seed + 1 if seed else 0, passes, views, cad_r.flat)
+                mv_cls = _vit_apply(cad_r, training, p_cad, seed + 1 if seed else 0, passes, views)
             return cad_cls, mv_cls
 
         # The CAD encoder sees B images against the frame encoder's B*T: its kernels fill a fraction of the SMs and are
@@ -1012,7 +1080,7 @@ class AutoRegressiveTransformer(_FlatOwner):
             n_img = ui_images.numel() // (ui_images.shape[-1] * ui_images.shape[-2])
             if n_img != B * T:
                 raise ValueError(f"frames carry {n_img} images but actions are [{B},{T}]")
-            state_cls = _VitFn.apply(st_r, training, p_st, seed, passes, ui_images, st_r.flat)
+            state_cls = _vit_apply(st_r, training, p_st, seed, passes, ui_images)
         if overlap:
             cur.wait_stream(side)
             cad_cls.record_stream(cur)
@@ -1020,7 +1088,7 @@ class AutoRegressiveTransformer(_FlatOwner):
                 mv_cls.record_stream(cur)
         else:
             cad_cls, mv_cls = cad_branch()
-        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, seq_r.flat)
+        cmds, params = _SeqFn.apply(seq_r, training, p, seed, passes, B, T, state_cls, cad_cls, mv_cls, actions, seq_r.flats[0])
         return cmds.view(B, T, self.num_classes), params.view(B, T, self.num_params, self.num_params_values)
 
     @torch.no_grad()

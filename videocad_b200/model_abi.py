@@ -64,6 +64,7 @@ L.EXTRA_PROTOS.update({
     "vc_vit_scratch_bytes": ([i32, i32], sz),
     "vc_vit_forward": ([C.POINTER(VitCall), vp], i32),
     "vc_vit_backward": ([C.POINTER(VitCall), vp, vp, sz, vp], i32),
+    "vc_vit_backward_layers": ([C.POINTER(VitCall), vp, vp, sz, i32, i32, vp], i32),
     "vc_seq_workspace_bytes": ([i32, i32, i32, i32, i32, i32, i32, i32], sz),
     "vc_seq_scratch_bytes": ([i32, i32, i32, i32, i32, i32], sz),
     "vc_seq_forward": ([C.POINTER(SeqCall), vp], i32),
