@@ -74,9 +74,12 @@ def test_module_contract_and_errors():
     sd["transformer.wte.weight"] = torch.zeros(1, 128)  # dead GPT-2 key of a reference checkpoint: ignored (strict=False)
     m2, _ = ModelFactory().create_model("x", dict(cfg, state_dim=1644, act_dim=7, encoder="vit"), "cpu", state_dict=sd)
     assert torch.equal(dict(m2.named_weights())["embed_action.weight"].data, sd["module._orig_mod.embed_action.weight"])
-    # one flat parameter for the sequence transformer, three (split by depth) per image encoder -- not the reference's ~320 tensors
+    # one flat parameter for the sequence transformer, two (split by depth) per image encoder -- not the reference's ~320 tensors
+    # (registered bottom-up, encoders interleaved, sequence transformer last: DDP's bucket order, see model._ParamOrder)
     vit_parts = [(n,) for n in m2.state_embedding_model._spec.part_totals]
-    assert len(vit_parts) == 3 and [tuple(p.shape) for p in m2.parameters()] == [(m2._spec.total,)] + vit_parts + vit_parts
+    assert len(vit_parts) == 2
+    assert [tuple(p.shape) for p in m2.parameters()] == [vit_parts[0]] * 2 + [vit_parts[1]] * 2 + [(m2._spec.total,)]
+    assert [tuple(p.shape) for p in m2.state_embedding_model.parameters()] == vit_parts  # trainer.py:244-245 (frozen lr groups)
     assert list(m.cad_embedding_model.parameters()) and list(m.state_embedding_model.parameters())
     with pytest.raises(ValueError):
         AutoRegressiveTransformer(state_dim=1644, act_dim=7, hidden_size=128, encoder="resnet")

@@ -165,7 +165,10 @@ class _FlatOwner(_NoForward):
             setattr(self, nm, nn.Parameter(f))
 
     def flats(self):
-        return [getattr(self, nm) for nm in self._flat_names]
+        own = self._parameters
+        if all(nm in own for nm in self._flat_names):
+            return [own[nm] for nm in self._flat_names]
+        return [self._ddp_order._parameters[f"p{len(self._ddp_order._parameters) - 1}"]]  # the top module: see _ParamOrder
 
     def _own_named_views(self):
         src = [f.detach() for f in self.flats()]  # detach(): same storage AND version counter (in-place loads invalidate caches)
@@ -223,16 +226,44 @@ class _FlatOwner(_NoForward):
                     unexpected_keys.append(key)
 
 
+class _ParamOrder(_NoForward):
+    """Registers the model's flat parameters a second time, as the FIRST child module, in the order that makes
+    DistributedDataParallel's buckets follow the backward.  DDP collects parameters by walking named_modules() (shared parameters
+    are taken at their first occurrence), gives every parameter above 25 MB a bucket of its own, numbers the buckets in REVERSE
+    parameter order and all-reduces them strictly in that order (torch/nn/parallel/distributed.py: `list(reversed(bucket_indices))`;
+    the Reducer skips a ready bucket until its predecessors have been launched).  Gradients become ready as: sequence transformer,
+    then the encoders' top, middle, bottom parts -- so the registration order here is bottom parts, middle, top, sequence
+    transformer.  With the natural module order the sequence transformer's bucket came LAST and every all-reduce of the step was
+    queued behind the encoders' bottom layers, i.e. after the end of the backward.  Holds no state of its own."""
+
+    def __init__(self, params):
+        super().__init__()
+        for i, prm in enumerate(params):
+            self.register_parameter(f"p{i}", prm)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        if destination is None:
+            import collections
+
+            destination = collections.OrderedDict()
+        return destination
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        return
+
+
 # The image encoders keep their weights in VIT_PARTS buffers, split by depth, so that the backward can hand the gradients of the
 # upper layers to DistributedDataParallel's all-reduce while the lower layers are still running (vc_vit_backward_layers):
-#   part 0: patch embedding, cls / pos, layers 0-1     part 1: layers 2-3     part 2: layers 4-5 + final LayerNorm
-VIT_PARTS = 3
-_VIT_PART_LAYERS = [(1, 0), (3, 2), (5, 4)]  # (l_hi, l_lo) of each part
+#   part 0: patch embedding, cls / pos, layers 0-2 (33.7 MB)     part 1: layers 3-5 + final LayerNorm (31.5 MB)
+# Both exceed DDP's 25 MB bucket cap, so every part is a bucket of its own (smaller parts would be merged with their neighbour in
+# registration order, i.e. with a part that becomes ready at another time).
+VIT_PARTS = 2
+_VIT_PART_LAYERS = [(2, 0), (5, 3)]  # (l_hi, l_lo) of each part
 
 
 def _vit_part_of(name: str) -> int:
     if name.startswith("transformer.layers."):
-        return int(name.split(".")[2]) // 2
+        return int(name.split(".")[2]) // 3
     if name.startswith("transformer.norm"):
         return VIT_PARTS - 1
     return 0
@@ -963,6 +994,16 @@ class AutoRegressiveTransformer(_FlatOwner):
         if self.enable_timestep_embedding:
             tmp.timestep_embedding = nn.Embedding(max_ep_len, hidden_size)
         self._init_flat(list(tmp.named_parameters()))
+        # registration order of the flat parameters for DistributedDataParallel (see _ParamOrder): encoder parts bottom-up, both
+        # encoders interleaved, the sequence transformer's parameter last; this module's own parameter lives only there
+        order = []
+        for k in range(VIT_PARTS):
+            for vit in (self.state_embedding_model, self.cad_embedding_model):
+                if vit is not None:
+                    order.append(vit.flats()[k])
+        order.append(self._parameters.pop("flat_params"))
+        self._ddp_order = _ParamOrder(order)
+        self._modules = {"_ddp_order": self._modules.pop("_ddp_order"), **self._modules}
         self.action_mask = torch.tensor([[1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 0, 0], [0, 0, 0, 0, 1, 0], [0, 0, 0, 0, 0, 1],
                                          [0, 0, 0, 0, 0, 0]]).float().to(device)
         if self.enable_past_states and self.state_embedding_model is None:
