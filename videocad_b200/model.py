@@ -3,16 +3,17 @@
 
 Same constructor kwargs, same parameter names/shapes, same
 ``forward(inputs: dict) -> (cmds [B,T,5], params [B,T,6,1000])`` and ``sequential_inference``; the arithmetic runs
-in libvideocad_b200.so (hand-written sm_100a kernels) through three autograd nodes (frame ViT, CAD ViT, sequence
-transformer) so that DDP can start all-reducing the decoder / CAD-encoder gradients while the frame encoder's
-backward is still running.  There is no eager/CPU fallback.
+in libvideocad_b200.so (hand-written sm_100a kernels) through five autograd nodes -- two per image encoder (lower / upper
+layers), one for the sequence transformer -- so that DistributedDataParallel all-reduces the gradients of whatever has
+finished while the rest of the backward is still running.  There is no eager/CPU fallback.
 
-Parameter storage: each of the three segments keeps ALL its weights in ONE flat fp32 nn.Parameter (`flat_params`,
-64-element aligned slices).  `state_dict()` / `load_state_dict()` speak the reference's key schema (views into the flat
-buffers), so checkpoints are interchangeable, while `parameters()` - what Adam, `clip_grad_norm_` and DDP iterate over -
-yields three large tensors instead of ~320 small ones: the optimizer runs three bandwidth-bound passes, DDP all-reduces
-three buckets (no per-parameter copy kernels), and a backward returns its whole gradient arena as one tensor.  The torch
-modules the reference would construct are built once, for their default initialisation and key names, and discarded.
+Parameter storage: the sequence transformer keeps ALL its weights in ONE flat fp32 nn.Parameter, each image encoder in TWO
+(split by depth; 64-element aligned slices).  `state_dict()` / `load_state_dict()` speak the reference's key schema (views into
+the flat buffers), so checkpoints are interchangeable, while `parameters()` - what Adam, `clip_grad_norm_` and DDP iterate over -
+yields five large tensors instead of ~320 small ones: the optimizer runs a few bandwidth-bound passes, every tensor is one DDP
+bucket (no per-parameter copy kernels), registered in the order the backward finishes them (`_ParamOrder`), and a backward node
+returns its slice of the gradient arena as one tensor.  The torch modules the reference would construct are built once, for their
+default initialisation and key names, and discarded.
 
 Not constructed (dead in the reference's forward): transformer.* (GPT2Model), embed_timestep,
 embed_ln, predict_action.  Checkpoints carrying those keys load with strict=False exactly as
