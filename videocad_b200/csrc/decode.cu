@@ -38,9 +38,13 @@ constexpr float DEC_LN_EPS = 1e-5f;
 inline cudaStream_t cs(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // global -> shared bulk copy (TMA, no tensor map): completion is counted in bytes on `bar`
+// L2 evict-first: the 293 MB of weight rows are read once per step and must not push the step's re-used data (cached keys / values,
+// LayerNorm parameters, activations) out of the 126 MB L2
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
 }
 
