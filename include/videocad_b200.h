@@ -385,18 +385,6 @@ int vc_seq_decode_dev_supported(const vc_seq_call* c);
 size_t vc_seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nhead);
 int vc_seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
                            float* params_all, void* stream);
-/* The same decode step as ONE persistent kernel (csrc/decode_mega.cu): 128 co-resident CTAs walk the phases of the step with a grid-wide
- * barrier after each instead of 66 dependent launches, and keep the fp32 weight rows of the next phases in flight through a shared-memory
- * ring of TMA bulk copies.  vc_seq_decode_mega_prepare() writes the step's phase program (vc_seq_decode_mega_program_bytes() bytes of
- * device memory, 16-byte aligned) once per rollout -- same arguments and the same zero-filled scratch as vc_seq_decode_step_dev; it is
- * the only call of the path that reads host memory (a pageable-source cudaMemcpyAsync) and must not be stream-captured.
- * vc_seq_decode_step_mega() then runs the position *t_dev exactly as vc_seq_decode_step_dev does (capturable; one graph serves every
- * position).  Replaces the same reference code: /root/reference/model/autoregressive_transformer.py:222-275. */
-int vc_seq_decode_mega_supported(const vc_seq_call* c);
-size_t vc_seq_decode_mega_program_bytes(void);
-int vc_seq_decode_mega_prepare(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
-                               float* params_all, void* program, size_t program_bytes, void* stream);
-int vc_seq_decode_step_mega(const vc_seq_call* c, const void* program, void* scratch, size_t scratch_bytes, int* t_dev, void* stream);
 /* dcmds [B*T,num_cmd], dparams [B*T,num_param_out]; d_state_cls [B*T,512] (may be null unless past_states),
  * d_cad_cls [B,512] and d_mv_cls [B*num_views,512] (may be null when num_views == 0) are OVERWRITTEN */
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,

@@ -7,7 +7,6 @@
 // Each function follows the contract documented in kernels.h; arithmetic mirrors the CUDA kernels (same split-bf16
 // operand model, same dropout masks) but accumulates in double.
 #include <math.h>
-#include <algorithm>
 #include <string.h>
 #include <vector>
 #include "kernels.h"
@@ -928,43 +927,6 @@ int dec_select(const DecSelect& a, stream_t) {
     for (int i = 0; i < a.NPAR; ++i) out[1 + i] = par[i] / 1000.0f;
   }
   *a.t_ptr = t + 1;
-  return 0;
-}
-
-// ---- CPU twin of the persistent decode kernel (videocad_b200/csrc/decode_mega.cu): the same program, phase by phase
-int dec_mega_ctas() { return 128; }
-int dec_mega_cols(int N) {
-  int cols = (N + 127) / 128;
-  cols = (cols + 3) / 4 * 4;
-  return cols <= 48 ? cols : 0;
-}
-int dec_mega_nsplit(int B, int nh) { return std::max(1, std::min(8, 128 / (B * nh))); }
-int dec_mega_upload(const MegaPhase* host, int nph, void* program_dev, stream_t) {
-  if (!host || !program_dev || nph < 1 || nph > VC_MEGA_MAX_PHASES) return set_error("dec_mega_upload: bad program");
-  memcpy(program_dev, host, (size_t)nph * sizeof(MegaPhase));
-  return 0;
-}
-int dec_mega(const void* program_dev, int nph, int M, int dh, unsigned int* sync, const int* t_ptr, stream_t s) {
-  if (!program_dev || !sync || !t_ptr || nph < 2 || nph > VC_MEGA_MAX_PHASES || M < 1 || M > 16 || (dh != 64 && dh != 128 && dh != 256))
-    return set_error("dec_mega: bad arguments");
-  const MegaPhase* prog = static_cast<const MegaPhase*>(program_dev);
-  if (prog[nph - 1].kind != VC_MEGA_SELECT) return set_error("dec_mega: the last phase must be the selection");
-  for (int i = 0; i < nph; ++i) {
-    const MegaPhase& P = prog[i];
-    int rc = 0;
-    if (P.kind == VC_MEGA_GEMV) {
-      if (P.g.cols_per_cta != dec_mega_cols(P.g.N) || P.g.cols_per_cta <= 0) return set_error("dec_mega: bad column share");
-      rc = dec_gemv(P.g, s);
-    } else if (P.kind == VC_MEGA_ATTN) {
-      rc = dec_attn(P.a, P.B, s);
-    } else if (P.kind == VC_MEGA_SELECT) {
-      rc = dec_select(P.s, s);
-    } else {
-      return set_error("dec_mega: unknown phase kind");
-    }
-    if (rc) return rc;
-  }
-  sync[2] += 1u;  // the epoch the kernel advances
   return 0;
 }
 

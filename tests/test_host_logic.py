@@ -263,17 +263,14 @@ def test_frame_ingestion_u8_bit_exact_and_model_equivalence(emu):
 
 # head dim 32 (nhead 4): the per-kernel step vc_seq_decode_step (17 sequences: its GEMM path, > 16 rows); head dim 64 (nhead 2): the
 # device-resident step vc_seq_decode_step_dev (<= 8 and 9..16 sequences: both row-count instantiations; Ff != H)
-# mega: the device-resident step as the phase program of the persistent kernel (vc_seq_decode_step_mega) or as 66 launches
-@pytest.mark.parametrize("layers,window,L_,B_,nhead,ff,mega", [(1, 2, 5, 2, 4, 128, "1"), (3, 3, 8, 2, 4, 128, "1"), (2, 2, 4, 17, 4, 128, "1"),
-                                                               (3, 3, 9, 3, 2, 256, "1"), (2, 2, 6, 9, 2, 128, "1"), (1, 4, 5, 17, 2, 128, "1"),
-                                                               (3, 3, 9, 3, 2, 256, "0"), (2, 2, 6, 9, 2, 128, "0")])
-def test_sequential_inference_matches_oracle(emu, monkeypatch, layers, window, L_, B_, nhead, ff, mega):
+@pytest.mark.parametrize("layers,window,L_,B_,nhead,ff", [(1, 2, 5, 2, 4, 128), (3, 3, 8, 2, 4, 128), (2, 2, 4, 17, 4, 128),
+                                                          (3, 3, 9, 3, 2, 256), (2, 2, 6, 9, 2, 128), (1, 4, 5, 17, 2, 128)])
+def test_sequential_inference_matches_oracle(emu, layers, window, L_, B_, nhead, ff):
     """Rollout with action feedback through the incremental decoder (one token per step against the key/value cache) against
     the oracle's O(T^2) recompute of the reference loop; three layers exercise the layer-output hand-over, T > window the
     clipping of the cross-attention window."""
     import videocad_b200.model as vm
 
-    monkeypatch.setenv("VIDEOCAD_B200_DECODE_MEGA", mega)
     cfg = dict(hidden_size=128, nhead=nhead, num_decoder_layers=layers, dim_feedforward=ff, window_size=window,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build_emu_model(emu, cfg)
@@ -281,13 +278,12 @@ def test_sequential_inference_matches_oracle(emu, monkeypatch, layers, window, L
     inp = to.model_inputs_from_batch(to.synthetic_batch(B_, L_, 64))
     used = []
     orig = vm._SeqRunner.decode_run
-    vm._SeqRunner.decode_run = lambda self, dec, T: (used.append((T, bool(dec.get("mega")))), orig(self, dec, T))[1]
+    vm._SeqRunner.decode_run = lambda self, dec, T: (used.append(T), orig(self, dec, T))[1]
     try:
         ac, ap = m.sequential_inference(inp["frames"], inp["cad_image"], action=True)
     finally:
         vm._SeqRunner.decode_run = orig
     assert bool(used) == (nhead == 2 and B_ <= 16), "which decode step ran"
-    assert all(flag == (mega == "1") for _, flag in used), "persistent-kernel program vs per-kernel launches"
     oc, op = to.rollout(sd, cfg, inp["frames"], inp["cad_image"], action=True)
     assert (ac - oc).abs().max() < 2e-4 and (ap - op).abs().max() < 2e-4
     assert (ac.argmax(-1) == oc.argmax(-1)).all()

@@ -167,11 +167,8 @@ def test_bf16_single_pass_mode_is_looser_but_close():
 
 # H = 256 (head dim 64), <= 16 sequences: the device-resident decode step (vc_seq_decode_step_dev; 9 sequences: its 16-row
 # instantiation); 18 sequences: the per-kernel step's tensor-core path; H = 128 (head dim 32): the per-kernel step's row kernels
-# mega: the device-resident step as ONE persistent kernel (vc_seq_decode_step_mega, the default) or as 66 launches ("0")
-@pytest.mark.parametrize("B,T,H,mega", [(2, 6, 256, "1"), (2, 19, 256, "1"), (9, 7, 256, "1"), (18, 5, 256, "1"), (2, 7, 128, "1"),
-                                        (2, 19, 256, "0"), (9, 7, 256, "0")])
-def test_prefix_invariance_and_rollout(monkeypatch, B, T, H, mega):
-    monkeypatch.setenv("VIDEOCAD_B200_DECODE_MEGA", mega)
+@pytest.mark.parametrize("B,T,H", [(2, 6, 256), (2, 19, 256), (9, 7, 256), (18, 5, 256), (2, 7, 128)])
+def test_prefix_invariance_and_rollout(B, T, H):
     cfg = dict(hidden_size=H, nhead=4, num_decoder_layers=3, dim_feedforward=256, window_size=2,
                enable_past_actions=True, enable_past_states=True, enable_timestep_embedding=True)
     m, sd = build(cfg)

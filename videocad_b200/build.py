@@ -11,7 +11,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvideocad_b200.so")
 
-CU_SOURCES = ["gemm_tc.cu", "rowops.cu", "attention.cu", "attention_small.cu", "attention_vit.cu", "decode.cu", "decode_mega.cu", "ingest.cu", "loss.cu", "optim.cu", "host_util_cuda.cu"]
+CU_SOURCES = ["gemm_tc.cu", "rowops.cu", "attention.cu", "attention_small.cu", "attention_vit.cu", "decode.cu", "ingest.cu", "loss.cu", "optim.cu", "host_util_cuda.cu"]
 CPP_SOURCES = ["host_util.cpp", "c_api.cpp", "model_vit.cpp", "model_seq.cpp"]
 
 NVCC_FLAGS = [

@@ -220,32 +220,6 @@ struct DecSelect {
 };
 int dec_select(const DecSelect& a, stream_t s);
 
-// ---- the whole decode step as ONE persistent kernel (decode_mega.cu; CPU twin in oracle/csrc/kernels_cpu.cpp) ----
-// A step is a fixed PROGRAM of phases -- the DecGemv / DecAttn / DecSelect calls of seq_decode_step_dev, in order -- that depends on the
-// position only through *t_ptr.  The program is written once per rollout into device memory (dec_mega_upload) and every position is one
-// launch of dec_mega_kernel: dec_mega_ctas() co-resident CTAs walk the phases with a grid-wide barrier after each, and a per-CTA
-// shared-memory ring keeps the fp32 weight rows of the NEXT phases in flight (TMA bulk copies) while the current phase and the barrier
-// run.  Each DecGemv of a program carries cols_per_cta = dec_mega_cols(N); each split DecAttn carries nsplit <= dec_mega_nsplit(...).
-enum { VC_MEGA_GEMV = 0, VC_MEGA_ATTN = 1, VC_MEGA_SELECT = 2 };
-constexpr int VC_MEGA_MAX_PHASES = 8 * 8 + 2;  // 8 decoder layers x 8 phases + parameter head + selection
-struct MegaPhase {
-  int kind;
-  int B;  // sequences (VC_MEGA_ATTN / VC_MEGA_SELECT work items)
-  union {
-    DecGemv g;
-    DecAttn a;
-    DecSelect s;
-  };
-};
-int dec_mega_ctas();                           // CTAs of the persistent grid (<= SM count, one per SM)
-int dec_mega_cols(int N);                      // output columns one CTA owns in a GEMV phase with N outputs (0: N too large)
-int dec_mega_nsplit(int B, int nh);            // key splits of the self-attention phase
-// copies `nph` phases to `program_dev` (nph * sizeof(MegaPhase) bytes); the host array may be released on return
-int dec_mega_upload(const MegaPhase* host, int nph, void* program_dev, stream_t s);
-// one position: sync = 4 zero-initialised words {barrier counter, error flag, epoch, -} owned by the rollout (8-byte aligned);
-// M = sequences, dh = head dim.  A barrier that does not complete within ~2 s sets the error flag and the step writes NaN command logits.
-int dec_mega(const void* program_dev, int nph, int M, int dh, unsigned int* sync, const int* t_ptr, stream_t s);
-
 // frame ingestion: uint8 grey-level frames -> the fp32 tensor the reference's loader hands the model,
 // i.e. torchvision ToTensor (u / 255) followed by Normalize(mean, std) (/root/reference/main.py:103-110: mean = std = 0.5):
 // dst[i] = (float(src[i]) / 255 - mean) / std, evaluated with the same fp32 operations in the same order (bit-exact)

@@ -13,8 +13,6 @@
 //   neither                 : tgt = memory = tanh(cad), both masks banded
 // Dropout sites (site_base + 7*l + i): 0 self-attn probs, 1 dropout1, 2 cross-attn probs, 3 dropout2, 4 FFN hidden, 5 dropout3.
 #include <math.h>
-#include <string.h>
-#include <algorithm>
 #include <vector>
 #include "model_common.h"
 
@@ -488,93 +486,11 @@ size_t seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nh) {
   return a.used();
 }
 
-namespace {
-// Where the phases of one decode step go: launched one after the other (decode.cu), or recorded as the program of the persistent
-// kernel (decode_mega.cu).  The phase list itself is the same.
-struct DecodeSink {
-  stream_t st;
-  MegaPhase* prog;  // null: launch
-  int n;
-  int gemv(DecGemv& g) {
-    if (!prog) return dec_gemv(g, st);
-    g.cols_per_cta = dec_mega_cols(g.N);
-    if (g.cols_per_cta <= 0 || n >= VC_MEGA_MAX_PHASES) return set_error("decode program: phase does not fit the persistent kernel");
-    MegaPhase& P = prog[n++];
-    P.kind = VC_MEGA_GEMV; P.B = g.M; P.g = g;
-    return 0;
-  }
-  int attn(DecAttn& a, int B) {
-    if (!prog) return dec_attn(a, B, st);
-    if (n >= VC_MEGA_MAX_PHASES) return set_error("decode program: too many phases");
-    if (a.nsplit > 1) a.nsplit = std::min(a.nsplit, dec_mega_nsplit(B, a.nh));
-    MegaPhase& P = prog[n++];
-    P.kind = VC_MEGA_ATTN; P.B = B; P.a = a;
-    return 0;
-  }
-  int select(DecSelect& s) {
-    if (!prog) return dec_select(s, st);
-    if (n >= VC_MEGA_MAX_PHASES) return set_error("decode program: too many phases");
-    MegaPhase& P = prog[n++];
-    P.kind = VC_MEGA_SELECT; P.B = s.B; P.s = s;
-    return 0;
-  }
-};
-
-int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all, float* params_all,
-                  DecodeSink& sink, DevStepWs* ws_out);
-}  // namespace
-
 int seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
                         float* params_all, stream_t st) {
-  DecodeSink sink = {st, nullptr, 0};
-  return decode_phases(c, t_dev, actions_io, scratch, scratch_bytes, cmds_all, params_all, sink, nullptr);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// The same step as ONE persistent kernel (decode_mega.cu): seq_decode_mega_prepare records the phases as a program in device memory
-// once per rollout; seq_decode_step_mega launches the kernel for the position *t_dev.
-// ---------------------------------------------------------------------------------------------------------------------
-int seq_decode_mega_supported(const vc_seq_call* c) {
-  if (!seq_decode_dev_supported(c)) return 0;
-  if (8 * c->w->num_layers + 2 > VC_MEGA_MAX_PHASES) return 0;
-  return dec_mega_cols(3 * c->H) > 0 && dec_mega_cols(c->H) > 0 && dec_mega_cols(c->Ff) > 0 && dec_mega_cols(c->num_param_out) > 0;
-}
-
-size_t seq_decode_mega_program_bytes() { return (size_t)VC_MEGA_MAX_PHASES * sizeof(MegaPhase); }
-
-int seq_decode_mega_prepare(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
-                            float* params_all, void* program, size_t program_bytes, stream_t st) {
-  VC_TRY(check_call(c));
-  if (!seq_decode_mega_supported(c)) return set_error("seq_decode_mega_prepare: unsupported configuration (use vc_seq_decode_step_dev)");
-  if (!program || program_bytes < seq_decode_mega_program_bytes()) return set_error("seq_decode_mega_prepare: program buffer too small");
-  std::vector<MegaPhase> prog(VC_MEGA_MAX_PHASES);
-  memset(prog.data(), 0, prog.size() * sizeof(MegaPhase));
-  DecodeSink sink = {st, prog.data(), 0};
-  VC_TRY(decode_phases(c, t_dev, actions_io, scratch, scratch_bytes, cmds_all, params_all, sink, nullptr));
-  if (sink.n != 8 * c->w->num_layers + 2 || prog[sink.n - 1].kind != VC_MEGA_SELECT) return set_error("seq_decode_mega_prepare: unexpected program");
-  return dec_mega_upload(prog.data(), sink.n, program, st);
-}
-
-int seq_decode_step_mega(const vc_seq_call* c, const void* program, void* scratch, size_t scratch_bytes, int* t_dev, stream_t st) {
-  VC_TRY(check_call(c));
-  if (!program || !scratch || !t_dev) return set_error("seq_decode_step_mega: null argument");
-  if (!seq_decode_mega_supported(c)) return set_error("seq_decode_step_mega: unsupported configuration");
-  const Dims d = dims_of(c);
-  Arena sa(scratch, scratch_bytes);
-  DevStepWs s;
-  dev_step_carve(sa, d.B, d.H, d.Ff, d.nh, s);
-  if (!sa.ok()) return set_error("seq_decode_step_mega: scratch too small");
-  return dec_mega(program, 8 * d.L + 2, d.B, d.dh, s.done + 16, t_dev, st);  // words 16..19 of the zero-filled counter block
-}
-
-namespace {
-int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all, float* params_all,
-                  DecodeSink& sink, DevStepWs* ws_out) {
   VC_TRY(check_call(c));
   if (!t_dev || !actions_io || !scratch || !cmds_all || !params_all) return set_error("seq_decode_step_dev: null argument");
   if (!seq_decode_dev_supported(c)) return set_error("seq_decode_step_dev: unsupported configuration (use vc_seq_decode_step)");
-  stream_t st = sink.st;
-  (void)st;
   const vc_seq_weights& W = *c->w;
   const Dims d = dims_of(c);
   const int B = d.B, T = d.T, H = d.H, Ff = d.Ff;
@@ -586,14 +502,13 @@ int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scr
   DevStepWs s;
   dev_step_carve(sa, B, H, Ff, d.nh, s);
   if (!sa.ok()) return set_error("seq_decode_step_dev: scratch too small");
-  if (ws_out) *ws_out = s;
   const float scale = 1.0f / sqrtf((float)d.dh);
 
   auto gemv = [&](DecGemv& g, const vc_linear& Lw, int64_t row0, int N, int K, float* out, int64_t row_stride, int64_t t_stride) -> int {
     g.M = B; g.N = N; g.K = K;
     g.W = Lw.w + row0 * K; g.bias = Lw.b ? Lw.b + row0 : nullptr;
     g.out = out; g.out_row_stride = row_stride; g.out_t_stride = t_stride; g.t_ptr = t_dev;
-    return sink.gemv(g);
+    return dec_gemv(g, st);
   };
   for (int l = 0; l < d.L; ++l) {
     const vc_dec_layer& LW = W.layers[l];
@@ -615,7 +530,7 @@ int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scr
       a.k = Y.qkv + H; a.v = Y.qkv + 2 * H; a.kv_bstride = (int64_t)T * 3 * H; a.kv_rstride = 3 * H;
       a.nh = d.nh; a.dh = d.dh; a.nsplit = DEC_SPLITS; a.window = 0; a.scale = scale; a.t_ptr = t_dev;
       a.out = s.sa; a.ld_out = H; a.part_o = s.part_o; a.part_ml = s.part_ml; a.counters = s.counters;
-      VC_TRY(sink.attn(a, B));
+      VC_TRY(dec_attn(a, B, st));
     }
     {  // K3
       DecGemv g = {};
@@ -634,7 +549,7 @@ int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scr
       a.k = Y.kv2; a.v = Y.kv2 + H; a.kv_bstride = (int64_t)T * 2 * H; a.kv_rstride = 2 * H;
       a.nh = d.nh; a.dh = d.dh; a.nsplit = 1; a.window = c->window; a.scale = scale; a.t_ptr = t_dev;
       a.out = s.ca; a.ld_out = H;
-      VC_TRY(sink.attn(a, B));
+      VC_TRY(dec_attn(a, B, st));
     }
     {  // K6
       DecGemv g = {};
@@ -668,11 +583,10 @@ int decode_phases(const vc_seq_call* c, int* t_dev, float* actions_io, void* scr
     a.H = H; a.B = B; a.NPAR = d.NP / 1000; a.NV = 1000; a.T = T;
     a.cmds_all = cmds_all; a.params_all = params_all; a.action_next = actions_io;
     a.t_ptr = t_dev; a.done_ctr = s.done;
-    VC_TRY(sink.select(a));
+    VC_TRY(dec_select(a, st));
   }
   return 0;
 }
-}  // namespace
 
 int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                  float* d_mv_cls, void* scratch, size_t scratch_bytes, stream_t st) {
@@ -894,15 +808,6 @@ size_t vc_seq_decode_dev_scratch_bytes(int B, int H, int Ff, int nhead) { return
 int vc_seq_decode_step_dev(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
                            float* params_all, void* stream) {
   return vck::seq_decode_step_dev(c, t_dev, actions_io, scratch, scratch_bytes, cmds_all, params_all, stream);
-}
-int vc_seq_decode_mega_supported(const vc_seq_call* c) { return vck::seq_decode_mega_supported(c); }
-size_t vc_seq_decode_mega_program_bytes(void) { return vck::seq_decode_mega_program_bytes(); }
-int vc_seq_decode_mega_prepare(const vc_seq_call* c, int* t_dev, float* actions_io, void* scratch, size_t scratch_bytes, float* cmds_all,
-                               float* params_all, void* program, size_t program_bytes, void* stream) {
-  return vck::seq_decode_mega_prepare(c, t_dev, actions_io, scratch, scratch_bytes, cmds_all, params_all, program, program_bytes, stream);
-}
-int vc_seq_decode_step_mega(const vc_seq_call* c, const void* program, void* scratch, size_t scratch_bytes, int* t_dev, void* stream) {
-  return vck::seq_decode_step_mega(c, program, scratch, scratch_bytes, t_dev, stream);
 }
 int vc_seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams, float* d_state_cls, float* d_cad_cls,
                     float* d_mv_cls, void* scratch, size_t scratch_bytes, void* stream) {

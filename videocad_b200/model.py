@@ -766,17 +766,6 @@ class _SeqRunner(_Segment):
                 dec["dsc_bytes"] = lib.vc_seq_decode_dev_scratch_bytes(B, H, Ff, nh)
                 dec["dscratch"] = torch.zeros(dec["dsc_bytes"], dtype=torch.uint8, device=dev)
                 dec["dgraph"], dec["duses"] = None, 0
-                # ... as ONE persistent kernel per position where the configuration allows (vc_seq_decode_step_mega): the step's phase
-                # program is written to device memory once, here
-                dec["mega"] = (bool(lib.vc_seq_decode_mega_supported(C.byref(c)))
-                               and os.environ.get("VIDEOCAD_B200_DECODE_MEGA", "1") != "0")
-                if dec["mega"]:
-                    dec["program_bytes"] = lib.vc_seq_decode_mega_program_bytes()
-                    dec["program"] = torch.zeros(dec["program_bytes"], dtype=torch.uint8, device=dev)
-                    L.check(lib.vc_seq_decode_mega_prepare(C.byref(c), dec["t_dev"].data_ptr(), dec["actions_io"].data_ptr(),
-                                                           dec["dscratch"].data_ptr(), dec["dsc_bytes"], dec["cmds_all"].data_ptr(),
-                                                           dec["params_all"].data_ptr(), dec["program"].data_ptr(), dec["program_bytes"],
-                                                           _stream_of(cad_cls)), lib)
             if persistent:
                 if len(self._dstates) >= 2:
                     self._dstates.pop(next(iter(self._dstates)))
@@ -799,10 +788,6 @@ class _SeqRunner(_Segment):
 
         def body():
             st = _stream_of(dec["cmds_all"])
-            if dec.get("mega"):
-                L.check(lib.vc_seq_decode_step_mega(C.byref(dec["call"]), dec["program"].data_ptr(), dec["dscratch"].data_ptr(),
-                                                    dec["dsc_bytes"], dec["t_dev"].data_ptr(), st), lib)
-                return
             L.check(lib.vc_seq_decode_step_dev(C.byref(dec["call"]), dec["t_dev"].data_ptr(), dec["actions_io"].data_ptr(),
                                                dec["dscratch"].data_ptr(), dec["dsc_bytes"], dec["cmds_all"].data_ptr(),
                                                dec["params_all"].data_ptr(), st), lib)

@@ -73,9 +73,5 @@ L.EXTRA_PROTOS.update({
     "vc_seq_decode_dev_supported": ([C.POINTER(SeqCall)], i32),
     "vc_seq_decode_dev_scratch_bytes": ([i32, i32, i32, i32], sz),
     "vc_seq_decode_step_dev": ([C.POINTER(SeqCall), vp, vp, vp, sz, vp, vp, vp], i32),
-    "vc_seq_decode_mega_supported": ([C.POINTER(SeqCall)], i32),
-    "vc_seq_decode_mega_program_bytes": ([], sz),
-    "vc_seq_decode_mega_prepare": ([C.POINTER(SeqCall), vp, vp, vp, sz, vp, vp, vp, sz, vp], i32),
-    "vc_seq_decode_step_mega": ([C.POINTER(SeqCall), vp, vp, sz, vp, vp], i32),
     "vc_seq_backward": ([C.POINTER(SeqCall), vp, vp, vp, vp, vp, vp, sz, vp], i32),
 })
