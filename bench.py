@@ -19,6 +19,8 @@ the named shape; frames = B*T model frames per step, summed over ranks (weak sca
              "kind": "reference" when the staged reference sources are present -- oracle/build_ref.py -- else the oracle's port)
   through_trainer  the UNMODIFIED reference trainer object (its compute_loss with the .item() syncs, torch clip + Adam) driving the
              drop-in on the GPU: what a user of trainer.py gets without touching it
+  through_trainer_fused  the same trainer object after videocad_b200.trainer_accel.accelerate_trainer(trainer): fused loss + metrics
+             kernels and ClipAdam behind the unmodified training loop; loss and metrics read on the host every step
   rollout    BASELINE config C4 on this GPU: 186-step action-feedback rollout of the H=1024 model, 8 sequences, with the decode
              step's HBM roofline (weight + cache bytes per step / step time / measured copy bandwidth)
   c3         (N > 1 only) BASELINE config C3 -- T=32, H=1024, 32 samples per GPU under DDP -- timed in the same launch
@@ -272,10 +274,12 @@ def measure_rollout(dev, peak, world=1, iters=3):
                                    "(mean over the 186 steps); the step's time includes the full-length pass that builds the cache"))
 
 
-def measure_through_trainer(net, dev_batches, B, T, world, steps):
+def measure_through_trainer(net, dev_batches, B, T, world, steps, accelerate=False):
     """frames/s of the UNMODIFIED reference trainer (oracle/_ref staged copy or /root/reference) driving the drop-in on the GPU:
     trainer._process_batch = zero_grad -> prepare_batch -> model -> its own compute_loss (argmax metrics with ~30 .item() syncs) ->
-    backward -> torch clip_grad_norm_ -> torch Adam."""
+    backward -> torch clip_grad_norm_ -> torch Adam.  `accelerate`: the same trainer object after
+    `videocad_b200.trainer_accel.accelerate_trainer` (fused loss + metrics, ClipAdam); the loss and the metrics dict are read on the
+    host every step, as the reference's training loop does (trainer.py:450-451)."""
     if not reference_available():
         return dict(unavailable="reference sources not staged (python -m oracle.build_ref in the build container)")
     import torch.distributed as dist
@@ -283,15 +287,25 @@ def measure_through_trainer(net, dev_batches, B, T, world, steps):
 
     dev = dev_batches[0]["frames"].device
     trainer = rt.make_trainer(net, dev, lr=1e-5)
+    if accelerate:
+        from videocad_b200.trainer_accel import accelerate_trainer
+
+        accelerate_trainer(trainer)
+
+    def one(i):
+        loss, metrics = trainer._process_batch(dev_batches[i % NUM_BATCHES])
+        if accelerate:  # what _train_epoch does with the two results (the unpatched compute_loss has synchronised ~30 times already)
+            return loss.item() + metrics["total_predictions"]
+
     for i in range(3):
-        trainer._process_batch(dev_batches[i % NUM_BATCHES])
+        one(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        trainer._process_batch(dev_batches[i % NUM_BATCHES])
+        one(i)
     e1.record()
     if world > 1:
         dist.barrier()
@@ -300,9 +314,11 @@ def measure_through_trainer(net, dev_batches, B, T, world, steps):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = ms.item()
-    return dict(value=world * B * T * steps / (ms / 1e3), unit="frames/s", ms_per_step=ms / steps, steps=steps,
-                note="unmodified trainer._process_batch (trainer.py:480-496) around the drop-in: the reference's compute_loss with its "
-                     ".item() syncs, torch clip_grad_norm_ and torch Adam; inputs resident in HBM")
+    note = ("unmodified trainer object after accelerate_trainer(): its _process_batch with the fused loss + metrics kernels and ClipAdam; "
+            "loss.item() and the metrics dict read on the host every step; inputs resident in HBM") if accelerate else \
+           ("unmodified trainer._process_batch (trainer.py:480-496) around the drop-in: the reference's compute_loss with its "
+            ".item() syncs, torch clip_grad_norm_ and torch Adam; inputs resident in HBM")
+    return dict(value=world * B * T * steps / (ms / 1e3), unit="frames/s", ms_per_step=ms / steps, steps=steps, note=note)
 
 
 def measure_c3(args, rank, world, local_rank, steps=10):
@@ -527,6 +543,7 @@ def main():
 
     # ---------------- through the unmodified reference trainer object (its own loss / metrics / clip / Adam)
     through_trainer = measure_through_trainer(net, dev_batches, B, T, world, max(5, args.steps // 2))
+    through_trainer_fused = measure_through_trainer(net, dev_batches, B, T, world, args.steps, accelerate=True)
 
     # ---------------- e2e: host (pinned) inputs, H2D + loss read-back inside the timed region
     del dev_batches
@@ -623,7 +640,8 @@ def main():
                 gpu_launches=launches_inst, gpu_launches_note="native kernels per %d steps (%d per step); with CUDA-graph replay "
                 "the same kernels run from 6 graph launches per step" % (args.steps, launches_inst // max(args.steps, 1)),
                 cuda_graphs=bool(graphs_were_on), segments_ms_per_step=segments, roofline=roofline,
-                cpu_baseline=cpu_baseline, through_trainer=through_trainer, rollout=rollout, c3=c3,
+                cpu_baseline=cpu_baseline, through_trainer=through_trainer, through_trainer_fused=through_trainer_fused,
+                rollout=rollout, c3=c3,
                 ms_per_step_without_allreduce=(ms_nosync / args.steps) if ms_nosync is not None else None,
                 exposed_allreduce_ms=((ms - ms_nosync) / args.steps) if ms_nosync is not None else None)
     emit(line)

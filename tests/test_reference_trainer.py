@@ -29,7 +29,7 @@ def _reference_step(batch, cfg=CFG):
     return loss.item(), metrics, grads, after
 
 
-def _dropin_step(batch, device, emu=None, cfg=CFG, compile_it=True):
+def _dropin_step(batch, device, emu=None, cfg=CFG, compile_it=True, accelerate=False):
     from oracle import ref_trainer as rt
     from videocad_b200 import ModelFactory
 
@@ -40,6 +40,10 @@ def _dropin_step(batch, device, emu=None, cfg=CFG, compile_it=True):
     model.eval()
     wrapped = torch.compile(model, dynamic=False) if compile_it else model  # experiment.py:92-93
     trainer = rt.make_trainer(wrapped, device, lr=1e-3)
+    if accelerate:
+        from videocad_b200.trainer_accel import accelerate_trainer
+
+        assert accelerate_trainer(trainer, _lib=emu) is trainer
     loss, metrics = trainer._process_batch(batch)
     grads = {k: w.grad.detach().cpu().clone() for k, w in model.named_weights() if w.grad is not None}
     after = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
@@ -72,6 +76,60 @@ def test_unmodified_trainer_drives_the_dropin_cpu_emulation():
     emu = L.load(build_emu.build(), require_cuda_build=False)
     batch = to.synthetic_batch(2, 5, 64, seed=21)
     _compare(_reference_step(batch), _dropin_step(batch, "cpu", emu=emu))
+
+
+def test_accelerated_trainer_cpu_emulation():
+    """`accelerate_trainer` on the unmodified trainer object: fused loss + lazily read metrics + ClipAdam behind the same
+    `_process_batch` call give the reference trainer's loss, metrics dict, clipped gradients and Adam-updated weights."""
+    from oracle import build_emu
+    from oracle import ref_trainer as rt
+    from videocad_b200 import lib as L
+    from videocad_b200.optim import ClipAdam
+    from videocad_b200.trainer_accel import LazyMetrics, accelerate_trainer
+
+    emu = L.load(build_emu.build(), require_cuda_build=False)
+    batch = to.synthetic_batch(2, 5, 64, seed=21)
+    ref = _reference_step(batch)
+    got = _dropin_step(batch, "cpu", emu=emu, accelerate=True)
+    assert isinstance(got[1], LazyMetrics) and dict(got[1]) == ref[1]
+    _compare(ref, got)
+    # what the patch refuses: a trainer on the plain-CE branch of compute_loss, a non-Adam optimizer
+    model = rt.build_reference_model(CFG, "cpu", seed=0)
+    tr = rt.make_trainer(model, "cpu")
+    tr.use_mse = False
+    with pytest.raises(ValueError):
+        accelerate_trainer(tr, _lib=emu)
+    tr.use_mse = True
+    tr.optimizer = torch.optim.SGD(model.parameters(), lr=0.1)
+    with pytest.raises(ValueError):
+        accelerate_trainer(tr, _lib=emu)
+    # loss only: the trainer keeps its own _process_batch (torch clip + Adam) and gets the fused loss
+    tr = rt.make_trainer(model, "cpu")
+    accelerate_trainer(tr, fuse_optimizer=False, _lib=emu)
+    assert not isinstance(tr.optimizer, ClipAdam) and "_process_batch" not in vars(tr) and "compute_loss" in vars(tr)
+
+
+@pytest.mark.gpu
+def test_accelerated_trainer_on_the_gpu():
+    """The same on the CUDA library, then three more steps next to the reference trainer (eager, capture, replay paths)."""
+    from oracle import ref_trainer as rt
+    from videocad_b200 import ModelFactory
+    from videocad_b200.trainer_accel import accelerate_trainer
+
+    batch = to.synthetic_batch(3, 7, 224, seed=22)
+    _compare(_reference_step(batch), _dropin_step(batch, "cuda", accelerate=True))
+    ref_model = rt.build_reference_model(CFG, "cpu", seed=0)
+    ref_model.eval()
+    ref_tr = rt.make_trainer(ref_model, "cpu", lr=1e-4)
+    model, _ = ModelFactory().create_model("autoregressive", dict(CFG, state_dim=1644, act_dim=7, encoder="vit"), "cuda",
+                                           state_dict=to.seeded_state_dict(CFG, 0))
+    model.eval()
+    got_tr = accelerate_trainer(rt.make_trainer(torch.compile(model, dynamic=False), "cuda", lr=1e-4))
+    for step in range(4):
+        l0, m0 = ref_tr._process_batch(batch)
+        l1, m1 = got_tr._process_batch(batch)
+        assert abs(l0.item() - l1.item()) < 2e-3 * abs(l0.item()), (step, l0.item(), l1.item())
+        assert m0["total_predictions"] == m1["total_predictions"] and len(m1) == len(m0)
 
 
 @pytest.mark.gpu
