@@ -1062,6 +1062,12 @@ class AutoRegressiveTransformer(_FlatOwner):
         masked[:, :, 3] = torch.where((masked[:, :, 2] >= 200) & (masked[:, :, 2] < 250), masked[:, :, 3], -1)
         return masked
 
+    def _check_length(self, T):
+        """timestep_embedding(arange(T)) (autoregressive_transformer.py:144-146) raises IndexError past its max_ep_len rows; the
+        native kernels index the table by position, so the same condition is checked here."""
+        if self.enable_timestep_embedding and T > self.max_ep_len:
+            raise IndexError(f"index out of range in self: sequence length {T} exceeds the timestep table (max_ep_len = {self.max_ep_len})")
+
     def _check_device(self, t):
         st, cad, seq = self._get_runners()
         if not t.is_cuda and cad._lib is None:
@@ -1084,7 +1090,15 @@ class AutoRegressiveTransformer(_FlatOwner):
         multiview_images = inputs.get("multiview_images", None)
         self._check_device(cad_image)
         st_r, cad_r, seq_r = self._get_runners()
+        if actions.dim() != 3 or actions.shape[-1] != self.act_dim:
+            # embed_action is Linear(act_dim, H): the reference fails in the matmul; the native kernels index act_dim columns per row
+            raise RuntimeError(f"actions must be [B, T, {self.act_dim}], got {tuple(actions.shape)}")
         B, T = actions.shape[0], actions.shape[1]
+        if B == 0 or T == 0:
+            raise ValueError(f"empty batch: actions are {tuple(actions.shape)}")
+        if cad_image.shape[0] != B:
+            raise RuntimeError(f"cad_image carries {cad_image.shape[0]} images for a batch of {B}")
+        self._check_length(T)
         training, p, passes = self.training, self.dropout_p, self._passes
         p_cad = cad_r.owner.dropout_p
         p_st = st_r.owner.dropout_p if st_r is not None else 0.0
@@ -1147,6 +1161,7 @@ class AutoRegressiveTransformer(_FlatOwner):
                 return self.sequential_inference(ui_images, cad_image, action)
         st_r, cad_r, seq_r = self._get_runners()
         B, T = ui_images.shape[:2]
+        self._check_length(T)
         dev, passes = ui_images.device, self._passes
         state_cls = None
         if self.enable_past_states:
