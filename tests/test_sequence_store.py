@@ -64,6 +64,31 @@ def test_errors(tmp_path):
     p.write_bytes(b"not a store at all")
     with pytest.raises(ValueError, match="not a videocad_b200 sequence store"):
         SequenceStore(str(p))
+    good_files, _, _ = _write_dataset(str(tmp_path / "ds2"), [3, 4])
+    with pytest.raises(ValueError, match="duplicate"):  # samples are looked up by id: two files with one id cannot both be stored
+        convert_pickles(good_files, str(tmp_path / "dup.vcseq"), ids=["a", "a"])
+    out = str(tmp_path / "ok.vcseq")
+    convert_pickles(good_files, out)
+    size = os.path.getsize(out)
+    with open(out, "r+b") as f:
+        f.truncate(size - 4096)  # a copy that was cut short must be refused at open time, not fail inside a DataLoader worker
+    with pytest.raises(ValueError, match="truncated"):
+        SequenceStore(out)
+
+
+def test_store_pickles_as_a_path_not_as_the_data(tmp_path):
+    """DataLoader workers started with `spawn` pickle the dataset (and its retriever): the store must travel as its path and
+    re-open the mapping, not serialise the mapped file."""
+    data_files, image_files, truth = _write_dataset(str(tmp_path / "ds"), [6, 40])
+    out = str(tmp_path / "ds.vcseq")
+    convert_pickles(data_files, out)
+    r = MmapSequenceRetriever(data_files, image_files, out)
+    blob = pickle.dumps(r)
+    assert len(blob) < 4096 < os.path.getsize(out)
+    r2 = pickle.loads(blob)
+    for i, (frames, actions, _, sid) in enumerate(truth):
+        f, a, got = r2.get_sequence(i)
+        assert got == sid and np.array_equal(f, frames) and np.array_equal(a, actions) and not f.flags.owndata
 
 
 @pytest.mark.skipif(not rm.available(), reason="reference sources neither under /root/reference nor staged in oracle/_ref")

@@ -48,6 +48,9 @@ def convert_pickles(data_files: Sequence[str], out_path: str, ids: Optional[Sequ
     ids = list(ids) if ids is not None else [sample_id_of(f) for f in data_files]
     if len(ids) != len(data_files):
         raise ValueError("ids and data_files must have the same length")
+    if len(set(ids)) != len(ids):
+        dup = sorted({i for i in ids if ids.count(i) > 1})
+        raise ValueError(f"duplicate sample ids {dup[:5]}: samples are looked up by id")
     # pass 1: shapes (a sample is unpickled twice; conversion is a one-off)
     metas = []
     H = W = C = act_dim = None
@@ -116,6 +119,17 @@ class SequenceStore:
     """Read side: one np.memmap over the file, zero-copy views per sample."""
 
     def __init__(self, path: str):
+        self._open(path)
+
+    # DataLoader workers started with `spawn` (and anything else that pickles the dataset) must re-open the mapping: pickling an
+    # np.memmap would serialise the whole file
+    def __getstate__(self):
+        return {"path": self.path}
+
+    def __setstate__(self, state):
+        self._open(state["path"])
+
+    def _open(self, path: str):
         self.path = path
         with open(path, "rb") as f:
             if f.read(8) != MAGIC:
@@ -131,6 +145,11 @@ class SequenceStore:
         self._fdtype, self._adtype = np.dtype(h["frame_dtype"]), np.dtype(h["action_dtype"])
         self.ids: List[str] = [s["id"] for s in h["samples"]]
         self._index = {sid: i for i, sid in enumerate(self.ids)}
+        per = int(np.prod(self._fshape)) * self._fdtype.itemsize
+        end = max([0] + [max(s["frame_off"] + s["n"] * per, s["action_off"] + s["n"] * h["act_dim"] * self._adtype.itemsize,
+                             s["time_off"] + s["nt"] * 8) for s in h["samples"]])
+        if self._data_start + end > self._mm.shape[0]:
+            raise ValueError(f"{path}: truncated store ({self._mm.shape[0]} bytes, the index needs {self._data_start + end})")
 
     def __len__(self) -> int:
         return len(self.ids)
