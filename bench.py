@@ -402,6 +402,9 @@ def main():
                          "torch calls of the reference trainer")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rollout", action="store_true", help="skip the C4 rollout leg")
+    ap.add_argument("--quick", action="store_true",
+                    help="A/B runs: only the `value` pass and the per-segment pass, then a short JSON line (no roofline / e2e / "
+                         "trainer / rollout / CPU legs)")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -511,6 +514,16 @@ def main():
         segments = {k: round(v[1] / args.steps, 4) for k, v in sorted(rep.items())}
         segments["step_ms"] = round(ms_seg / args.steps, 4)
         segments["outside_graphs_ms"] = round(ms_seg / args.steps - sum(v[1] for v in rep.values()) / args.steps, 4)
+
+    if args.quick:
+        if rank == 0:
+            emit(dict(metric="train frames/sec", value=value, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                      ms_per_step=ms / args.steps, quick=True, clocks=clocks, segments_ms_per_step=segments,
+                      env={k: v for k, v in os.environ.items() if k.startswith(("VC_", "VIDEOCAD_B200_"))}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---------------- roofline pass: the same K steps with the native segments launched kernel by kernel (CUDA-graph
     # replay off) so that a CUDA-event pair can be recorded around every GEMM launch on the launching stream

@@ -27,7 +27,12 @@ extern "C" {
 
 typedef uint16_t vc_bf16;
 
-enum { VC_ACT_NONE = 0, VC_ACT_GELU = 1, VC_ACT_RELU = 2, VC_ACT_TANH = 3 };
+enum { VC_ACT_NONE = 0, VC_ACT_GELU = 1, VC_ACT_RELU = 2, VC_ACT_TANH = 3,
+       /* GEMM epilogues only.  VC_ACT_GELU_DSTORE (forward, needs preact): like VC_ACT_GELU, but `preact` receives
+        * D = gelu'(v) * dropout_mask * dropout_scale instead of the pre-activation v -- the factor the backward multiplies by,
+        * computed where erf(v) and the mask exist anyway.  VC_ACT_MUL_AUX (act_backward, needs act_aux): v *= act_aux[m,n],
+        * i.e. the dgrad epilogue reads that D and needs neither erf nor the dropout hash. */
+       VC_ACT_GELU_DSTORE = 4, VC_ACT_MUL_AUX = 5 };
 enum { VC_MASK_NONE = 0, VC_MASK_CAUSAL = 1, VC_MASK_WINDOW = 2 };
 
 /* one dropout call site: keep-mask is a pure function of (seed, site, element index); p == 0 disables.
@@ -48,8 +53,9 @@ typedef struct vc_drop {
  * epilogue order: +bias[n], +rowadd[(m/rowadd_div)%rowadd_mod, n], store preact, act, dropout, +residual,
  *   store out_f32 (atomicAdd when splitk > 1) and/or split (out_hi, out_lo).
  * backward-activation mode (act_backward != 0; used by dgrad GEMMs): instead of "act, dropout" the epilogue applies
- *   v = dropout_mask(v) * act'(.)  with act' taken from act_aux (GELU: pre-activation fp32; TANH: forward output fp32) or
- *   act_aux_hi (RELU: forward output hi != 0), and colsum[n] += sum_m v[m,n] (atomic, caller-zeroed) if colsum != NULL. */
+ *   v = dropout_mask(v) * act'(.)  with act' taken from act_aux (GELU: pre-activation fp32; TANH: forward output fp32;
+ *   MUL_AUX: the stored factor itself) or act_aux_hi (RELU: forward output hi != 0), and colsum[n] += sum_m v[m,n]
+ *   (atomic, caller-zeroed) if colsum != NULL. */
 typedef struct vc_gemm_desc {
   const vc_bf16 *a_hi, *a_lo; int64_t lda; int a_mn_major;
   const vc_bf16 *b_hi, *b_lo; int64_t ldb; int b_mn_major;

@@ -46,6 +46,7 @@ inline double gelu_grad_d(double x) {
 inline double act_d(double x, int act) {
   switch (act) {
     case VC_ACT_GELU: return gelu_d(x);
+    case VC_ACT_GELU_DSTORE: return gelu_d(x);
     case VC_ACT_RELU: return x > 0 ? x : 0;
     case VC_ACT_TANH: return tanh(x);
     default: return x;
@@ -74,8 +75,10 @@ int gemm(const GemmDesc& d, stream_t) {
   if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
   if (!d.a_hi || !d.b_hi) return set_error("gemm: null operand");
   if (d.passes == 3 && (!d.a_lo || !d.b_lo)) return set_error("gemm: passes=3 needs lo operands");
-  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH) && !d.act_aux)) return set_error("gemm: act_aux required");
+  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH || d.act == VC_ACT_MUL_AUX) && !d.act_aux)) return set_error("gemm: act_aux required");
   if (d.act_backward && d.act == VC_ACT_RELU && !d.act_aux_hi) return set_error("gemm: act_aux_hi required");
+  if (d.act == VC_ACT_GELU_DSTORE && (d.act_backward || !d.preact)) return set_error("gemm: VC_ACT_GELU_DSTORE is a forward activation and needs preact");
+  if (d.act == VC_ACT_MUL_AUX && !d.act_backward) return set_error("gemm: VC_ACT_MUL_AUX is a backward-activation mode");
   if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact || d.colsum))
     return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");
   if (!d.out_f32 && !d.out_hi) return set_error("gemm: no output");
@@ -118,11 +121,16 @@ int gemm(const GemmDesc& d, stream_t) {
       double v = acc;
       if (d.bias) v += d.bias[n];
       if (d.rowadd) v += d.rowadd[(size_t)((m / rdiv) % rmod) * d.ld_rowadd + n];
-      if (d.preact) d.preact[(size_t)m * d.ld_preact + n] = (float)v;
+      const bool dstore = d.act == VC_ACT_GELU_DSTORE;  // preact receives gelu'(v) * mask * scale instead of v
+      if (d.preact && !dstore) d.preact[(size_t)m * d.ld_preact + n] = (float)v;
+      double dv = dstore ? gelu_grad_d((double)(float)v) : 0.0;
       if (!d.act_backward) v = act_d(v, d.act);
-      v *= keep_scale(d.drop, (uint64_t)m * d.N + n);
+      const double ks = keep_scale(d.drop, (uint64_t)m * d.N + n);
+      v *= ks;
+      if (dstore) d.preact[(size_t)m * d.ld_preact + n] = (float)(dv * ks);
       if (d.act_backward) {
         if (d.act == VC_ACT_GELU) v *= gelu_grad_d(d.act_aux[(size_t)m * d.ld_act_aux + n]);
+        else if (d.act == VC_ACT_MUL_AUX) v *= d.act_aux[(size_t)m * d.ld_act_aux + n];
         else if (d.act == VC_ACT_TANH) { const double t = d.act_aux[(size_t)m * d.ld_act_aux + n]; v *= 1.0 - t * t; }
         else if (d.act == VC_ACT_RELU) { if ((d.act_aux_hi[(size_t)m * d.ld_act_aux_hi + n] & 0x7fffu) == 0) v = 0; }
       }

@@ -2,7 +2,7 @@
 """Per-kernel table from an `ncu --metrics <list> --csv` launch list (one CSV row per launch and metric): launches, device time,
 DRAM bytes -> achieved GB/s and fraction of the measured copy bandwidth (MEASURED_PEAKS.json), tensor-pipe activity, occupancy.
 
-    python scripts/summarize_kernel_metrics.py gpurun_out/kernels.csv [peak_GBs] > profiles/rNN_per_kernel_ncu.txt
+    python scripts/summarize_kernel_metrics.py gpurun_out/kernels.csv [peak_GBs] [--split-by-read] > profiles/rNN_per_kernel_ncu.txt
 
 Times under ncu are cold-cache and serialised; bytes and pipe activity per launch are what the table is for."""
 import collections
@@ -18,14 +18,13 @@ BYTES = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 def short(name):
     name = re.sub(r"^void ", "", name)
-    name = name.replace("vck::<unnamed>::", "").replace("(anonymous namespace)::", "")
-    m = re.match(r"(at::native::)?([A-Za-z_0-9:]+)(<.*)?", name)
+    name = name.replace("vck::<unnamed>::", "").replace("(anonymous namespace)::", "").replace("unnamed>::", "")
     if name.startswith("at::"):
         return ("torch " + re.sub(r"\(.*", "", name))[:48]
     return re.sub(r"\(.*", "", name)[:60]
 
 
-def main(path, peak_gbs):
+def main(path, peak_gbs, split_by_read=False):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     launches = collections.OrderedDict()
@@ -44,6 +43,8 @@ def main(path, peak_gbs):
         d[m] = v
     agg = collections.OrderedDict()
     for d in launches.values():
+        if split_by_read:  # kernels that serve several problem sizes (the decode GEMV): one line per amount of DRAM read
+            d["name"] += f" [{d.get('dram__bytes_read.sum', 0.0) / 1e6:.0f} MB read]"
         a = agg.setdefault(d["name"], collections.defaultdict(float))
         a["n"] += 1
         for k, v in d.items():
@@ -74,9 +75,12 @@ def main(path, peak_gbs):
 
 if __name__ == "__main__":
     peak = None
+    split = "--split-by-read" in sys.argv
+    if split:
+        sys.argv.remove("--split-by-read")
     if len(sys.argv) > 2:
         peak = float(sys.argv[2])
     else:
         p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
         peak = json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6555.0
-    main(sys.argv[1], peak)
+    main(sys.argv[1], peak, split)

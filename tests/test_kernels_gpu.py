@@ -121,6 +121,46 @@ def test_gemm_backward_activation_epilogue(act):
     assert _relerr(cs, ref.sum(0)) < 3e-5
 
 
+@pytest.mark.parametrize("M,N,Kd,p_drop", [(520, 264, 192, 0.1), (520, 264, 192, 0.0), (2560, 1024, 512, 0.1)])
+def test_gemm_gelu_derivative_store_and_mul_aux(M, N, Kd, p_drop):
+    """VC_ACT_GELU_DSTORE / VC_ACT_MUL_AUX: the forward epilogue leaves D = gelu'(z) * mask * scale in `preact`, the dgrad epilogue
+    multiplies by it -- same outputs as VC_ACT_GELU forward, same gradient as the act_backward GELU mode that recomputes erf and
+    the mask (single-CTA and 2-SM kernels)."""
+    A, B = _rand(M, Kd, seed=6, scale=0.5), _rand(N, Kd, seed=7, scale=0.2)
+    bias = _rand(N, seed=8)
+    drop = L.make_drop(p_drop, 17, 1234) if p_drop > 0 else None
+    mask = K.dropout_mask(drop, M * N).reshape(M, N).double() if drop is not None else torch.ones(M, N, device="cuda").double()
+    z = A.double() @ B.double().t() + bias.double()
+    zt = z.clone().requires_grad_(True)
+    torch.nn.functional.gelu(zt).sum().backward()
+    D = torch.full((M, N), float("nan"), device="cuda")
+    outs, outs_ref = K.bf16_pair((M, N)), K.bf16_pair((M, N))
+    pre = torch.empty(M, N, device="cuda")
+    L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, preact=D, act=L.ACT_GELU_DSTORE, drop=drop, out_split=outs)
+    L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, preact=pre, act=L.ACT_GELU, drop=drop, out_split=outs_ref)
+    fo, fr = K.join(outs), K.join(outs_ref)
+    assert (fo - fr).abs().max() <= 1e-6 * fr.abs().max()  # the forward output does not change
+    assert _relerr(D, zt.grad * mask) < 3e-5
+    assert (D[mask == 0] == 0).all()
+    # backward: dX = (G W) * D, column sums for the bias gradient
+    G, W = _rand(M, Kd, seed=70, scale=0.5), _rand(Kd, N, seed=71, scale=0.2)
+    got, ref = K.bf16_pair((M, N)), K.bf16_pair((M, N))
+    cs, cs_ref = torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")
+    L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=L.ACT_MUL_AUX, act_backward=True, act_aux=D, out_split=got, colsum=cs)
+    L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=L.ACT_GELU, act_backward=True, act_aux=pre, drop=drop, out_split=ref,
+           colsum=cs_ref)
+    exact = (G.double() @ W.double()) * mask * zt.grad
+    assert _relerr(K.join(got), exact) < 3e-5 and _relerr(K.join(ref), exact) < 3e-5
+    assert _relerr(cs, exact.sum(0)) < 3e-5
+    # misuse is refused
+    with pytest.raises(RuntimeError):
+        L.gemm(L.split(A), L.split(B), M, N, Kd, act=L.ACT_GELU_DSTORE, out_split=outs)                      # no preact
+    with pytest.raises(RuntimeError):
+        L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=L.ACT_MUL_AUX, act_backward=True, out_split=got)  # no act_aux
+    with pytest.raises(RuntimeError):
+        L.gemm(L.split(A), L.split(B), M, N, Kd, act=L.ACT_MUL_AUX, out_split=outs)                          # forward
+
+
 def test_gemm_rowadd_div():
     M, N, K, T = 64, 128, 64, 8
     A, B = _rand(M, K, seed=11), _rand(N, K, seed=12)

@@ -40,7 +40,7 @@ __device__ __forceinline__ void split4(const float v[4], uint2& hi, uint2& lo) {
 // ---------------------------------------------------------------------------------------------
 // activations (forward value and derivative), matching torch: exact-erf GELU, ReLU, tanh
 // ---------------------------------------------------------------------------------------------
-enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3 };
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_TANH = 3, ACT_GELU_DSTORE = 4, ACT_MUL_AUX = 5 };
 
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -48,9 +48,18 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// gelu(x) and gelu'(x) together (same expressions as gelu_f / gelu_grad_f: one erf serves both)
+__device__ __forceinline__ void gelu_with_grad(float x, float& g, float& d) {
+  const float e = erff(x * 0.70710678118654752440f);
+  g = 0.5f * x * (1.0f + e);
+  const float cdf = 0.5f * (1.0f + e);
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  d = cdf + x * pdf;
+}
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
     case ACT_GELU: return gelu_f(x);
+    case ACT_GELU_DSTORE: return gelu_f(x);
     case ACT_RELU: return fmaxf(x, 0.0f);
     case ACT_TANH: return tanhf(x);
     default: return x;

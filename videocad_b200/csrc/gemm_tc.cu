@@ -124,22 +124,54 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
       v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
     }
   }
-  if constexpr ((F & EF_PREACT) != 0) {
-    if (p.preact != nullptr)
-      *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
-  }
-  if constexpr ((F & EF_ACT) != 0) {
-    if (p.act != ACT_NONE && !p.act_backward) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+  // ACT_GELU_DSTORE: `preact` receives gelu'(v) * dropout mask * dropout scale (what the backward multiplies by) instead of v.
+  // Two elements at a time, each pair stored as soon as it is finished: the kernel is register-capped (96), four more live
+  // values per quad spilled.
+  constexpr bool kDStore = (F & EF_PREACT) != 0 && (F & EF_ACT) != 0;
+  bool dstore = false;
+  if constexpr (kDStore) dstore = p.preact != nullptr && p.act == ACT_GELU_DSTORE && !p.act_backward;
+  if (kDStore && dstore) {
+    uint32_t w[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    float scale = 1.0f;
+    uint32_t thresh = 0u;
+    if constexpr ((F & EF_DROP) != 0) {
+      if (p.drop_on) {
+        const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
+        const Rand4 r4 = dropout_words(dkey, idx >> 2);
+        w[0] = r4.v[0]; w[1] = r4.v[1]; w[2] = r4.v[2]; w[3] = r4.v[3];
+        scale = p.drop_scale;
+        thresh = p.drop_thresh;
+      }
     }
-  }
-  if constexpr ((F & EF_DROP) != 0) {
-    if (p.drop_on) {
-      const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
-      const Rand4 w = dropout_words(dkey, idx >> 2);
+    float* dptr = p.preact + row * p.ld_preact + col;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+    for (int h = 0; h < 2; ++h) {
+      float d0, d1;
+      gelu_with_grad(v[2 * h], v[2 * h], d0);
+      gelu_with_grad(v[2 * h + 1], v[2 * h + 1], d1);
+      const bool k0 = w[2 * h] >= thresh, k1 = w[2 * h + 1] >= thresh;
+      v[2 * h] = k0 ? v[2 * h] * scale : 0.0f;
+      v[2 * h + 1] = k1 ? v[2 * h + 1] * scale : 0.0f;
+      *reinterpret_cast<float2*>(dptr + 2 * h) = make_float2(k0 ? d0 * scale : 0.0f, k1 ? d1 * scale : 0.0f);
+    }
+  } else {
+    if constexpr ((F & EF_PREACT) != 0) {
+      if (p.preact != nullptr)
+        *reinterpret_cast<float4*>(p.preact + row * p.ld_preact + col) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if constexpr ((F & EF_ACT) != 0) {
+      if (p.act != ACT_NONE && !p.act_backward) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = apply_act(v[i], p.act);
+      }
+    }
+    if constexpr ((F & EF_DROP) != 0) {
+      if (p.drop_on) {
+        const unsigned long long idx = (unsigned long long)row * (unsigned long long)p.N + (unsigned long long)col;
+        const Rand4 w = dropout_words(dkey, idx >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (w.v[i] >= p.drop_thresh) ? v[i] * p.drop_scale : 0.0f;
+      }
     }
   }
   if constexpr ((F & EF_ACTBWD) != 0) {
@@ -150,6 +182,9 @@ __device__ __forceinline__ void epilogue_quad(const GemmParams& p, float (&v)[4]
       } else if (p.act == ACT_TANH) {
         const float4 a = use_pre_aux ? pre_aux : *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
         v[0] *= 1.f - a.x * a.x; v[1] *= 1.f - a.y * a.y; v[2] *= 1.f - a.z * a.z; v[3] *= 1.f - a.w * a.w;
+      } else if (p.act == ACT_MUL_AUX) {  // the forward stored the whole factor (ACT_GELU_DSTORE)
+        const float4 a = use_pre_aux ? pre_aux : *reinterpret_cast<const float4*>(p.act_aux + row * p.ld_act_aux + col);
+        v[0] *= a.x; v[1] *= a.y; v[2] *= a.z; v[3] *= a.w;
       } else if (p.act == ACT_RELU) {
         const uint2 a = use_pre_relu ? pre_relu : *reinterpret_cast<const uint2*>(p.act_aux_hi + row * p.ld_act_aux_hi + col);
         if ((a.x & 0x7fffu) == 0u) v[0] = 0.f;
@@ -401,7 +436,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float4 bias;
     };
     const bool has_res = kPreRes && p.residual != nullptr;
-    const bool has_aux = kPreAux && p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+    const bool has_aux = kPreAux && p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH || p.act == ACT_MUL_AUX);
     const bool has_relu = kPreAux && p.act_backward && p.act == ACT_RELU;
     const bool has_bias = kPreBias && p.bias != nullptr;
     auto preload = [&](Pre& P, int m0, int col0) {
@@ -784,7 +819,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_con
         {
           const int pcol = n0 + c * P_CW + 4 * (lane & 3);
           if constexpr (kPreRes) has_res = p.residual != nullptr;
-          if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH);
+          if constexpr (kPreAux) has_aux = p.act_backward && (p.act == ACT_GELU || p.act == ACT_TANH || p.act == ACT_MUL_AUX);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const long long prow = (long long)m0 + g * 32 + it * 8 + (lane >> 2);
@@ -1227,7 +1262,9 @@ int gemm(const GemmDesc& d, stream_t stream) {
   if (d.passes != 1 && d.passes != 3) return set_error("gemm: passes must be 1 or 3");
   if (d.a_hi == nullptr || d.b_hi == nullptr) return set_error("gemm: null operand");
   if (d.passes == 3 && (d.a_lo == nullptr || d.b_lo == nullptr)) return set_error("gemm: passes=3 needs lo operands");
-  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH) && !d.act_aux)) return set_error("gemm: act_aux required");
+  if (d.act_backward && ((d.act == VC_ACT_GELU || d.act == VC_ACT_TANH || d.act == VC_ACT_MUL_AUX) && !d.act_aux)) return set_error("gemm: act_aux required");
+  if (d.act == VC_ACT_GELU_DSTORE && (d.act_backward || !d.preact)) return set_error("gemm: VC_ACT_GELU_DSTORE is a forward activation and needs preact");
+  if (d.act == VC_ACT_MUL_AUX && !d.act_backward) return set_error("gemm: VC_ACT_MUL_AUX is a backward-activation mode");
   if (d.act_backward && d.act == VC_ACT_RELU && !d.act_aux_hi) return set_error("gemm: act_aux_hi required");
   if (d.splitk > 1 && (d.act != VC_ACT_NONE || d.drop.p > 0.f || d.residual || d.out_hi || d.preact || d.colsum))
     return set_error("gemm: split-K supports only the bias epilogue with an fp32 (atomic) output");

@@ -10,11 +10,20 @@
 //   GEMM A-operands           split-bf16 [M,K]        (written directly by the producing LN / epilogue / attention)
 //   qkv                       split-bf16 [M,3072]     (written by the to_qkv GEMM epilogue, read by the attention kernels)
 // Dropout sites (site_base + i): 0 embedding; layer l: 1+4l attention probs, 2+4l to_out, 3+4l MLP hidden, 4+4l MLP out.
+#include <stdlib.h>
 #include "model_common.h"
 
 namespace vck {
 
 namespace {
+
+// MLP hidden activation: the fc1 epilogue stores gelu'(pre) * dropout mask * scale for the backward (VC_ACT_GELU_DSTORE /
+// VC_ACT_MUL_AUX) instead of the pre-activation; VC_GELU_DSTORE=0 keeps the pre-activation and recomputes erf + mask in the fc2
+// dgrad epilogue (the two give the same gradients to rounding; A/B switch for measurements, read once per process)
+bool gelu_dstore() {
+  static const bool on = [] { const char* e = getenv("VC_GELU_DSTORE"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 
 constexpr int D = VC_VIT_DIM;        // 512
 constexpr int DI = VC_VIT_HEADS * VC_VIT_DHEAD;  // 1024
@@ -168,7 +177,9 @@ int vit_forward(const vc_vit_call* c, stream_t st) {
     {
       GemmDesc d;
       gemm_linear_fwd(d, L.h2, wsplit(LW.fc1, D), M, VC_VIT_MLP, D, P);
-      d.bias = LW.fc1.b; d.preact = L.pre1; d.ld_preact = VC_VIT_MLP; d.act = VC_ACT_GELU;
+      // L.pre1 receives gelu'(pre) * mask * scale of this dropout site (VC_ACT_GELU_DSTORE) -- the factor the fc2 dgrad epilogue
+      // multiplies by -- instead of the pre-activation: erf and the mask exist here anyway, the backward then needs neither
+      d.bias = LW.fc1.b; d.preact = L.pre1; d.ld_preact = VC_VIT_MLP; d.act = gelu_dstore() ? VC_ACT_GELU_DSTORE : VC_ACT_GELU;
       d.drop = site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev);
       d.out_hi = L.ud.hi; d.out_lo = L.ud.lo; d.ldo_split = VC_VIT_MLP;
       VC_TRY(gemm(d, st));
@@ -239,8 +250,13 @@ int vit_backward_layers(const vc_vit_call* c, const float* dcls, void* scratch, 
       // d pre1 = (g W2) * mask(MLP hidden site) * gelu'(pre1): activation backward + fc1 bias gradient fused in the epilogue
       GemmDesc d;
       gemm_linear_dgrad(d, s.g, wsplit(LW.fc2, VC_VIT_MLP), M, D, VC_VIT_MLP, P);
-      d.act_backward = 1; d.act = VC_ACT_GELU; d.act_aux = L.pre1; d.ld_act_aux = VC_VIT_MLP;
-      d.drop = site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev);
+      d.act_backward = 1; d.act_aux = L.pre1; d.ld_act_aux = VC_VIT_MLP;
+      if (gelu_dstore()) {
+        d.act = VC_ACT_MUL_AUX;  // L.pre1 already holds mask * scale * gelu'(pre1)
+      } else {
+        d.act = VC_ACT_GELU;
+        d.drop = site_drop(p, c->training, c->seed, s0 + 2, c->seed_dev);
+      }
       d.out_hi = s.dpre.hi; d.out_lo = s.dpre.lo; d.ldo_split = VC_VIT_MLP; d.colsum = LW.fc1.db;
       VC_TRY(gemm(d, st));
     }

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VIDEOCAD_B200_LIB", os.path.join(_HERE, "libvideocad_b200.so"))
 
-ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_TANH, ACT_GELU_DSTORE, ACT_MUL_AUX = 0, 1, 2, 3, 4, 5
 MASK_NONE, MASK_CAUSAL, MASK_WINDOW = 0, 1, 2
 
 vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
