@@ -139,8 +139,11 @@ def test_gemm_gelu_derivative_store_and_mul_aux(M, N, Kd, p_drop):
     L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, preact=D, act=L.ACT_GELU_DSTORE, drop=drop, out_split=outs)
     L.gemm(L.split(A), L.split(B), M, N, Kd, bias=bias, preact=pre, act=L.ACT_GELU, drop=drop, out_split=outs_ref)
     fo, fr = K.join(outs), K.join(outs_ref)
-    assert (fo - fr).abs().max() <= 1e-6 * fr.abs().max()  # the forward output does not change
-    assert _relerr(D, zt.grad * mask) < 3e-5
+    assert (fo - fr).abs().max() <= 2.0 ** -15 * fr.abs().max()  # the forward output does not change (one split-bf16 rounding step)
+    assert _relerr(D, zt.grad * mask) < 1e-4  # gelu' of the fp32-grade GEMM result against gelu' of the exact product
+    pt = pre.double().requires_grad_(True)     # against gelu' of the kernel's own pre-activation: fp32 erf / exp rounding only
+    torch.nn.functional.gelu(pt).sum().backward()
+    assert _relerr(D, pt.grad * mask) < 3e-6
     assert (D[mask == 0] == 0).all()
     # backward: dX = (G W) * D, column sums for the bias gradient
     G, W = _rand(M, Kd, seed=70, scale=0.5), _rand(Kd, N, seed=71, scale=0.2)
@@ -150,8 +153,9 @@ def test_gemm_gelu_derivative_store_and_mul_aux(M, N, Kd, p_drop):
     L.gemm(L.split(G), L.split(W), M, N, Kd, b_mn=True, act=L.ACT_GELU, act_backward=True, act_aux=pre, drop=drop, out_split=ref,
            colsum=cs_ref)
     exact = (G.double() @ W.double()) * mask * zt.grad
-    assert _relerr(K.join(got), exact) < 3e-5 and _relerr(K.join(ref), exact) < 3e-5
-    assert _relerr(cs, exact.sum(0)) < 3e-5
+    assert _relerr(K.join(got), exact) < 1e-4 and _relerr(K.join(ref), exact) < 3e-5
+    assert _relerr(K.join(got), K.join(ref)) < 2.0 ** -15  # the two backward modes agree to one split-bf16 rounding step
+    assert _relerr(cs, exact.sum(0)) < 1e-4 and _relerr(cs, cs_ref) < 3e-6
     # misuse is refused
     with pytest.raises(RuntimeError):
         L.gemm(L.split(A), L.split(B), M, N, Kd, act=L.ACT_GELU_DSTORE, out_split=outs)                      # no preact

@@ -14,6 +14,7 @@
 // Dropout sites (site_base + 7*l + i): 0 self-attn probs, 1 dropout1, 2 cross-attn probs, 3 dropout2, 4 FFN hidden, 5 dropout3.
 #include <math.h>
 #include <vector>
+#include <stdlib.h>
 #include "model_common.h"
 
 namespace vck {
@@ -620,9 +621,17 @@ int seq_backward(const vc_seq_call* c, const float* dcmds, const float* dparams,
   VC_TRY(stream_fork(st, 0, &side));
   VC_TRY(linear_wgrad(s.dparS, last.x3S, R, d.NP, H, W.head_params.dw, P, side));
   {
+    // d x_last = dparams [R, 6000] W [6000, H]: K = 6000 on R / 128 x H / 64 tiles is a chain of 94 k-blocks on 16 CTAs (C1: 37 us at
+    // the head of the backward's critical path, profiles/r02ab_ncu_full_in_step_summary.txt); split-K spreads it over the chip
+    // (atomic accumulation into the zeroed s.A, like the weight-gradient GEMMs).  VC_HEAD_DGRAD_SPLITK=1 restores the single pass.
+    static const int head_splitk = [] { const char* e = getenv("VC_HEAD_DGRAD_SPLITK"); const int v = e ? atoi(e) : 8; return v < 1 ? 1 : v; }();
     GemmDesc g;
     gemm_linear_dgrad(g, s.dparS, wsplit(W.head_params, H), R, d.NP, H, P);
     g.out_f32 = s.A; g.ldo = H;
+    if (head_splitk > 1 && d.NP >= 64 * 4 * head_splitk) {
+      VC_TRY(zero_f32(s.A, (int64_t)R * H, st));
+      g.splitk = head_splitk;
+    }
     VC_TRY(gemm(g, st));
   }
   VC_TRY(head_small_bwd(dcmds, last.x3, R, H, W.head_cmd_w, d.NC, s.A, 1, W.d_head_cmd_w, W.d_head_cmd_b, st));
