@@ -113,12 +113,16 @@ def _end_to_end(tmp_path, device, lib=None, H=224, W=224):
     store_path = str(tmp_path / "ds.vcseq")
     convert_dataset_dir(root, store_path)
     retr = MmapSequenceRetriever(ds.data_files, ds.image_files, store_path)
-    samples = []
-    for i in range(len(retr)):
-        frames, actions, sid = retr.get_sequence(i)
-        cad = ingest.cad_to_gray_u8(cv2.imread(os.path.join(root, sid[:4], f"{sid}_frame.png")), (224, 224))
-        samples.append({"frames": frames, "actions": actions, "cad_image": cad})
+    raw = ingest.RawSequenceDataset(retr, ds.image_loader, (224, 224))  # the reference's own ImageLoader finds the CAD images
+    assert len(raw) == len(ds)
+    with pytest.raises(IndexError):
+        raw[len(raw)]
+    samples = [raw[i] for i in range(len(raw))]
+    assert samples[1]["frames"].dtype == np.uint8 and not samples[1]["frames"].flags.owndata  # still a view into the mapping
     hb = ingest.collate_u8(samples, pin=False)
+    loader = torch.utils.data.DataLoader(raw, batch_size=len(raw), collate_fn=lambda b: ingest.collate_u8(b, pin=False))
+    for k, v in next(iter(loader)).items():  # the same batch through a torch DataLoader
+        assert torch.equal(v, hb[k]), k
     got = ingest.transform_batch({k: v.to(device) for k, v in hb.items()}, ingest.FrameTransform((224, 224), _lib=lib), _lib=lib)
     for k in ("frames", "actions", "cad_image", "timesteps"):
         assert got[k].shape == want[k].shape, k

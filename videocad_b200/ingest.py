@@ -10,6 +10,7 @@ trainer copies them to the GPU synchronously (`prepare_batch`, trainer.py:307-31
                        no CPU transform -- instead of 4 B per grey pixel after it;
   * `cad_to_gray_u8`   keeps the reference's own cv2 code for the ONE target image per sample (BGR -> grey -> resize, uint8;
                        data_loader.py:468-474) and leaves `/ 255` + Normalize to the device (`vc_frames_u8_normalize`);
+  * `RawSequenceDataset` is `DatasetBase.__getitem__` (data_loader.py:434-508) minus the CPU transforms: the stored bytes of a sample;
   * `collate_u8`       is `DatasetBase.collate_with_padding` (data_loader.py:319-366) for uint8 samples: pads with the frame
                        count instead of -1 values (the -1 fill is applied on the device after normalisation);
   * `DevicePrefetcher` double-buffers pinned host batches -> device on a copy stream while the previous step computes, and
@@ -127,6 +128,31 @@ def normalize_u8(img_u8: torch.Tensor, mean: float = 0.5, std: float = 0.5, _lib
     stream = torch.cuda.current_stream(src.device).cuda_stream if src.is_cuda else None
     L.check(lib.vc_frames_u8_normalize(src.data_ptr(), src.numel(), float(mean), float(std), out.data_ptr(), stream), lib)
     return out
+
+
+class RawSequenceDataset(torch.utils.data.Dataset):
+    """`DatasetBase.__getitem__` (data_loader.py:434-508) without its CPU transforms: a sample is the bytes the dataset stores --
+    {"frames": uint8 [n, H, W, 3] (a zero-copy view when the retriever is a `MmapSequenceRetriever`), "actions": [n, 7],
+    "cad_image": uint8 [S, S] grey (the reference's own cv2 steps, `cad_to_gray_u8`)} -- for `collate_u8` + `DevicePrefetcher`.
+
+    `sequence_retriever`: anything with the reference's retriever interface (`get_sequence(idx) -> (frames, actions, base_file_id)`,
+    `__len__`; sequence_retriver.py:25-36); `image_loader`: the reference's `ImageLoader` (`get_image(base_file_id)` -> BGR array,
+    image_loader.py:30-43).  Multi-view samples are not covered (the reference loads them with a third code path, :416-429)."""
+
+    def __init__(self, sequence_retriever, image_loader, image_size: Tuple[int, int] = (224, 224)):
+        self.sequence_retriever, self.image_loader, self.image_size = sequence_retriever, image_loader, tuple(image_size)
+
+    def __len__(self) -> int:
+        return len(self.sequence_retriever)
+
+    def __getitem__(self, idx: int) -> dict:
+        if idx < 0 or idx >= len(self):
+            raise IndexError("Index out of range")  # as DatasetBase.__getitem__ (data_loader.py:435-436)
+        frames, actions, base_file_id = self.sequence_retriever.get_sequence(idx)
+        cad = self.image_loader.get_image(base_file_id)
+        if cad is None:
+            raise ValueError(f"Missing CAD image for sample {base_file_id}")
+        return {"frames": frames, "actions": actions, "cad_image": cad_to_gray_u8(cad, self.image_size)}
 
 
 def collate_u8(samples: Sequence[dict], pin: bool = True) -> dict:
