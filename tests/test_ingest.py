@@ -151,3 +151,28 @@ def test_data_path_equals_reference_dataset_gpu_and_prefetcher(tmp_path):
             assert torch.equal(batch[k].cpu(), want[k]), k
         seen += 1
     assert seen == 3
+
+
+def test_frame_transform_random_sizes_property():
+    """Any stored frame size: the device transform's arithmetic (restated on the CPU in the emulation library behind the same host
+    code: Pillow's coefficient tables, fixed-point passes, rgb2l, ToTensor, Normalize) equals torchvision on PIL images bit for bit --
+    up- and down-scaling, odd sizes, single rows / columns."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from PIL import Image
+
+    from oracle import build_emu
+
+    lib = L.load(build_emu.build(), require_cuda_build=False)
+    ref_t = _reference_transform()
+    ft = ingest.FrameTransform((224, 224), _lib=lib)
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(h=st.integers(1, 500), w=st.integers(1, 500), seed=st.integers(0, 2 ** 16))
+    def check(h, w, seed):
+        fr = np.random.default_rng(seed).integers(0, 256, size=(1, h, w, 3), dtype=np.uint8)
+        want = ref_t(Image.fromarray(fr[0])).unsqueeze(0)
+        got = ft(torch.from_numpy(fr))
+        assert torch.equal(got, want), f"{(h, w)}: {(got != want).sum().item()} pixels differ"
+
+    check()
