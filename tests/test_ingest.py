@@ -94,8 +94,7 @@ def _write_dataset(root, lengths, H, W, seed=0):
 
 def _end_to_end(tmp_path, device, lib=None, H=224, W=224):
     """reference: DatasetBase.__getitem__ + collate_with_padding with main.py's transforms;
-    here: SequenceStore -> collate_u8 -> transform_batch (device)."""
-    import cv2
+    here: SequenceStore -> RawSequenceDataset -> collate_u8 -> transform_batch (device)."""
     from torchvision import transforms
 
     from videocad_b200.sequence_store import MmapSequenceRetriever, convert_dataset_dir

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn

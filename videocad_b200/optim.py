@@ -10,7 +10,6 @@ torch.optim.Optimizer's (state: step, exp_avg, exp_avg_sq), so checkpoints round
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 
