@@ -326,3 +326,16 @@ def test_image_input_gradient_is_refused_loudly(emu):
     inp["cad_image"] = inp["cad_image"].clone().requires_grad_(True)  # trainer.generate_saliency_batch (trainer.py:621-645)
     with pytest.raises(RuntimeError, match="input images"):
         m(inp)
+
+
+def test_ab_switches_keep_the_previous_paths_working():
+    """VC_GELU_DSTORE=0 (fc2 dgrad recomputes erf + mask from the stored pre-activation) and VC_HEAD_DGRAD_SPLITK=1 (heads dgrad in
+    one pass) are read once per process: the orchestration-vs-oracle check is repeated in a child process with both switched off."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, VC_GELU_DSTORE="0", VC_HEAD_DGRAD_SPLITK="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "test_orchestration_forward_backward_vs_fp64_oracle and mode0"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=600)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
